@@ -1,0 +1,240 @@
+"""ctypes binding of libbmf_b200.so (include/bmf_b200.h) -- the harness-side view of the C ABI used by
+tests/, bench.py and __graft_entry__.py.  Host buffers are numpy arrays; nothing here computes.
+
+The library is the product; this file fails loudly when it is missing or when no CUDA device is
+usable -- there is no CPU fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libbmf_b200.so")
+
+SPHERE, TORUS_Z, CUBOID, PLANE_Y, CSG = 0, 1, 2, 3, 4
+TERRAIN2D, TERRAIN2D_PERT, TERRAIN3D, TERRAIN3D_PERT = 10, 11, 12, 13
+HOST_DENSITY = 100
+CSG_UNION, CSG_INTERSECT, CSG_SUBTRACT = 0, 1, 2
+STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
+
+# symbols include/bmf_b200.h declares (tests check that the library exports every one of them)
+EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
+           "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
+           "bmf_batch_download", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_batch_device_ptrs",
+           "bmf_mesh_process", "bmf_qef_solve")
+
+
+class SamplerDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("world_size", C.c_float), ("g_scale", C.c_float), ("height", C.c_float),
+                ("octaves", C.c_int32), ("amp", C.c_float), ("frequency", C.c_float), ("gain", C.c_float),
+                ("seed", C.c_int32), ("csg_op", C.c_int32), ("csg_kind_a", C.c_int32), ("csg_kind_b", C.c_int32),
+                ("csg_world_size_a", C.c_float), ("csg_world_size_b", C.c_float),
+                ("csg_offset_a", C.c_float * 3), ("csg_offset_b", C.c_float * 3)]
+
+
+class ChunkDesc(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("size", C.c_float), ("level", C.c_int32), ("overlap", C.c_float), ("morton", C.c_uint64)]
+
+
+class Params(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("iters", C.c_int32), ("process_boundary", C.c_int32), ("smooth_normals", C.c_int32),
+                ("qef", C.c_int32), ("keep_density", C.c_int32), ("keep_masks", C.c_int32), ("density_on_device", C.c_int32)]
+
+
+class ChunkInfo(C.Structure):
+    _fields_ = [("contains_mesh", C.c_int32), ("n_cells", C.c_int32), ("n_verts", C.c_int32), ("n_inds", C.c_int32),
+                ("vert_offset", C.c_int64), ("ind_offset", C.c_int64), ("overlap_pos", C.c_float * 3), ("scale", C.c_float)]
+
+
+CHUNK_DESC_DTYPE = np.dtype([("pos", "<f4", 3), ("size", "<f4"), ("level", "<i4"), ("overlap", "<f4"), ("morton", "<u8")])
+CHUNK_INFO_DTYPE = np.dtype([("contains_mesh", "<i4"), ("n_cells", "<i4"), ("n_verts", "<i4"), ("n_inds", "<i4"),
+                             ("vert_offset", "<i8"), ("ind_offset", "<i8"), ("overlap_pos", "<f4", 3), ("scale", "<f4")])
+assert CHUNK_DESC_DTYPE.itemsize == C.sizeof(ChunkDesc) and CHUNK_INFO_DTYPE.itemsize == C.sizeof(ChunkInfo)
+
+DUALVERTEX_DTYPE = np.dtype({
+    "names": ["boundary", "mask", "index", "valence", "init_valence", "adj_next", "adj_offset", "edge_mask", "s", "xyz", "p", "n", "avg", "color"],
+    "formats": ["u1", "u1", "<u4", "u1", "u1", "u1", "<u4", "<u2", "<f4", ("<i4", 3), ("<f4", 3), ("<f4", 3), ("<f4", 3), ("<f4", 3)],
+    "offsets": [0, 1, 4, 8, 9, 10, 12, 16, 20, 24, 36, 48, 60, 72],
+    "itemsize": 84,
+})
+
+
+class BmfError(RuntimeError):
+    pass
+
+
+def load_library(path=SO):
+    if not os.path.exists(path):
+        raise BmfError("libbmf_b200.so is missing (%s): build it with `python -m binarymeshfitting_b200.build`; "
+                       "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.bmf_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.bmf_ctx_destroy.argtypes = [vp]
+    lib.bmf_ctx_destroy.restype = None
+    lib.bmf_last_error.argtypes = [vp]
+    lib.bmf_last_error.restype = C.c_char_p
+    lib.bmf_version.restype = C.c_char_p
+    lib.bmf_sampler_defaults.argtypes = [C.POINTER(SamplerDesc), C.c_int]
+    lib.bmf_sampler_defaults.restype = None
+    lib.bmf_sampler_set.argtypes = [vp, C.POINTER(SamplerDesc)]
+    lib.bmf_batch_submit.argtypes = [vp, vp, C.c_int, C.POINTER(Params), vp]
+    lib.bmf_batch_wait.argtypes = [vp]
+    lib.bmf_batch_totals.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.bmf_batch_chunk_info.argtypes = [vp, C.c_int, C.POINTER(ChunkInfo)]
+    lib.bmf_batch_chunk_infos.argtypes = [vp, vp]
+    lib.bmf_batch_download.argtypes = [vp] * 7
+    lib.bmf_batch_copy_chunk.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.bmf_batch_stage_ms.argtypes = [vp, vp]
+    lib.bmf_ctx_launch_count.argtypes = [vp]
+    lib.bmf_ctx_launch_count.restype = C.c_int64
+    lib.bmf_batch_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_chunk_descs(pos_size, overlaps=0.0, levels=0):
+    ps = np.asarray(pos_size, np.float32).reshape(-1, 4)
+    d = np.zeros(len(ps), CHUNK_DESC_DTYPE)
+    d["pos"] = ps[:, :3]
+    d["size"] = ps[:, 3]
+    d["overlap"] = overlaps
+    d["level"] = levels
+    d["morton"] = np.arange(1, len(ps) + 1)
+    return d
+
+
+class Context:
+    """One bmf_ctx (one GPU).  Mirrors the C ABI one to one."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        h = C.c_void_p()
+        rc = self.lib.bmf_ctx_create(device, C.byref(h))
+        if rc != 0 or not h:
+            raise BmfError("bmf_ctx_create(device=%d) failed with %d: no usable CUDA device (no CPU fallback)" % (device, rc))
+        self.h = h
+        self.n = 0
+        self.dim = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bmf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BmfError("bmf error %d: %s" % (rc, self.lib.bmf_last_error(self.h).decode()))
+
+    def sampler_desc(self, kind, **kw):
+        s = SamplerDesc()
+        self.lib.bmf_sampler_defaults(C.byref(s), kind)
+        for k, v in kw.items():
+            if k in ("csg_offset_a", "csg_offset_b"):
+                setattr(s, k, (C.c_float * 3)(*v))
+            else:
+                setattr(s, k, v)
+        return s
+
+    def set_sampler(self, kind_or_desc, **kw):
+        s = kind_or_desc if isinstance(kind_or_desc, SamplerDesc) else self.sampler_desc(kind_or_desc, **kw)
+        self._check(self.lib.bmf_sampler_set(self.h, C.byref(s)))
+        return s
+
+    def submit(self, descs, dim, iters=0, process_boundary=False, smooth_normals=False, qef=False, keep_density=False, keep_masks=False,
+               density=None, density_device_ptr=None):
+        descs = np.ascontiguousarray(descs, CHUNK_DESC_DTYPE)
+        p = Params(dim, iters, int(process_boundary), int(smooth_normals), int(qef), int(keep_density), int(keep_masks), 1 if density_device_ptr else 0)
+        dptr = None
+        if density_device_ptr:
+            dptr = C.c_void_p(density_device_ptr)
+        elif density is not None:
+            self._density_keepalive = np.ascontiguousarray(density, np.float32).reshape(-1)
+            dptr = _p(self._density_keepalive)
+        self._check(self.lib.bmf_batch_submit(self.h, _p(descs), len(descs), C.byref(p), dptr))
+        self.n, self.dim = len(descs), dim
+
+    def wait(self):
+        self._check(self.lib.bmf_batch_wait(self.h))
+
+    def totals(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.bmf_batch_totals(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def chunk_infos(self):
+        out = np.zeros(self.n, CHUNK_INFO_DTYPE)
+        self._check(self.lib.bmf_batch_chunk_infos(self.h, _p(out)))
+        return out
+
+    def download(self, want=("pos", "normal", "color", "boundary", "valence", "inds"), out=None):
+        _, V, I = self.totals()
+        out = out or {}
+        def buf(name, shape, dt):
+            if name not in want:
+                return None
+            if name not in out:
+                out[name] = np.empty(shape, dt)
+            return out[name]
+        pos = buf("pos", (V, 3), np.float32)
+        nrm = buf("normal", (V, 3), np.float32)
+        col = buf("color", (V, 3), np.float32)
+        bnd = buf("boundary", (V,), np.uint8)
+        val = buf("valence", (V,), np.uint8)
+        ind = buf("inds", (I,), np.uint32)
+        self._check(self.lib.bmf_batch_download(self.h, _p(pos), _p(nrm), _p(col), _p(bnd), _p(val), _p(ind)))
+        return out
+
+    def copy_chunk(self, i, want=("verts", "inds", "bits")):
+        info = ChunkInfo()
+        self._check(self.lib.bmf_batch_chunk_info(self.h, i, C.byref(info)))
+        n = self.dim ** 3
+        verts = np.zeros(info.n_verts, DUALVERTEX_DTYPE) if "verts" in want else None
+        inds = np.zeros(info.n_inds, np.uint32) if "inds" in want else None
+        bits = np.zeros(n // 32, np.uint32) if "bits" in want else None
+        masks = np.zeros(n, np.uint8) if "masks" in want else None
+        dens = np.zeros(n, np.float32) if "density" in want else None
+        self._check(self.lib.bmf_batch_copy_chunk(self.h, i, _p(verts), _p(inds), _p(bits), _p(masks), _p(dens)))
+        return {"contains_mesh": bool(info.contains_mesh), "n_cells": info.n_cells, "n_verts": info.n_verts, "n_inds": info.n_inds,
+                "overlap_pos": np.array(info.overlap_pos[:], np.float32), "scale": info.scale,
+                "verts": verts, "inds": inds, "bits": bits, "masks": masks, "density": dens}
+
+    def stage_ms(self):
+        ms = np.zeros(len(STAGES), np.float32)
+        self._check(self.lib.bmf_batch_stage_ms(self.h, _p(ms)))
+        return dict(zip(STAGES, ms.tolist()))
+
+    def launch_count(self):
+        return int(self.lib.bmf_ctx_launch_count(self.h))
+
+    def mesh_process(self, pos, color, normal, boundary, inds, prim_n=3, iters=2, process_boundary=False, smooth_normals=False):
+        pos = np.array(pos, np.float32, copy=True).reshape(-1, 3)
+        color = np.array(color, np.float32, copy=True).reshape(-1, 3)
+        normal = None if normal is None else np.array(normal, np.float32, copy=True).reshape(-1, 3)
+        boundary = np.ascontiguousarray(boundary, np.uint8)
+        inds = np.ascontiguousarray(inds, np.uint32)
+        self._check(self.lib.bmf_mesh_process(self.h, _p(pos), _p(color), _p(normal), _p(boundary), None, len(pos), _p(inds), len(inds), prim_n, iters,
+                                              int(process_boundary), int(smooth_normals)))
+        return pos, color, normal
+
+    def qef_solve(self, positions, normals, counts):
+        """positions/normals: [m,12,3]; counts: [m]."""
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 12, 3)
+        n = np.ascontiguousarray(normals, np.float32).reshape(-1, 12, 3)
+        c = np.ascontiguousarray(counts, np.int32)
+        out = np.zeros((len(c), 3), np.float32)
+        err = np.zeros(len(c), np.float32)
+        self._check(self.lib.bmf_qef_solve(self.h, _p(p), _p(n), _p(c), len(c), _p(out), _p(err)))
+        return out, err

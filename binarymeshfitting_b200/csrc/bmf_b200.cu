@@ -1,0 +1,763 @@
+// bmf_b200.cu -- the C ABI of include/bmf_b200.h: context, device arenas, stage orchestration.
+// Everything that computes is a hand-written sm_100a kernel in noise.cuh / extract.cuh / smooth.cuh;
+// this file only owns memory, streams, events and the launch sequence.  There is no CPU fallback:
+// a missing device or a failed launch is an error (BMF_ERR_CUDA).
+#include "../../include/bmf_b200.h"
+#include "extract.cuh"
+#include "smooth.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bmf;
+
+namespace
+{
+
+template <typename T>
+struct DevBuf
+{
+	T* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct HostTotals
+{
+	unsigned long long v[4];
+};
+
+} // namespace
+
+struct bmf_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	int64_t launches = 0;
+
+	bool sampler_set = false;
+	bmf_sampler_desc sampler_desc;
+	SamplerDev sampler;
+
+	// resident batch
+	int n = 0;
+	bool have_batch = false;
+	bool finished = false;
+	bmf_params params;
+	Layout L;
+	std::vector<bmf_chunk_desc> descs;
+	std::vector<ChunkGeom> geom_host;
+	std::vector<ChunkCounts> counts_host;
+	unsigned long long totals[3] = { 0, 0, 0 };
+	const float* ext_density = nullptr; // caller-owned device density (density_on_device)
+	bool density_valid = false, masks_valid = false;
+
+	DevBuf<ChunkGeom> geom;
+	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base;
+	DevBuf<float> density, hmap;
+	DevBuf<uint8_t> masks;
+	DevBuf<ChunkCounts> counts;
+	DevBuf<unsigned long long> totals_dev;
+	DevBuf<float> pos, color, normal;
+	DevBuf<uint8_t> boundary, valence;
+	DevBuf<uint32_t> inds;
+	// smoothing temporaries
+	DevBuf<uint32_t> adj_off, cursor, adj, prim_vbase, block_sums;
+	DevBuf<float> dp, dc, dn;
+	// qef scratch
+	DevBuf<float> qp, qn, qo, qe;
+	DevBuf<int32_t> qc;
+
+	HostTotals* totals_pinned = nullptr;
+	ChunkCounts* counts_pinned = nullptr;
+	size_t counts_pinned_cap = 0;
+
+	cudaEvent_t ev[BMF_NUM_STAGES + 1] = {};
+	float stage_ms[BMF_NUM_STAGES] = {};
+};
+
+namespace
+{
+
+int fail(bmf_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+	if (c)
+	{
+		c->err = what;
+		if (e != cudaSuccess)
+		{
+			c->err += ": ";
+			c->err += cudaGetErrorString(e);
+		}
+	}
+	return code;
+}
+
+#define BMF_CUDA(call)                                                   \
+	do                                                                   \
+	{                                                                    \
+		cudaError_t e__ = (call);                                        \
+		if (e__ != cudaSuccess) return fail(ctx, BMF_ERR_CUDA, #call, e__); \
+	} while (0)
+
+#define BMF_LAUNCH(kernel, grid, block, smem, ...)                              \
+	do                                                                          \
+	{                                                                           \
+		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);          \
+		ctx->launches++;                                                        \
+		cudaError_t e__ = cudaGetLastError();                                   \
+		if (e__ != cudaSuccess) return fail(ctx, BMF_ERR_CUDA, #kernel, e__);   \
+	} while (0)
+
+float bounding(float gain, int octaves)
+{
+	float amp = gain, amp_fractal = 1.0f;
+	for (int i = 1; i < octaves; i++)
+	{
+		amp_fractal += amp;
+		amp *= gain;
+	}
+	return 1.0f / amp_fractal;
+}
+
+// FastNoiseSIMD object state after the setter sequence of each terrain block function
+// (NoiseSampler.cpp:120-125, 160-167, 203-206, 236-242) on a fresh per-thread sampler (library defaults).
+void build_sampler(const bmf_sampler_desc& d, SamplerDev* s)
+{
+	memset(s, 0, sizeof(*s));
+	s->kind = d.kind;
+	s->world_size = d.world_size;
+	NoiseState& ns = s->ns;
+	ns.seed = d.seed;
+	ns.frequency = 0.01f;
+	ns.base = NT_SIMPLEX;
+	ns.fractal = 1;
+	ns.octaves = 3;
+	ns.lacunarity = 2.0f;
+	ns.gain = 0.5f;
+	ns.fractal_type = FT_FBM;
+	ns.perturb = 0;
+	ns.perturb_amp = 1.0f / 511.5f;
+	ns.perturb_frequency = 0.5f;
+	ns.perturb_octaves = 3;
+	ns.perturb_lacunarity = 2.0f;
+	ns.perturb_gain = 0.5f;
+	s->n_mul = 1;
+	switch (d.kind)
+	{
+	case BMF_SAMPLER_TERRAIN2D:
+		s->g = 1.0f; s->nm = 64.0f;
+		ns.base = NT_VALUE; ns.octaves = 12; ns.gain = 0.5f; ns.lacunarity = 2.0f; ns.fractal_type = FT_FBM;
+		break;
+	case BMF_SAMPLER_TERRAIN2D_PERT:
+		s->g = d.g_scale; s->nm = d.height;
+		ns.base = NT_VALUE; ns.perturb = 2; ns.perturb_octaves = d.octaves; ns.perturb_amp = d.amp / 511.5f;
+		ns.perturb_frequency = d.frequency; ns.perturb_gain = d.gain; ns.fractal_type = FT_FBM;
+		break;
+	case BMF_SAMPLER_TERRAIN3D:
+		s->g = 0.15f; s->nm = 1.0f; s->dy_half = 1; s->n_mul = 0;
+		ns.base = NT_VALUE; ns.octaves = 4; ns.fractal_type = FT_RIGIDMULTI;
+		break;
+	case BMF_SAMPLER_TERRAIN3D_PERT:
+		s->g = 0.15f; s->nm = 48.0f;
+		ns.base = NT_SIMPLEX; ns.perturb = 2; ns.octaves = 8; ns.perturb_amp = 1.0f / 511.5f; ns.perturb_frequency = 0.05f;
+		ns.fractal_type = FT_RIGIDMULTI;
+		break;
+	default: break;
+	}
+	ns.fractal_bounding = bounding(ns.gain, ns.octaves);
+	ns.perturb_bounding = bounding(ns.perturb_gain, ns.perturb_octaves);
+	s->csg_op = d.csg_op; s->csg_kind_a = d.csg_kind_a; s->csg_kind_b = d.csg_kind_b;
+	s->csg_ws_a = d.csg_world_size_a; s->csg_ws_b = d.csg_world_size_b;
+	for (int i = 0; i < 3; i++)
+	{
+		s->csg_off_a[i] = d.csg_offset_a[i];
+		s->csg_off_b[i] = d.csg_offset_b[i];
+	}
+}
+
+bool valid_dim(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+bool is_terrain2d(int k) { return k == BMF_SAMPLER_TERRAIN2D || k == BMF_SAMPLER_TERRAIN2D_PERT; }
+bool is_terrain3d(int k) { return k == BMF_SAMPLER_TERRAIN3D || k == BMF_SAMPLER_TERRAIN3D_PERT; }
+bool is_implicit(int k) { return k >= BMF_SAMPLER_SPHERE && k <= BMF_SAMPLER_CSG; }
+
+inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// MeshProcessor<N> on device arrays (all batch-wide); chunks_dev maps index positions to vertex bases.
+template <int N>
+int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* color, float* normal, const uint8_t* boundary,
+               const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef)
+{
+	if (n_verts == 0 || n_inds < (size_t)N || iters <= 0) return BMF_OK;
+	const size_t n_prims = n_inds / N;
+	BMF_CUDA(ctx->adj_off.reserve(n_verts));
+	BMF_CUDA(ctx->cursor.reserve(n_verts));
+	BMF_CUDA(ctx->adj.reserve(n_inds));
+	BMF_CUDA(ctx->prim_vbase.reserve(n_prims));
+	BMF_CUDA(ctx->dp.reserve(3 * n_prims));
+	BMF_CUDA(ctx->dc.reserve(3 * n_prims));
+	const bool need_dn = smooth || qef;
+	if (need_dn) BMF_CUDA(ctx->dn.reserve(3 * n_prims));
+	const size_t per_block = (size_t)CTA * SCAN_ITEMS;
+	const unsigned nblk = grid_for(n_verts, (int)per_block);
+	BMF_CUDA(ctx->block_sums.reserve(nblk));
+
+	// init: adj_offset = exclusive prefix of init_valence (MeshProcessor.cpp:33-39)
+	BMF_LAUNCH(k_scan8_partial, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p);
+	BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
+	BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
+	BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, n_verts * sizeof(uint32_t), ctx->stream));
+	BMF_LAUNCH(k_csr_fill<N>, grid_for(n_prims, CTA), CTA, 0, inds, n_prims, chunks_dev, n_chunks, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
+	BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
+
+	// optimize_dual_grid (MeshProcessor.cpp:130-236)
+	const int hard_norm_max = 10;
+	const int max_norms = (iters / 2 - 3 < hard_norm_max ? iters / 2 - 3 : hard_norm_max);
+	for (int m = 0; m < iters; m++)
+	{
+		const int face = (m == 0 || m < max_norms || m < 3) ? 1 : 0;
+		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, ctx->dc.p,
+		           need_dn ? ctx->dn.p : nullptr, smooth, face);
+		if (m < iters - 1)
+		{
+			const int set_colors = (m == 3) || (m == 0 && iters <= 3);
+			BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p,
+			           ctx->dn.p, pos, color, normal, smooth, set_colors, pb);
+		}
+	}
+	// the driver's extra primal call (ChunkGenerator.cpp:120)
+	BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p, ctx->dn.p, pos,
+	           color, normal, smooth, 0, pb);
+	if (qef)
+	{
+		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
+		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, ctx->dc.p, ctx->dn.p, 1, 1);
+		BMF_LAUNCH(k_qef_place, grid_for(n_verts, 128), 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb);
+	}
+	return BMF_OK;
+}
+
+__global__ void __launch_bounds__(CTA) k_valence_from_inds(const uint32_t* __restrict__ inds, size_t n, uint8_t* __restrict__ valence)
+{
+	const size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (i >= n) return;
+	const size_t gv = inds[i];
+	atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
+}
+
+int elapsed(bmf_ctx* ctx, int a, int b, float* out)
+{
+	cudaError_t e = cudaEventElapsedTime(out, ctx->ev[a], ctx->ev[b]);
+	if (e != cudaSuccess) *out = 0.0f;
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* bmf_version(void) { return "bmf_b200 0.1 (sm_100a)"; }
+
+const char* bmf_last_error(const bmf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int bmf_ctx_create(int device, bmf_ctx** out)
+{
+	if (!out) return BMF_ERR_INVALID;
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0 || device < 0 || device >= count)
+	{
+		fprintf(stderr, "bmf_b200: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+		        e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+		return BMF_ERR_CUDA;
+	}
+	bmf_ctx* ctx = new bmf_ctx();
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+	{
+		delete ctx;
+		return BMF_ERR_CUDA;
+	}
+	for (int i = 0; i <= BMF_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+	cudaMallocHost((void**)&ctx->totals_pinned, sizeof(HostTotals));
+	*out = ctx;
+	return BMF_OK;
+}
+
+void bmf_ctx_destroy(bmf_ctx* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->geom.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
+	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
+	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
+	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cursor.release();
+	ctx->adj.release(); ctx->prim_vbase.release(); ctx->block_sums.release(); ctx->dp.release(); ctx->dc.release(); ctx->dn.release();
+	ctx->qp.release(); ctx->qn.release(); ctx->qo.release(); ctx->qe.release(); ctx->qc.release();
+	if (ctx->totals_pinned) cudaFreeHost(ctx->totals_pinned);
+	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
+	for (int i = 0; i <= BMF_NUM_STAGES; i++)
+		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+void bmf_sampler_defaults(bmf_sampler_desc* d, int kind)
+{
+	if (!d) return;
+	memset(d, 0, sizeof(*d));
+	d->kind = kind;
+	d->world_size = 256.0f;
+	// WorldOctree.cpp:47-54
+	d->g_scale = 0.25f;
+	d->height = 75.0f;
+	d->octaves = 13;
+	d->amp = 0.87f;
+	d->frequency = 0.585f;
+	d->gain = 0.488f;
+	d->seed = 1337;
+	d->csg_op = BMF_CSG_UNION;
+	d->csg_kind_a = BMF_SAMPLER_SPHERE;
+	d->csg_kind_b = BMF_SAMPLER_TORUS_Z;
+	d->csg_world_size_a = d->csg_world_size_b = 256.0f;
+}
+
+int bmf_sampler_set(bmf_ctx* ctx, const bmf_sampler_desc* desc)
+{
+	if (!ctx || !desc) return BMF_ERR_INVALID;
+	const int k = desc->kind;
+	if (!(is_implicit(k) || is_terrain2d(k) || is_terrain3d(k) || k == BMF_SAMPLER_HOST_DENSITY))
+		return fail(ctx, BMF_ERR_INVALID, "bmf_sampler_set: unknown sampler kind");
+	if (k == BMF_SAMPLER_CSG && !(desc->csg_kind_a >= 0 && desc->csg_kind_a <= 3 && desc->csg_kind_b >= 0 && desc->csg_kind_b <= 3 && desc->csg_op >= 0 && desc->csg_op <= 2))
+		return fail(ctx, BMF_ERR_INVALID, "bmf_sampler_set: CSG operands must be primitive kinds 0..3 and op 0..2");
+	if (k == BMF_SAMPLER_TERRAIN2D_PERT && desc->octaves < 1)
+		return fail(ctx, BMF_ERR_INVALID, "bmf_sampler_set: octaves must be >= 1");
+	ctx->sampler_desc = *desc;
+	build_sampler(*desc, &ctx->sampler);
+	ctx->sampler_set = true;
+	return BMF_OK;
+}
+
+int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bmf_params* params, const float* density_in)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!chunks || !params || n <= 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: null argument or empty batch");
+	if (!ctx->sampler_set) return fail(ctx, BMF_ERR_STATE, "bmf_batch_submit: no sampler set");
+	if (!valid_dim(params->dim)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: dim must be 32, 64, 128 or 256");
+	if (params->iters < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: iters < 0");
+	const int kind = ctx->sampler.kind;
+	if (kind == BMF_SAMPLER_HOST_DENSITY && !density_in) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: HOST_DENSITY needs a density block");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+
+	ctx->have_batch = false;
+	ctx->finished = false;
+	ctx->n = n;
+	ctx->params = *params;
+	ctx->descs.assign(chunks, chunks + n);
+	const Layout L = ctx->L = make_layout(params->dim);
+	const int d = L.d;
+	const size_t nvox = (size_t)d * d * d;
+	const size_t n_words = (size_t)n * L.wc;
+	const int nseg = n * L.S;
+
+	// DMCChunk::label_grid geometry (DMCChunk.cpp:94-98), IEEE single ops in this order
+	ctx->geom_host.resize(n);
+	for (int i = 0; i < n; i++)
+	{
+		const bmf_chunk_desc& c = chunks[i];
+		ChunkGeom g;
+		g.delta = c.size * (1.0f + c.overlap * 2.0f) / (float)(d - 1);
+		const float so = c.size * c.overlap;
+		g.ox = c.pos[0] - so;
+		g.oy = c.pos[1] - so;
+		g.oz = c.pos[2] - so;
+		ctx->geom_host[i] = g;
+	}
+	BMF_CUDA(ctx->geom.reserve(n));
+	BMF_CUDA(ctx->flags.reserve(n));
+	BMF_CUDA(ctx->bits.reserve(n_words));
+	BMF_CUDA(ctx->wcnt.reserve(n_words));
+	BMF_CUDA(ctx->wvb.reserve(n_words));
+	BMF_CUDA(ctx->wib.reserve(n_words));
+	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
+	BMF_CUDA(ctx->seg_base.reserve(3 * ((size_t)nseg + 1)));
+	BMF_CUDA(ctx->counts.reserve(n));
+	BMF_CUDA(ctx->totals_dev.reserve(4));
+	if ((size_t)n > ctx->counts_pinned_cap)
+	{
+		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
+		ctx->counts_pinned = nullptr;
+		BMF_CUDA(cudaMallocHost((void**)&ctx->counts_pinned, sizeof(ChunkCounts) * (size_t)n));
+		ctx->counts_pinned_cap = n;
+	}
+
+	const bool host_density = kind == BMF_SAMPLER_HOST_DENSITY;
+	const bool need_density = host_density || is_terrain3d(kind) || params->keep_density;
+	const float* density_dev = nullptr;
+	ctx->ext_density = nullptr;
+	if (host_density && params->density_on_device)
+	{
+		density_dev = density_in;
+		ctx->ext_density = density_in;
+	}
+	else if (need_density)
+	{
+		BMF_CUDA(ctx->density.reserve(n * nvox));
+		density_dev = ctx->density.p;
+	}
+	ctx->density_valid = need_density;
+	ctx->masks_valid = params->keep_masks != 0;
+	if (params->keep_masks) BMF_CUDA(ctx->masks.reserve(n * nvox));
+	if (is_terrain2d(kind)) BMF_CUDA(ctx->hmap.reserve((size_t)n * d * d));
+
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(cudaMemcpyAsync(ctx->geom.p, ctx->geom_host.data(), sizeof(ChunkGeom) * n, cudaMemcpyHostToDevice, st));
+	if (host_density && !params->density_on_device)
+		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
+
+	// ---- K1 / K2
+	BMF_CUDA(cudaEventRecord(ctx->ev[0], st));
+	float* dens_w = need_density ? ctx->density.p : nullptr;
+	if (is_implicit(kind))
+	{
+		BMF_LAUNCH(k_sample_implicit, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->bits.p, dens_w, ctx->flags.p);
+	}
+	else if (is_terrain2d(kind))
+	{
+		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n * d * d, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->hmap.p, n);
+		BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->bits.p, dens_w, ctx->flags.p);
+	}
+	else if (kind == BMF_SAMPLER_TERRAIN3D)
+	{
+		BMF_LAUNCH(k_terrain3d<NT_VALUE>, (unsigned)(n_words / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->bits.p, dens_w, ctx->flags.p);
+	}
+	else if (kind == BMF_SAMPLER_TERRAIN3D_PERT)
+	{
+		BMF_LAUNCH(k_terrain3d<NT_SIMPLEX>, (unsigned)(n_words / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->bits.p, dens_w, ctx->flags.p);
+	}
+	else
+	{
+		BMF_LAUNCH(k_pack_density, (unsigned)(n_words / (PACK_UNROLL * (CTA / 32))), CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.wc);
+	}
+	BMF_CUDA(cudaEventRecord(ctx->ev[1], st));
+
+	// ---- K3
+	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
+	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
+	if (L.wpt == 4)
+		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+	else
+		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+	BMF_CUDA(cudaEventRecord(ctx->ev[2], st));
+
+	// ---- scan + the one host round trip (output sizes)
+	BMF_LAUNCH(k_scan_segments, 1, SCAN_CTA, 0, ctx->seg_tot.p, ctx->flags.p, nseg, L.S, ctx->seg_base.p, ctx->counts.p, n, ctx->totals_dev.p);
+	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, ctx->totals_dev.p, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	if (ctx->totals_pinned->v[3]) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: batch exceeds 2^32 cells/vertices/indices; split it");
+	ctx->totals[0] = ctx->totals_pinned->v[0];
+	ctx->totals[1] = ctx->totals_pinned->v[1];
+	ctx->totals[2] = ctx->totals_pinned->v[2];
+	ctx->counts_host.assign(ctx->counts_pinned, ctx->counts_pinned + n);
+	const size_t V = ctx->totals[1], I = ctx->totals[2];
+
+	BMF_CUDA(ctx->pos.reserve(3 * V + 4));
+	BMF_CUDA(ctx->color.reserve(3 * V + 4));
+	BMF_CUDA(ctx->normal.reserve(3 * V + 4));
+	BMF_CUDA(ctx->boundary.reserve(V + 16));
+	BMF_CUDA(ctx->valence.reserve(V + 16));
+	BMF_CUDA(ctx->inds.reserve(I + 4));
+
+	// ---- K4
+	DensitySource src;
+	src.density = density_dev;
+	src.hmap = (!density_dev && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
+	if (L.wpt == 4)
+		BMF_LAUNCH(k_verts<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_base.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->wvb.p,
+		           ctx->wib.p, ctx->pos.p, ctx->boundary.p);
+	else
+		BMF_LAUNCH(k_verts<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_base.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->wvb.p,
+		           ctx->wib.p, ctx->pos.p, ctx->boundary.p);
+	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+	if (V)
+	{
+		BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, V + 16, st));
+		BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
+		BMF_LAUNCH(k_fill_f32, grid_for(3 * V, CTA), CTA, 0, ctx->color.p, 3 * V, 1.0f); // calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681)
+	}
+	if (I)
+	{
+		const size_t smem_inds = (size_t)(2 * L.P + 3) * L.wp * sizeof(uint32_t);
+		if (L.wpt == 4)
+			BMF_LAUNCH(k_inds<4>, nseg, CTA, smem_inds, ctx->bits.p, L, ctx->wcnt.p, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->inds.p, ctx->valence.p);
+		else
+			BMF_LAUNCH(k_inds<8>, nseg, CTA, smem_inds, ctx->bits.p, L, ctx->wcnt.p, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->inds.p, ctx->valence.p);
+	}
+	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+
+	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it
+	if (params->iters > 0 && V && I)
+	{
+		int rc = run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
+		                       params->iters, params->process_boundary, params->smooth_normals, params->qef);
+		if (rc) return rc;
+	}
+	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+	ctx->have_batch = true;
+	return BMF_OK;
+}
+
+int bmf_batch_wait(bmf_ctx* ctx)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_wait: no batch submitted");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (!ctx->finished)
+	{
+		for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
+		elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
+		ctx->finished = true;
+	}
+	return BMF_OK;
+}
+
+int bmf_batch_totals(bmf_ctx* ctx, int64_t* n_cells, int64_t* n_verts, int64_t* n_inds)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_totals: no batch submitted");
+	if (n_cells) *n_cells = (int64_t)ctx->totals[0];
+	if (n_verts) *n_verts = (int64_t)ctx->totals[1];
+	if (n_inds) *n_inds = (int64_t)ctx->totals[2];
+	return BMF_OK;
+}
+
+int bmf_batch_chunk_info(bmf_ctx* ctx, int i, bmf_chunk_info* out)
+{
+	if (!ctx || !out) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_chunk_info: no batch submitted");
+	if (i < 0 || i >= ctx->n) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_chunk_info: chunk index out of range");
+	const ChunkCounts& c = ctx->counts_host[i];
+	const ChunkGeom& g = ctx->geom_host[i];
+	out->contains_mesh = (int32_t)c.contains_mesh;
+	out->n_cells = (int32_t)c.n_cells;
+	out->n_verts = (int32_t)c.n_verts;
+	out->n_inds = (int32_t)c.n_inds;
+	out->vert_offset = (int64_t)c.vert_base;
+	out->ind_offset = (int64_t)c.ind_base;
+	out->overlap_pos[0] = g.ox; out->overlap_pos[1] = g.oy; out->overlap_pos[2] = g.oz;
+	out->scale = g.delta;
+	return BMF_OK;
+}
+
+int bmf_batch_chunk_infos(bmf_ctx* ctx, bmf_chunk_info* out)
+{
+	if (!ctx || !out) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_chunk_infos: no batch submitted");
+	for (int i = 0; i < ctx->n; i++)
+	{
+		int rc = bmf_batch_chunk_info(ctx, i, out + i);
+		if (rc) return rc;
+	}
+	return BMF_OK;
+}
+
+int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download: no batch submitted");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	const size_t V = ctx->totals[1], I = ctx->totals[2];
+	cudaStream_t st = ctx->stream;
+	if (V)
+	{
+		if (pos) BMF_CUDA(cudaMemcpyAsync(pos, ctx->pos.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (normal) BMF_CUDA(cudaMemcpyAsync(normal, ctx->normal.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (color) BMF_CUDA(cudaMemcpyAsync(color, ctx->color.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (boundary) BMF_CUDA(cudaMemcpyAsync(boundary, ctx->boundary.p, V, cudaMemcpyDeviceToHost, st));
+		if (valence) BMF_CUDA(cudaMemcpyAsync(valence, ctx->valence.p, V, cudaMemcpyDeviceToHost, st));
+	}
+	if (I && indices) BMF_CUDA(cudaMemcpyAsync(indices, ctx->inds.p, sizeof(uint32_t) * I, cudaMemcpyDeviceToHost, st));
+	return bmf_batch_wait(ctx);
+}
+
+int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* indices, uint32_t* bits, uint8_t* masks, float* density)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_copy_chunk: no batch submitted");
+	if (i < 0 || i >= ctx->n) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_copy_chunk: chunk index out of range");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	const ChunkCounts& c = ctx->counts_host[i];
+	const Layout& L = ctx->L;
+	const size_t nvox = (size_t)L.d * L.d * L.d;
+	cudaStream_t st = ctx->stream;
+	if (bits) BMF_CUDA(cudaMemcpyAsync(bits, ctx->bits.p + (size_t)i * L.wc, sizeof(uint32_t) * L.wc, cudaMemcpyDeviceToHost, st));
+	if (masks)
+	{
+		if (!ctx->masks_valid) return fail(ctx, BMF_ERR_STATE, "bmf_batch_copy_chunk: masks were not kept (params.keep_masks)");
+		BMF_CUDA(cudaMemcpyAsync(masks, ctx->masks.p + (size_t)i * nvox, nvox, cudaMemcpyDeviceToHost, st));
+	}
+	if (density)
+	{
+		if (!ctx->density_valid) return fail(ctx, BMF_ERR_STATE, "bmf_batch_copy_chunk: density was not kept (params.keep_density)");
+		const float* src = ctx->ext_density ? ctx->ext_density : ctx->density.p;
+		BMF_CUDA(cudaMemcpyAsync(density, src + (size_t)i * nvox, sizeof(float) * nvox, cudaMemcpyDeviceToHost, st));
+	}
+	if (indices && c.n_inds) BMF_CUDA(cudaMemcpyAsync(indices, ctx->inds.p + c.ind_base, sizeof(uint32_t) * c.n_inds, cudaMemcpyDeviceToHost, st));
+	std::vector<float> p, nn, col;
+	std::vector<uint8_t> bd, val;
+	if (dual_vertices && c.n_verts)
+	{
+		const size_t nv = c.n_verts;
+		p.resize(3 * nv); nn.resize(3 * nv); col.resize(3 * nv); bd.resize(nv); val.resize(nv);
+		BMF_CUDA(cudaMemcpyAsync(p.data(), ctx->pos.p + 3 * c.vert_base, sizeof(float) * 3 * nv, cudaMemcpyDeviceToHost, st));
+		BMF_CUDA(cudaMemcpyAsync(nn.data(), ctx->normal.p + 3 * c.vert_base, sizeof(float) * 3 * nv, cudaMemcpyDeviceToHost, st));
+		BMF_CUDA(cudaMemcpyAsync(col.data(), ctx->color.p + 3 * c.vert_base, sizeof(float) * 3 * nv, cudaMemcpyDeviceToHost, st));
+		BMF_CUDA(cudaMemcpyAsync(bd.data(), ctx->boundary.p + c.vert_base, nv, cudaMemcpyDeviceToHost, st));
+		BMF_CUDA(cudaMemcpyAsync(val.data(), ctx->valence.p + c.vert_base, nv, cudaMemcpyDeviceToHost, st));
+	}
+	int rc = bmf_batch_wait(ctx);
+	if (rc) return rc;
+	if (dual_vertices && c.n_verts)
+	{
+		// DualVertex, 84 bytes (Vertices.hpp:5-24): boundary@0 index@4 valence@8 init_valence@9 adj_next@10
+		// adj_offset@12 s@20 p@36 n@48 color@72; fields the reference leaves uninitialised are zero here
+		uint8_t* out = (uint8_t*)dual_vertices;
+		const bool processed = ctx->params.iters > 0 && c.n_inds > 0;
+		uint32_t off = 0;
+		for (size_t v = 0; v < c.n_verts; v++)
+		{
+			uint8_t* r = out + 84 * v;
+			memset(r, 0, 84);
+			r[0] = bd[v];
+			uint32_t idx = (uint32_t)v;
+			memcpy(r + 4, &idx, 4);
+			r[8] = processed ? val[v] : 0;
+			r[9] = val[v];
+			r[10] = processed ? val[v] : 0;
+			uint32_t ao = processed ? off : 0;
+			memcpy(r + 12, &ao, 4);
+			memcpy(r + 36, &p[3 * v], 12);
+			memcpy(r + 48, &nn[3 * v], 12);
+			memcpy(r + 72, &col[3 * v], 12);
+			off += val[v];
+		}
+	}
+	return BMF_OK;
+}
+
+int bmf_batch_stage_ms(bmf_ctx* ctx, float* ms)
+{
+	if (!ctx || !ms) return BMF_ERR_INVALID;
+	int rc = bmf_batch_wait(ctx);
+	if (rc) return rc;
+	memcpy(ms, ctx->stage_ms, sizeof(ctx->stage_ms));
+	return BMF_OK;
+}
+
+int64_t bmf_ctx_launch_count(const bmf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits, void** density)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_device_ptrs: no batch submitted");
+	if (pos) *pos = ctx->pos.p;
+	if (indices) *indices = ctx->inds.p;
+	if (bits) *bits = ctx->bits.p;
+	if (density) *density = ctx->density_valid ? (void*)(ctx->ext_density ? ctx->ext_density : ctx->density.p) : nullptr;
+	return BMF_OK;
+}
+
+int bmf_mesh_process(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence_in, int n_verts,
+                     const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals)
+{
+	(void)valence_in; // init_valence is recomputed from the index buffer (identical whenever the caller's was consistent)
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!pos || !color || !boundary || !indices || n_verts < 0 || n_inds < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: null argument");
+	if (prim_n != 3 && prim_n != 4) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: prim_n must be 3 or 4");
+	if (smooth_normals && !normal) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: smooth_normals needs a normal array");
+	if (n_verts == 0 || n_inds < prim_n || iters <= 0) return BMF_OK;
+	for (int i = 0; i < n_inds; i++)
+		if (indices[i] >= (uint32_t)n_verts) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: index out of range");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	ctx->have_batch = false; // the arenas are reused
+	const size_t V = n_verts, I = (size_t)(n_inds / prim_n) * prim_n;
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(ctx->pos.reserve(3 * V + 4));
+	BMF_CUDA(ctx->color.reserve(3 * V + 4));
+	BMF_CUDA(ctx->normal.reserve(3 * V + 4));
+	BMF_CUDA(ctx->boundary.reserve(V + 16));
+	BMF_CUDA(ctx->valence.reserve(V + 16));
+	BMF_CUDA(ctx->inds.reserve(I + 4));
+	BMF_CUDA(ctx->counts.reserve(1));
+	BMF_CUDA(cudaMemcpyAsync(ctx->pos.p, pos, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->color.p, color, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, st));
+	if (normal) BMF_CUDA(cudaMemcpyAsync(ctx->normal.p, normal, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, st));
+	else BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->boundary.p, boundary, V, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->inds.p, indices, sizeof(uint32_t) * I, cudaMemcpyHostToDevice, st));
+	ChunkCounts one;
+	memset(&one, 0, sizeof(one));
+	one.contains_mesh = 1; one.n_verts = (uint32_t)V; one.n_inds = (uint32_t)I;
+	BMF_CUDA(cudaMemcpyAsync(ctx->counts.p, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, V + 16, st));
+	BMF_LAUNCH(k_valence_from_inds, grid_for(I, CTA), CTA, 0, ctx->inds.p, I, ctx->valence.p);
+	int rc = (prim_n == 3)
+		? run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0)
+		: run_smooth<4>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0);
+	if (rc) return rc;
+	BMF_CUDA(cudaMemcpyAsync(pos, ctx->pos.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(color, ctx->color.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+	if (normal) BMF_CUDA(cudaMemcpyAsync(normal, ctx->normal.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!positions || !normals || !counts || !out_pos || !out_err || m < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_qef_solve: null argument");
+	if (m == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const size_t M = m;
+	BMF_CUDA(ctx->qp.reserve(36 * M));
+	BMF_CUDA(ctx->qn.reserve(36 * M));
+	BMF_CUDA(ctx->qc.reserve(M));
+	BMF_CUDA(ctx->qo.reserve(3 * M));
+	BMF_CUDA(ctx->qe.reserve(M));
+	BMF_CUDA(cudaMemcpyAsync(ctx->qp.p, positions, sizeof(float) * 36 * M, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->qn.p, normals, sizeof(float) * 36 * M, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->qc.p, counts, sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+	BMF_LAUNCH(k_qef_batch, grid_for(M, 128), 128, 0, ctx->qp.p, ctx->qn.p, ctx->qc.p, m, ctx->qo.p, ctx->qe.p);
+	BMF_CUDA(cudaMemcpyAsync(out_pos, ctx->qo.p, sizeof(float) * 3 * M, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(out_err, ctx->qe.p, sizeof(float) * M, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,679 @@
+// extract.cuh -- K1 sampling front-ends, K2 sign pack, K3 cell-mask/count, segment scan, K4 vertex and
+// index emission.  What they compute is the closed form of DMCChunk::label_grid / label_edges /
+// polygonize (DMCChunk.cpp:79-166, 168-508, 514-576); how they compute it is
+// B200-first:
+//   * a 32-bit sign word is one __ballot_sync over 32 consecutive z (the reference's inner loop
+//     DMCChunk.cpp:132-143 collapses to one instruction);
+//   * cell masks are never materialised per cell on the hot path: 32 cells are classified at once with
+//     word-wide logic on the four row words and their z+1 funnel shifts ("pseudo-SIMD" at warp-word width),
+//     popc gives the cell / vertex counts, only ACTIVE cells touch the triangle table;
+//   * the reference's serial x->y->z scan (DMCChunk.cpp:449-498) becomes count -> exclusive scan -> emit
+//     over fixed-size segments of whole x-planes staged in shared memory, so vertex ids, cell order and
+//     the index buffer are bit-identical to the serial order;
+//   * the dense IndexesBlock (4 B/voxel) and the 124-byte DMC_Cell records are not produced at all: a
+//     4-byte vertex base per 32-cell word replaces them.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "noise.cuh"
+#include "mc_tables.h"
+
+namespace bmf
+{
+
+static constexpr int CTA = 256;
+
+struct ChunkGeom
+{
+	float ox, oy, oz; // DMCChunk::overlap_pos
+	float delta;      // DMCChunk::scale
+};
+
+// chunk flags accumulated by the sampling / pack kernels (DMCChunk.cpp:141-162)
+enum { CF_MIXED = 1, CF_ZERO = 2, CF_ONES = 4 };
+__host__ __device__ __forceinline__ bool flags_contain_mesh(uint32_t f) { return (f & CF_MIXED) || ((f & CF_ZERO) && (f & CF_ONES)); }
+
+struct SamplerDev
+{
+	int32_t kind; // bmf_sampler_kind
+	float world_size;
+	float g, nm;       // terrain: g_scale, height multiplier
+	int32_t dy_half;   // terrain3d: dy * 0.5
+	int32_t n_mul;     // 1: density = -dy - n*nm ; 0: -dy - n
+	NoiseState ns;
+	int32_t csg_op, csg_kind_a, csg_kind_b;
+	float csg_ws_a, csg_ws_b;
+	float csg_off_a[3], csg_off_b[3];
+};
+
+struct Layout
+{
+	int d;       // dim
+	int zc;      // words per row = d/32
+	int wp;      // words per plane = d*zc
+	int wc;      // words per chunk
+	int P;       // planes per segment
+	int ws;      // words per segment
+	int S;       // segments per chunk
+	int wpt;     // words per thread in segment kernels = ws / CTA
+};
+
+__host__ inline Layout make_layout(int d)
+{
+	Layout L;
+	L.d = d; L.zc = d / 32; L.wp = d * L.zc; L.wc = d * L.wp;
+	L.P = (d == 32) ? 32 : (d == 64) ? 8 : (d == 128) ? 2 : 1;
+	L.ws = L.P * L.wp; L.S = d / L.P; L.wpt = L.ws / CTA;
+	return L;
+}
+
+__constant__ uint64_t c_tri_pack[256] = BMF_TRI_PACK_INIT;
+
+// ---- density of one grid point for the analytic / heightmap samplers ----------------------------------
+// implicit_block (ImplicitSampler.hpp:14-36): coordinate = p + (float)i * scale
+__device__ __forceinline__ float implicit_point(const SamplerDev& s, const ChunkGeom& g, int x, int y, int z)
+{
+	float px = g.ox + (float)x * g.delta;
+	float py = g.oy + (float)y * g.delta;
+	float pz = g.oz + (float)z * g.delta;
+	if (s.kind == 4)
+	{
+		float a = implicit_value(s.csg_kind_a, s.csg_ws_a, px - s.csg_off_a[0], py - s.csg_off_a[1], pz - s.csg_off_a[2]);
+		float b = implicit_value(s.csg_kind_b, s.csg_ws_b, px - s.csg_off_b[0], py - s.csg_off_b[1], pz - s.csg_off_b[2]);
+		return s.csg_op == 0 ? fmaxf(a, b) : s.csg_op == 1 ? fminf(a, b) : fminf(a, -b);
+	}
+	return implicit_value(s.kind, s.world_size, px, py, pz);
+}
+
+// terrain*_block tail (NoiseSampler.cpp:136-143, 180-187, 216-223, 250-257): density from a noise value
+__device__ __forceinline__ float terrain_density(const SamplerDev& s, const ChunkGeom& g, int y, float n)
+{
+	float dy = ((float)y * g.delta + g.oy) * s.g;
+	if (s.dy_half) dy = dy * 0.5f;
+	return s.n_mul ? (-dy - n * s.nm) : (-dy - n);
+}
+
+// where the emitters read a density sample back from
+struct DensitySource
+{
+	const float* density; // [n][d^3] or null
+	const float* hmap;    // [n][d*d] noise sheet of the 2-D terrains, or null
+};
+
+__device__ __forceinline__ float density_at(const SamplerDev& s, const DensitySource& src, const ChunkGeom& g, int d, int chunk, int x, int y, int z)
+{
+	if (src.density) return src.density[(size_t)chunk * d * d * d + ((size_t)x * d + y) * d + z];
+	if (src.hmap) return terrain_density(s, g, y, src.hmap[(size_t)chunk * d * d + (size_t)x * d + z]);
+	return implicit_point(s, g, x, y, z);
+}
+
+// block-level flag merge: one atomicOr per CTA
+__device__ __forceinline__ void merge_flags(uint32_t f, uint32_t* chunk_flags)
+{
+	__shared__ uint32_t s_f;
+	if (threadIdx.x == 0) s_f = 0;
+	__syncthreads();
+	f |= __shfl_xor_sync(0xffffffffu, f, 16);
+	f |= __shfl_xor_sync(0xffffffffu, f, 8);
+	f |= __shfl_xor_sync(0xffffffffu, f, 4);
+	f |= __shfl_xor_sync(0xffffffffu, f, 2);
+	f |= __shfl_xor_sync(0xffffffffu, f, 1);
+	if ((threadIdx.x & 31) == 0 && f) atomicOr(&s_f, f);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_f) atomicOr(chunk_flags, s_f);
+}
+
+__device__ __forceinline__ uint32_t word_flags(uint32_t w) { return w == 0 ? CF_ZERO : (w == 0xFFFFFFFFu ? CF_ONES : CF_MIXED); }
+
+// ---- K1a: implicit primitives -> (density) + sign words.  One warp per 32-z word, WORDS_PER_CTA words per CTA.
+static constexpr int SAMPLE_WORDS_PER_CTA = 64;
+
+__global__ void __launch_bounds__(CTA) k_sample_implicit(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L,
+                                                          uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ctas_per_chunk = L.wc / SAMPLE_WORDS_PER_CTA;
+	const int chunk = blockIdx.x / ctas_per_chunk;
+	const int w0 = (blockIdx.x % ctas_per_chunk) * SAMPLE_WORDS_PER_CTA;
+	const ChunkGeom g = geom[chunk];
+	uint32_t f = 0;
+	for (int k = warp; k < SAMPLE_WORDS_PER_CTA; k += CTA / 32)
+	{
+		int w = w0 + k;
+		int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+		int z = zb * 32 + lane;
+		float v = implicit_point(s, g, x, y, z);
+		if (density) density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
+		uint32_t word = __ballot_sync(0xffffffffu, v < 0.0f);
+		if (lane == 0)
+		{
+			bits[(size_t)chunk * L.wc + w] = word;
+			f |= word_flags(word);
+		}
+	}
+	merge_flags(f, flags + chunk);
+}
+
+// ---- K1b: 2-D terrains.  Noise sheet: one thread per (ix, iz) column (NOISE_BLOCK with size_y = 1,
+// NoiseSampler.cpp:117,152), then density = -dy - n*height per voxel and the sign word.
+template <int BASE>
+__global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, float* __restrict__ hmap, int n_chunks)
+{
+	size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
+	size_t per = (size_t)d * d;
+	if (i >= per * n_chunks) return;
+	int chunk = (int)(i / per);
+	int r = (int)(i % per);
+	int ix = r / d, iz = r % d;
+	const ChunkGeom g = geom[chunk];
+	float sg = g.delta * s.g;
+	float vx = (float)ix * sg + g.ox * s.g;
+	float vy = (float)0 * sg + 0.0f;
+	float vz = (float)iz * sg + g.oz * s.g;
+	hmap[i] = noise_eval<BASE>(s.ns, vx, vy, vz);
+}
+
+__global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
+                                                            uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ctas_per_chunk = L.wc / SAMPLE_WORDS_PER_CTA;
+	const int chunk = blockIdx.x / ctas_per_chunk;
+	const int w0 = (blockIdx.x % ctas_per_chunk) * SAMPLE_WORDS_PER_CTA;
+	const ChunkGeom g = geom[chunk];
+	const float* hm = hmap + (size_t)chunk * L.d * L.d;
+	uint32_t f = 0;
+	for (int k = warp; k < SAMPLE_WORDS_PER_CTA; k += CTA / 32)
+	{
+		int w = w0 + k;
+		int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+		int z = zb * 32 + lane;
+		float v = terrain_density(s, g, y, hm[x * L.d + z]);
+		if (density) density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
+		uint32_t word = __ballot_sync(0xffffffffu, v < 0.0f);
+		if (lane == 0)
+		{
+			bits[(size_t)chunk * L.wc + w] = word;
+			f |= word_flags(word);
+		}
+	}
+	merge_flags(f, flags + chunk);
+}
+
+// ---- K1c: 3-D terrains: one noise evaluation per voxel, density always materialised (4 B/voxel is
+// noise next to ~1.5 k ALU ops/voxel) so the emitters can read crossing-edge samples back.
+template <int BASE>
+__global__ void __launch_bounds__(CTA) k_terrain3d(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L,
+                                                    uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int words_per_cta = CTA / 32;
+	const int ctas_per_chunk = L.wc / words_per_cta;
+	const int chunk = blockIdx.x / ctas_per_chunk;
+	const int w = (blockIdx.x % ctas_per_chunk) * words_per_cta + warp;
+	const ChunkGeom g = geom[chunk];
+	int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+	int z = zb * 32 + lane;
+	float sg = g.delta * s.g;
+	float vx = (float)x * sg + g.ox * s.g;
+	float vy = (float)y * sg + g.oy * s.g;
+	float vz = (float)z * sg + g.oz * s.g;
+	float n = noise_eval<BASE>(s.ns, vx, vy, vz);
+	float v = terrain_density(s, g, y, n);
+	density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
+	uint32_t word = __ballot_sync(0xffffffffu, v < 0.0f);
+	uint32_t f = 0;
+	if (lane == 0)
+	{
+		bits[(size_t)chunk * L.wc + w] = word;
+		f = word_flags(word);
+	}
+	merge_flags(f, flags + chunk);
+}
+
+// ---- K2: density block -> sign words (label_grid's pack, DMCChunk.cpp:118-157).  Pure streaming:
+// the density of a batch is one flat array of 32-float groups, each group is one word.  Every lane issues
+// PACK_UNROLL independent coalesced 4-byte loads before the first ballot so enough bytes are in flight.
+static constexpr int PACK_UNROLL = 8;
+
+__global__ void __launch_bounds__(CTA) k_pack_density(const float* __restrict__ density, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags,
+                                                       size_t n_words, int words_per_chunk)
+{
+	const int lane = threadIdx.x & 31;
+	const size_t warp_global = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5;
+	const size_t w0 = warp_global * PACK_UNROLL;
+	if (w0 >= n_words) return; // n_words is a multiple of PACK_UNROLL * (CTA/32): whole CTAs leave together
+	float v[PACK_UNROLL];
+#pragma unroll
+	for (int k = 0; k < PACK_UNROLL; k++) v[k] = __ldcs(density + (w0 + k) * 32 + lane);
+	uint32_t f = 0, mine = 0;
+#pragma unroll
+	for (int k = 0; k < PACK_UNROLL; k++)
+	{
+		uint32_t word = __ballot_sync(0xffffffffu, v[k] < 0.0f);
+		if (lane == k) mine = word;
+		f |= word_flags(word);
+	}
+	if (lane < PACK_UNROLL) bits[w0 + lane] = mine;
+	// all PACK_UNROLL words of a warp lie in one chunk (words_per_chunk is a multiple of 1024)
+	merge_flags(lane == 0 ? f : 0, flags + (w0 / words_per_chunk));
+}
+
+// ---- shared-memory staging of sign planes ----------------------------------------------------------------
+// Copies `planes` x-planes starting at x0 of one chunk into smem, zero-filling planes at x >= d (the
+// closed form's B == 0 outside the grid).
+__device__ __forceinline__ void stage_planes(uint32_t* sb, const uint32_t* __restrict__ chunk_bits, const Layout& L, int x0, int planes)
+{
+	const int total = planes * L.wp;
+	const int valid = min(planes, L.d - x0) * L.wp;
+	const uint4* src = reinterpret_cast<const uint4*>(chunk_bits + (size_t)x0 * L.wp);
+	uint4* dst = reinterpret_cast<uint4*>(sb);
+	for (int i = threadIdx.x; i < total / 4; i += CTA)
+		dst[i] = (i < valid / 4) ? src[i] : make_uint4(0, 0, 0, 0);
+}
+
+struct WordBits
+{
+	uint32_t A, A1, B, B1, C, C1, D, D1; // rows (x,y) (x,y+1) (x+1,y) (x+1,y+1); *1 = shifted so bit z holds sample z+1
+};
+
+// lx = plane index inside the staged window (plane lx+1 must be staged too)
+__device__ __forceinline__ WordBits load_word_bits(const uint32_t* sb, const Layout& L, int lx, int y, int zb)
+{
+	WordBits r;
+	const int base = (lx * L.d + y) * L.zc + zb;
+	const bool zn = zb + 1 < L.zc, yn = y + 1 < L.d;
+	r.A = sb[base];
+	r.A1 = __funnelshift_r(r.A, zn ? sb[base + 1] : 0u, 1);
+	r.B = yn ? sb[base + L.zc] : 0u;
+	r.B1 = __funnelshift_r(r.B, (yn && zn) ? sb[base + L.zc + 1] : 0u, 1);
+	r.C = sb[base + L.wp];
+	r.C1 = __funnelshift_r(r.C, zn ? sb[base + L.wp + 1] : 0u, 1);
+	r.D = yn ? sb[base + L.wp + L.zc] : 0u;
+	r.D1 = __funnelshift_r(r.D, (yn && zn) ? sb[base + L.wp + L.zc + 1] : 0u, 1);
+	return r;
+}
+
+struct WordClass
+{
+	uint32_t active;   // cells with mask8 not in {0,255}
+	uint32_t ex, ey, ez; // cells owning an X / Y / Z edge vertex
+	uint32_t interior; // cells that polygonize (x,y,z < d-1)
+};
+
+__device__ __forceinline__ WordClass classify(const WordBits& b, const Layout& L, int x, int y, int zb)
+{
+	WordClass c;
+	const uint32_t any = b.A | b.A1 | b.B | b.B1 | b.C | b.C1 | b.D | b.D1;
+	const uint32_t all = b.A & b.A1 & b.B & b.B1 & b.C & b.C1 & b.D & b.D1;
+	const uint32_t zvalid = (zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu;
+	const bool xn = x + 1 < L.d, yn = y + 1 < L.d;
+	c.active = any & ~all;
+	c.ex = xn ? (b.A ^ b.C) : 0u;
+	c.ey = yn ? (b.A ^ b.B) : 0u;
+	c.ez = (b.A ^ b.A1) & zvalid;
+	c.interior = (xn && yn) ? zvalid : 0u;
+	return c;
+}
+
+__device__ __forceinline__ uint32_t mask8_of(const WordBits& b, int bit)
+{
+	return ((b.A >> bit) & 1u) | (((b.A1 >> bit) & 1u) << 1) | (((b.B >> bit) & 1u) << 2) | (((b.B1 >> bit) & 1u) << 3) |
+	       (((b.C >> bit) & 1u) << 4) | (((b.C1 >> bit) & 1u) << 5) | (((b.D >> bit) & 1u) << 6) | (((b.D1 >> bit) & 1u) << 7);
+}
+
+// packed per-word counts: cells [0,8) verts [8,16) indices [16,32)
+__device__ __forceinline__ uint32_t pack_counts(uint32_t nc, uint32_t nv, uint32_t ni) { return nc | (nv << 8) | (ni << 16); }
+
+// exclusive scan of three counters over the CTA (thread order); totals returned through tot[3] (valid in all threads)
+__device__ __forceinline__ void block_scan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t tot[3])
+{
+	__shared__ uint32_t s_w[3][CTA / 32];
+	__shared__ uint32_t s_t[3];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+		if (lane >= o) { ia += ta; ib += tb; ic += tc; }
+	}
+	if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t va = lane < CTA / 32 ? s_w[0][lane] : 0, vb = lane < CTA / 32 ? s_w[1][lane] : 0, vc = lane < CTA / 32 ? s_w[2][lane] : 0;
+		uint32_t ja = va, jb = vb, jc = vc;
+#pragma unroll
+		for (int o = 1; o < CTA / 32; o <<= 1)
+		{
+			uint32_t ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
+			if (lane >= o) { ja += ta; jb += tb; jc += tc; }
+		}
+		if (lane < CTA / 32) { s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc; }
+		if (lane == CTA / 32 - 1) { s_t[0] = ja; s_t[1] = jb; s_t[2] = jc; }
+	}
+	__syncthreads();
+	a = ia - a + s_w[0][warp];
+	b = ib - b + s_w[1][warp];
+	c = ic - c + s_w[2][warp];
+	tot[0] = s_t[0]; tot[1] = s_t[1]; tot[2] = s_t[2];
+	__syncthreads();
+}
+
+// ---- K3: cell-mask build + counts.  One CTA per segment (P whole x-planes); each thread owns wpt
+// consecutive words.  Writes one packed count per word and one (cells, verts, indices) total per segment;
+// optionally the 8-bit mask image (MasksBlock, DMCChunk.cpp:184-438) when the caller wants it back.
+template <int WPT>
+__global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits, Layout L, uint32_t* __restrict__ wcnt,
+                                                uint32_t* __restrict__ seg_tot, uint8_t* __restrict__ masks)
+{
+	extern __shared__ uint32_t sb[];
+	const int seg = blockIdx.x;
+	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
+	__syncthreads();
+
+	uint32_t tc = 0, tv = 0, ti = 0;
+	uint32_t packed[WPT];
+#pragma unroll
+	for (int k = 0; k < WPT; k++)
+	{
+		const int lw = threadIdx.x * WPT + k; // word inside the segment
+		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp;
+		const WordBits b = load_word_bits(sb, L, lx, y, zb);
+		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		uint32_t nc = __popc(c.active);
+		uint32_t nv = __popc(c.ex) + __popc(c.ey) + __popc(c.ez);
+		uint32_t ni = 0;
+		uint32_t m = c.active & c.interior;
+		while (m)
+		{
+			int bit = __ffs(m) - 1;
+			m &= m - 1;
+			ni += (uint32_t)(c_tri_pack[mask8_of(b, bit)] >> 60);
+		}
+		packed[k] = pack_counts(nc, nv, ni);
+		tc += nc; tv += nv; ti += ni;
+		if (masks)
+		{
+			// MasksBlock byte image: 32 cells of this word, little-endian, 8 cells per uint64
+			uint8_t* mrow = masks + (size_t)chunk * L.wc * 32 + ((size_t)(x0 + lx) * L.d + y) * L.d + zb * 32;
+#pragma unroll
+			for (int q = 0; q < 8; q++)
+			{
+				uint32_t v4 = mask8_of(b, 4 * q) | (mask8_of(b, 4 * q + 1) << 8) | (mask8_of(b, 4 * q + 2) << 16) | (mask8_of(b, 4 * q + 3) << 24);
+				reinterpret_cast<uint32_t*>(mrow)[q] = v4;
+			}
+		}
+	}
+	uint32_t* out = wcnt + (size_t)seg * L.ws + threadIdx.x * WPT;
+	if (WPT == 4) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+	else
+	{
+		*reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+		*reinterpret_cast<uint4*>(out + 4) = make_uint4(packed[4 % WPT], packed[5 % WPT], packed[6 % WPT], packed[7 % WPT]);
+	}
+	// CTA totals
+	uint32_t tot[3];
+	block_scan3(tc, tv, ti, tot);
+	if (threadIdx.x == 0)
+	{
+		seg_tot[3 * (size_t)seg + 0] = tot[0];
+		seg_tot[3 * (size_t)seg + 1] = tot[1];
+		seg_tot[3 * (size_t)seg + 2] = tot[2];
+	}
+}
+
+// ---- segment scan: one CTA.  seg_base[3*(nseg+1)] = exclusive prefix of seg_tot with segments of chunks
+// that do not contain a mesh (DMCChunk.cpp:159-162, label_edges :170-171) forced to zero.
+struct ChunkCounts
+{
+	uint32_t contains_mesh;
+	uint32_t n_cells, n_verts, n_inds;
+	uint64_t cell_base, vert_base, ind_base;
+};
+
+static constexpr int SCAN_CTA = 1024;
+
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __restrict__ seg_tot, const uint32_t* __restrict__ flags, int nseg, int S,
+                                                             uint32_t* __restrict__ seg_base, ChunkCounts* __restrict__ chunks, int n_chunks,
+                                                             unsigned long long* __restrict__ totals /* cells, verts, inds, overflow */)
+{
+	__shared__ unsigned long long s_w[3][SCAN_CTA / 32];
+	__shared__ unsigned long long s_tot[3];
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const int per = (nseg + SCAN_CTA - 1) / SCAN_CTA;
+	const int lo = min(nseg, t * per), hi = min(nseg, lo + per);
+	unsigned long long a = 0, b = 0, c = 0;
+	for (int i = lo; i < hi; i++)
+	{
+		if (!flags_contain_mesh(flags[i / S])) continue;
+		a += seg_tot[3 * (size_t)i]; b += seg_tot[3 * (size_t)i + 1]; c += seg_tot[3 * (size_t)i + 2];
+	}
+	unsigned long long ia = a, ib = b, ic = c;
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+		if (lane >= o) { ia += ta; ib += tb; ic += tc; }
+	}
+	if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
+	__syncthreads();
+	if (warp == 0)
+	{
+		unsigned long long va = s_w[0][lane], vb = s_w[1][lane], vc = s_w[2][lane];
+		unsigned long long ja = va, jb = vb, jc = vc;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			unsigned long long ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
+			if (lane >= o) { ja += ta; jb += tb; jc += tc; }
+		}
+		s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc;
+		if (lane == 31) { s_tot[0] = ja; s_tot[1] = jb; s_tot[2] = jc; }
+	}
+	__syncthreads();
+	unsigned long long ea = ia - a + s_w[0][warp], eb = ib - b + s_w[1][warp], ec = ic - c + s_w[2][warp];
+	const bool overflow = s_tot[0] >= 0xFFFFFFFFull || s_tot[1] >= 0xFFFFFFFFull || s_tot[2] >= 0xFFFFFFFFull;
+	for (int i = lo; i < hi; i++)
+	{
+		seg_base[3 * (size_t)i] = (uint32_t)ea; seg_base[3 * (size_t)i + 1] = (uint32_t)eb; seg_base[3 * (size_t)i + 2] = (uint32_t)ec;
+		if (flags_contain_mesh(flags[i / S]))
+		{
+			ea += seg_tot[3 * (size_t)i]; eb += seg_tot[3 * (size_t)i + 1]; ec += seg_tot[3 * (size_t)i + 2];
+		}
+	}
+	if (t == 0)
+	{
+		seg_base[3 * (size_t)nseg] = (uint32_t)s_tot[0]; seg_base[3 * (size_t)nseg + 1] = (uint32_t)s_tot[1]; seg_base[3 * (size_t)nseg + 2] = (uint32_t)s_tot[2];
+		totals[0] = s_tot[0]; totals[1] = s_tot[1]; totals[2] = s_tot[2]; totals[3] = overflow ? 1ull : 0ull;
+	}
+	__syncthreads(); // seg_base complete (single CTA; global writes visible after the barrier)
+	__threadfence_block();
+	for (int ch = t; ch < n_chunks; ch += SCAN_CTA)
+	{
+		ChunkCounts cc;
+		const uint32_t* b0 = seg_base + 3 * (size_t)ch * S;
+		const uint32_t* b1 = seg_base + 3 * (size_t)(ch + 1) * S;
+		cc.contains_mesh = flags_contain_mesh(flags[ch]) ? 1u : 0u;
+		cc.cell_base = b0[0]; cc.vert_base = b0[1]; cc.ind_base = b0[2];
+		cc.n_cells = b1[0] - b0[0]; cc.n_verts = b1[1] - b0[1]; cc.n_inds = b1[2] - b0[2];
+		chunks[ch] = cc;
+	}
+}
+
+// ---- K4a: per-word bases + vertex emission.  One CTA per segment.
+// wvb[word] = chunk-local id of the word's first vertex; wib[word] = batch-wide position of its first index.
+// Vertices: calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674).
+template <int WPT>
+__global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt,
+                                                const uint32_t* __restrict__ seg_base, const ChunkCounts* __restrict__ chunks,
+                                                SamplerDev s, DensitySource src, const ChunkGeom* __restrict__ geom,
+                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib,
+                                                float* __restrict__ pos, uint8_t* __restrict__ boundary)
+{
+	extern __shared__ uint32_t sb[];
+	const int seg = blockIdx.x;
+	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	const ChunkCounts cc = chunks[chunk];
+	uint32_t cnt[WPT];
+	{
+		const uint32_t* in = wcnt + (size_t)seg * L.ws + threadIdx.x * WPT;
+#pragma unroll
+		for (int k = 0; k < WPT; k += 4)
+		{
+			uint4 v = *reinterpret_cast<const uint4*>(in + k);
+			cnt[k] = v.x; cnt[k + 1] = v.y; cnt[k + 2] = v.z; cnt[k + 3] = v.w;
+		}
+	}
+	if (!cc.contains_mesh)
+	{
+#pragma unroll
+		for (int k = 0; k < WPT; k++) cnt[k] = 0;
+	}
+	uint32_t tv = 0, ti = 0, tc = 0;
+#pragma unroll
+	for (int k = 0; k < WPT; k++) { tc += cnt[k] & 0xFF; tv += (cnt[k] >> 8) & 0xFF; ti += cnt[k] >> 16; }
+	uint32_t tot[3];
+	block_scan3(tc, tv, ti, tot);
+	const uint32_t seg_v_local = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base;
+	const uint32_t seg_i = seg_base[3 * (size_t)seg + 2];
+	uint32_t vb[WPT];
+	{
+		uint32_t rv = seg_v_local + tv, ri = seg_i + ti;
+		uint32_t ob[WPT], oi[WPT];
+#pragma unroll
+		for (int k = 0; k < WPT; k++)
+		{
+			ob[k] = rv; oi[k] = ri; vb[k] = rv;
+			rv += (cnt[k] >> 8) & 0xFF; ri += cnt[k] >> 16;
+		}
+		uint32_t* o1 = wvb + (size_t)seg * L.ws + threadIdx.x * WPT;
+		uint32_t* o2 = wib + (size_t)seg * L.ws + threadIdx.x * WPT;
+#pragma unroll
+		for (int k = 0; k < WPT; k += 4)
+		{
+			*reinterpret_cast<uint4*>(o1 + k) = make_uint4(ob[k], ob[k + 1], ob[k + 2], ob[k + 3]);
+			*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oi[k], oi[k + 1], oi[k + 2], oi[k + 3]);
+		}
+	}
+	if (tot[1] == 0) return; // no vertex in this segment (uniform across the CTA)
+
+	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
+	__syncthreads();
+	const ChunkGeom g = geom[chunk];
+	const int d = L.d;
+#pragma unroll
+	for (int k = 0; k < WPT; k++)
+	{
+		if (((cnt[k] >> 8) & 0xFF) == 0) continue;
+		const int lw = threadIdx.x * WPT + k;
+		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp, x = x0 + lx;
+		const WordBits b = load_word_bits(sb, L, lx, y, zb);
+		const WordClass c = classify(b, L, x, y, zb);
+		uint32_t m = c.ex | c.ey | c.ez;
+		size_t v = (size_t)cc.vert_base + vb[k];
+		while (m)
+		{
+			const int bit = __ffs(m) - 1;
+			m &= m - 1;
+			const int z = zb * 32 + bit;
+			const float s0 = density_at(s, src, g, d, chunk, x, y, z);
+			const bool b0 = x == 0 || y == 0 || z == 0 || x == d - 1 || y == d - 1 || z == d - 1;
+#pragma unroll
+			for (int axis = 0; axis < 3; axis++)
+			{
+				const uint32_t e = axis == 0 ? c.ex : axis == 1 ? c.ey : c.ez;
+				if (!((e >> bit) & 1u)) continue;
+				const int x1 = x + (axis == 0), y1 = y + (axis == 1), z1 = z + (axis == 2);
+				const float s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
+				const float mu = (0.0f - s0) / (s1 - s0);
+				// (p1 - p0) * mu + p0 per component, p in grid units
+				pos[3 * v + 0] = ((float)x1 - (float)x) * mu + (float)x;
+				pos[3 * v + 1] = ((float)y1 - (float)y) * mu + (float)y;
+				pos[3 * v + 2] = ((float)z1 - (float)z) * mu + (float)z;
+				boundary[v] = (b0 || x1 == d - 1 || y1 == d - 1 || z1 == d - 1) ? 1 : 0;
+				v++;
+			}
+		}
+	}
+}
+
+// chunk-local id of the vertex on `axis` of cell (lx,y,z) inside the staged window
+__device__ __forceinline__ uint32_t vertex_id(const uint32_t* sb, const uint32_t* svb, const Layout& L, int x0, int lx, int y, int z, int axis)
+{
+	const int zb = z >> 5, bit = z & 31;
+	const int base = (lx * L.d + y) * L.zc + zb;
+	const bool zn = zb + 1 < L.zc, yn = y + 1 < L.d, xn = x0 + lx + 1 < L.d;
+	const uint32_t A = sb[base];
+	const uint32_t A1 = __funnelshift_r(A, zn ? sb[base + 1] : 0u, 1);
+	const uint32_t ex = xn ? (A ^ sb[base + L.wp]) : 0u;
+	const uint32_t ey = yn ? (A ^ sb[base + L.zc]) : 0u;
+	const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+	const uint32_t lt = (1u << bit) - 1u;
+	uint32_t id = svb[base] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
+	if (axis >= 1) id += (ex >> bit) & 1u;
+	if (axis >= 2) id += (ey >> bit) & 1u;
+	return id;
+}
+
+// ---- K4b: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence.
+// Staged: sign planes x0 .. x0+P+1 and vertex bases of planes x0 .. x0+P.
+template <int WPT>
+__global__ void __launch_bounds__(CTA) k_inds(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt,
+                                               const uint32_t* __restrict__ wvb, const uint32_t* __restrict__ wib,
+                                               const ChunkCounts* __restrict__ chunks, uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
+{
+	extern __shared__ uint32_t sb[];
+	const int seg = blockIdx.x;
+	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	const ChunkCounts cc = chunks[chunk];
+	if (!cc.contains_mesh || cc.n_inds == 0) return;
+	uint32_t* svb = sb + (L.P + 2) * L.wp;
+	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 2);
+	{
+		// vertex bases: planes x0 .. x0+P (the halo plane belongs to the next segment of the same chunk)
+		const int planes = min(L.P + 1, L.d - x0);
+		const uint4* srcv = reinterpret_cast<const uint4*>(wvb + (size_t)chunk * L.wc + (size_t)x0 * L.wp);
+		uint4* dst = reinterpret_cast<uint4*>(svb);
+		for (int i = threadIdx.x; i < (L.P + 1) * L.wp / 4; i += CTA)
+			dst[i] = (i < planes * L.wp / 4) ? srcv[i] : make_uint4(0, 0, 0, 0);
+	}
+	__syncthreads();
+
+#pragma unroll
+	for (int k = 0; k < WPT; k++)
+	{
+		const int lw = threadIdx.x * WPT + k;
+		const size_t gw = (size_t)seg * L.ws + lw;
+		if ((wcnt[gw] >> 16) == 0) continue;
+		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp;
+		const WordBits b = load_word_bits(sb, L, lx, y, zb);
+		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		uint32_t m = c.active & c.interior;
+		uint32_t o = wib[gw];
+		while (m)
+		{
+			const int bit = __ffs(m) - 1;
+			m &= m - 1;
+			const int z = zb * 32 + bit;
+			const uint64_t tp = c_tri_pack[mask8_of(b, bit)];
+			const int n = (int)(tp >> 60);
+			for (int t = 0; t < n; t++)
+			{
+				const int e = (int)(tp >> (4 * t)) & 15;
+				// EDGE_V (DMCChunk.cpp:32, 543-565): e0-3 X-edges at (y,z) offsets, e4-7 Y-edges at (x,z), e8-11 Z-edges at (x,y)
+				const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
+				const int dx = axis == 0 ? 0 : hi;
+				const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
+				const int dz = axis == 2 ? 0 : lo;
+				const uint32_t vid = vertex_id(sb, svb, L, x0, lx + dx, y + dy, z + dz, axis);
+				inds[o++] = vid;
+				// init_valence++ (DMCChunk.cpp:573): byte-wise add through the aligned 32-bit word
+				const size_t gv = (size_t)cc.vert_base + vid;
+				atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
+			}
+		}
+	}
+}
+
+} // namespace bmf

@@ -1,0 +1,411 @@
+// smooth.cuh -- K5: Processing::MeshProcessor<N> on the device (MeshProcessor.cpp:25-55 init,
+// 98-128 init_primitives, 130-236 optimize_dual_grid, 238-306 optimize_primal_grid), batch-wide:
+// all chunks' vertices / primitives are processed by one launch per step.
+//
+// The reference sums a vertex's adjacent duals in CSR order = ascending primitive id
+// (init_primitives fills (primitive, corner) order).  The CSR here is filled with atomics and then each
+// (short) list is sorted, so the float summation order -- and therefore every bit of the result -- is the
+// reference's.  Jacobi structure is kept: all duals from the old positions, then all vertices.
+//
+// K6: qef_solve_from_points_3d (qef_simd.h:550-579) as one thread per system, everything in registers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "extract.cuh"
+
+namespace bmf
+{
+
+// ---- device-wide exclusive scan of uint8 -> uint32 (adj_offset = prefix of init_valence, MeshProcessor.cpp:33-39)
+static constexpr int SCAN_ITEMS = 16; // per thread
+
+__global__ void __launch_bounds__(CTA) k_scan8_partial(const uint8_t* __restrict__ in, size_t n, uint32_t* __restrict__ block_sums)
+{
+	const size_t base = ((size_t)blockIdx.x * CTA + threadIdx.x) * SCAN_ITEMS;
+	uint32_t s = 0;
+	if (base + SCAN_ITEMS <= n)
+	{
+		uint4 v = *reinterpret_cast<const uint4*>(in + base);
+		uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+		for (int k = 0; k < 4; k++) s += (w[k] & 0xFF) + ((w[k] >> 8) & 0xFF) + ((w[k] >> 16) & 0xFF) + (w[k] >> 24);
+	}
+	else
+		for (size_t i = base; i < n; i++) s += in[i];
+	uint32_t a = s, b = 0, c = 0, tot[3];
+	block_scan3(a, b, c, tot);
+	if (threadIdx.x == 0) block_sums[blockIdx.x] = tot[0];
+}
+
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_block_sums(uint32_t* __restrict__ sums, int n)
+{
+	__shared__ uint32_t s_w[SCAN_CTA / 32];
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const int per = (n + SCAN_CTA - 1) / SCAN_CTA;
+	const int lo = min(n, t * per), hi = min(n, lo + per);
+	uint32_t a = 0;
+	for (int i = lo; i < hi; i++) a += sums[i];
+	uint32_t ia = a;
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o);
+		if (lane >= o) ia += ta;
+	}
+	if (lane == 31) s_w[warp] = ia;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t v = s_w[lane], j = v;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t tj = __shfl_up_sync(0xffffffffu, j, o);
+			if (lane >= o) j += tj;
+		}
+		s_w[lane] = j - v;
+	}
+	__syncthreads();
+	uint32_t e = ia - a + s_w[warp];
+	for (int i = lo; i < hi; i++)
+	{
+		uint32_t v = sums[i];
+		sums[i] = e;
+		e += v;
+	}
+}
+
+__global__ void __launch_bounds__(CTA) k_scan8_final(const uint8_t* __restrict__ in, size_t n, const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ out)
+{
+	const size_t base = ((size_t)blockIdx.x * CTA + threadIdx.x) * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	uint32_t s = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++)
+	{
+		v[k] = (base + k < n) ? in[base + k] : 0;
+		s += v[k];
+	}
+	uint32_t a = s, b = 0, c = 0, tot[3];
+	block_scan3(a, b, c, tot);
+	uint32_t run = block_sums[blockIdx.x] + a;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++)
+	{
+		if (base + k < n) out[base + k] = run;
+		run += v[k];
+	}
+}
+
+// chunk that owns batch-wide index position p (chunks' ind_base are ascending)
+__device__ __forceinline__ int chunk_of_index(const ChunkCounts* __restrict__ chunks, int n_chunks, uint64_t p)
+{
+	int lo = 0, hi = n_chunks - 1;
+	while (lo < hi)
+	{
+		int mid = (lo + hi + 1) >> 1;
+		if (chunks[mid].ind_base <= p) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+
+// ---- CSR build: adj[adj_off[v] + k] = primitive ids of v, ascending (init_primitives :114-127)
+template <int N>
+__global__ void __launch_bounds__(CTA) k_csr_fill(const uint32_t* __restrict__ inds, size_t n_prims, const ChunkCounts* __restrict__ chunks, int n_chunks,
+                                                   const uint32_t* __restrict__ adj_off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ adj,
+                                                   uint32_t* __restrict__ prim_vbase)
+{
+	const size_t t = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (t >= n_prims) return;
+	const int ch = chunk_of_index(chunks, n_chunks, (uint64_t)t * N);
+	const uint32_t vbase = (uint32_t)chunks[ch].vert_base;
+	prim_vbase[t] = vbase;
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		const uint32_t v = vbase + inds[t * N + k];
+		const uint32_t slot = atomicAdd(cursor + v, 1u);
+		adj[adj_off[v] + slot] = (uint32_t)t;
+	}
+}
+
+__global__ void __launch_bounds__(CTA) k_csr_sort(const uint32_t* __restrict__ adj_off, const uint8_t* __restrict__ valence, size_t n_verts, uint32_t* __restrict__ adj)
+{
+	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (v >= n_verts) return;
+	const int n = valence[v];
+	uint32_t* a = adj + adj_off[v];
+	for (int i = 1; i < n; i++)
+	{
+		uint32_t key = a[i];
+		int j = i - 1;
+		while (j >= 0 && a[j] > key)
+		{
+			a[j + 1] = a[j];
+			j--;
+		}
+		a[j + 1] = key;
+	}
+}
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 ld3(const float* p, size_t i) { return { p[3 * i], p[3 * i + 1], p[3 * i + 2] }; }
+__device__ __forceinline__ void st3(float* p, size_t i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ f3 div3(f3 a, float s) { return { a.x / s, a.y / s, a.z / s }; }
+__device__ __forceinline__ f3 mul3(f3 a, float s) { return { a.x * s, a.y * s, a.z * s }; }
+// glm::normalize = v * (1 / sqrt(dot)), dot = x*x + y*y + z*z left to right
+__device__ __forceinline__ f3 normalize3(f3 v) { float inv = 1.0f / sqrtf((v.x * v.x + v.y * v.y) + v.z * v.z); return mul3(v, inv); }
+__device__ __forceinline__ f3 cross3(f3 x, f3 y) { return { x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y }; }
+
+// ---- dual step (optimize_dual_grid :141-227): centroid, colour mean and (optionally) normal per primitive
+template <int N>
+__global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds, const uint32_t* __restrict__ prim_vbase, size_t n_prims,
+                                               const float* __restrict__ pos, const float* __restrict__ color, const float* __restrict__ normal,
+                                               float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals)
+{
+	const size_t t = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (t >= n_prims) return;
+	const uint32_t vb = prim_vbase[t];
+	size_t v[N];
+#pragma unroll
+	for (int k = 0; k < N; k++) v[k] = (size_t)vb + inds[t * N + k];
+	f3 sp = { 0, 0, 0 }, sc = { 0, 0, 0 };
+	f3 p[N];
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		p[k] = ld3(pos, v[k]);
+		sp = add3(sp, p[k]);
+		sc = add3(sc, ld3(color, v[k]));
+	}
+	st3(dp, t, div3(sp, (float)N));
+	st3(dc, t, div3(sc, (float)N));
+	if (!smooth) return;
+	if (face_normals)
+	{
+		if (N == 3)
+		{
+			f3 a = normalize3(sub3(p[0], p[1])), b = normalize3(sub3(p[0], p[2]));
+			f3 c = cross3(a, b);
+			st3(dn, t, { -c.x, -c.y, -c.z });
+		}
+		else
+		{
+			f3 n1 = cross3(normalize3(sub3(p[0], p[1])), normalize3(sub3(p[0], p[2 % N])));
+			f3 n2 = cross3(normalize3(sub3(p[2 % N], p[3 % N])), normalize3(sub3(p[2 % N], p[0])));
+			if (isnan(n1.x))
+			{
+				n1 = n2;
+				if (isnan(n1.x)) n1 = { 0.0f, 1.0f, 0.0f };
+			}
+			if (isnan(n2.x)) n2 = n1;
+			f3 h = normalize3(mul3(add3(n1, n2), 0.5f));
+			st3(dn, t, { -h.x, -h.y, -h.z });
+		}
+	}
+	else
+	{
+		f3 sn = { 0, 0, 0 };
+#pragma unroll
+		for (int k = 0; k < N; k++) sn = add3(sn, ld3(normal, v[k]));
+		st3(dn, t, sn); // not averaged (:211-213)
+	}
+}
+
+// ---- primal step (optimize_primal_grid :238-306)
+__global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                                 const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dc,
+                                                 const float* __restrict__ dn, float* __restrict__ pos, float* __restrict__ color, float* __restrict__ normal,
+                                                 int smooth, int set_colors, int process_boundary)
+{
+	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (v >= n_verts) return;
+	const int cnt = valence[v];
+	if (cnt == 0 || (!process_boundary && boundary[v])) return;
+	const uint32_t* a = adj + adj_off[v];
+	f3 p = { 0, 0, 0 }, n = { 0, 0, 0 }, c = { 0, 0, 0 };
+	for (int k = 0; k < cnt; k++)
+	{
+		const size_t t = a[k];
+		p = add3(p, ld3(dp, t));
+		c = add3(c, ld3(dc, t));
+		if (smooth) n = add3(n, ld3(dn, t));
+	}
+	const float fc = (float)cnt;
+	p = div3(p, fc);
+	c = div3(c, fc);
+	if (smooth) n = div3(n, fc);
+	if (set_colors) n = normalize3(n);
+	st3(pos, v, p);
+	st3(color, v, c);
+	if (n.y != 0 && normal) st3(normal, v, n);
+}
+
+__global__ void __launch_bounds__(CTA) k_fill_f32(float* __restrict__ p, size_t n, float v)
+{
+	const size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+
+// ---- K6: QEF, one thread per system (scalar form of qef_simd.h).  The reference's single
+// _mm_rsqrt_ps (x86 12-bit approximation, CPU-specific) is an exact 1/sqrt here.
+__device__ __forceinline__ float dot4(const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + (a[3] * b[3] + a[2] * b[2]); }
+
+__device__ __forceinline__ float qef_solve_device(const float* __restrict__ P, const float* __restrict__ Nn, int count, float out[3])
+{
+	if (count < 2 || count > 12)
+	{
+		out[0] = out[1] = out[2] = 0.0f;
+		return 0.0f;
+	}
+	float ATA[4][4], ATb[4] = { 0, 0, 0, 0 }, acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) ATA[r][j] = 0.0f;
+	for (int i = 0; i < count; i++)
+	{
+		const float p[4] = { P[3 * i], P[3 * i + 1], P[3 * i + 2], 1.0f };
+		const float n[4] = { Nn[3 * i], Nn[3 * i + 1], Nn[3 * i + 2], 0.0f };
+#pragma unroll
+		for (int r = 0; r < 3; r++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) ATA[r][j] += n[r] * n[j];
+		const float d = dot4(p, n);
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			ATb[j] += (j < 3 ? d : 0.0f) * n[j];
+			acc[j] += p[j];
+		}
+	}
+	float mp[4], b[4], tmp[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) mp[j] = acc[j] / acc[3];
+#pragma unroll
+	for (int j = 0; j < 4; j++) tmp[j] = ((mp[0] * ATA[0][j] + mp[1] * ATA[1][j]) + mp[2] * ATA[2][j]) + mp[3] * ATA[3][j];
+#pragma unroll
+	for (int j = 0; j < 4; j++) b[j] = ATb[j] - tmp[j];
+
+	float A[4][4], V[4][4];
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) { A[r][j] = ATA[r][j]; V[r][j] = (r == j && r < 3) ? 1.0f : 0.0f; }
+
+#define BMF_QEF_ROT(a, q)                                                                                         \
+	if (A[a][q] != 0.0f)                                                                                          \
+	{                                                                                                             \
+		const float pp = A[a][a], pq = A[a][q], qq = A[q][q];                                                     \
+		const float tau = (qq - pp) / (pq * 2.0f);                                                                \
+		const float stt = sqrtf(tau * tau + 1.0f);                                                                \
+		const float tn = 1.0f / ((tau >= 0.0f) ? (tau + stt) : (tau - stt));                                      \
+		float c = 1.0f / sqrtf(1.0f + tn * tn);                                                                   \
+		float s = tn * c;                                                                                         \
+		if (pq == 0.0f) { c = 1.0f; s = 0.0f; }                                                                   \
+		const float cc = c * c, ss = s * s;                                                                       \
+		const float mx = ((2.0f * c) * s) * pq;                                                                   \
+		A[a][a] = (cc * pp - mx) + ss * qq;                                                                       \
+		A[q][q] = (ss * pp + mx) + cc * qq;                                                                       \
+		float u[4] = { V[0][a], V[1][a], V[2][a], A[0][3 - q] };                                                  \
+		float w[4] = { V[0][q], V[1][q], V[2][q], A[1 - a][2] };                                                  \
+		float xr[4], yr[4];                                                                                       \
+		_Pragma("unroll") for (int k = 0; k < 4; k++) { xr[k] = c * u[k] - s * w[k]; yr[k] = s * u[k] + c * w[k]; } \
+		V[0][a] = xr[0]; V[1][a] = xr[1]; V[2][a] = xr[2]; A[0][3 - q] = xr[3];                                   \
+		V[0][q] = yr[0]; V[1][q] = yr[1]; V[2][q] = yr[2]; A[1 - a][2] = yr[3];                                   \
+		A[a][q] = 0.0f;                                                                                           \
+	}
+#pragma unroll
+	for (int sweep = 0; sweep < 5; sweep++)
+	{
+		BMF_QEF_ROT(0, 1)
+		BMF_QEF_ROT(0, 2)
+		BMF_QEF_ROT(1, 2)
+	}
+#undef BMF_QEF_ROT
+	const float sigma[4] = { A[0][0], A[1][1], A[2][2], 0.0f };
+	float inv[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		const float one_over = 1.0f / sigma[j];
+		const float mn = fminf(fabsf(sigma[j]), fabsf(one_over));
+		inv[j] = (mn >= 0.001f) ? one_over : 0.0f;
+	}
+	float M[3][4], Pm[4][4];
+#pragma unroll
+	for (int r = 0; r < 3; r++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) M[r][j] = V[r][j] * inv[j];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) Pm[i][j] = (i < 3 && j < 3) ? dot4(M[j], V[i]) : 0.0f;
+	float x[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) x[j] = ((b[0] * Pm[0][j] + b[1] * Pm[1][j]) + b[2] * Pm[2][j]) + b[3] * Pm[3][j];
+#pragma unroll
+	for (int j = 0; j < 4; j++) tmp[j] = ((x[0] * ATA[0][j] + x[1] * ATA[1][j]) + x[2] * ATA[2][j]) + x[3] * ATA[3][j];
+	float e[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) e[j] = ATb[j] - tmp[j];
+	out[0] = x[0] + mp[0];
+	out[1] = x[1] + mp[1];
+	out[2] = x[2] + mp[2];
+	return dot4(e, e);
+}
+
+__global__ void __launch_bounds__(128) k_qef_batch(const float* __restrict__ positions, const float* __restrict__ normals, const int32_t* __restrict__ counts,
+                                                    int m, float* __restrict__ out_pos, float* __restrict__ out_err)
+{
+	const int j = blockIdx.x * 128 + threadIdx.x;
+	if (j >= m) return;
+	float P[36], Nn[36];
+	const int cnt = counts[j];
+	const int c = cnt < 0 ? 0 : (cnt > 12 ? 12 : cnt);
+	for (int i = 0; i < 3 * c; i++)
+	{
+		P[i] = positions[(size_t)j * 36 + i];
+		Nn[i] = normals[(size_t)j * 36 + i];
+	}
+	float o[3];
+	const float err = qef_solve_device(P, Nn, cnt, o);
+	out_pos[3 * (size_t)j] = o[0];
+	out_pos[3 * (size_t)j + 1] = o[1];
+	out_pos[3 * (size_t)j + 2] = o[2];
+	out_err[j] = err;
+}
+
+// Build-defined QEF placement (config 5; the reference never calls its solver, MeshProcessor.cpp:239):
+// each processed vertex is re-placed at the QEF minimiser of the planes (dual_p, dual_n) of its first <= 12
+// adjacent primitives, clamped to the bounding box of those dual points.
+__global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                                    const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dn,
+                                                    float* __restrict__ pos, int process_boundary)
+{
+	const size_t v = (size_t)blockIdx.x * 128 + threadIdx.x;
+	if (v >= n_verts) return;
+	int cnt = valence[v];
+	if (cnt < 2 || (!process_boundary && boundary[v])) return;
+	if (cnt > 12) cnt = 12;
+	const uint32_t* a = adj + adj_off[v];
+	float P[36], Nn[36];
+	f3 lo = { 3.0e38f, 3.0e38f, 3.0e38f }, hi = { -3.0e38f, -3.0e38f, -3.0e38f };
+	for (int k = 0; k < cnt; k++)
+	{
+		const size_t t = a[k];
+		f3 p = ld3(dp, t), n = ld3(dn, t);
+		P[3 * k] = p.x; P[3 * k + 1] = p.y; P[3 * k + 2] = p.z;
+		Nn[3 * k] = n.x; Nn[3 * k + 1] = n.y; Nn[3 * k + 2] = n.z;
+		lo = { fminf(lo.x, p.x), fminf(lo.y, p.y), fminf(lo.z, p.z) };
+		hi = { fmaxf(hi.x, p.x), fmaxf(hi.y, p.y), fmaxf(hi.z, p.z) };
+	}
+	float o[3];
+	qef_solve_device(P, Nn, cnt, o);
+	if (isnan(o[0]) || isnan(o[1]) || isnan(o[2])) return;
+	pos[3 * v] = fminf(fmaxf(o[0], lo.x), hi.x);
+	pos[3 * v + 1] = fminf(fmaxf(o[1], lo.y), hi.y);
+	pos[3 * v + 2] = fminf(fmaxf(o[2], lo.z), hi.z);
+}
+
+} // namespace bmf

@@ -1,0 +1,166 @@
+/*
+ * bmf_b200.h -- C ABI of the B200-native chunk-extraction path (libbmf_b200.so).
+ *
+ * The reference (Lin20/BinaryMeshFitting) has no FFI: the hot path sits behind C++ classes compiled
+ * into one executable.  This header is the drop-in boundary those classes are re-hosted
+ * on: plain pointers and sizes, no C++ or torch types.  Each entry point names the reference
+ * interface it replaces (file:line under /root/reference/BinaryMeshFitting).  The C++ mirror of the
+ * reference classes (Sampler / DMCChunk / ChunkGenerator / Processing::MeshProcessor) that sits on
+ * top of this ABI is binarymeshfitting_b200/host/bmf_host.hpp; INTEGRATION.md shows the binding.
+ *
+ * Conventions: every function returns 0 on success, a negative bmf_status otherwise;
+ * bmf_last_error(ctx) holds the message.  One bmf_ctx per GPU; a ctx is single-threaded (the
+ * reference calls ChunkGenerator::process_queue from exactly one thread, WorldWatcher.cpp:71).
+ * The caller owns host buffers; the library owns device arenas.  There is NO CPU fallback: without a
+ * CUDA device every compute entry point fails with BMF_ERR_CUDA.
+ */
+#ifndef BMF_B200_H
+#define BMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bmf_status
+{
+	BMF_OK = 0,
+	BMF_ERR_INVALID = -1, /* bad argument (dim not in {32,64,128,256}, null pointer, count out of range ...) */
+	BMF_ERR_CUDA = -2,    /* CUDA runtime error (message in bmf_last_error) */
+	BMF_ERR_STATE = -3,   /* call order (no batch submitted, sampler not set ...) */
+	BMF_ERR_NOMEM = -4
+} bmf_status;
+
+/* Sampler.hpp:24-34 -- a GPU can only run *known* samplers, so the callback bundle becomes a
+ * descriptor.  HOST_DENSITY is the escape hatch for arbitrary `Sampler::block` callbacks: the host
+ * fills the density block, the device does everything after it (also the bit-exact parity mode). */
+typedef enum bmf_sampler_kind
+{
+	BMF_SAMPLER_SPHERE = 0,          /* ImplicitSampler.cpp:46-50 */
+	BMF_SAMPLER_TORUS_Z = 1,         /* ImplicitSampler.cpp:27-34 */
+	BMF_SAMPLER_CUBOID = 2,          /* ImplicitSampler.cpp:52-60 */
+	BMF_SAMPLER_PLANE_Y = 3,         /* ImplicitSampler.cpp:62-65 */
+	BMF_SAMPLER_CSG = 4,             /* two primitives combined (config 5; build-defined, unpinned) */
+	BMF_SAMPLER_TERRAIN2D = 10,      /* NoiseSampler.cpp:113-146 */
+	BMF_SAMPLER_TERRAIN2D_PERT = 11, /* NoiseSampler.cpp:148-194 (the reference world's default) */
+	BMF_SAMPLER_TERRAIN3D = 12,      /* NoiseSampler.cpp:196-227 */
+	BMF_SAMPLER_TERRAIN3D_PERT = 13, /* NoiseSampler.cpp:229-263 */
+	BMF_SAMPLER_HOST_DENSITY = 100
+} bmf_sampler_kind;
+
+typedef enum bmf_csg_op { BMF_CSG_UNION = 0, BMF_CSG_INTERSECT = 1, BMF_CSG_SUBTRACT = 2 } bmf_csg_op;
+
+typedef struct bmf_sampler_desc
+{
+	int32_t kind;     /* bmf_sampler_kind */
+	float world_size; /* Sampler::world_size (Sampler.hpp:26) */
+	/* NoiseSamplers::NoiseSamplerProperties (NoiseSampler.hpp:7-22); defaults WorldOctree.cpp:47-54 */
+	float g_scale, height;
+	int32_t octaves;
+	float amp, frequency, gain;
+	int32_t seed; /* FastNoiseSIMD::NewFastNoiseSIMD(seed), library default 1337 */
+	/* BMF_SAMPLER_CSG: value = op(a(p - offset_a), b(p - offset_b)), positive = inside */
+	int32_t csg_op, csg_kind_a, csg_kind_b;
+	float csg_world_size_a, csg_world_size_b;
+	float csg_offset_a[3], csg_offset_b[3];
+} bmf_sampler_desc;
+
+/* DMCChunk::init(pos, size, level, sampler, parent_code) (DMCChunk.cpp:58-77) + the per-chunk overlap
+ * ChunkGenerator::extract_chunk derives (ChunkGenerator.cpp:98) */
+typedef struct bmf_chunk_desc
+{
+	float pos[3];
+	float size;
+	int32_t level;
+	float overlap;
+	uint64_t morton; /* WorldOctreeNode::morton_code (carried through, not interpreted) */
+} bmf_chunk_desc;
+
+/* WorldProperties / DefaultOptions knobs that reach the hot path (WorldOctree.cpp:20-33,
+ * DefaultOptions.h:7-8, ChunkGenerator.cpp:112-124) */
+typedef struct bmf_params
+{
+	int32_t dim;              /* chunk_resolution: 32, 64, 128 or 256 */
+	int32_t iters;            /* process_iters: MeshProcessor<3> iterations, 0 = none */
+	int32_t process_boundary; /* boundary_processing */
+	int32_t smooth_normals;   /* SMOOTH_NORMALS */
+	int32_t qef;              /* 1: after smoothing, re-place each vertex by the QEF of its adjacent primitives (build-defined policy) */
+	int32_t keep_density;     /* 1: materialise the f32 density block (DMCChunk::density_block) so it can be copied out */
+	int32_t keep_masks;       /* 1: materialise the 8-bit cell masks (MasksBlock image) so they can be copied out */
+	int32_t density_on_device; /* HOST_DENSITY only: the density pointer passed to submit is a device pointer */
+} bmf_params;
+
+typedef struct bmf_chunk_info
+{
+	int32_t contains_mesh; /* DMCChunk::contains_mesh (DMCChunk.cpp:159-162) */
+	int32_t n_cells, n_verts, n_inds;
+	int64_t vert_offset, ind_offset; /* into the batch-wide SoA arrays */
+	float overlap_pos[3];            /* DMCChunk::overlap_pos (DMCChunk.cpp:97) */
+	float scale;                     /* DMCChunk::scale = delta (DMCChunk.cpp:94,98) */
+} bmf_chunk_info;
+
+enum
+{
+	BMF_STAGE_SAMPLE = 0, /* K1 sampling + sign pack (or K2 pack from a supplied density block) */
+	BMF_STAGE_COUNT = 1,  /* K3 cell-mask build + per-word counts */
+	BMF_STAGE_SCAN = 2,   /* segment scan */
+	BMF_STAGE_VERTS = 3,  /* K4 vertex emission */
+	BMF_STAGE_INDS = 4,   /* K4 index emission + valence */
+	BMF_STAGE_SMOOTH = 5, /* K5 CSR + dual/primal iterations (+K6 QEF placement) */
+	BMF_STAGE_TOTAL = 6,  /* first kernel start to last kernel end */
+	BMF_NUM_STAGES = 7
+};
+
+typedef struct bmf_ctx bmf_ctx;
+
+/* library */
+int bmf_ctx_create(int device, bmf_ctx** out);
+void bmf_ctx_destroy(bmf_ctx* ctx);
+const char* bmf_last_error(const bmf_ctx* ctx);
+const char* bmf_version(void);
+
+/* Sampler (Sampler.hpp:24-34; factories ImplicitSampler.hpp:51-59, NoiseSampler.hpp:82-140) */
+void bmf_sampler_defaults(bmf_sampler_desc* desc, int kind);
+int bmf_sampler_set(bmf_ctx* ctx, const bmf_sampler_desc* desc);
+
+/* ChunkGenerator::process_queue / extract_chunk (ChunkGenerator.cpp:27-60, 80-147): the whole batch
+ * through label_grid -> label_edges -> polygonize -> MeshProcessor<3>.  Asynchronous on the ctx stream.
+ * `density` is required (n * dim^3 floats, chunk-major, [x][y][z] z fastest) for HOST_DENSITY, else NULL.
+ * One batch per ctx is resident at a time; submitting again recycles the arenas. */
+int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bmf_params* params, const float* density);
+int bmf_batch_wait(bmf_ctx* ctx);
+int bmf_batch_totals(bmf_ctx* ctx, int64_t* n_cells, int64_t* n_verts, int64_t* n_inds);
+int bmf_batch_chunk_info(bmf_ctx* ctx, int i, bmf_chunk_info* out);
+int bmf_batch_chunk_infos(bmf_ctx* ctx, bmf_chunk_info* out /* [n] */);
+
+/* The renderer-facing SoA of the whole batch (what GLChunk::format_data packs, GLChunk.cpp:278-296:
+ * p_data / n_data / c_data + the index buffer), chunk i at [vert_offset, +n_verts) / [ind_offset, +n_inds).
+ * Indices are chunk-local like DMCChunk::vi->mesh_indexes.  Any pointer may be NULL. */
+int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices);
+
+/* One chunk in the reference's own layouts: DualVertex[n_verts] (84-byte records, Vertices.hpp:5-24),
+ * mesh_indexes, BinaryBlock words (dim^3/32), MasksBlock byte image (dim^3, needs keep_masks),
+ * DensityBlock (dim^3 floats, needs keep_density or HOST_DENSITY).  Any pointer may be NULL. */
+int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* indices, uint32_t* bits, uint8_t* masks, float* density);
+
+/* per-stage device times of the last batch (CUDA events on the ctx stream), milliseconds */
+int bmf_batch_stage_ms(bmf_ctx* ctx, float* ms /* [BMF_NUM_STAGES] */);
+/* kernels launched by this ctx since creation (bench.py's gpu_launches) */
+int64_t bmf_ctx_launch_count(const bmf_ctx* ctx);
+/* device pointers of the resident batch (for zero-copy consumers / profiling); valid until next submit */
+int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits, void** density);
+
+/* Processing::MeshProcessor<N> stand-alone (MeshProcessor.hpp:55-84): init + optimize_dual_grid(iters,
+ * pb) + optimize_primal_grid(false,false,pb) + flush, on caller arrays (updated in place).  N = 3 or 4. */
+int bmf_mesh_process(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence,
+                     int n_verts, const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals);
+
+/* qef_solve_from_points_3d (qef_simd.h:550-579), m independent systems: system j reads counts[j]
+ * (2..12) planes from positions/normals[j*12*3 ...]; writes out_pos[3*j..], out_err[j]. */
+int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMF_B200_H */

@@ -107,9 +107,9 @@ class RefLib:
     def qef_solve(self, positions, normals):
         p = np.ascontiguousarray(positions, np.float32)
         n = np.ascontiguousarray(normals, np.float32)
-        out = np.zeros(3, np.float32)
+        out = np.zeros(4, np.float32)  # the reference zeroes solved[3] too when count is out of range (qef_simd.h:558)
         err = self.lib.ref_qef_solve(_fp(p), _fp(n), len(p), _fp(out))
-        return out, float(err)
+        return out[:3].copy(), float(err)
 
     def implicit_value(self, kind, p, world_size=256.0):
         p = np.asarray(p, np.float32)

@@ -1,0 +1,230 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): sign words, cell masks, cell/vertex/index counts, vertex ids, index buffer,
+boundary flags and valences BIT-EXACT; vertex positions bit-exact (contract: 1e-4 of chunk extent);
+noise within 1e-5 absolute with sign flips counted (measured: 0 ulp, 0 flips against the restatement).
+"""
+import numpy as np
+import pytest
+
+from binarymeshfitting_b200 import capi
+from oracle import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_chunk(gpu, kind, pos, size, dim, overlap=0.0, iters=0, pb=False, sn=False, density=None, want_density=True, **kw):
+    gpu.set_sampler(kind, **kw)
+    descs = capi.make_chunk_descs([[pos[0], pos[1], pos[2], size]], overlaps=overlap)
+    gpu.submit(descs, dim, iters=iters, process_boundary=pb, smooth_normals=sn, keep_density=want_density, keep_masks=True, density=density)
+    gpu.wait()
+    want = ("verts", "inds", "bits", "masks") + (("density",) if (want_density or density is not None) else ())
+    return gpu.copy_chunk(0, want=want)
+
+
+def assert_same_topology(g, o):
+    assert g["contains_mesh"] == o["contains_mesh"]
+    np.testing.assert_array_equal(g["bits"], o["bits"])
+    if not o["contains_mesh"]:
+        assert g["n_verts"] == 0 and g["n_inds"] == 0 and g["n_cells"] == 0
+        return
+    np.testing.assert_array_equal(g["masks"], o["masks"])
+    assert (g["n_cells"], g["n_verts"], g["n_inds"]) == (o["n_cells"], o["n_verts"], o["n_inds"])
+    np.testing.assert_array_equal(g["inds"], o["inds"])
+    np.testing.assert_array_equal(g["verts"]["boundary"], o["boundary"])
+    np.testing.assert_array_equal(g["verts"]["init_valence"], o["valence"])
+    np.testing.assert_array_equal(g["verts"]["index"], np.arange(o["n_verts"], dtype=np.uint32))
+
+
+def assert_same_positions(g, o, dim, exact=True):
+    gp, op = g["verts"]["p"], o["pos"]
+    if exact:
+        np.testing.assert_array_equal(gp.view(np.uint32), op.view(np.uint32))
+    else:
+        assert np.abs(gp - op).max() <= 1e-4 * (dim - 1)  # tolerance: 1e-4 of chunk extent (north_star)
+
+
+@pytest.mark.parametrize("kind", [ob.SPHERE, ob.TORUS_Z, ob.CUBOID, ob.PLANE_Y])
+@pytest.mark.parametrize("dim,overlap", [(32, 0.0), (64, 0.0), (64, 0.045), (128, 0.045)])
+def test_implicit_chunk_bit_exact(gpu, oracle, kind, dim, overlap):
+    pos, size = (-128.0, -128.0, -128.0), 256.0
+    g = gpu_chunk(gpu, kind, pos, size, dim, overlap)
+    o = oracle.chunk(oracle.sampler(kind), pos, size, dim, overlap)
+    np.testing.assert_array_equal(g["density"].view(np.uint32), o["density"].view(np.uint32))
+    assert_same_topology(g, o)
+    assert_same_positions(g, o, dim)
+    np.testing.assert_array_equal(g["verts"]["color"], np.ones((o["n_verts"], 3), np.float32))
+
+
+def test_sphere_256(gpu, oracle):
+    pos, size = (-128.0, -128.0, -128.0), 256.0
+    g = gpu_chunk(gpu, ob.SPHERE, pos, size, 256)
+    o = oracle.chunk(oracle.sampler(ob.SPHERE), pos, size, 256)
+    assert (o["n_cells"], o["n_verts"], o["n_inds"]) == (272619, 76776, 460644)
+    assert_same_topology(g, o)
+    assert_same_positions(g, o, 256)
+
+
+def test_recompute_path_matches_materialised(gpu, oracle):
+    """keep_density=0: the emitters re-evaluate crossing-edge samples instead of reading a density block."""
+    pos, size = (-100.0, -90.0, -80.0), 200.0
+    for kind in (ob.TORUS_Z, ob.TERRAIN2D_PERT):
+        a = gpu_chunk(gpu, kind, pos, size, 64, 0.02, want_density=True)
+        b = gpu_chunk(gpu, kind, pos, size, 64, 0.02, want_density=False)
+        np.testing.assert_array_equal(a["inds"], b["inds"])
+        np.testing.assert_array_equal(a["verts"]["p"].view(np.uint32), b["verts"]["p"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed,dim", [(1, 32), (2, 64), (3, 64), (4, 128)])
+def test_host_density_random_fields(gpu, oracle, seed, dim):
+    """HOST_DENSITY: arbitrary density (smooth random field + specials) -> everything downstream bit-exact."""
+    rng = np.random.default_rng(seed)
+    n = dim ** 3
+    x = np.linspace(-1, 1, dim, dtype=np.float32)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    f = (np.sin(3 * X + rng.normal()) * np.cos(4 * Y + rng.normal()) + 0.5 * np.sin(5 * Z * X + rng.normal()) + 0.2 * rng.normal(size=(dim,) * 3)).astype(np.float32)
+    f = f.reshape(-1)
+    # specials: +0, -0 (both "not air"), tiny denormals, exact zeros next to negatives
+    idx = rng.integers(0, n, 64)
+    f[idx[:16]] = 0.0
+    f[idx[16:32]] = -0.0
+    f[idx[32:48]] = np.float32(1e-42)
+    f[idx[48:]] = np.float32(-1e-42)
+    g = gpu_chunk(gpu, ob.HOST_DENSITY, (0, 0, 0), 1.0, dim, density=f)
+    o = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), (0, 0, 0), 1.0, dim, host_density=f)
+    assert_same_topology(g, o)
+    assert_same_positions(g, o, dim)
+
+
+def test_host_density_nan_and_degenerate(gpu, oracle):
+    dim = 32
+    f = np.full(dim ** 3, 1.0, np.float32)
+    f[::7] = -1.0
+    f[5::11] = np.nan  # NaN compares false -> bit 0 (DMCChunk.cpp:136)
+    g = gpu_chunk(gpu, ob.HOST_DENSITY, (0, 0, 0), 1.0, dim, density=f)
+    o = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), (0, 0, 0), 1.0, dim, host_density=f)
+    assert_same_topology(g, o)
+    gp, op = g["verts"]["p"], o["pos"]
+    np.testing.assert_array_equal(np.isnan(gp), np.isnan(op))
+    m = ~np.isnan(op)
+    np.testing.assert_array_equal(gp[m].view(np.uint32), op[m].view(np.uint32))
+
+
+@pytest.mark.parametrize("fill,expect_mesh", [(1.0, False), (-1.0, False)])
+def test_empty_chunks(gpu, oracle, fill, expect_mesh):
+    """all-solid / all-air chunks: contains_mesh false, no cells even though all-air border cells have partial masks."""
+    dim = 32
+    f = np.full(dim ** 3, fill, np.float32)
+    g = gpu_chunk(gpu, ob.HOST_DENSITY, (0, 0, 0), 1.0, dim, density=f)
+    o = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), (0, 0, 0), 1.0, dim, host_density=f)
+    assert o["contains_mesh"] == expect_mesh
+    assert_same_topology(g, o)
+
+
+def test_half_air_half_solid_words(gpu, oracle):
+    """no mixed word, but both all-ones and all-zero words -> contains_mesh true (DMCChunk.cpp:159-160)."""
+    dim = 32
+    f = np.full((dim, dim, dim), 1.0, np.float32)
+    f[:, dim // 2:, :] = -1.0
+    g = gpu_chunk(gpu, ob.HOST_DENSITY, (0, 0, 0), 1.0, dim, density=f)
+    o = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), (0, 0, 0), 1.0, dim, host_density=f.reshape(-1))
+    assert o["contains_mesh"]
+    assert_same_topology(g, o)
+    assert_same_positions(g, o, dim)
+
+
+@pytest.mark.parametrize("kind,dim", [(ob.TERRAIN2D, 64), (ob.TERRAIN2D_PERT, 64), (ob.TERRAIN3D, 64), (ob.TERRAIN3D_PERT, 64),
+                                      (ob.TERRAIN2D_PERT, 128), (ob.TERRAIN3D_PERT, 32)])
+def test_noise_terrain(gpu, oracle, kind, dim):
+    """Noise vs the (unpinned) restatement: <= 1e-5 abs, sign flips counted; topology exact on the GPU's own density."""
+    pos, size, overlap = (-64.0, -64.0, -64.0), 128.0, 0.045
+    g = gpu_chunk(gpu, kind, pos, size, dim, overlap)
+    s = oracle.sampler(kind)
+    o = oracle.chunk(s, pos, size, dim, overlap)
+    diff = np.abs(g["density"] - o["density"])
+    flips = int(((g["density"] < 0) != (o["density"] < 0)).sum())
+    print("kind %d dim %d: max |d_gpu - d_oracle| = %.3g, sign flips = %d of %d" % (kind, dim, diff.max(), flips, dim ** 3))
+    assert diff.max() <= 1e-5 * max(1.0, float(np.abs(o["density"]).max()) / 75.0) or diff.max() <= 1e-5
+    # topology must be exact given identical density samples: feed the GPU's density to the oracle
+    o2 = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), pos, size, dim, overlap, host_density=g["density"])
+    assert_same_topology(g, o2)
+    assert_same_positions(g, o2, dim)
+    if flips == 0:
+        assert_same_topology(g, o)
+
+
+@pytest.mark.parametrize("iters,pb,sn", [(1, False, False), (2, False, False), (2, True, False), (4, False, True), (5, True, True), (10, False, True)])
+def test_smoothing_matches_oracle(gpu, oracle, iters, pb, sn):
+    pos, size, dim = (-128.0, -128.0, -128.0), 256.0, 64
+    overlap = 0.035 + 0.005 * iters
+    g = gpu_chunk(gpu, ob.TORUS_Z, pos, size, dim, overlap, iters=iters, pb=pb, sn=sn)
+    o = oracle.chunk(oracle.sampler(ob.TORUS_Z), pos, size, dim, overlap, iters=iters, process_boundary=pb, smooth_normals=sn)
+    np.testing.assert_array_equal(g["inds"], o["inds"])
+    # contract: 1e-4 of chunk extent; measured: identical bits (same summation order)
+    assert np.abs(g["verts"]["p"] - o["pos"]).max() <= 1e-4 * (dim - 1)
+    np.testing.assert_array_equal(g["verts"]["p"].view(np.uint32), o["pos"].view(np.uint32))
+    np.testing.assert_array_equal(g["verts"]["color"].view(np.uint32), o["color"].view(np.uint32))
+    if sn:
+        gn, on = g["verts"]["n"], o["normal"]
+        np.testing.assert_array_equal(np.isnan(gn), np.isnan(on))
+        m = ~np.isnan(on)
+        assert np.abs(gn[m] - on[m]).max() <= 1e-5
+
+
+def test_batch_of_chunks_matches_per_chunk_oracle(gpu, oracle):
+    """A 4x4x4 grid of 32^3 terrain chunks in one submit: per-chunk results equal the one-chunk oracle."""
+    dim, size = 32, 32.0
+    ps = [[-64.0 + size * i, -64.0 + size * j, -64.0 + size * k, size] for i in range(4) for j in range(4) for k in range(4)]
+    descs = capi.make_chunk_descs(ps, overlaps=0.045)
+    gpu.set_sampler(ob.TERRAIN2D_PERT)
+    gpu.submit(descs, dim, iters=2)
+    gpu.wait()
+    infos = gpu.chunk_infos()
+    out = gpu.download()
+    s = oracle.sampler(ob.TERRAIN2D_PERT)
+    n_mesh = 0
+    for i, p in enumerate(ps):
+        o = oracle.chunk(s, p[:3], p[3], dim, 0.045, iters=2)
+        inf = infos[i]
+        assert bool(inf["contains_mesh"]) == o["contains_mesh"]
+        assert (inf["n_verts"], inf["n_inds"]) == (o["n_verts"], o["n_inds"])
+        if o["n_verts"]:
+            n_mesh += 1
+            v0, i0 = int(inf["vert_offset"]), int(inf["ind_offset"])
+            np.testing.assert_array_equal(out["inds"][i0:i0 + o["n_inds"]], o["inds"])
+            np.testing.assert_array_equal(out["pos"][v0:v0 + o["n_verts"]].view(np.uint32), o["pos"].view(np.uint32))
+            np.testing.assert_array_equal(out["valence"][v0:v0 + o["n_verts"]], o["valence"])
+    assert n_mesh > 4
+    tot = gpu.totals()
+    assert tot[1] == int(infos["n_verts"].sum()) and tot[2] == int(infos["n_inds"].sum())
+
+
+def test_qef_matches_oracle(gpu, oracle):
+    rng = np.random.default_rng(7)
+    m = 2000
+    counts = rng.integers(2, 13, m).astype(np.int32)
+    P = rng.random((m, 12, 3), dtype=np.float32)
+    N = rng.normal(size=(m, 12, 3)).astype(np.float32)
+    N /= np.linalg.norm(N, axis=2, keepdims=True)
+    out, err = gpu.qef_solve(P, N, counts)
+    worst = 0.0
+    for j in range(m):
+        o, e = oracle.qef_solve(P[j, :counts[j]], N[j, :counts[j]])
+        worst = max(worst, float(np.abs(out[j] - o).max()))
+        np.testing.assert_array_equal(out[j].view(np.uint32), o.view(np.uint32))
+        assert np.float32(e).view(np.uint32) == err[j].view(np.uint32)
+    # out-of-range counts -> zeros (qef_simd.h:556-560)
+    out2, err2 = gpu.qef_solve(P[:2], N[:2], np.array([1, 13], np.int32))
+    assert not out2.any() and not err2.any()
+
+
+def test_errors_are_reported(gpu):
+    gpu.set_sampler(ob.SPHERE)
+    descs = capi.make_chunk_descs([[0, 0, 0, 1.0]])
+    with pytest.raises(capi.BmfError):
+        gpu.submit(descs, 48)  # dim must be 32/64/128/256
+    with pytest.raises(capi.BmfError):
+        gpu.set_sampler(55)
+    gpu.set_sampler(ob.HOST_DENSITY)
+    with pytest.raises(capi.BmfError):
+        gpu.submit(descs, 32)  # HOST_DENSITY without a density block
