@@ -21,7 +21,7 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 # symbols include/bmf_b200.h declares (tests check that the library exports every one of them)
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
-           "bmf_batch_download", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_batch_device_ptrs",
+           "bmf_batch_download", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_qef_solve")
 
 
@@ -89,6 +89,10 @@ def load_library(path=SO):
     lib.bmf_batch_stage_ms.argtypes = [vp, vp]
     lib.bmf_ctx_launch_count.argtypes = [vp]
     lib.bmf_ctx_launch_count.restype = C.c_int64
+    lib.bmf_ctx_set_kernel_timing.argtypes = [vp, C.c_int]
+    lib.bmf_ctx_kernel_times.argtypes = [vp, C.c_int, vp, vp]
+    lib.bmf_ctx_stream.argtypes = [vp]
+    lib.bmf_ctx_stream.restype = vp
     lib.bmf_batch_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
@@ -215,6 +219,21 @@ class Context:
         ms = np.zeros(len(STAGES), np.float32)
         self._check(self.lib.bmf_batch_stage_ms(self.h, _p(ms)))
         return dict(zip(STAGES, ms.tolist()))
+
+    def set_kernel_timing(self, on):
+        self._check(self.lib.bmf_ctx_set_kernel_timing(self.h, int(on)))
+
+    def kernel_times(self, cap=512):
+        """[(kernel name, ms)] for every launch of the last batch (needs set_kernel_timing(True) before submit)."""
+        names = (C.c_char_p * cap)()
+        ms = np.zeros(cap, np.float32)
+        n = self.lib.bmf_ctx_kernel_times(self.h, cap, names, _p(ms))
+        if n < 0:
+            self._check(n)
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
+
+    def stream_ptr(self):
+        return int(self.lib.bmf_ctx_stream(self.h) or 0)
 
     def launch_count(self):
         return int(self.lib.bmf_ctx_launch_count(self.h))

@@ -7,7 +7,9 @@
 #include "smooth.cuh"
 
 #include <cstdio>
+#include <array>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -71,7 +73,10 @@ struct bmf_ctx
 	const float* ext_density = nullptr; // caller-owned device density (density_on_device)
 	bool density_valid = false, masks_valid = false;
 
-	DevBuf<ChunkGeom> geom;
+	DevBuf<ChunkGeom> geom, sheet_geom;
+	DevBuf<int> sheet_of;
+	std::vector<ChunkGeom> sheet_geom_host;
+	std::vector<int> sheet_of_host;
 	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base;
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
@@ -93,6 +98,12 @@ struct bmf_ctx
 
 	cudaEvent_t ev[BMF_NUM_STAGES + 1] = {};
 	float stage_ms[BMF_NUM_STAGES] = {};
+
+	// optional per-launch timing (bmf_ctx_set_kernel_timing): one event pair per launch of the last batch
+	bool ktiming = false;
+	std::vector<cudaEvent_t> kev;
+	std::vector<const char*> kname;
+	size_t kused = 0;
 };
 
 namespace
@@ -119,10 +130,27 @@ int fail(bmf_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
 		if (e__ != cudaSuccess) return fail(ctx, BMF_ERR_CUDA, #call, e__); \
 	} while (0)
 
+void ktime_mark(bmf_ctx* ctx, const char* name)
+{
+	if (ctx->kev.size() < 2 * (ctx->kused + 1))
+	{
+		cudaEvent_t a, b;
+		cudaEventCreate(&a);
+		cudaEventCreate(&b);
+		ctx->kev.push_back(a);
+		ctx->kev.push_back(b);
+		ctx->kname.push_back(name);
+	}
+	ctx->kname[ctx->kused] = name;
+	cudaEventRecord(ctx->kev[2 * ctx->kused], ctx->stream);
+}
+
 #define BMF_LAUNCH(kernel, grid, block, smem, ...)                              \
 	do                                                                          \
 	{                                                                           \
+		if (ctx->ktiming) ktime_mark(ctx, #kernel);                             \
 		kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);          \
+		if (ctx->ktiming) cudaEventRecord(ctx->kev[2 * ctx->kused++ + 1], ctx->stream); \
 		ctx->launches++;                                                        \
 		cudaError_t e__ = cudaGetLastError();                                   \
 		if (e__ != cudaSuccess) return fail(ctx, BMF_ERR_CUDA, #kernel, e__);   \
@@ -309,7 +337,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->geom.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
+	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
 	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cursor.release();
@@ -319,6 +347,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	for (int i = 0; i <= BMF_NUM_STAGES; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -372,6 +401,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	ctx->have_batch = false;
 	ctx->finished = false;
+	ctx->kused = 0;
 	ctx->n = n;
 	ctx->params = *params;
 	ctx->descs.assign(chunks, chunks + n);
@@ -429,13 +459,42 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	ctx->density_valid = need_density;
 	ctx->masks_valid = params->keep_masks != 0;
 	if (params->keep_masks) BMF_CUDA(ctx->masks.reserve(n * nvox));
-	if (is_terrain2d(kind)) BMF_CUDA(ctx->hmap.reserve((size_t)n * d * d));
+	int n_sheets = 0;
+	if (is_terrain2d(kind))
+	{
+		// the noise sheet is a function of (overlap_pos.x, overlap_pos.z, delta) only: one sheet per unique triple
+		std::map<std::array<uint32_t, 3>, int> seen;
+		ctx->sheet_of_host.resize(n);
+		ctx->sheet_geom_host.clear();
+		for (int i = 0; i < n; i++)
+		{
+			const ChunkGeom& g = ctx->geom_host[i];
+			std::array<uint32_t, 3> key;
+			memcpy(&key[0], &g.ox, 4); memcpy(&key[1], &g.oz, 4); memcpy(&key[2], &g.delta, 4);
+			auto it = seen.find(key);
+			if (it == seen.end())
+			{
+				it = seen.emplace(key, (int)ctx->sheet_geom_host.size()).first;
+				ctx->sheet_geom_host.push_back(g);
+			}
+			ctx->sheet_of_host[i] = it->second;
+		}
+		n_sheets = (int)ctx->sheet_geom_host.size();
+		BMF_CUDA(ctx->hmap.reserve((size_t)n_sheets * d * d));
+		BMF_CUDA(ctx->sheet_geom.reserve(n_sheets));
+		BMF_CUDA(ctx->sheet_of.reserve(n));
+	}
 
 	cudaStream_t st = ctx->stream;
 	BMF_CUDA(cudaMemcpyAsync(ctx->geom.p, ctx->geom_host.data(), sizeof(ChunkGeom) * n, cudaMemcpyHostToDevice, st));
 	if (host_density && !params->density_on_device)
 		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
+	if (n_sheets)
+	{
+		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_geom.p, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * n_sheets, cudaMemcpyHostToDevice, st));
+		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_of.p, ctx->sheet_of_host.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+	}
 
 	// ---- K1 / K2
 	BMF_CUDA(cudaEventRecord(ctx->ev[0], st));
@@ -446,8 +505,9 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	else if (is_terrain2d(kind))
 	{
-		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n * d * d, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->hmap.p, n);
-		BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->bits.p, dens_w, ctx->flags.p);
+		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n_sheets * d * d, CTA), CTA, 0, ctx->sampler, ctx->sheet_geom.p, d, L.ld, ctx->hmap.p, n_sheets);
+		BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p, ctx->bits.p,
+		           dens_w, ctx->flags.p);
 	}
 	else if (kind == BMF_SAMPLER_TERRAIN3D)
 	{
@@ -459,7 +519,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	else
 	{
-		BMF_LAUNCH(k_pack_density, (unsigned)(n_words / (PACK_UNROLL * (CTA / 32))), CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.wc);
+		BMF_LAUNCH(k_pack_density, (unsigned)(n_words / (PACK_UNROLL * (CTA / 32))), CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.lwc);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[1], st));
 
@@ -496,6 +556,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	DensitySource src;
 	src.density = density_dev;
 	src.hmap = (!density_dev && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
+	src.sheet_of = ctx->sheet_of.p;
 	if (L.wpt == 4)
 		BMF_LAUNCH(k_verts<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_base.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->wvb.p,
 		           ctx->wib.p, ctx->pos.p, ctx->boundary.p);
@@ -680,6 +741,32 @@ int bmf_batch_stage_ms(bmf_ctx* ctx, float* ms)
 }
 
 int64_t bmf_ctx_launch_count(const bmf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bmf_ctx_set_kernel_timing(bmf_ctx* ctx, int on)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	ctx->ktiming = on != 0;
+	return BMF_OK;
+}
+
+int bmf_ctx_kernel_times(bmf_ctx* ctx, int cap, const char** names, float* ms)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_ctx_kernel_times: no batch submitted");
+	int rc = bmf_batch_wait(ctx);
+	if (rc) return rc;
+	int n = (int)ctx->kused;
+	for (int i = 0; i < n && i < cap; i++)
+	{
+		float t = 0.0f;
+		cudaEventElapsedTime(&t, ctx->kev[2 * i], ctx->kev[2 * i + 1]);
+		if (names) names[i] = ctx->kname[i];
+		if (ms) ms[i] = t;
+	}
+	return n;
+}
+
+void* bmf_ctx_stream(const bmf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits, void** density)
 {

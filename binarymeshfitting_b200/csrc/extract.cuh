@@ -56,7 +56,10 @@ struct Layout
 	int ws;      // words per segment
 	int S;       // segments per chunk
 	int wpt;     // words per thread in segment kernels = ws / CTA
+	int lzc, ld, lwp, lwc, lS; // log2 of zc, d, wp, wc, S (all powers of two: index math is shifts and masks)
 };
+
+__host__ __device__ __forceinline__ int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 __host__ inline Layout make_layout(int d)
 {
@@ -64,6 +67,7 @@ __host__ inline Layout make_layout(int d)
 	L.d = d; L.zc = d / 32; L.wp = d * L.zc; L.wc = d * L.wp;
 	L.P = (d == 32) ? 32 : (d == 64) ? 8 : (d == 128) ? 2 : 1;
 	L.ws = L.P * L.wp; L.S = d / L.P; L.wpt = L.ws / CTA;
+	L.lzc = ilog2(L.zc); L.ld = ilog2(d); L.lwp = ilog2(L.wp); L.lwc = ilog2(L.wc); L.lS = ilog2(L.S);
 	return L;
 }
 
@@ -97,13 +101,14 @@ __device__ __forceinline__ float terrain_density(const SamplerDev& s, const Chun
 struct DensitySource
 {
 	const float* density; // [n][d^3] or null
-	const float* hmap;    // [n][d*d] noise sheet of the 2-D terrains, or null
+	const float* hmap;    // [n_sheets][d*d] noise sheets of the 2-D terrains, or null
+	const int* sheet_of;  // [n] sheet index of each chunk (chunks stacked in y share one sheet)
 };
 
 __device__ __forceinline__ float density_at(const SamplerDev& s, const DensitySource& src, const ChunkGeom& g, int d, int chunk, int x, int y, int z)
 {
 	if (src.density) return src.density[(size_t)chunk * d * d * d + ((size_t)x * d + y) * d + z];
-	if (src.hmap) return terrain_density(s, g, y, src.hmap[(size_t)chunk * d * d + (size_t)x * d + z]);
+	if (src.hmap) return terrain_density(s, g, y, src.hmap[(size_t)src.sheet_of[chunk] * d * d + (size_t)x * d + z]);
 	return implicit_point(s, g, x, y, z);
 }
 
@@ -132,15 +137,15 @@ __global__ void __launch_bounds__(CTA) k_sample_implicit(SamplerDev s, const Chu
                                                           uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int ctas_per_chunk = L.wc / SAMPLE_WORDS_PER_CTA;
-	const int chunk = blockIdx.x / ctas_per_chunk;
-	const int w0 = (blockIdx.x % ctas_per_chunk) * SAMPLE_WORDS_PER_CTA;
+	const int lcpc = L.lwc - 6; // log2(CTAs per chunk), SAMPLE_WORDS_PER_CTA == 64
+	const int chunk = blockIdx.x >> lcpc;
+	const int w0 = (blockIdx.x & ((1 << lcpc) - 1)) * SAMPLE_WORDS_PER_CTA;
 	const ChunkGeom g = geom[chunk];
 	uint32_t f = 0;
 	for (int k = warp; k < SAMPLE_WORDS_PER_CTA; k += CTA / 32)
 	{
 		int w = w0 + k;
-		int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+		int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
 		int z = zb * 32 + lane;
 		float v = implicit_point(s, g, x, y, z);
 		if (density) density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
@@ -156,15 +161,16 @@ __global__ void __launch_bounds__(CTA) k_sample_implicit(SamplerDev s, const Chu
 
 // ---- K1b: 2-D terrains.  Noise sheet: one thread per (ix, iz) column (NOISE_BLOCK with size_y = 1,
 // NoiseSampler.cpp:117,152), then density = -dy - n*height per voxel and the sign word.
+// The sheet depends only on (overlap_pos.x, overlap_pos.z, delta): chunks stacked in y get the same
+// floats, so the host deduplicates and `geom` here holds one entry per UNIQUE sheet.
 template <int BASE>
-__global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, float* __restrict__ hmap, int n_chunks)
+__global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, int ld, float* __restrict__ hmap, int n_chunks)
 {
 	size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
-	size_t per = (size_t)d * d;
-	if (i >= per * n_chunks) return;
-	int chunk = (int)(i / per);
-	int r = (int)(i % per);
-	int ix = r / d, iz = r % d;
+	if (i >= ((size_t)n_chunks << (2 * ld))) return;
+	int chunk = (int)(i >> (2 * ld));
+	int r = (int)(i & (((size_t)1 << (2 * ld)) - 1));
+	int ix = r >> ld, iz = r & (d - 1);
 	const ChunkGeom g = geom[chunk];
 	float sg = g.delta * s.g;
 	float vx = (float)ix * sg + g.ox * s.g;
@@ -174,19 +180,20 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 }
 
 __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
-                                                            uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
+                                                            const int* __restrict__ sheet_of, uint32_t* __restrict__ bits, float* __restrict__ density,
+                                                            uint32_t* __restrict__ flags)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int ctas_per_chunk = L.wc / SAMPLE_WORDS_PER_CTA;
-	const int chunk = blockIdx.x / ctas_per_chunk;
-	const int w0 = (blockIdx.x % ctas_per_chunk) * SAMPLE_WORDS_PER_CTA;
+	const int lcpc = L.lwc - 6; // log2(CTAs per chunk), SAMPLE_WORDS_PER_CTA == 64
+	const int chunk = blockIdx.x >> lcpc;
+	const int w0 = (blockIdx.x & ((1 << lcpc) - 1)) * SAMPLE_WORDS_PER_CTA;
 	const ChunkGeom g = geom[chunk];
-	const float* hm = hmap + (size_t)chunk * L.d * L.d;
+	const float* hm = hmap + ((size_t)sheet_of[chunk] << (2 * L.ld));
 	uint32_t f = 0;
 	for (int k = warp; k < SAMPLE_WORDS_PER_CTA; k += CTA / 32)
 	{
 		int w = w0 + k;
-		int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+		int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
 		int z = zb * 32 + lane;
 		float v = terrain_density(s, g, y, hm[x * L.d + z]);
 		if (density) density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
@@ -207,12 +214,11 @@ __global__ void __launch_bounds__(CTA) k_terrain3d(SamplerDev s, const ChunkGeom
                                                     uint32_t* __restrict__ bits, float* __restrict__ density, uint32_t* __restrict__ flags)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int words_per_cta = CTA / 32;
-	const int ctas_per_chunk = L.wc / words_per_cta;
-	const int chunk = blockIdx.x / ctas_per_chunk;
-	const int w = (blockIdx.x % ctas_per_chunk) * words_per_cta + warp;
+	const int lcpc = L.lwc - 3; // log2(CTAs per chunk), CTA/32 == 8 words per CTA
+	const int chunk = blockIdx.x >> lcpc;
+	const int w = (blockIdx.x & ((1 << lcpc) - 1)) * (CTA / 32) + warp;
 	const ChunkGeom g = geom[chunk];
-	int zb = w % L.zc, y = (w / L.zc) % L.d, x = w / L.wp;
+	int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
 	int z = zb * 32 + lane;
 	float sg = g.delta * s.g;
 	float vx = (float)x * sg + g.ox * s.g;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(CTA) k_terrain3d(SamplerDev s, const ChunkGeom
 static constexpr int PACK_UNROLL = 8;
 
 __global__ void __launch_bounds__(CTA) k_pack_density(const float* __restrict__ density, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags,
-                                                       size_t n_words, int words_per_chunk)
+                                                       size_t n_words, int lwc)
 {
 	const int lane = threadIdx.x & 31;
 	const size_t warp_global = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(CTA) k_pack_density(const float* __restrict__ 
 	}
 	if (lane < PACK_UNROLL) bits[w0 + lane] = mine;
 	// all PACK_UNROLL words of a warp lie in one chunk (words_per_chunk is a multiple of 1024)
-	merge_flags(lane == 0 ? f : 0, flags + (w0 / words_per_chunk));
+	merge_flags(lane == 0 ? f : 0, flags + (w0 >> lwc));
 }
 
 // ---- shared-memory staging of sign planes ----------------------------------------------------------------
@@ -281,7 +287,7 @@ struct WordBits
 __device__ __forceinline__ WordBits load_word_bits(const uint32_t* sb, const Layout& L, int lx, int y, int zb)
 {
 	WordBits r;
-	const int base = (lx * L.d + y) * L.zc + zb;
+	const int base = (((lx << L.ld) + y) << L.lzc) + zb;
 	const bool zn = zb + 1 < L.zc, yn = y + 1 < L.d;
 	r.A = sb[base];
 	r.A1 = __funnelshift_r(r.A, zn ? sb[base + 1] : 0u, 1);
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits
 {
 	extern __shared__ uint32_t sb[];
 	const int seg = blockIdx.x;
-	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
 	__syncthreads();
 
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits
 	for (int k = 0; k < WPT; k++)
 	{
 		const int lw = threadIdx.x * WPT + k; // word inside the segment
-		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp;
+		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x0 + lx, y, zb);
 		uint32_t nc = __popc(c.active);
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits
 {
 	extern __shared__ uint32_t sb[];
 	const int seg = blockIdx.x;
-	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	const ChunkCounts cc = chunks[chunk];
 	uint32_t cnt[WPT];
 	{
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits
 	{
 		if (((cnt[k] >> 8) & 0xFF) == 0) continue;
 		const int lw = threadIdx.x * WPT + k;
-		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp, x = x0 + lx;
+		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp, x = x0 + lx;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x, y, zb);
 		uint32_t m = c.ex | c.ey | c.ez;
@@ -602,7 +608,7 @@ __global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits
 __device__ __forceinline__ uint32_t vertex_id(const uint32_t* sb, const uint32_t* svb, const Layout& L, int x0, int lx, int y, int z, int axis)
 {
 	const int zb = z >> 5, bit = z & 31;
-	const int base = (lx * L.d + y) * L.zc + zb;
+	const int base = (((lx << L.ld) + y) << L.lzc) + zb;
 	const bool zn = zb + 1 < L.zc, yn = y + 1 < L.d, xn = x0 + lx + 1 < L.d;
 	const uint32_t A = sb[base];
 	const uint32_t A1 = __funnelshift_r(A, zn ? sb[base + 1] : 0u, 1);
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(CTA) k_inds(const uint32_t* __restrict__ bits,
 {
 	extern __shared__ uint32_t sb[];
 	const int seg = blockIdx.x;
-	const int chunk = seg / L.S, x0 = (seg % L.S) * L.P;
+	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	const ChunkCounts cc = chunks[chunk];
 	if (!cc.contains_mesh || cc.n_inds == 0) return;
 	uint32_t* svb = sb + (L.P + 2) * L.wp;
@@ -646,7 +652,7 @@ __global__ void __launch_bounds__(CTA) k_inds(const uint32_t* __restrict__ bits,
 		const int lw = threadIdx.x * WPT + k;
 		const size_t gw = (size_t)seg * L.ws + lw;
 		if ((wcnt[gw] >> 16) == 0) continue;
-		const int zb = lw % L.zc, y = (lw / L.zc) % L.d, lx = lw / L.wp;
+		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x0 + lx, y, zb);
 		uint32_t m = c.active & c.interior;

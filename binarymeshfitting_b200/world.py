@@ -1,0 +1,115 @@
+"""Host-side LOD leaf enumeration and multi-GPU partitioning -- the caller that feeds the hot path.
+
+Mirrors WorldOctree::init / split_leaves / split_node / node_needs_split / create_chunk
+(WorldOctree.cpp:117-127, 129-173, 175-210, 239-249, 263-269) and the per-chunk overlap rule of
+ChunkGenerator::extract_chunk (ChunkGenerator.cpp:98).  Pure host logic in float32 (numpy scalars) so
+leaf sets, positions, sizes, levels and Morton codes are identical to the reference's; pinned by
+tests/test_world.py against the compiled reference and the committed golden leaf list.
+"""
+import numpy as np
+
+from . import capi
+
+F = np.float32
+
+# Tables::MCDX/MCDY/MCDZ (Tables.hpp:7-9): octree children are enumerated in MC-corner order
+MCDX = (0, 1, 1, 0, 0, 1, 1, 0)
+MCDY = (0, 0, 0, 0, 1, 1, 1, 1)
+MCDZ = (0, 0, 1, 1, 0, 0, 1, 1)
+
+
+class WorldProperties:
+    """WorldProperties() defaults (WorldOctree.cpp:20-33)."""
+
+    def __init__(self, **kw):
+        self.split_multiplier = 1.0
+        self.size_modifier = 0.0
+        self.max_level = 7
+        self.min_level = 1
+        self.process_iters = 0
+        self.chunk_resolution = 32
+        self.overlap = 0.035
+        self.boundary_processing = False
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+def node_needs_split(props, focus, pos, size, level):
+    """WorldOctree::node_needs_split (WorldOctree.cpp:239-249); middle = pos + size*0.5 (WorldOctreeNode.cpp:26)."""
+    if level >= props.max_level:
+        return False
+    if level < props.min_level:
+        return True
+    half = F(size) * F(0.5)
+    mid = (F(pos[0]) + half, F(pos[1]) + half, F(pos[2]) + half)
+    # glm::distance(middle, center) = length(center - middle), dot summed x,y,z left to right
+    dx, dy, dz = F(focus[0]) - mid[0], F(focus[1]) - mid[1], F(focus[2]) - mid[2]
+    d = np.sqrt(F(F(dx * dx) + F(dy * dy)) + F(dz * dz), dtype=F)
+    rhs = F(F(F(size) * F(props.split_multiplier)) + F(props.size_modifier)) + half
+    return bool(d < rhs)
+
+
+def split_leaves(props, world_size=256, focus=(0.0, 0.0, 0.0)):
+    """Static LOD build.  Returns (pos_size[n,4] f32, level[n] i32, morton[n] u64) in the reference's leaf order
+    (stack DFS, children pushed 0..7 and popped LIFO -- not Morton order)."""
+    size = F(world_size * 2)  # WorldOctree::init doubles the size (WorldOctree.cpp:119)
+    p = F(1) * size * F(-0.5)
+    stack = [((p, p, p), size, 0, 1)]
+    out_ps, out_lv, out_mc = [], [], []
+    while stack:
+        pos, sz, level, code = stack.pop()
+        if not node_needs_split(props, focus, pos, sz, level):
+            out_ps.append((pos[0], pos[1], pos[2], sz))
+            out_lv.append(level)
+            out_mc.append(code)
+            continue
+        c_size = F(sz * F(0.5))
+        for i in range(8):
+            cpos = (F(pos[0] + F(MCDX[i]) * c_size), F(pos[1] + F(MCDY[i]) * c_size), F(pos[2] + F(MCDZ[i]) * c_size))
+            ccode = (code << 3) | (MCDX[i] | (MCDY[i] << 1) | (MCDZ[i] << 2))
+            stack.append((cpos, c_size, level + 1, ccode))
+    return np.array(out_ps, np.float32).reshape(-1, 4), np.array(out_lv, np.int32), np.array(out_mc, np.uint64)
+
+
+def chunk_overlap(props, level):
+    """ChunkGenerator.cpp:98."""
+    iters = props.process_iters
+    if level == props.max_level and (not props.boundary_processing or iters == 0):
+        return F(0.0)
+    return F(F(props.overlap) + F(F(0.005) * F(iters)))
+
+
+def make_descs(props, pos_size, levels, mortons=None):
+    d = capi.make_chunk_descs(pos_size)
+    d["level"] = levels
+    d["overlap"] = [chunk_overlap(props, int(l)) for l in levels]
+    if mortons is not None:
+        d["morton"] = mortons
+    return d
+
+
+def grid_chunks(n_per_axis=16, chunk_size=16.0, origin=(-128.0, -128.0, -128.0)):
+    """Config 3: n^3 grid of equal chunks (x-major like the reference's own loops)."""
+    i = np.arange(n_per_axis, dtype=np.float32)
+    X, Y, Z = np.meshgrid(i, i, i, indexing="ij")
+    ps = np.stack([F(origin[0]) + X.ravel() * F(chunk_size), F(origin[1]) + Y.ravel() * F(chunk_size),
+                   F(origin[2]) + Z.ravel() * F(chunk_size), np.full(X.size, chunk_size, np.float32)], axis=1)
+    return np.ascontiguousarray(ps, np.float32)
+
+
+def partition(mortons, costs, n_parts):
+    """Multi-GPU sharding by octree node: sort leaves by Morton code and deal contiguous,
+    cost-balanced ranges.  Returns a list of index arrays (into the original order), one per part."""
+    order = np.argsort(np.asarray(mortons, np.uint64), kind="stable")
+    c = np.asarray(costs, np.float64)[order]
+    cum = np.cumsum(c)
+    total = cum[-1] if len(cum) else 0.0
+    bounds = [int(np.searchsorted(cum, total * k / n_parts, side="left")) for k in range(1, n_parts)]
+    parts, lo = [], 0
+    for b in bounds + [len(order)]:
+        b = max(b, lo)
+        parts.append(order[lo:b])
+        lo = b
+    return parts

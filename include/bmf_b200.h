@@ -148,6 +148,12 @@ int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* ind
 int bmf_batch_stage_ms(bmf_ctx* ctx, float* ms /* [BMF_NUM_STAGES] */);
 /* kernels launched by this ctx since creation (bench.py's gpu_launches) */
 int64_t bmf_ctx_launch_count(const bmf_ctx* ctx);
+/* optional per-launch timing: when on, every kernel of the next batches is bracketed by its own event pair;
+ * bmf_ctx_kernel_times returns the number of launches of the last batch and fills up to `cap` (name, ms) */
+int bmf_ctx_set_kernel_timing(bmf_ctx* ctx, int on);
+int bmf_ctx_kernel_times(bmf_ctx* ctx, int cap, const char** names, float* ms);
+/* the cudaStream_t every kernel of this ctx is launched on (so a harness can record its own events there) */
+void* bmf_ctx_stream(const bmf_ctx* ctx);
 /* device pointers of the resident batch (for zero-copy consumers / profiling); valid until next submit */
 int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits, void** density);
 
