@@ -506,8 +506,12 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	else if (is_terrain2d(kind))
 	{
 		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n_sheets * d * d, CTA), CTA, 0, ctx->sampler, ctx->sheet_geom.p, d, L.ld, ctx->hmap.p, n_sheets);
-		BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p, ctx->bits.p,
-		           dens_w, ctx->flags.p);
+		if (dens_w)
+			BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p, ctx->bits.p,
+			           dens_w, ctx->flags.p);
+		else // no density block wanted: compare-only sign words (32 voxels per ballot, no per-voxel arithmetic)
+			BMF_LAUNCH(k_terrain2d_bits, (unsigned)((size_t)n * L.d * L.zc * L.zc / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
+			           ctx->bits.p, ctx->flags.p);
 	}
 	else if (kind == BMF_SAMPLER_TERRAIN3D)
 	{

@@ -207,6 +207,40 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const C
 	merge_flags(f, flags + chunk);
 }
 
+// ---- K1b': sign words of a 2-D terrain WITHOUT evaluating the density per voxel.
+// density(x,y,z) = (-dy(y)) - t(x,z) with t = n(x,z)*height: in IEEE arithmetic with gradual underflow
+// a - b < 0  <=>  a < b (the difference of two floats is zero only if they are equal; NaN compares false
+// either way), so bit(x,y,z) = (-dy(y) < t(x,z)): one compare + ballot per 32 voxels.  A warp owns a
+// 32(y) x 32(z) tile of one x-plane: every lane keeps t for its z and -dy for its y, the y value is
+// broadcast by shuffle, and after 32 ballots lane j holds the word of row y0+j -> one coalesced store.
+__global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
+                                                         const int* __restrict__ sheet_of, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
+{
+	const int lane = threadIdx.x & 31;
+	const size_t task = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5; // (chunk, x, yb, zb); tasks per chunk = d * zc^2, a multiple of 8
+	const int zb = (int)task & (L.zc - 1);
+	const int yb = (int)(task >> L.lzc) & (L.zc - 1);
+	const int x = (int)(task >> (2 * L.lzc)) & (L.d - 1);
+	const int chunk = (int)(task >> (2 * L.lzc + L.ld));
+	const ChunkGeom g = geom[chunk];
+	const float n = hmap[((size_t)sheet_of[chunk] << (2 * L.ld)) + ((size_t)x << L.ld) + zb * 32 + lane];
+	const float t = n * s.nm;
+	const int y = yb * 32 + lane;
+	float dy = ((float)y * g.delta + g.oy) * s.g;
+	if (s.dy_half) dy = dy * 0.5f;
+	const float ndy = -dy;
+	uint32_t mine = 0;
+#pragma unroll
+	for (int j = 0; j < 32; j++)
+	{
+		const float a = __shfl_sync(0xffffffffu, ndy, j);
+		const uint32_t word = __ballot_sync(0xffffffffu, a < t);
+		if (lane == j) mine = word;
+	}
+	bits[(size_t)chunk * L.wc + ((((size_t)x << L.ld) + y) << L.lzc) + zb] = mine;
+	merge_flags(word_flags(mine), flags + chunk);
+}
+
 // ---- K1c: 3-D terrains: one noise evaluation per voxel, density always materialised (4 B/voxel is
 // noise next to ~1.5 k ALU ops/voxel) so the emitters can read crossing-edge samples back.
 template <int BASE>

@@ -71,8 +71,21 @@ def test_recompute_path_matches_materialised(gpu, oracle):
     for kind in (ob.TORUS_Z, ob.TERRAIN2D_PERT):
         a = gpu_chunk(gpu, kind, pos, size, 64, 0.02, want_density=True)
         b = gpu_chunk(gpu, kind, pos, size, 64, 0.02, want_density=False)
+        np.testing.assert_array_equal(a["bits"], b["bits"])
         np.testing.assert_array_equal(a["inds"], b["inds"])
         np.testing.assert_array_equal(a["verts"]["p"].view(np.uint32), b["verts"]["p"].view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", [ob.TERRAIN2D, ob.TERRAIN2D_PERT])
+@pytest.mark.parametrize("pos,size,dim,overlap", [((-64.0, -64.0, -64.0), 128.0, 64, 0.045), ((-256.0, -40.0, 100.0), 64.0, 32, 0.0),
+                                                  ((3.5, -7.25, 11.0), 16.0, 128, 0.035), ((-16.0, 0.0, -16.0), 16.0, 64, 0.045)])
+def test_terrain2d_compare_only_sign_words(gpu, oracle, kind, pos, size, dim, overlap):
+    """The production 2-D terrain path never evaluates a density per voxel (bit = (-dy < n*height)); its sign
+    words, topology and positions must equal the oracle's, which evaluates -dy - n*height < 0 per voxel."""
+    g = gpu_chunk(gpu, kind, pos, size, dim, overlap, want_density=False)
+    o = oracle.chunk(oracle.sampler(kind), pos, size, dim, overlap)
+    assert_same_topology(g, o)
+    assert_same_positions(g, o, dim)
 
 
 @pytest.mark.parametrize("seed,dim", [(1, 32), (2, 64), (3, 64), (4, 128)])
