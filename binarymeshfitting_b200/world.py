@@ -106,7 +106,7 @@ def partition(mortons, costs, n_parts):
     c = np.asarray(costs, np.float64)[order]
     cum = np.cumsum(c)
     total = cum[-1] if len(cum) else 0.0
-    bounds = [int(np.searchsorted(cum, total * k / n_parts, side="left")) for k in range(1, n_parts)]
+    bounds = [int(np.searchsorted(cum, total * k / n_parts, side="right")) for k in range(1, n_parts)]
     parts, lo = [], 0
     for b in bounds + [len(order)]:
         b = max(b, lo)

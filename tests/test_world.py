@@ -1,0 +1,106 @@
+"""CPU: host-side LOD enumeration / partitioning (binarymeshfitting_b200/world.py) against the golden leaf lists
+of the compiled reference, and the N>1 sharding logic over gloo with world_size 2."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from binarymeshfitting_b200 import world as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+ARR = np.load(os.path.join(HERE, "golden", "golden_arrays.npz"))
+
+
+@pytest.mark.parametrize("w", GOLD["worlds"], ids=lambda w: w["key"])
+def test_split_leaves_matches_reference(w):
+    props = W.WorldProperties(max_level=w["max_level"], chunk_resolution=w["dim"], process_iters=w["iters"])
+    ps, lv, mc = W.split_leaves(props, 256, tuple(w["focus"]))
+    gold = ARR[w["key"] + "_leaves"]
+    assert len(ps) == w["leaves"]
+    np.testing.assert_array_equal(ps, gold[:, :4])
+    np.testing.assert_array_equal(lv, gold[:, 4].astype(np.int32))
+    np.testing.assert_array_equal(mc, ARR[w["key"] + "_morton"])
+
+
+def test_default_world_leaf_counts():
+    for ml, n in ((5, 232), (6, 288), (7, 344)):
+        assert len(W.split_leaves(W.WorldProperties(max_level=ml))[0]) == n
+
+
+def test_overlap_rule():
+    p = W.WorldProperties(max_level=5, process_iters=2)
+    assert W.chunk_overlap(p, 3) == np.float32(np.float32(0.035) + np.float32(0.005) * np.float32(2))
+    assert W.chunk_overlap(p, 5) == 0.0  # at max level without boundary processing (ChunkGenerator.cpp:98)
+    p.boundary_processing = True
+    assert W.chunk_overlap(p, 5) > 0
+    p.process_iters = 0
+    assert W.chunk_overlap(p, 5) == 0.0 and W.chunk_overlap(p, 2) == np.float32(0.035)
+
+
+def test_partition_is_a_balanced_cover():
+    ps, lv, mc = W.split_leaves(W.WorldProperties(max_level=6))
+    for n in (1, 2, 4, 8):
+        parts = W.partition(mc, np.ones(len(mc)), n)
+        allidx = np.concatenate(parts)
+        assert sorted(allidx.tolist()) == list(range(len(mc)))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        # contiguous in Morton order
+        for p in parts:
+            if len(p):
+                assert (np.diff(mc[p].astype(np.int64)) > 0).all()
+    assert W.partition(mc[:3], np.ones(3), 8)[0].size <= 1  # more parts than chunks: empty parts allowed
+
+
+def test_grid_chunks():
+    ps = W.grid_chunks(16, 16.0)
+    assert ps.shape == (4096, 4) and ps[0].tolist() == [-128, -128, -128, 16] and ps[-1].tolist() == [112, 112, 112, 16]
+    assert ps[1].tolist() == [-128, -128, -112, 16]  # z fastest
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch.distributed as dist
+from binarymeshfitting_b200 import world as W
+from oracle import oracle_binding as ob   # CPU stand-in for the per-rank extraction: this test is about the sharding
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+props = W.WorldProperties(max_level=5, chunk_resolution=32)
+ps, lv, mc = W.split_leaves(props)
+parts = W.partition(mc, np.ones(len(mc)), ws)
+mine = parts[rank]
+O = ob.Oracle()
+total, counts = O.batch(O.sampler(ob.SPHERE), ps[mine], 32, overlaps=[W.chunk_overlap(props, int(l)) for l in lv[mine]], threads=2)
+# final host gather of per-chunk results, back in the original batch order
+gathered = [None] * ws
+dist.all_gather_object(gathered, (mine.tolist(), counts.tolist()))
+if rank == 0:
+    per = np.zeros((len(ps), 2), np.int64)
+    for idx, c in gathered:
+        per[np.array(idx, int)] = np.array(c).reshape(-1, 2)
+    print("TOTALS", int(per[:, 0].sum()), int(per[:, 1].sum()), len(ps))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("TOTALS")][0].split()
+    assert (int(line[1]), int(line[2]), int(line[3])) == (79992, 452400, 232)  # the single-process reference totals (Appendix A)
