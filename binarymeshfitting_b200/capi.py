@@ -22,7 +22,7 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
-           "bmf_mesh_process", "bmf_qef_solve")
+           "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve")
 
 
 class SamplerDesc(C.Structure):
@@ -95,6 +95,7 @@ def load_library(path=SO):
     lib.bmf_ctx_stream.restype = vp
     lib.bmf_batch_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.bmf_mesh_process_steps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     return lib
 

@@ -233,7 +233,7 @@ inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1
 // MeshProcessor<N> on device arrays (all batch-wide); chunks_dev maps index positions to vertex bases.
 template <int N>
 int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* color, float* normal, const uint8_t* boundary,
-               const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef)
+               const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef, int final_primal = 1)
 {
 	if (n_verts == 0 || n_inds < (size_t)N || iters <= 0) return BMF_OK;
 	const size_t n_prims = n_inds / N;
@@ -273,8 +273,9 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		}
 	}
 	// the driver's extra primal call (ChunkGenerator.cpp:120)
-	BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p, ctx->dn.p, pos,
-	           color, normal, smooth, 0, pb);
+	if (final_primal)
+		BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p, ctx->dn.p, pos,
+		           color, normal, smooth, 0, pb);
 	if (qef)
 	{
 		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
@@ -783,8 +784,17 @@ int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits,
 	return BMF_OK;
 }
 
+int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence_in, int n_verts,
+                           const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals, int final_primal);
+
 int bmf_mesh_process(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence_in, int n_verts,
                      const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals)
+{
+	return bmf_mesh_process_steps(ctx, pos, color, normal, boundary, valence_in, n_verts, indices, n_inds, prim_n, iters, process_boundary, smooth_normals, 1);
+}
+
+int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence_in, int n_verts,
+                           const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals, int final_primal)
 {
 	(void)valence_in; // init_valence is recomputed from the index buffer (identical whenever the caller's was consistent)
 	if (!ctx) return BMF_ERR_INVALID;
@@ -818,8 +828,8 @@ int bmf_mesh_process(bmf_ctx* ctx, float* pos, float* color, float* normal, cons
 	BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, V + 16, st));
 	BMF_LAUNCH(k_valence_from_inds, grid_for(I, CTA), CTA, 0, ctx->inds.p, I, ctx->valence.p);
 	int rc = (prim_n == 3)
-		? run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0)
-		: run_smooth<4>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0);
+		? run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0, final_primal)
+		: run_smooth<4>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, 1, iters, process_boundary, smooth_normals, 0, final_primal);
 	if (rc) return rc;
 	BMF_CUDA(cudaMemcpyAsync(pos, ctx->pos.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(color, ctx->color.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));

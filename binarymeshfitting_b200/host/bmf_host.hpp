@@ -1,0 +1,765 @@
+// bmf_host.hpp -- C++ host side above the C ABI (include/bmf_b200.h): the reference's operator interface for
+// the extraction path -- Sampler / DMCChunk / ChunkGenerator / Processing::MeshProcessor<N> -- with the same
+// names, argument meaning, public fields and (absent) error behaviour, re-hosted on libbmf_b200.so.
+//
+// What each class replaces (reference file:line under BinaryMeshFitting/):
+//   SmartContainer<T>              SmartContainer.hpp:8-139      POD vector (count / size / elements)
+//   DualVertex                     Vertices.hpp:5-24             84-byte vertex record (layout asserted below)
+//   Sampler, SamplerProperties     Sampler.hpp:8-34              callback bundle + the device descriptor a GPU needs
+//   ImplicitFunctions / NoiseSamplers factories  ImplicitSampler.hpp:51-59, NoiseSampler.hpp:82-140
+//   BinaryBlock / DensityBlock / VerticesIndicesBlock / ...      ChunkBlocks.hpp:9-227
+//   ResourceAllocator<T>           ResourceAllocator.hpp:8-69    mutex-guarded free list of blocks
+//   DMCChunk                       DMCChunk.hpp:21-85, DMCChunk.cpp:58-166, 168-508, 514-591
+//   WorldProperties / WorldOctreeNode / WorldOctree (the slice process_queue touches)  WorldOctree.hpp:18-33,
+//                                  WorldOctreeNode.hpp:30-170, WorldOctree.cpp:20-33, 263-269
+//   ChunkGenerator                 ChunkGenerator.hpp:15-57, ChunkGenerator.cpp:19-147
+//   Processing::MeshProcessor<N>   MeshProcessor.hpp:55-84, MeshProcessor.cpp:25-306
+//
+// Differences a maintainer must know (also in INTEGRATION.md):
+//   * Sampler carries `device` (bmf_sampler_desc).  The factories below fill it.  A Sampler whose `block`
+//     is an arbitrary host callback keeps working through kind = BMF_SAMPLER_HOST_DENSITY: the shim calls
+//     `block` on the host, uploads the density block and the GPU does everything after it.
+//   * ChunkGenerator::process_queue runs the whole batch as ONE device submission (the reference loops
+//     chunks under `#pragma omp parallel for`); results land in the same fields (chunk->vi, contains_mesh, ...).
+//   * DMCChunk's staged calls stay valid, but label_grid already runs the fused device pipeline for the chunk;
+//     label_edges / polygonize publish its results (vertices, then indices + init_valence) at the same points.
+//   * There is no CPU fallback: without libbmf_b200.so / a CUDA device the constructors report the error and
+//     every compute call returns false.
+#pragma once
+
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+#include "../../include/bmf_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<glm/glm.hpp>)
+#include <glm/glm.hpp>
+#define BMF_HAVE_GLM 1
+#endif
+#endif
+#ifndef BMF_HAVE_GLM
+namespace glm
+{
+// the few glm types the interface exposes, for builds without GLM
+template <typename T>
+struct tvec3
+{
+	T x, y, z;
+	tvec3() : x(0), y(0), z(0) {}
+	tvec3(T a, T b, T c) : x(a), y(b), z(c) {}
+	T& operator[](int i) { return (&x)[i]; }
+	const T& operator[](int i) const { return (&x)[i]; }
+};
+typedef tvec3<float> vec3;
+typedef tvec3<int> ivec3;
+inline vec3 operator+(const vec3& a, float s) { return vec3(a.x + s, a.y + s, a.z + s); }
+inline vec3 operator-(const vec3& a, float s) { return vec3(a.x - s, a.y - s, a.z - s); }
+} // namespace glm
+#endif
+
+// ---- SmartContainer ------------------------------------------------------------------------------------
+template <class T>
+class SmartContainer
+{
+public:
+	size_t size;
+	size_t count;
+	T* elements;
+	int scale;
+
+	SmartContainer() : size(0), count(0), elements(nullptr), scale(2) {}
+	SmartContainer(const SmartContainer&) = delete;
+	SmartContainer& operator=(const SmartContainer&) = delete;
+	~SmartContainer() { reset(); }
+
+	T& operator[](int index) { return elements[index]; }
+	bool resize(size_t new_size)
+	{
+		T* p = static_cast<T*>(std::realloc((void*)elements, sizeof(T) * new_size));
+		if (!p && new_size) return false;
+		elements = p;
+		size = new_size;
+		return true;
+	}
+	bool prepare(size_t amount)
+	{
+		if (count + amount <= size) return true;
+		size_t want = 32;
+		while (want < size + amount) want *= 2;
+		return resize(want);
+	}
+	bool prepare_exact(size_t amount) { return count + amount <= size ? true : resize(size + amount); }
+	bool push_back(const T& v)
+	{
+		if (count >= size && !resize(size ? size * (size_t)scale : 32)) return false;
+		elements[count++] = v;
+		return true;
+	}
+	bool push_back(const T* other, size_t n)
+	{
+		if (!n) return true;
+		if (!prepare(n)) return false;
+		std::memcpy((void*)(elements + count), (const void*)other, sizeof(T) * n);
+		count += n;
+		return true;
+	}
+	bool push_back(const SmartContainer<T>& other) { return push_back(other.elements, other.count); }
+	void zero()
+	{
+		if (elements && size) std::memset((void*)elements, 0, sizeof(T) * size);
+	}
+	void reset()
+	{
+		std::free((void*)elements);
+		elements = nullptr;
+		size = count = 0;
+	}
+};
+
+// ---- vertex record -------------------------------------------------------------------------------------
+struct DualVertex
+{
+	bool boundary;
+	uint8_t mask;
+	uint32_t index;
+	uint8_t valence;
+	uint8_t init_valence;
+	uint8_t adj_next;
+	uint32_t adj_offset;
+	uint16_t edge_mask;
+	float s;
+	glm::ivec3 xyz;
+	glm::vec3 p;
+	glm::vec3 n;
+	glm::vec3 avg;
+	glm::vec3 color;
+};
+static_assert(sizeof(DualVertex) == 84, "DualVertex must keep the reference's 84-byte layout");
+static_assert(offsetof(DualVertex, p) == 36 && offsetof(DualVertex, n) == 48 && offsetof(DualVertex, color) == 72, "DualVertex field offsets");
+
+// ---- Sampler --------------------------------------------------------------------------------------------
+struct FastNoiseVectorSet; // opaque here: the noise library is replaced by the device kernels
+class FastNoiseSIMD;
+
+class SamplerProperties
+{
+public:
+	int thread_id;
+	SamplerProperties() : thread_id(0) {}
+	explicit SamplerProperties(int t) : thread_id(t) {}
+	virtual ~SamplerProperties() {}
+};
+
+typedef const float (*SamplerValueFunction)(const float world_size, const glm::vec3& p);
+typedef std::function<void(const float world_size, const glm::vec3& p, const glm::ivec3& size, const float scale, void** out, FastNoiseVectorSet* vectorset_out,
+                           float* dest_noise, int offset, int stride, SamplerProperties* properties)>
+	SamplerBlockFunction;
+typedef std::function<glm::vec3(const float world_size, const glm::vec3& p, float h)> SamplerGradientFunction;
+
+struct Sampler
+{
+	float world_size;
+	SamplerValueFunction value;
+	SamplerBlockFunction block;
+	SamplerGradientFunction gradient;
+	FastNoiseSIMD* noise_samplers[8];
+	bmf_sampler_desc device; // what the GPU runs; kind == BMF_SAMPLER_HOST_DENSITY -> `block` is called on the host
+
+	Sampler() : world_size(256.0f), value(nullptr)
+	{
+		for (int i = 0; i < 8; i++) noise_samplers[i] = nullptr;
+		bmf_sampler_defaults(&device, BMF_SAMPLER_HOST_DENSITY);
+	}
+	virtual ~Sampler() {}
+};
+
+namespace NoiseSamplers
+{
+class NoiseSamplerProperties : public SamplerProperties
+{
+public:
+	int level;
+	float g_scale, height;
+	int octaves;
+	float amp, frequency, gain;
+	int noise_type, fractal_type;
+	NoiseSamplerProperties() : SamplerProperties(), level(0), g_scale(0.25f), height(75.0f), octaves(13), amp(0.87f), frequency(0.585f), gain(0.488f), noise_type(1), fractal_type(0) {}
+};
+inline const float noise3d(const float, const glm::vec3&) { return 0; }
+inline void make(Sampler* s, int kind)
+{
+	s->value = noise3d;
+	bmf_sampler_defaults(&s->device, kind);
+	s->device.world_size = s->world_size;
+}
+inline void create_sampler_terrain_2d(Sampler* s) { make(s, BMF_SAMPLER_TERRAIN2D); }
+inline void create_sampler_terrain_pert_2d(Sampler* s) { make(s, BMF_SAMPLER_TERRAIN2D_PERT); }
+inline void create_sampler_terrain_3d(Sampler* s) { make(s, BMF_SAMPLER_TERRAIN3D); }
+inline void create_sampler_terrain_pert_3d(Sampler* s) { make(s, BMF_SAMPLER_TERRAIN3D_PERT); }
+} // namespace NoiseSamplers
+
+namespace ImplicitFunctions
+{
+// value callbacks keep their reference meaning (density = -SDF, positive inside); they are only evaluated on the
+// host by callers that use Sampler::value / gradient directly -- the device evaluates its own copy per voxel
+inline const float sphere(const float r, const glm::vec3& p) { return -(std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z) - r * 0.25f); }
+inline const float torus_z(const float r, const glm::vec3& p)
+{
+	float qx = std::fabs(std::sqrt(p.x * p.x + p.y * p.y)) - r / 4.0f;
+	return -(std::sqrt(qx * qx + p.z * p.z) - r / 10.0f);
+}
+inline const float cuboid(const float res, const glm::vec3& p)
+{
+	float r = res / 8.0f, dx = std::fabs(p.x) - r, dy = std::fabs(p.y) - r, dz = std::fabs(p.z) - r;
+	return -std::fmin(std::fmax(dx, std::fmax(dy, dz)), std::sqrt(dx * dx + dy * dy + dz * dz));
+}
+inline const float plane_y(const float, const glm::vec3& p) { return -p.y; }
+inline glm::vec3 implicit_gradient(SamplerValueFunction f, const float res, const glm::vec3& p, float h = 0.01f)
+{
+	return glm::vec3(f(res, glm::vec3(p.x + h, p.y, p.z)) - f(res, glm::vec3(p.x - h, p.y, p.z)), f(res, glm::vec3(p.x, p.y + h, p.z)) - f(res, glm::vec3(p.x, p.y - h, p.z)),
+	                 f(res, glm::vec3(p.x, p.y, p.z + h)) - f(res, glm::vec3(p.x, p.y, p.z - h)));
+}
+inline Sampler create_sampler(const SamplerValueFunction& f)
+{
+	Sampler s;
+	s.value = f;
+	s.gradient = [f](const float ws, const glm::vec3& p, float h) { return implicit_gradient(f, ws, p, h); };
+	int kind = f == sphere ? BMF_SAMPLER_SPHERE : f == torus_z ? BMF_SAMPLER_TORUS_Z : f == cuboid ? BMF_SAMPLER_CUBOID : f == plane_y ? BMF_SAMPLER_PLANE_Y : BMF_SAMPLER_HOST_DENSITY;
+	bmf_sampler_defaults(&s.device, kind);
+	if (kind == BMF_SAMPLER_HOST_DENSITY)
+	{
+		// unknown analytic function: evaluate it on the host like implicit_block (ImplicitSampler.hpp:14-36)
+		s.block = [f](const float ws, const glm::vec3& p, const glm::ivec3& size, const float scale, void** out, FastNoiseVectorSet*, float*, int, int, SamplerProperties*) {
+			float* o = (float*)*out;
+			for (int x = 0; x < size.x; x++)
+				for (int y = 0; y < size.y; y++)
+					for (int z = 0; z < size.z; z++) o[((size_t)x * size.y + y) * size.z + z] = f(ws, glm::vec3(p.x + (float)x * scale, p.y + (float)y * scale, p.z + (float)z * scale));
+		};
+	}
+	return s;
+}
+} // namespace ImplicitFunctions
+
+// ---- pooled blocks ---------------------------------------------------------------------------------------
+template <typename T>
+struct PodBlock
+{
+	uint32_t size = 0;
+	T* data = nullptr;
+	bool initialized = false;
+	~PodBlock() { std::free(data); }
+	void init(uint32_t n)
+	{
+		if (initialized && n <= size) return;
+		std::free(data);
+		data = (T*)std::malloc(sizeof(T) * (size_t)n);
+		size = n;
+		initialized = true;
+	}
+};
+struct BinaryBlock : PodBlock<uint32_t>
+{
+	void init(uint32_t /*raw*/, uint32_t binary_size) { PodBlock<uint32_t>::init(binary_size); }
+};
+struct DensityBlock : PodBlock<float> {};
+struct MasksBlock : PodBlock<uint64_t> {};
+struct IndexesBlock : PodBlock<uint32_t> {};
+struct NoiseBlock : PodBlock<float> {};
+struct DMC_Cell { uint16_t mask; };
+struct DMC_CellsBlock
+{
+	SmartContainer<DMC_Cell> cells; // only the count is meaningful: the device path has no per-cell records
+	void init() { cells.count = 0; }
+};
+struct VerticesIndicesBlock
+{
+	SmartContainer<DualVertex> vertices;
+	SmartContainer<uint32_t> mesh_indexes;
+	void init() { vertices.count = 0; mesh_indexes.count = 0; }
+};
+
+template <class T>
+class ResourceAllocator
+{
+public:
+	~ResourceAllocator()
+	{
+		for (T* e : all) delete e;
+	}
+	T* new_element(bool no_lock = false)
+	{
+		std::unique_lock<std::mutex> l(_mutex, std::defer_lock);
+		if (!no_lock) l.lock();
+		if (!free_list.empty())
+		{
+			T* e = free_list.back();
+			free_list.pop_back();
+			return e;
+		}
+		T* e = new T();
+		all.push_back(e);
+		return e;
+	}
+	void free_element(T* e, bool no_lock = false)
+	{
+		if (!e) return;
+		std::unique_lock<std::mutex> l(_mutex, std::defer_lock);
+		if (!no_lock) l.lock();
+		free_list.push_back(e);
+	}
+	std::mutex _mutex;
+
+private:
+	std::vector<T*> all, free_list;
+};
+
+// ---- device context shared by the classes below ------------------------------------------------------------
+class BmfDevice
+{
+public:
+	static BmfDevice& get(int device = 0)
+	{
+		static BmfDevice d(device);
+		return d;
+	}
+	bmf_ctx* ctx = nullptr;
+	bool ok() const { return ctx != nullptr; }
+	const char* error() const { return ctx ? bmf_last_error(ctx) : "no CUDA device / libbmf_b200 context (no CPU fallback)"; }
+
+private:
+	explicit BmfDevice(int device)
+	{
+		if (bmf_ctx_create(device, &ctx) != BMF_OK) ctx = nullptr;
+	}
+	~BmfDevice() { bmf_ctx_destroy(ctx); }
+};
+
+namespace bmf_detail
+{
+inline void fill_dual_vertices(SmartContainer<DualVertex>& out, const float* pos, const float* nrm, const float* col, const uint8_t* bnd, const uint8_t* val, size_t n,
+                               bool with_valence, bool processed)
+{
+	out.count = 0;
+	out.prepare(n);
+	uint32_t off = 0;
+	for (size_t i = 0; i < n; i++)
+	{
+		DualVertex v;
+		std::memset((void*)&v, 0, sizeof(v));
+		v.boundary = bnd[i] != 0;
+		v.index = (uint32_t)i;
+		v.init_valence = with_valence ? val[i] : 0;
+		v.valence = processed ? val[i] : 0;
+		v.adj_next = processed ? val[i] : 0;
+		v.adj_offset = processed ? off : 0;
+		v.p = glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		if (nrm) v.n = glm::vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+		v.color = glm::vec3(col[3 * i], col[3 * i + 1], col[3 * i + 2]);
+		out.elements[out.count++] = v;
+		off += val[i];
+	}
+}
+} // namespace bmf_detail
+
+// ---- DMCChunk ----------------------------------------------------------------------------------------------
+class DMCChunk
+{
+public:
+	bool pem = false;
+	int id = 0;
+	int level = 0;
+	uint32_t dim = 32; // RESOLUTION (DMCChunk.cpp:34)
+	float size = 0;
+	glm::vec3 pos;
+	bool contains_mesh = false;
+	uint32_t mesh_offset = 0;
+	uint64_t parent_code = 0;
+	Sampler sampler;
+	VerticesIndicesBlock* vi = nullptr;
+	DensityBlock* density_block = nullptr;
+	BinaryBlock* binary_block = nullptr;
+	DMC_CellsBlock* cell_block = nullptr;
+	IndexesBlock* indexes_block = nullptr;
+	glm::vec3 overlap_pos, bound_start;
+	float bound_size = 0, scale = 0;
+
+	DMCChunk() {}
+	DMCChunk(glm::vec3 p, float s, int lvl, Sampler& smp, uint64_t code) { init(p, s, lvl, smp, code); }
+
+	void init(glm::vec3 p, float s, int lvl, Sampler& smp, uint64_t code)
+	{
+		pos = p; dim = 32; size = s; level = lvl; pem = false; contains_mesh = false; mesh_offset = 0; sampler = smp;
+		vi = nullptr; cell_block = nullptr; indexes_block = nullptr; density_block = nullptr; binary_block = nullptr; parent_code = code;
+	}
+
+	// sample + sign pack (+ the fused device pipeline of this one chunk).  Fills binary_block, density_block,
+	// contains_mesh, overlap_pos, scale, bound_start, bound_size like DMCChunk.cpp:79-166.
+	bool label_grid(ResourceAllocator<BinaryBlock>* binary_allocator, ResourceAllocator<DensityBlock>* density_allocator, ResourceAllocator<NoiseBlock>* /*noise_allocator*/, float overlap,
+	                NoiseSamplers::NoiseSamplerProperties properties)
+	{
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok()) return false;
+		const size_t n = (size_t)dim * dim * dim;
+		binary_block = binary_allocator->new_element();
+		binary_block->init((uint32_t)n, (uint32_t)(n / 32));
+		density_block = density_allocator->new_element();
+		density_block->init((uint32_t)n);
+		const float delta = size * (1.0f + overlap * 2.0f) / (float)(dim - 1);
+		overlap_pos = pos - size * overlap;
+		scale = delta;
+		bound_size = size * (1.0f + overlap * 2.0f) * 0.5f;
+		bound_start = overlap_pos + bound_size;
+
+		bmf_sampler_desc d = sampler.device;
+		d.world_size = sampler.world_size;
+		if (d.kind == BMF_SAMPLER_TERRAIN2D_PERT)
+		{
+			d.g_scale = properties.g_scale; d.height = properties.height; d.octaves = properties.octaves;
+			d.amp = properties.amp; d.frequency = properties.frequency; d.gain = properties.gain;
+		}
+		const float* host_density = nullptr;
+		if (d.kind == BMF_SAMPLER_HOST_DENSITY)
+		{
+			if (!sampler.block) return false;
+			void* out = density_block->data;
+			sampler.block(sampler.world_size, overlap_pos, glm::ivec3((int)dim, (int)dim, (int)dim), delta, &out, nullptr, nullptr, 0, sizeof(float), &properties);
+			host_density = density_block->data;
+		}
+		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
+		bmf_chunk_desc c;
+		c.pos[0] = pos.x; c.pos[1] = pos.y; c.pos[2] = pos.z; c.size = size; c.level = level; c.overlap = overlap; c.morton = parent_code;
+		bmf_params p;
+		std::memset(&p, 0, sizeof(p));
+		p.dim = (int32_t)dim;
+		p.keep_density = 1;
+		if (bmf_batch_submit(dev.ctx, &c, 1, &p, host_density) != BMF_OK) return false;
+		bmf_chunk_info info;
+		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
+		contains_mesh = info.contains_mesh != 0;
+		return bmf_batch_copy_chunk(dev.ctx, 0, nullptr, nullptr, binary_block->data, nullptr, d.kind == BMF_SAMPLER_HOST_DENSITY ? nullptr : density_block->data) == BMF_OK;
+	}
+
+	// publishes the iso-vertices (positions, boundary flags; valences still 0) -- DMCChunk.cpp:168-508
+	bool label_edges(ResourceAllocator<VerticesIndicesBlock>* vi_allocator, ResourceAllocator<DMC_CellsBlock>* cell_allocator, ResourceAllocator<IndexesBlock>* /*inds_allocator*/,
+	                 ResourceAllocator<DensityBlock>* /*density_allocator*/, ResourceAllocator<MasksBlock>* /*masks_allocator*/)
+	{
+		if (!contains_mesh) return true;
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok()) return false;
+		if (!vi) { vi = vi_allocator->new_element(); vi->init(); }
+		if (!cell_block) { cell_block = cell_allocator->new_element(); cell_block->init(); }
+		bmf_chunk_info info;
+		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
+		cell_block->cells.count = 0;
+		cell_block->cells.prepare((size_t)info.n_cells);
+		cell_block->cells.count = (size_t)info.n_cells;
+		return fetch(dev, info, false);
+	}
+
+	// publishes the index buffer and init_valence -- DMCChunk.cpp:514-576
+	bool polygonize()
+	{
+		if (!contains_mesh) return true;
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok() || !vi) return false;
+		bmf_chunk_info info;
+		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
+		vi->mesh_indexes.count = 0;
+		vi->mesh_indexes.prepare((size_t)info.n_inds);
+		vi->mesh_indexes.count = (size_t)info.n_inds;
+		if (bmf_batch_copy_chunk(dev.ctx, 0, nullptr, vi->mesh_indexes.elements, nullptr, nullptr, nullptr) != BMF_OK) return false;
+		return fetch(dev, info, true);
+	}
+
+	void copy_verts_and_inds(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& i_out)
+	{
+		if (!contains_mesh || !vi) return;
+		mesh_offset = (uint32_t)v_out.count;
+		size_t start = i_out.count;
+		v_out.push_back(vi->vertices);
+		i_out.push_back(vi->mesh_indexes);
+		for (size_t i = start; i < i_out.count; i++) i_out.elements[i] += mesh_offset;
+	}
+
+private:
+	bool fetch(BmfDevice& dev, const bmf_chunk_info& info, bool with_valence)
+	{
+		std::vector<uint8_t> rec((size_t)info.n_verts * 84);
+		if (bmf_batch_copy_chunk(dev.ctx, 0, rec.data(), nullptr, nullptr, nullptr, nullptr) != BMF_OK) return false;
+		vi->vertices.count = 0;
+		vi->vertices.prepare((size_t)info.n_verts);
+		std::memcpy((void*)vi->vertices.elements, rec.data(), rec.size());
+		vi->vertices.count = (size_t)info.n_verts;
+		if (!with_valence)
+			for (size_t i = 0; i < vi->vertices.count; i++) vi->vertices.elements[i].init_valence = 0;
+		return true;
+	}
+};
+
+// ---- the slice of the world the generator touches -------------------------------------------------------------
+enum GENERATION_STAGES
+{
+	GENERATION_STAGES_UNHANDLED = 0, GENERATION_STAGES_WATCHER_QUEUED = 1, GENERATION_STAGES_GENERATOR_QUEUED = 2, GENERATION_STAGES_GENERATOR_ACKNOWLEDGED = 3,
+	GENERATION_STAGES_GENERATING = 4, GENERATION_STAGES_NEEDS_FORMAT = 5, GENERATION_STAGES_NEEDS_UPLOAD = 6, GENERATION_STAGES_UPLOADING = 7,
+	GENERATION_STAGES_AWAITING_STITCHING = 8, GENERATION_STAGES_AWAITING_STITCHING_UPLOAD = 9, GENERATION_STAGES_DONE = 10
+};
+
+struct WorldProperties
+{
+	float split_multiplier = 1.0f, group_multiplier = 2.0f, size_modifier = 0.0f;
+	int max_level = 7, min_level = 1, num_threads = 4, process_iters = 0, chunk_resolution = 32;
+	bool enable_stitching = false;
+	float overlap = 0.035f;
+	bool boundary_processing = false;
+};
+
+// GLChunk's CPU side: the SoA the renderer uploads (GLChunk.hpp:32-34, format_data GLChunk.cpp:278-296)
+struct GLChunk
+{
+	SmartContainer<glm::vec3> p_data, n_data, c_data;
+};
+
+class WorldOctreeNode
+{
+public:
+	float size = 0;
+	uint8_t level = 0;
+	glm::vec3 pos;
+	uint64_t morton_code = 0;
+	int generation_stage = GENERATION_STAGES_UNHANDLED;
+	DMCChunk* chunk = nullptr;
+	GLChunk* gl_chunk = nullptr;
+	WorldOctreeNode() {}
+	WorldOctreeNode(float s, glm::vec3 p, uint8_t l, uint64_t code) : size(s), level(l), pos(p), morton_code(code) {}
+};
+
+class WorldOctree
+{
+public:
+	Sampler sampler;
+	WorldProperties properties;
+	NoiseSamplers::NoiseSamplerProperties noise_properties;
+	std::mutex chunk_mutex;
+	int next_chunk_id = 0;
+	std::vector<DMCChunk*> chunks;
+	~WorldOctree()
+	{
+		for (DMCChunk* c : chunks) delete c;
+	}
+	void create_chunk(WorldOctreeNode* n)
+	{
+		n->chunk = new DMCChunk();
+		chunks.push_back(n->chunk);
+		n->chunk->init(n->pos, n->size, n->level, sampler, n->morton_code);
+		n->chunk->dim = (uint32_t)properties.chunk_resolution;
+		n->chunk->id = next_chunk_id++;
+	}
+};
+
+// ---- ChunkGenerator ---------------------------------------------------------------------------------------------
+class ChunkGenerator
+{
+public:
+	ResourceAllocator<GLChunk> gl_allocator;
+	ResourceAllocator<DensityBlock> density_allocator;
+	ResourceAllocator<BinaryBlock> binary_allocator;
+	ResourceAllocator<MasksBlock> masks_allocator;
+	ResourceAllocator<VerticesIndicesBlock> vi_allocator;
+	ResourceAllocator<DMC_CellsBlock> cell_allocator;
+	ResourceAllocator<IndexesBlock> inds_allocator;
+	ResourceAllocator<NoiseBlock> noise_allocator;
+
+	void init(WorldOctree* w) { world = w; }
+
+	// ChunkGenerator.cpp:27-60 + extract_chunk :80-147, the whole batch as one device submission
+	bool process_queue(SmartContainer<WorldOctreeNode*>& batch)
+	{
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok() || !world) return false;
+		const int count = (int)batch.count;
+		{
+			std::unique_lock<std::mutex> lock(world->chunk_mutex);
+			for (int i = 0; i < count; i++)
+				if (!batch[i]->chunk) world->create_chunk(batch[i]);
+		}
+		const int iters = world->properties.process_iters, max_level = world->properties.max_level;
+		const bool pb = world->properties.boundary_processing;
+		const float base_overlap = world->properties.overlap;
+		std::vector<bmf_chunk_desc> descs;
+		std::vector<int> who;
+		for (int i = 0; i < count; i++)
+		{
+			WorldOctreeNode* n = batch[i];
+			if (n->generation_stage != GENERATION_STAGES_GENERATING) continue;
+			bmf_chunk_desc c;
+			c.pos[0] = n->pos.x; c.pos[1] = n->pos.y; c.pos[2] = n->pos.z; c.size = n->size; c.level = n->level; c.morton = n->morton_code;
+			c.overlap = (n->level == max_level && (!pb || iters == 0)) ? 0.0f : base_overlap + 0.005f * (float)iters; // ChunkGenerator.cpp:98
+			descs.push_back(c);
+			who.push_back(i);
+		}
+		if (!descs.empty())
+		{
+			bmf_sampler_desc d = world->sampler.device;
+			d.world_size = world->sampler.world_size;
+			if (d.kind == BMF_SAMPLER_TERRAIN2D_PERT)
+			{
+				const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
+				d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
+			}
+			if (d.kind == BMF_SAMPLER_HOST_DENSITY) return false; // host callbacks go through DMCChunk::label_grid one chunk at a time
+			if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
+			bmf_params p;
+			std::memset(&p, 0, sizeof(p));
+			p.dim = world->properties.chunk_resolution;
+			p.iters = iters;
+			p.process_boundary = pb ? 1 : 0;
+			p.smooth_normals = 0; // SMOOTH_NORMALS 0 (DefaultOptions.h:8)
+			if (bmf_batch_submit(dev.ctx, descs.data(), (int)descs.size(), &p, nullptr) != BMF_OK) return false;
+			int64_t nc = 0, nv = 0, ni = 0;
+			bmf_batch_totals(dev.ctx, &nc, &nv, &ni);
+			std::vector<float> pos(3 * (size_t)nv + 3), col(3 * (size_t)nv + 3), nrm(3 * (size_t)nv + 3);
+			std::vector<uint8_t> bnd((size_t)nv + 1), val((size_t)nv + 1);
+			std::vector<uint32_t> idx((size_t)ni + 1);
+			if (bmf_batch_download(dev.ctx, pos.data(), nrm.data(), col.data(), bnd.data(), val.data(), idx.data()) != BMF_OK) return false;
+			std::vector<bmf_chunk_info> infos(descs.size());
+			bmf_batch_chunk_infos(dev.ctx, infos.data());
+			for (size_t k = 0; k < descs.size(); k++)
+			{
+				WorldOctreeNode* n = batch[who[k]];
+				DMCChunk* c = n->chunk;
+				const bmf_chunk_info& inf = infos[k];
+				c->contains_mesh = inf.contains_mesh != 0;
+				c->overlap_pos = glm::vec3(inf.overlap_pos[0], inf.overlap_pos[1], inf.overlap_pos[2]);
+				c->scale = inf.scale;
+				c->bound_size = c->size * (1.0f + descs[k].overlap * 2.0f) * 0.5f;
+				c->bound_start = c->overlap_pos + c->bound_size;
+				if (!c->contains_mesh) continue;
+				if (!c->vi) { c->vi = vi_allocator.new_element(); c->vi->init(); }
+				const size_t v0 = (size_t)inf.vert_offset, i0 = (size_t)inf.ind_offset;
+				const bool processed = iters > 0 && inf.n_verts > 0 && inf.n_inds > 0;
+				bmf_detail::fill_dual_vertices(c->vi->vertices, &pos[3 * v0], &nrm[3 * v0], &col[3 * v0], &bnd[v0], &val[v0], (size_t)inf.n_verts, true, processed);
+				c->vi->mesh_indexes.count = 0;
+				c->vi->mesh_indexes.push_back(&idx[i0], (size_t)inf.n_inds);
+				// WorldOctreeNode::format -> GLChunk::format_data(vertices, indexes, false, false) (WorldOctreeNode.cpp:72-88)
+				if (!n->gl_chunk) n->gl_chunk = gl_allocator.new_element();
+				GLChunk* g = n->gl_chunk;
+				g->p_data.count = g->n_data.count = g->c_data.count = 0;
+				g->p_data.push_back((const glm::vec3*)&pos[3 * v0], (size_t)inf.n_verts);
+				g->n_data.push_back((const glm::vec3*)&nrm[3 * v0], (size_t)inf.n_verts);
+				g->c_data.push_back((const glm::vec3*)&col[3 * v0], (size_t)inf.n_verts);
+			}
+		}
+		for (int i = 0; i < count; i++)
+			batch[i]->generation_stage = (batch[i]->chunk && batch[i]->chunk->vi) ? GENERATION_STAGES_NEEDS_UPLOAD : GENERATION_STAGES_DONE; // ChunkGenerator.cpp:137-143
+		return true;
+	}
+
+private:
+	WorldOctree* world = nullptr;
+};
+
+// ---- MeshProcessor -------------------------------------------------------------------------------------------------
+namespace Processing
+{
+template <int N>
+class MeshProcessor
+{
+public:
+	bool simple_quality;
+	MeshProcessor(bool simple_quality_, bool smooth_normals_) : simple_quality(simple_quality_), smooth_normals(smooth_normals_) {}
+
+	// copies the vertices and the index buffer (MeshProcessor.cpp:25-55); CSR adjacency is built on the device
+	bool init(SmartContainer<DualVertex>& v, SmartContainer<uint32_t>& inds, Sampler& /*sampler*/)
+	{
+		if (v.count == 0 || inds.count < (size_t)N) return true;
+		vertices.count = 0;
+		vertices.push_back(v);
+		indices.assign(inds.elements, inds.elements + inds.count / N * N);
+		uint32_t a = 0;
+		for (size_t i = 0; i < vertices.count; i++)
+		{
+			DualVertex& dv = vertices.elements[i];
+			dv.adj_offset = a; dv.adj_next = dv.init_valence; dv.valence = dv.init_valence;
+			a += dv.init_valence;
+		}
+		pending_iters = 0;
+		return a != 0;
+	}
+	// recorded; executed by the following optimize_primal_grid (the reference driver's sequence,
+	// ChunkGenerator.cpp:119-120) or, without it, by flush
+	void optimize_dual_grid(int iterations, bool process_boundary = true)
+	{
+		pending_iters = iterations;
+		pending_pb = process_boundary;
+	}
+	void optimize_primal_grid(bool /*qef: ignored by the reference too, MeshProcessor.cpp:239*/, bool /*set_colors*/, bool process_boundary = true)
+	{
+		(void)process_boundary; // the driver passes the same flag to both calls
+		if (pending_iters > 0) run(pending_iters, pending_pb, 1);
+		pending_iters = 0;
+	}
+	void flush(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& inds)
+	{
+		if (pending_iters > 0) run(pending_iters, pending_pb, 0);
+		pending_iters = 0;
+		v_out.push_back(vertices);
+		inds.push_back(indices.data(), indices.size());
+	}
+	void flush_to_tris(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& inds) // quad -> (0,1,2),(2,3,0), MeshProcessor.cpp:73-91
+	{
+		if (pending_iters > 0) run(pending_iters, pending_pb, 0);
+		pending_iters = 0;
+		v_out.push_back(vertices);
+		for (size_t t = 0; t + 3 < indices.size() + 1 && N == 4; t += 4)
+		{
+			const uint32_t* q = &indices[t];
+			const uint32_t tri[6] = { q[0], q[1], q[2], q[2], q[3], q[0] };
+			inds.push_back(tri, 6);
+		}
+	}
+
+private:
+	bool run(int iters, bool pb, int final_primal)
+	{
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok() || vertices.count == 0) return false;
+		const size_t n = vertices.count;
+		std::vector<float> pos(3 * n), col(3 * n), nrm(3 * n);
+		std::vector<uint8_t> bnd(n);
+		for (size_t i = 0; i < n; i++)
+		{
+			const DualVertex& v = vertices.elements[i];
+			pos[3 * i] = v.p.x; pos[3 * i + 1] = v.p.y; pos[3 * i + 2] = v.p.z;
+			col[3 * i] = v.color.x; col[3 * i + 1] = v.color.y; col[3 * i + 2] = v.color.z;
+			nrm[3 * i] = v.n.x; nrm[3 * i + 1] = v.n.y; nrm[3 * i + 2] = v.n.z;
+			bnd[i] = v.boundary ? 1 : 0;
+		}
+		if (bmf_mesh_process_steps(dev.ctx, pos.data(), col.data(), nrm.data(), bnd.data(), nullptr, (int)n, indices.data(), (int)indices.size(), N, iters, pb ? 1 : 0,
+		                           smooth_normals ? 1 : 0, final_primal) != BMF_OK)
+			return false;
+		for (size_t i = 0; i < n; i++)
+		{
+			DualVertex& v = vertices.elements[i];
+			v.p = glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			v.color = glm::vec3(col[3 * i], col[3 * i + 1], col[3 * i + 2]);
+			if (smooth_normals) v.n = glm::vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+			v.s = 0.0f;
+		}
+		return true;
+	}
+
+	SmartContainer<DualVertex> vertices;
+	std::vector<uint32_t> indices;
+	bool smooth_normals;
+	int pending_iters = 0;
+	bool pending_pb = true;
+};
+} // namespace Processing

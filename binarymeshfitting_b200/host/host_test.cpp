@@ -1,0 +1,184 @@
+// host_test.cpp -- drives the C++ mirror (bmf_host.hpp) exactly the way the reference's own callers do and prints
+// counts + zlib-compatible CRC32s of the produced buffers; tests/test_gpu_host_shim.py compares them with the oracle.
+//   host_test chunk <kind> <dim> <overlap> <iters>          DMCChunk staged calls + MeshProcessor<3> (ChunkGenerator.cpp:98-124)
+//   host_test world <kind> <dim> <max_level> <iters> <file> ChunkGenerator::process_queue over the leaves listed in <file>
+//   host_test hostfn <dim> [density.bin]                                a Sampler with an arbitrary host callback (HOST_DENSITY escape path)
+#include "bmf_host.hpp"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+static uint32_t crc32_of(const void* data, size_t n, uint32_t crc = 0)
+{
+	static uint32_t table[256];
+	static bool init = false;
+	if (!init)
+	{
+		for (uint32_t i = 0; i < 256; i++)
+		{
+			uint32_t c = i;
+			for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+			table[i] = c;
+		}
+		init = true;
+	}
+	crc = ~crc;
+	const uint8_t* p = (const uint8_t*)data;
+	for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xFF] ^ (crc >> 8);
+	return ~crc;
+}
+
+static Sampler make_sampler(int kind)
+{
+	Sampler s;
+	switch (kind)
+	{
+	case 0: s = ImplicitFunctions::create_sampler(ImplicitFunctions::sphere); break;
+	case 1: s = ImplicitFunctions::create_sampler(ImplicitFunctions::torus_z); break;
+	case 2: s = ImplicitFunctions::create_sampler(ImplicitFunctions::cuboid); break;
+	case 3: s = ImplicitFunctions::create_sampler(ImplicitFunctions::plane_y); break;
+	case 10: NoiseSamplers::create_sampler_terrain_2d(&s); break;
+	case 11: NoiseSamplers::create_sampler_terrain_pert_2d(&s); break;
+	case 12: NoiseSamplers::create_sampler_terrain_3d(&s); break;
+	default: NoiseSamplers::create_sampler_terrain_pert_3d(&s); break;
+	}
+	s.world_size = 256;
+	return s;
+}
+
+static void print_chunk(const char* tag, DMCChunk& c)
+{
+	std::vector<float> p;
+	std::vector<uint8_t> bnd, val;
+	size_t nv = c.vi ? c.vi->vertices.count : 0, ni = c.vi ? c.vi->mesh_indexes.count : 0;
+	for (size_t i = 0; i < nv; i++)
+	{
+		const DualVertex& v = c.vi->vertices.elements[i];
+		p.push_back(v.p.x); p.push_back(v.p.y); p.push_back(v.p.z);
+		bnd.push_back(v.boundary ? 1 : 0);
+		val.push_back(v.init_valence);
+	}
+	size_t n = (size_t)c.dim * c.dim * c.dim;
+	printf("%s contains_mesh=%d cells=%zu verts=%zu inds=%zu bits_crc=%u density_crc=%u inds_crc=%u pos_crc=%u boundary_crc=%u valence_crc=%u scale=%.9g\n", tag, (int)c.contains_mesh,
+	       c.cell_block ? c.cell_block->cells.count : (size_t)0, nv, ni, c.binary_block ? crc32_of(c.binary_block->data, n / 8) : 0u,
+	       c.density_block ? crc32_of(c.density_block->data, n * 4) : 0u, ni ? crc32_of(c.vi->mesh_indexes.elements, ni * 4) : 0u, nv ? crc32_of(p.data(), p.size() * 4) : 0u,
+	       nv ? crc32_of(bnd.data(), nv) : 0u, nv ? crc32_of(val.data(), nv) : 0u, c.scale);
+}
+
+static const float wavy(const float ws, const glm::vec3& p) { return 20.0f * std::sin(p.x * 0.05f) * std::cos(p.z * 0.07f) - p.y + ws * 0.0f; }
+
+int main(int argc, char** argv)
+{
+	if (argc < 2) return 2;
+	if (!BmfDevice::get().ok())
+	{
+		fprintf(stderr, "host_test: %s\n", BmfDevice::get().error());
+		return 3;
+	}
+	ResourceAllocator<BinaryBlock> binary_allocator;
+	ResourceAllocator<DensityBlock> density_allocator;
+	ResourceAllocator<NoiseBlock> noise_allocator;
+	ResourceAllocator<VerticesIndicesBlock> vi_allocator;
+	ResourceAllocator<DMC_CellsBlock> cell_allocator;
+	ResourceAllocator<IndexesBlock> inds_allocator;
+	ResourceAllocator<MasksBlock> masks_allocator;
+	NoiseSamplers::NoiseSamplerProperties props;
+
+	if (!strcmp(argv[1], "chunk") && argc >= 6)
+	{
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), iters = atoi(argv[5]);
+		float overlap = (float)atof(argv[4]);
+		Sampler s = make_sampler(kind);
+		DMCChunk c(glm::vec3(-128, -128, -128), 256.0f, 0, s, 1);
+		c.dim = dim;
+		c.label_grid(&binary_allocator, &density_allocator, &noise_allocator, overlap, props);
+		c.label_edges(&vi_allocator, &cell_allocator, &inds_allocator, &density_allocator, &masks_allocator);
+		size_t valence_before = 0;
+		if (c.vi)
+			for (size_t i = 0; i < c.vi->vertices.count; i++) valence_before += c.vi->vertices.elements[i].init_valence;
+		c.polygonize();
+		print_chunk("extract", c);
+		printf("valence_sum_before_polygonize=%zu\n", valence_before);
+		if (iters > 0 && c.contains_mesh && c.vi->vertices.count && c.vi->mesh_indexes.count)
+		{
+			// verbatim shape of ChunkGenerator.cpp:112-123
+			auto& v_out = c.vi->vertices;
+			auto& i_out = c.vi->mesh_indexes;
+			Processing::MeshProcessor<3> mp(true, false);
+			mp.init(c.vi->vertices, c.vi->mesh_indexes, s);
+			mp.optimize_dual_grid(iters, false);
+			mp.optimize_primal_grid(false, false, false);
+			v_out.count = 0;
+			i_out.count = 0;
+			mp.flush(v_out, i_out);
+			print_chunk("processed", c);
+		}
+		return 0;
+	}
+	if (!strcmp(argv[1], "hostfn") && argc >= 3)
+	{
+		int dim = atoi(argv[2]);
+		Sampler s = ImplicitFunctions::create_sampler(wavy); // not a known primitive -> host callback + HOST_DENSITY
+		s.world_size = 256;
+		DMCChunk c(glm::vec3(-64, -64, -64), 128.0f, 0, s, 1);
+		c.dim = dim;
+		c.label_grid(&binary_allocator, &density_allocator, &noise_allocator, 0.0f, props);
+		c.label_edges(&vi_allocator, &cell_allocator, &inds_allocator, &density_allocator, &masks_allocator);
+		c.polygonize();
+		print_chunk("hostfn", c);
+		if (argc >= 4)
+		{
+			FILE* f = fopen(argv[3], "wb"); // the host-evaluated density, so the test can feed the same samples to the oracle
+			fwrite(c.density_block->data, sizeof(float), (size_t)dim * dim * dim, f);
+			fclose(f);
+		}
+		return 0;
+	}
+	if (!strcmp(argv[1], "world") && argc >= 7)
+	{
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), iters = atoi(argv[5]);
+		WorldOctree world;
+		world.sampler = make_sampler(kind);
+		world.properties.chunk_resolution = dim;
+		world.properties.max_level = max_level;
+		world.properties.process_iters = iters;
+		ChunkGenerator gen;
+		gen.init(&world);
+		FILE* f = fopen(argv[6], "r");
+		if (!f) return 4;
+		std::vector<WorldOctreeNode*> nodes;
+		float x, y, z, sz;
+		int lvl;
+		unsigned long long code;
+		SmartContainer<WorldOctreeNode*> batch;
+		while (fscanf(f, "%f %f %f %f %d %llu", &x, &y, &z, &sz, &lvl, &code) == 6)
+		{
+			WorldOctreeNode* n = new WorldOctreeNode(sz, glm::vec3(x, y, z), (uint8_t)lvl, code);
+			n->generation_stage = GENERATION_STAGES_GENERATING;
+			nodes.push_back(n);
+			batch.push_back(n);
+		}
+		fclose(f);
+		if (!gen.process_queue(batch))
+		{
+			fprintf(stderr, "process_queue failed: %s\n", BmfDevice::get().error());
+			return 5;
+		}
+		size_t nm = 0, nv = 0, ni = 0, upload = 0;
+		uint32_t hi = 0, hp = 0;
+		for (WorldOctreeNode* n : nodes)
+		{
+			DMCChunk* c = n->chunk;
+			if (n->generation_stage == GENERATION_STAGES_NEEDS_UPLOAD) upload++;
+			if (!(c->contains_mesh && c->vi)) continue;
+			nm += c->vi->vertices.count ? 1 : 0;
+			nv += c->vi->vertices.count;
+			ni += c->vi->mesh_indexes.count;
+			hi = crc32_of(c->vi->mesh_indexes.elements, c->vi->mesh_indexes.count * 4, hi);
+			hp = crc32_of(n->gl_chunk->p_data.elements, n->gl_chunk->p_data.count * 12, hp);
+		}
+		printf("world chunks=%zu with_mesh=%zu verts=%zu inds=%zu inds_crc=%u pdata_crc=%u needs_upload=%zu\n", nodes.size(), nm, nv, ni, hi, hp, upload);
+		return 0;
+	}
+	return 2;
+}

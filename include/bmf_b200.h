@@ -162,6 +162,12 @@ int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits,
 int bmf_mesh_process(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence,
                      int n_verts, const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals);
 
+/* same, with the trailing optimize_primal_grid(false,false,pb) of ChunkGenerator.cpp:120 optional (final_primal = 0:
+ * optimize_dual_grid alone, MeshProcessor.cpp:130-236) */
+int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal, const uint8_t* boundary, const uint8_t* valence,
+                           int n_verts, const uint32_t* indices, int n_inds, int prim_n, int iters, int process_boundary, int smooth_normals,
+                           int final_primal);
+
 /* qef_solve_from_points_3d (qef_simd.h:550-579), m independent systems: system j reads counts[j]
  * (2..12) planes from positions/normals[j*12*3 ...]; writes out_pos[3*j..], out_err[j]. */
 int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err);

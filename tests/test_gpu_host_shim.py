@@ -1,0 +1,84 @@
+"""GPU: the C++ mirror of the reference classes (binarymeshfitting_b200/host/bmf_host.hpp) driven by a C++ program
+written like the reference's own callers (DMCChunk staged calls, MeshProcessor<3> sequence of ChunkGenerator.cpp:112-123,
+ChunkGenerator::process_queue over a leaf list), checked against the oracle."""
+import json
+import os
+import re
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from binarymeshfitting_b200 import world as W
+from oracle import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "binarymeshfitting_b200", "host", "host_test")
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+
+
+def crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+
+
+def run(*args):
+    if not os.path.exists(EXE):
+        subprocess.run(["bash", os.path.join(ROOT, "binarymeshfitting_b200", "host", "build_host_test.sh")], check=True)
+    r = subprocess.run([EXE] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = {}
+    for line in r.stdout.splitlines():
+        parts = line.split()
+        tag = parts[0] if "=" not in parts[0] else "misc"
+        out.setdefault(tag, {}).update({k: v for k, v in (p.split("=") for p in parts if "=" in p)})
+    return out
+
+
+def check(rec, o, processed=False):
+    assert int(rec["contains_mesh"]) == int(o["contains_mesh"])
+    assert (int(rec["verts"]), int(rec["inds"])) == (o["n_verts"], o["n_inds"])
+    assert int(rec["bits_crc"]) == crc(o["bits"])
+    if o["n_verts"]:
+        assert int(rec["inds_crc"]) == crc(o["inds"]) and int(rec["pos_crc"]) == crc(o["pos"])
+        assert int(rec["boundary_crc"]) == crc(o["boundary"]) and int(rec["valence_crc"]) == crc(o["valence"])
+    if not processed:
+        assert int(rec["cells"]) == o["n_cells"]
+
+
+@pytest.mark.parametrize("kind,dim,overlap,iters", [(ob.SPHERE, 64, 0.0, 0), (ob.TORUS_Z, 64, 0.045, 2), (ob.TERRAIN2D_PERT, 32, 0.045, 2), (ob.TERRAIN3D_PERT, 32, 0.055, 4)])
+def test_dmcchunk_staged_calls_and_meshprocessor(oracle, kind, dim, overlap, iters):
+    out = run("chunk", kind, dim, overlap, iters)
+    pos, size = (-128, -128, -128), 256.0
+    o0 = oracle.chunk(oracle.sampler(kind), pos, size, dim, np.float32(overlap))
+    check(out["extract"], o0)
+    assert int(out["extract"]["density_crc"]) == crc(o0["density"])
+    assert abs(float(out["extract"]["scale"]) - o0["scale"]) == 0
+    assert int(out["misc"]["valence_sum_before_polygonize"]) == 0  # label_edges publishes vertices, polygonize the valences
+    if iters:
+        o1 = oracle.chunk(oracle.sampler(kind), pos, size, dim, np.float32(overlap), iters=iters)
+        check(out["processed"], o1, processed=True)
+
+
+def test_arbitrary_host_callback_sampler(oracle, tmp_path):
+    f = tmp_path / "density.bin"
+    out = run("hostfn", 32, f)
+    dens = np.fromfile(f, np.float32)
+    o = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), (-64, -64, -64), 128.0, 32, 0.0, host_density=dens)
+    assert o["n_verts"] > 100
+    check(out["hostfn"], o)
+
+
+@pytest.mark.parametrize("w", [g for g in GOLD["worlds"] if g["dim"] == 32], ids=lambda w: w["key"])
+def test_chunkgenerator_process_queue(tmp_path, w):
+    props = W.WorldProperties(max_level=w["max_level"], chunk_resolution=w["dim"], process_iters=w["iters"])
+    ps, lv, mc = W.split_leaves(props, 256, tuple(w["focus"]))
+    f = tmp_path / "leaves.txt"
+    with open(f, "w") as fh:
+        for p, l, m in zip(ps, lv, mc):
+            fh.write("%r %r %r %r %d %d\n" % (float(p[0]), float(p[1]), float(p[2]), float(p[3]), int(l), int(m)))
+    out = run("world", w["kind"], w["dim"], w["max_level"], w["iters"], f)["world"]
+    assert (int(out["chunks"]), int(out["with_mesh"]), int(out["verts"]), int(out["inds"])) == (w["leaves"], w["chunks_with_mesh"], w["verts"], w["inds"])
+    assert int(out["inds_crc"]) == w["inds_crc"]  # golden: the compiled reference's ChunkGenerator::process_queue
+    assert int(out["needs_upload"]) == w["chunks_with_mesh"]
