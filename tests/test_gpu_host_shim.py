@@ -54,7 +54,7 @@ def test_dmcchunk_staged_calls_and_meshprocessor(oracle, kind, dim, overlap, ite
     o0 = oracle.chunk(oracle.sampler(kind), pos, size, dim, np.float32(overlap))
     check(out["extract"], o0)
     assert int(out["extract"]["density_crc"]) == crc(o0["density"])
-    assert abs(float(out["extract"]["scale"]) - o0["scale"]) == 0
+    assert np.float32(out["extract"]["scale"]) == np.float32(o0["scale"])
     assert int(out["misc"]["valence_sum_before_polygonize"]) == 0  # label_edges publishes vertices, polygonize the valences
     if iters:
         o1 = oracle.chunk(oracle.sampler(kind), pos, size, dim, np.float32(overlap), iters=iters)
