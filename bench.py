@@ -121,15 +121,18 @@ def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
     words = nvox / 32.0
     algo = {
         # sign words out (+ noise sheet in for the 2-D terrains)
+        "k_terrain2d_bits": words * 4 + nvox * 4.0 / dim,
         "k_terrain2d_density": words * 4 + nvox * 4.0 / dim,
         "k_sample_implicit": words * 4,
         "k_pack_density": nvox * 4 + words * 4,
         # bits in, packed counts out
         "k_count<4>": words * 8, "k_count<8>": words * 8,
-        # counts in, two bases out, bits in, 13 B per vertex out
-        "k_verts<4>": words * 16 + 13.0 * V, "k_verts<8>": words * 16 + 13.0 * V,
-        # bits + vertex bases + counts + index bases in, 4 B per index out, 1 B valence per vertex
-        "k_inds<4>": words * 16 + 4.0 * I + V, "k_inds<8>": words * 16 + 4.0 * I + V,
+        # counts in, two bases out
+        "k_bases<4>": words * 12, "k_bases<8>": words * 12,
+        # 13 B per vertex out (position + boundary flag), two crossing-edge samples in
+        "k_verts2": 13.0 * V + 8.0 * V,
+        # 4 B per index out, 1 B valence per vertex
+        "k_inds2": 4.0 * I + V,
     }
     if name in algo:
         ach = algo[name] / (ms * 1e-3) / 1e9

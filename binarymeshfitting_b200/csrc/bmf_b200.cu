@@ -77,7 +77,8 @@ struct bmf_ctx
 	DevBuf<int> sheet_of;
 	std::vector<ChunkGeom> sheet_geom_host;
 	std::vector<int> sheet_of_host;
-	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base;
+	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base, vlist, ilist;
+	int sm_count = 148;
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
 	DevBuf<ChunkCounts> counts;
@@ -328,6 +329,8 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 		return BMF_ERR_CUDA;
 	}
 	for (int i = 0; i <= BMF_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+	if (ctx->sm_count <= 0) ctx->sm_count = 148;
 	cudaMallocHost((void**)&ctx->totals_pinned, sizeof(HostTotals));
 	*out = ctx;
 	return BMF_OK;
@@ -339,7 +342,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
-	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
+	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->vlist.release(); ctx->ilist.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cursor.release();
 	ctx->adj.release(); ctx->prim_vbase.release(); ctx->block_sums.release(); ctx->dp.release(); ctx->dc.release(); ctx->dn.release();
@@ -434,7 +437,9 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
 	BMF_CUDA(ctx->seg_base.reserve(3 * ((size_t)nseg + 1)));
 	BMF_CUDA(ctx->counts.reserve(n));
-	BMF_CUDA(ctx->totals_dev.reserve(4));
+	BMF_CUDA(ctx->totals_dev.reserve(8));
+	BMF_CUDA(ctx->vlist.reserve(n_words));
+	BMF_CUDA(ctx->ilist.reserve(n_words));
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
 		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
@@ -532,13 +537,13 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
 	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
 	else
-		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
 	BMF_CUDA(cudaEventRecord(ctx->ev[2], st));
 
 	// ---- scan + the one host round trip (output sizes)
-	BMF_LAUNCH(k_scan_segments, 1, SCAN_CTA, 0, ctx->seg_tot.p, ctx->flags.p, nseg, L.S, ctx->seg_base.p, ctx->counts.p, n, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_segments, 1, SCAN_CTA, 0, ctx->seg_tot.p, ctx->flags.p, nseg, L.lS, ctx->seg_base.p, ctx->counts.p, n, ctx->totals_dev.p);
 	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, ctx->totals_dev.p, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -562,12 +567,14 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	src.density = density_dev;
 	src.hmap = (!density_dev && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
 	src.sheet_of = ctx->sheet_of.p;
+	unsigned long long* list_count = ctx->totals_dev.p + 4;
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_verts<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_base.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->wvb.p,
-		           ctx->wib.p, ctx->pos.p, ctx->boundary.p);
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, 0, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vlist.p, ctx->ilist.p, list_count);
 	else
-		BMF_LAUNCH(k_verts<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_base.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->wvb.p,
-		           ctx->wib.p, ctx->pos.p, ctx->boundary.p);
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, 0, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vlist.p, ctx->ilist.p, list_count);
+	if (V)
+		BMF_LAUNCH(k_verts2, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vlist.p, list_count, ctx->pos.p,
+		           ctx->boundary.p);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 	if (V)
 	{
@@ -577,11 +584,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	if (I)
 	{
-		const size_t smem_inds = (size_t)(2 * L.P + 3) * L.wp * sizeof(uint32_t);
-		if (L.wpt == 4)
-			BMF_LAUNCH(k_inds<4>, nseg, CTA, smem_inds, ctx->bits.p, L, ctx->wcnt.p, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->inds.p, ctx->valence.p);
-		else
-			BMF_LAUNCH(k_inds<8>, nseg, CTA, smem_inds, ctx->bits.p, L, ctx->wcnt.p, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->inds.p, ctx->valence.p);
+		BMF_LAUNCH(k_inds2, ctx->sm_count * 6, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->ilist.p, list_count, ctx->inds.p, ctx->valence.p);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 

@@ -405,12 +405,18 @@ __device__ __forceinline__ void block_scan3(uint32_t& a, uint32_t& b, uint32_t& 
 // consecutive words.  Writes one packed count per word and one (cells, verts, indices) total per segment;
 // optionally the 8-bit mask image (MasksBlock, DMCChunk.cpp:184-438) when the caller wants it back.
 template <int WPT>
-__global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits, Layout L, uint32_t* __restrict__ wcnt,
+__global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, uint32_t* __restrict__ wcnt,
                                                 uint32_t* __restrict__ seg_tot, uint8_t* __restrict__ masks)
 {
 	extern __shared__ uint32_t sb[];
 	const int seg = blockIdx.x;
 	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
+	if (!flags_contain_mesh(flags[chunk]))
+	{
+		// label_edges returns at once for a chunk without a mesh (DMCChunk.cpp:170-171): nothing downstream reads its words
+		if (threadIdx.x < 3) seg_tot[3 * (size_t)seg + threadIdx.x] = 0;
+		return;
+	}
 	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
 	__syncthreads();
 
@@ -465,8 +471,9 @@ __global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits
 	}
 }
 
-// ---- segment scan: one CTA.  seg_base[3*(nseg+1)] = exclusive prefix of seg_tot with segments of chunks
-// that do not contain a mesh (DMCChunk.cpp:159-162, label_edges :170-171) forced to zero.
+// ---- segment scan: one CTA walks the segment totals in coalesced tiles of SCAN_CTA with a running carry.
+// seg_base[3*(nseg+1)] = exclusive prefix of seg_tot; segments of chunks that do not contain a mesh
+// (DMCChunk.cpp:159-162, label_edges :170-171) count as zero.
 struct ChunkCounts
 {
 	uint32_t contains_mesh;
@@ -476,64 +483,67 @@ struct ChunkCounts
 
 static constexpr int SCAN_CTA = 1024;
 
-__global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __restrict__ seg_tot, const uint32_t* __restrict__ flags, int nseg, int S,
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __restrict__ seg_tot, const uint32_t* __restrict__ flags, int nseg, int lS,
                                                              uint32_t* __restrict__ seg_base, ChunkCounts* __restrict__ chunks, int n_chunks,
                                                              unsigned long long* __restrict__ totals /* cells, verts, inds, overflow */)
 {
-	__shared__ unsigned long long s_w[3][SCAN_CTA / 32];
-	__shared__ unsigned long long s_tot[3];
+	__shared__ uint32_t s_w[3][SCAN_CTA / 32];
+	__shared__ uint32_t s_tot[3];
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	const int per = (nseg + SCAN_CTA - 1) / SCAN_CTA;
-	const int lo = min(nseg, t * per), hi = min(nseg, lo + per);
-	unsigned long long a = 0, b = 0, c = 0;
-	for (int i = lo; i < hi; i++)
+	unsigned long long carry0 = 0, carry1 = 0, carry2 = 0;
+	for (int base = 0; base < nseg; base += SCAN_CTA)
 	{
-		if (!flags_contain_mesh(flags[i / S])) continue;
-		a += seg_tot[3 * (size_t)i]; b += seg_tot[3 * (size_t)i + 1]; c += seg_tot[3 * (size_t)i + 2];
-	}
-	unsigned long long ia = a, ib = b, ic = c;
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
-		if (lane >= o) { ia += ta; ib += tb; ic += tc; }
-	}
-	if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
-	__syncthreads();
-	if (warp == 0)
-	{
-		unsigned long long va = s_w[0][lane], vb = s_w[1][lane], vc = s_w[2][lane];
-		unsigned long long ja = va, jb = vb, jc = vc;
+		const int i = base + t;
+		uint32_t a = 0, b = 0, c = 0;
+		if (i < nseg && flags_contain_mesh(flags[i >> lS]))
+		{
+			a = seg_tot[3 * (size_t)i]; b = seg_tot[3 * (size_t)i + 1]; c = seg_tot[3 * (size_t)i + 2];
+		}
+		uint32_t ia = a, ib = b, ic = c;
+#pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
-			unsigned long long ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
-			if (lane >= o) { ja += ta; jb += tb; jc += tc; }
+			uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+			if (lane >= o) { ia += ta; ib += tb; ic += tc; }
 		}
-		s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc;
-		if (lane == 31) { s_tot[0] = ja; s_tot[1] = jb; s_tot[2] = jc; }
-	}
-	__syncthreads();
-	unsigned long long ea = ia - a + s_w[0][warp], eb = ib - b + s_w[1][warp], ec = ic - c + s_w[2][warp];
-	const bool overflow = s_tot[0] >= 0xFFFFFFFFull || s_tot[1] >= 0xFFFFFFFFull || s_tot[2] >= 0xFFFFFFFFull;
-	for (int i = lo; i < hi; i++)
-	{
-		seg_base[3 * (size_t)i] = (uint32_t)ea; seg_base[3 * (size_t)i + 1] = (uint32_t)eb; seg_base[3 * (size_t)i + 2] = (uint32_t)ec;
-		if (flags_contain_mesh(flags[i / S]))
+		if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
+		__syncthreads();
+		if (warp == 0)
 		{
-			ea += seg_tot[3 * (size_t)i]; eb += seg_tot[3 * (size_t)i + 1]; ec += seg_tot[3 * (size_t)i + 2];
+			uint32_t va = s_w[0][lane], vb = s_w[1][lane], vc = s_w[2][lane];
+			uint32_t ja = va, jb = vb, jc = vc;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				uint32_t ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
+				if (lane >= o) { ja += ta; jb += tb; jc += tc; }
+			}
+			s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc;
+			if (lane == 31) { s_tot[0] = ja; s_tot[1] = jb; s_tot[2] = jc; }
 		}
+		__syncthreads();
+		if (i < nseg)
+		{
+			seg_base[3 * (size_t)i] = (uint32_t)(carry0 + (ia - a + s_w[0][warp]));
+			seg_base[3 * (size_t)i + 1] = (uint32_t)(carry1 + (ib - b + s_w[1][warp]));
+			seg_base[3 * (size_t)i + 2] = (uint32_t)(carry2 + (ic - c + s_w[2][warp]));
+		}
+		carry0 += s_tot[0]; carry1 += s_tot[1]; carry2 += s_tot[2];
+		__syncthreads();
 	}
 	if (t == 0)
 	{
-		seg_base[3 * (size_t)nseg] = (uint32_t)s_tot[0]; seg_base[3 * (size_t)nseg + 1] = (uint32_t)s_tot[1]; seg_base[3 * (size_t)nseg + 2] = (uint32_t)s_tot[2];
-		totals[0] = s_tot[0]; totals[1] = s_tot[1]; totals[2] = s_tot[2]; totals[3] = overflow ? 1ull : 0ull;
+		seg_base[3 * (size_t)nseg] = (uint32_t)carry0; seg_base[3 * (size_t)nseg + 1] = (uint32_t)carry1; seg_base[3 * (size_t)nseg + 2] = (uint32_t)carry2;
+		const bool overflow = carry0 >= 0xFFFFFFFFull || carry1 >= 0xFFFFFFFFull || carry2 >= 0xFFFFFFFFull;
+		totals[0] = carry0; totals[1] = carry1; totals[2] = carry2; totals[3] = overflow ? 1ull : 0ull;
+		totals[4] = 0; totals[5] = 0; // active-word list counters (k_bases)
 	}
-	__syncthreads(); // seg_base complete (single CTA; global writes visible after the barrier)
-	__threadfence_block();
+	__syncthreads(); // seg_base complete (single CTA)
 	for (int ch = t; ch < n_chunks; ch += SCAN_CTA)
 	{
 		ChunkCounts cc;
-		const uint32_t* b0 = seg_base + 3 * (size_t)ch * S;
-		const uint32_t* b1 = seg_base + 3 * (size_t)(ch + 1) * S;
+		const uint32_t* b0 = seg_base + 3 * ((size_t)ch << lS);
+		const uint32_t* b1 = seg_base + 3 * ((size_t)(ch + 1) << lS);
 		cc.contains_mesh = flags_contain_mesh(flags[ch]) ? 1u : 0u;
 		cc.cell_base = b0[0]; cc.vert_base = b0[1]; cc.ind_base = b0[2];
 		cc.n_cells = b1[0] - b0[0]; cc.n_verts = b1[1] - b0[1]; cc.n_inds = b1[2] - b0[2];
@@ -541,20 +551,22 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __re
 	}
 }
 
-// ---- K4a: per-word bases + vertex emission.  One CTA per segment.
-// wvb[word] = chunk-local id of the word's first vertex; wib[word] = batch-wide position of its first index.
-// Vertices: calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674).
+// ---- K4a: per-word output bases + compaction of the words that emit anything.  One CTA per segment with
+// active cells (everything else leaves at once).  wvb[word] = chunk-local id of the word's first vertex,
+// wib[word] = batch-wide position of its first index.  Words with vertices / indices are appended to two
+// lists (a range per CTA reserved with one atomic; list order does not matter, every entry carries its own
+// output position), so the emitters below only ever touch words on the surface.
 template <int WPT>
-__global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt,
+__global__ void __launch_bounds__(CTA) k_bases(Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
                                                 const uint32_t* __restrict__ seg_base, const ChunkCounts* __restrict__ chunks,
-                                                SamplerDev s, DensitySource src, const ChunkGeom* __restrict__ geom,
-                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib,
-                                                float* __restrict__ pos, uint8_t* __restrict__ boundary)
+                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib, uint32_t* __restrict__ vlist,
+                                                uint32_t* __restrict__ ilist, unsigned long long* __restrict__ list_count /* [2] */)
 {
-	extern __shared__ uint32_t sb[];
+	__shared__ uint32_t s_base[2];
 	const int seg = blockIdx.x;
-	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
+	const int chunk = seg >> L.lS;
 	const ChunkCounts cc = chunks[chunk];
+	if (!cc.contains_mesh || seg_tot[3 * (size_t)seg] == 0) return;
 	uint32_t cnt[WPT];
 	{
 		const uint32_t* in = wcnt + (size_t)seg * L.ws + threadIdx.x * WPT;
@@ -565,154 +577,213 @@ __global__ void __launch_bounds__(CTA) k_verts(const uint32_t* __restrict__ bits
 			cnt[k] = v.x; cnt[k + 1] = v.y; cnt[k + 2] = v.z; cnt[k + 3] = v.w;
 		}
 	}
-	if (!cc.contains_mesh)
+	uint32_t tv = 0, ti = 0, tw = 0; // tw: words with vertices (low 16 bits) and words with indices (high 16 bits)
+#pragma unroll
+	for (int k = 0; k < WPT; k++)
 	{
-#pragma unroll
-		for (int k = 0; k < WPT; k++) cnt[k] = 0;
+		const uint32_t nv = (cnt[k] >> 8) & 0xFF, ni = cnt[k] >> 16;
+		tv += nv; ti += ni;
+		tw += (nv ? 1u : 0u) + (ni ? 0x10000u : 0u);
 	}
-	uint32_t tv = 0, ti = 0, tc = 0;
-#pragma unroll
-	for (int k = 0; k < WPT; k++) { tc += cnt[k] & 0xFF; tv += (cnt[k] >> 8) & 0xFF; ti += cnt[k] >> 16; }
 	uint32_t tot[3];
-	block_scan3(tc, tv, ti, tot);
-	const uint32_t seg_v_local = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base;
-	const uint32_t seg_i = seg_base[3 * (size_t)seg + 2];
-	uint32_t vb[WPT];
+	block_scan3(tv, ti, tw, tot);
+	if (threadIdx.x == 0)
 	{
-		uint32_t rv = seg_v_local + tv, ri = seg_i + ti;
-		uint32_t ob[WPT], oi[WPT];
-#pragma unroll
-		for (int k = 0; k < WPT; k++)
-		{
-			ob[k] = rv; oi[k] = ri; vb[k] = rv;
-			rv += (cnt[k] >> 8) & 0xFF; ri += cnt[k] >> 16;
-		}
-		uint32_t* o1 = wvb + (size_t)seg * L.ws + threadIdx.x * WPT;
-		uint32_t* o2 = wib + (size_t)seg * L.ws + threadIdx.x * WPT;
-#pragma unroll
-		for (int k = 0; k < WPT; k += 4)
-		{
-			*reinterpret_cast<uint4*>(o1 + k) = make_uint4(ob[k], ob[k + 1], ob[k + 2], ob[k + 3]);
-			*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oi[k], oi[k + 1], oi[k + 2], oi[k + 3]);
-		}
+		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)(tot[2] & 0xFFFF));
+		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)(tot[2] >> 16));
 	}
-	if (tot[1] == 0) return; // no vertex in this segment (uniform across the CTA)
-
-	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
 	__syncthreads();
-	const ChunkGeom g = geom[chunk];
+	uint32_t rv = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base + tv;
+	uint32_t ri = seg_base[3 * (size_t)seg + 2] + ti;
+	uint32_t ov = s_base[0] + (tw & 0xFFFF), oi = s_base[1] + (tw >> 16);
+	const uint32_t gw0 = (uint32_t)((size_t)seg * L.ws + threadIdx.x * WPT);
+	uint32_t ob[WPT], oix[WPT];
+#pragma unroll
+	for (int k = 0; k < WPT; k++)
+	{
+		const uint32_t nv = (cnt[k] >> 8) & 0xFF, ni = cnt[k] >> 16;
+		ob[k] = rv; oix[k] = ri;
+		if (nv) vlist[ov++] = gw0 + k;
+		if (ni) ilist[oi++] = gw0 + k;
+		rv += nv; ri += ni;
+	}
+	uint32_t* o1 = wvb + gw0;
+	uint32_t* o2 = wib + gw0;
+#pragma unroll
+	for (int k = 0; k < WPT; k += 4)
+	{
+		*reinterpret_cast<uint4*>(o1 + k) = make_uint4(ob[k], ob[k + 1], ob[k + 2], ob[k + 3]);
+		*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oix[k], oix[k + 1], oix[k + 2], oix[k + 3]);
+	}
+}
+
+// ---- K4b: vertex emission, one WARP per word that owns vertices, one LANE per cell (z).
+// calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674): X, Y, Z edge of a cell in that
+// order; the id of a lane's first vertex is the word base plus the popcounts of the edge flags below the lane.
+// Neighbour samples along z are consecutive floats of one row, so the crossing-edge reads are coalesced.
+__global__ void __launch_bounds__(CTA) k_verts2(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb,
+                                                 const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
+                                                 const ChunkGeom* __restrict__ geom, const uint32_t* __restrict__ vlist,
+                                                 const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t n_words = (uint32_t)list_count[0];
+	const uint32_t stride = gridDim.x * (CTA / 32);
 	const int d = L.d;
-#pragma unroll
-	for (int k = 0; k < WPT; k++)
+	for (uint32_t i = blockIdx.x * (CTA / 32) + (threadIdx.x >> 5); i < n_words; i += stride)
 	{
-		if (((cnt[k] >> 8) & 0xFF) == 0) continue;
-		const int lw = threadIdx.x * WPT + k;
-		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp, x = x0 + lx;
-		const WordBits b = load_word_bits(sb, L, lx, y, zb);
-		const WordClass c = classify(b, L, x, y, zb);
-		uint32_t m = c.ex | c.ey | c.ez;
-		size_t v = (size_t)cc.vert_base + vb[k];
-		while (m)
-		{
-			const int bit = __ffs(m) - 1;
-			m &= m - 1;
-			const int z = zb * 32 + bit;
-			const float s0 = density_at(s, src, g, d, chunk, x, y, z);
-			const bool b0 = x == 0 || y == 0 || z == 0 || x == d - 1 || y == d - 1 || z == d - 1;
+		const uint32_t gw = vlist[i];
+		const int chunk = (int)(gw >> L.lwc);
+		const int w = (int)(gw & (uint32_t)(L.wc - 1));
+		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
+		const uint32_t* cb = bits + (size_t)chunk * L.wc;
+		const bool zn = zb + 1 < L.zc, yn = y + 1 < d, xn = x + 1 < d;
+		const uint32_t A = cb[w];
+		const uint32_t A1 = __funnelshift_r(A, zn ? cb[w + 1] : 0u, 1);
+		const uint32_t ex = xn ? (A ^ cb[w + L.wp]) : 0u;
+		const uint32_t ey = yn ? (A ^ cb[w + L.zc]) : 0u;
+		const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+		const uint32_t any = ex | ey | ez;
+		if (!((any >> lane) & 1u)) continue;
+		const uint32_t lt = (1u << lane) - 1u;
+		const ChunkGeom g = geom[chunk];
+		const int z = zb * 32 + lane;
+		size_t v = (size_t)chunks[chunk].vert_base + wvb[gw] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
+		const float s0 = density_at(s, src, g, d, chunk, x, y, z);
+		const bool b0 = x == 0 || y == 0 || z == 0 || x == d - 1 || y == d - 1 || z == d - 1;
 #pragma unroll
-			for (int axis = 0; axis < 3; axis++)
-			{
-				const uint32_t e = axis == 0 ? c.ex : axis == 1 ? c.ey : c.ez;
-				if (!((e >> bit) & 1u)) continue;
-				const int x1 = x + (axis == 0), y1 = y + (axis == 1), z1 = z + (axis == 2);
-				const float s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
-				const float mu = (0.0f - s0) / (s1 - s0);
-				// (p1 - p0) * mu + p0 per component, p in grid units
-				pos[3 * v + 0] = ((float)x1 - (float)x) * mu + (float)x;
-				pos[3 * v + 1] = ((float)y1 - (float)y) * mu + (float)y;
-				pos[3 * v + 2] = ((float)z1 - (float)z) * mu + (float)z;
-				boundary[v] = (b0 || x1 == d - 1 || y1 == d - 1 || z1 == d - 1) ? 1 : 0;
-				v++;
-			}
+		for (int axis = 0; axis < 3; axis++)
+		{
+			const uint32_t e = axis == 0 ? ex : axis == 1 ? ey : ez;
+			if (!((e >> lane) & 1u)) continue;
+			const int x1 = x + (axis == 0), y1 = y + (axis == 1), z1 = z + (axis == 2);
+			const float s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
+			const float mu = (0.0f - s0) / (s1 - s0);
+			// (p1 - p0) * mu + p0 per component, p in grid units
+			pos[3 * v + 0] = ((float)x1 - (float)x) * mu + (float)x;
+			pos[3 * v + 1] = ((float)y1 - (float)y) * mu + (float)y;
+			pos[3 * v + 2] = ((float)z1 - (float)z) * mu + (float)z;
+			boundary[v] = (b0 || x1 == d - 1 || y1 == d - 1 || z1 == d - 1) ? 1 : 0;
+			v++;
 		}
 	}
 }
 
-// chunk-local id of the vertex on `axis` of cell (lx,y,z) inside the staged window
-__device__ __forceinline__ uint32_t vertex_id(const uint32_t* sb, const uint32_t* svb, const Layout& L, int x0, int lx, int y, int z, int axis)
+// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence, one WARP per
+// word that emits indices, one LANE per cell.  The 16 sign words of the 8 neighbouring rows (x..x+2, y..y+2) x
+// (zb, zb+1) and the 8 vertex bases of rows (x..x+1, y..y+1) are fetched by 24 lanes in one load and broadcast by
+// shuffle; every lane then derives its cell mask and the ids of its 12 edge vertices with popcounts
+// (EDGE_V, DMCChunk.cpp:32, 543-565), the warp scans the per-cell index counts and the word's indices leave
+// shared memory as one coalesced run.
+__global__ void __launch_bounds__(CTA) k_inds2(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb,
+                                                const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
+                                                const uint32_t* __restrict__ ilist, const unsigned long long* __restrict__ list_count,
+                                                uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
 {
-	const int zb = z >> 5, bit = z & 31;
-	const int base = (((lx << L.ld) + y) << L.lzc) + zb;
-	const bool zn = zb + 1 < L.zc, yn = y + 1 < L.d, xn = x0 + lx + 1 < L.d;
-	const uint32_t A = sb[base];
-	const uint32_t A1 = __funnelshift_r(A, zn ? sb[base + 1] : 0u, 1);
-	const uint32_t ex = xn ? (A ^ sb[base + L.wp]) : 0u;
-	const uint32_t ey = yn ? (A ^ sb[base + L.zc]) : 0u;
-	const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
-	const uint32_t lt = (1u << bit) - 1u;
-	uint32_t id = svb[base] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
-	if (axis >= 1) id += (ex >> bit) & 1u;
-	if (axis >= 2) id += (ey >> bit) & 1u;
-	return id;
-}
-
-// ---- K4b: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence.
-// Staged: sign planes x0 .. x0+P+1 and vertex bases of planes x0 .. x0+P.
-template <int WPT>
-__global__ void __launch_bounds__(CTA) k_inds(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt,
-                                               const uint32_t* __restrict__ wvb, const uint32_t* __restrict__ wib,
-                                               const ChunkCounts* __restrict__ chunks, uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
-{
-	extern __shared__ uint32_t sb[];
-	const int seg = blockIdx.x;
-	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
-	const ChunkCounts cc = chunks[chunk];
-	if (!cc.contains_mesh || cc.n_inds == 0) return;
-	uint32_t* svb = sb + (L.P + 2) * L.wp;
-	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 2);
-	{
-		// vertex bases: planes x0 .. x0+P (the halo plane belongs to the next segment of the same chunk)
-		const int planes = min(L.P + 1, L.d - x0);
-		const uint4* srcv = reinterpret_cast<const uint4*>(wvb + (size_t)chunk * L.wc + (size_t)x0 * L.wp);
-		uint4* dst = reinterpret_cast<uint4*>(svb);
-		for (int i = threadIdx.x; i < (L.P + 1) * L.wp / 4; i += CTA)
-			dst[i] = (i < planes * L.wp / 4) ? srcv[i] : make_uint4(0, 0, 0, 0);
-	}
+	__shared__ uint64_t s_tri[256];
+	__shared__ uint32_t s_id[CTA / 32][12][32];
+	__shared__ uint32_t s_out[CTA / 32][480];
+	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
-
-#pragma unroll
-	for (int k = 0; k < WPT; k++)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t n_words = (uint32_t)list_count[1];
+	const uint32_t stride = gridDim.x * (CTA / 32);
+	const int d = L.d;
+	for (uint32_t i = blockIdx.x * (CTA / 32) + warp; i < n_words; i += stride)
 	{
-		const int lw = threadIdx.x * WPT + k;
-		const size_t gw = (size_t)seg * L.ws + lw;
-		if ((wcnt[gw] >> 16) == 0) continue;
-		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
-		const WordBits b = load_word_bits(sb, L, lx, y, zb);
-		const WordClass c = classify(b, L, x0 + lx, y, zb);
-		uint32_t m = c.active & c.interior;
-		uint32_t o = wib[gw];
-		while (m)
+		const uint32_t gw = ilist[i];
+		const int chunk = (int)(gw >> L.lwc);
+		const int w = (int)(gw & (uint32_t)(L.wc - 1));
+		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
+		// lanes 0..15: sign word of row r = lane>>1 in {(0,0),(0,1),(0,2),(1,0),(1,1),(1,2),(2,0),(2,1)}, z-word zb + (lane&1)
+		// lanes 16..23: vertex base of row (dx,dy) in {0,1}^2, z-word zb + (lane&1)
+		uint32_t mine = 0;
 		{
-			const int bit = __ffs(m) - 1;
-			m &= m - 1;
-			const int z = zb * 32 + bit;
-			const uint64_t tp = c_tri_pack[mask8_of(b, bit)];
-			const int n = (int)(tp >> 60);
-			for (int t = 0; t < n; t++)
-			{
-				const int e = (int)(tp >> (4 * t)) & 15;
-				// EDGE_V (DMCChunk.cpp:32, 543-565): e0-3 X-edges at (y,z) offsets, e4-7 Y-edges at (x,z), e8-11 Z-edges at (x,y)
-				const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
-				const int dx = axis == 0 ? 0 : hi;
-				const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
-				const int dz = axis == 2 ? 0 : lo;
-				const uint32_t vid = vertex_id(sb, svb, L, x0, lx + dx, y + dy, z + dz, axis);
-				inds[o++] = vid;
-				// init_valence++ (DMCChunk.cpp:573): byte-wise add through the aligned 32-bit word
-				const size_t gv = (size_t)cc.vert_base + vid;
-				atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
-			}
+			const int k = lane & 1;
+			int dx, dy;
+			const uint32_t* base;
+			if (lane < 16) { const int r = lane >> 1; dx = r / 3; dy = r - 3 * dx; base = bits; }
+			else { const int r = (lane - 16) >> 1; dx = r >> 1; dy = r & 1; base = wvb; }
+			if (lane < 24 && x + dx < d && y + dy < d && zb + k < L.zc) mine = base[(size_t)chunk * L.wc + w + dx * L.wp + dy * L.zc + k];
 		}
+#define BMF_ROW(dx, dy, k) __shfl_sync(0xffffffffu, mine, ((dx) * 3 + (dy)) * 2 + (k))
+#define BMF_VB(dx, dy, k) __shfl_sync(0xffffffffu, mine, 16 + ((dx) * 2 + (dy)) * 2 + (k))
+		const uint32_t zvalid = (zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu;
+		// per row (dx,dy) in {0,1}^2 and z-word k: the sign word, the edge-owner words and the vertex base
+		uint32_t rb[2][2][2], rex[2][2][2], rey[2][2][2], rez[2][2], rvb[2][2][2];
+#pragma unroll
+		for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+			for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+				for (int k = 0; k < 2; k++)
+				{
+					const uint32_t b = BMF_ROW(dx, dy, k);
+					rb[dx][dy][k] = b;
+					rex[dx][dy][k] = (x + dx + 1 < d) ? (b ^ BMF_ROW(dx + 1, dy, k)) : 0u;
+					rey[dx][dy][k] = (y + dy + 1 < d) ? (b ^ BMF_ROW(dx, dy + 1, k)) : 0u;
+					rvb[dx][dy][k] = BMF_VB(dx, dy, k);
+				}
+#pragma unroll
+		for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+			for (int dy = 0; dy < 2; dy++)
+				rez[dx][dy] = (rb[dx][dy][0] ^ __funnelshift_r(rb[dx][dy][0], rb[dx][dy][1], 1)) & zvalid;
+#undef BMF_ROW
+#undef BMF_VB
+		// this lane's cell: corner mask (x high bit, z low bit) and whether it polygonizes
+		WordBits wb;
+		wb.A = rb[0][0][0]; wb.A1 = __funnelshift_r(rb[0][0][0], rb[0][0][1], 1);
+		wb.B = rb[0][1][0]; wb.B1 = __funnelshift_r(rb[0][1][0], rb[0][1][1], 1);
+		wb.C = rb[1][0][0]; wb.C1 = __funnelshift_r(rb[1][0][0], rb[1][0][1], 1);
+		wb.D = rb[1][1][0]; wb.D1 = __funnelshift_r(rb[1][1][0], rb[1][1][1], 1);
+		const WordClass c = classify(wb, L, x, y, zb);
+		const bool emits = ((c.active & c.interior) >> lane) & 1u;
+		const uint64_t tp = emits ? s_tri[mask8_of(wb, lane)] : 0ull;
+		const uint32_t n_l = (uint32_t)(tp >> 60);
+		// ids of the 12 edge vertices of this cell (only meaningful where the table uses them)
+#pragma unroll
+		for (int e = 0; e < 12; e++)
+		{
+			const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
+			const int dx = axis == 0 ? 0 : hi;
+			const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
+			const int dz = axis == 2 ? 0 : lo;
+			const int zz = lane + dz;          // 0..32: bit 32 is bit 0 of the next z-word
+			const int k = zz >> 5, bit = zz & 31;
+			const uint32_t exw = k ? rex[dx][dy][1] : rex[dx][dy][0];
+			const uint32_t eyw = k ? rey[dx][dy][1] : rey[dx][dy][0];
+			const uint32_t ezw = k ? 0u : rez[dx][dy]; // k == 1 only with bit == 0: nothing below it
+			const uint32_t lt = (1u << bit) - 1u;
+			uint32_t id = (k ? rvb[dx][dy][1] : rvb[dx][dy][0]) + __popc(exw & lt) + __popc(eyw & lt) + __popc(ezw & lt);
+			if (axis >= 1) id += (exw >> bit) & 1u;
+			if (axis >= 2) id += (eyw >> bit) & 1u;
+			s_id[warp][e][lane] = id;
+		}
+		// exclusive scan of the per-cell index counts across the warp
+		uint32_t incl = n_l;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+		uint32_t o = incl - n_l;
+		__syncwarp();
+		for (uint32_t t = 0; t < n_l; t++) s_out[warp][o + t] = s_id[warp][(tp >> (4 * t)) & 15][lane];
+		__syncwarp();
+		const size_t out0 = wib[gw];
+		const size_t vbase = (size_t)chunks[chunk].vert_base;
+		for (uint32_t j = lane; j < total; j += 32)
+		{
+			const uint32_t vid = s_out[warp][j];
+			inds[out0 + j] = vid;
+			// init_valence++ (DMCChunk.cpp:573): byte-wise add through the aligned 32-bit word
+			const size_t gv = vbase + vid;
+			atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
+		}
+		__syncwarp();
 	}
 }
 
