@@ -130,9 +130,9 @@ def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
         # counts in, two bases out
         "k_bases<4>": words * 12, "k_bases<8>": words * 12,
         # 13 B per vertex out (position + boundary flag), two crossing-edge samples in
-        "k_verts2": 13.0 * V + 8.0 * V,
+        "k_verts3": 13.0 * V + 8.0 * V,
         # 4 B per index out, 1 B valence per vertex
-        "k_inds2": 4.0 * I + V,
+        "k_inds3": 4.0 * I + V,
     }
     if name in algo:
         ach = algo[name] / (ms * 1e-3) / 1e9

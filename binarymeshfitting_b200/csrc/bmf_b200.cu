@@ -77,7 +77,8 @@ struct bmf_ctx
 	DevBuf<int> sheet_of;
 	std::vector<ChunkGeom> sheet_geom_host;
 	std::vector<int> sheet_of_host;
-	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base, vlist, ilist;
+	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base;
+	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	int sm_count = 148;
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
@@ -342,7 +343,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
-	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->vlist.release(); ctx->ilist.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
+	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cursor.release();
 	ctx->adj.release(); ctx->prim_vbase.release(); ctx->block_sums.release(); ctx->dp.release(); ctx->dc.release(); ctx->dn.release();
@@ -438,8 +439,6 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->seg_base.reserve(3 * ((size_t)nseg + 1)));
 	BMF_CUDA(ctx->counts.reserve(n));
 	BMF_CUDA(ctx->totals_dev.reserve(8));
-	BMF_CUDA(ctx->vlist.reserve(n_words));
-	BMF_CUDA(ctx->ilist.reserve(n_words));
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
 		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
@@ -568,13 +567,17 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	src.hmap = (!density_dev && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
 	src.sheet_of = ctx->sheet_of.p;
 	unsigned long long* list_count = ctx->totals_dev.p + 4;
+	// every vertex cell and every polygonizing cell is an active cell: totals[0] bounds both lists
+	BMF_CUDA(ctx->vcells.reserve(ctx->totals[0] + 1));
+	BMF_CUDA(ctx->icells.reserve(ctx->totals[0] + 1));
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_bases<4>, nseg, CTA, 0, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vlist.p, ctx->ilist.p, list_count);
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		           ctx->icells.p, list_count);
 	else
-		BMF_LAUNCH(k_bases<8>, nseg, CTA, 0, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vlist.p, ctx->ilist.p, list_count);
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		           ctx->icells.p, list_count);
 	if (V)
-		BMF_LAUNCH(k_verts2, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vlist.p, list_count, ctx->pos.p,
-		           ctx->boundary.p);
+		BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wvb.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 	if (V)
 	{
@@ -584,7 +587,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	if (I)
 	{
-		BMF_LAUNCH(k_inds2, ctx->sm_count * 6, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->ilist.p, list_count, ctx->inds.p, ctx->valence.p);
+		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->valence.p);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 

@@ -210,9 +210,11 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const C
 // ---- K1b': sign words of a 2-D terrain WITHOUT evaluating the density per voxel.
 // density(x,y,z) = (-dy(y)) - t(x,z) with t = n(x,z)*height: in IEEE arithmetic with gradual underflow
 // a - b < 0  <=>  a < b (the difference of two floats is zero only if they are equal; NaN compares false
-// either way), so bit(x,y,z) = (-dy(y) < t(x,z)): one compare + ballot per 32 voxels.  A warp owns a
-// 32(y) x 32(z) tile of one x-plane: every lane keeps t for its z and -dy for its y, the y value is
-// broadcast by shuffle, and after 32 ballots lane j holds the word of row y0+j -> one coalesced store.
+// either way), so bit(x,y,z) = (-dy(y) < t(x,z)).  A warp owns a 32(y) x 32(z) tile of one x-plane; lane j
+// holds -dy(y0+j) and t(z0+j).  -dy is monotone in y (checked per tile, NaN-safe), so every lane finds the
+// first y of ITS column where the bit turns on with a 5-step shuffle binary search, forms the column's 32-bit
+// y-mask with one shift, and a 5-stage warp bit-matrix transpose turns the 32 column masks into the 32 row
+// words -> one coalesced store.  ~70 instructions per 1024 voxels; a non-monotone tile falls back to 32 ballots.
 __global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
                                                          const int* __restrict__ sheet_of, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
 {
@@ -229,13 +231,42 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const Chun
 	float dy = ((float)y * g.delta + g.oy) * s.g;
 	if (s.dy_half) dy = dy * 0.5f;
 	const float ndy = -dy;
-	uint32_t mine = 0;
-#pragma unroll
-	for (int j = 0; j < 32; j++)
+	uint32_t mine;
+	const float nxt = __shfl_down_sync(0xffffffffu, ndy, 1);
+	const bool monotone = __all_sync(0xffffffffu, lane == 31 || ndy >= nxt); // false if any NaN
+	if (monotone)
 	{
-		const float a = __shfl_sync(0xffffffffu, ndy, j);
-		const uint32_t word = __ballot_sync(0xffffffffu, a < t);
-		if (lane == j) mine = word;
+		// number of rows y (from the bottom of the tile) whose bit is still 0 in this lane's column
+		int cnt = 0;
+#pragma unroll
+		for (int st = 16; st >= 1; st >>= 1)
+		{
+			const float a = __shfl_sync(0xffffffffu, ndy, cnt + st - 1);
+			if (!(a < t)) cnt += st;
+		}
+		const float a31 = __shfl_sync(0xffffffffu, ndy, 31);
+		if (cnt == 31 && !(a31 < t)) cnt = 32;
+		uint32_t v = cnt >= 32 ? 0u : (0xFFFFFFFFu << cnt); // lane = z, bit = y
+		// 32x32 bit-matrix transpose across the warp: afterwards lane = y, bit = z
+#pragma unroll
+		for (int j = 16; j >= 1; j >>= 1)
+		{
+			const uint32_t m0 = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+			const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+			v = (lane & j) ? ((v & ~m0) | ((o >> j) & m0)) : ((v & m0) | ((o << j) & ~m0));
+		}
+		mine = v;
+	}
+	else
+	{
+		mine = 0;
+#pragma unroll
+		for (int j = 0; j < 32; j++)
+		{
+			const float a = __shfl_sync(0xffffffffu, ndy, j);
+			const uint32_t word = __ballot_sync(0xffffffffu, a < t);
+			if (lane == j) mine = word;
+		}
 	}
 	bits[(size_t)chunk * L.wc + ((((size_t)x << L.ld) + y) << L.lzc) + zb] = mine;
 	merge_flags(word_flags(mine), flags + chunk);
@@ -365,40 +396,65 @@ __device__ __forceinline__ uint32_t mask8_of(const WordBits& b, int bit)
 // packed per-word counts: cells [0,8) verts [8,16) indices [16,32)
 __device__ __forceinline__ uint32_t pack_counts(uint32_t nc, uint32_t nv, uint32_t ni) { return nc | (nv << 8) | (ni << 16); }
 
-// exclusive scan of three counters over the CTA (thread order); totals returned through tot[3] (valid in all threads)
-__device__ __forceinline__ void block_scan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t tot[3])
+// exclusive scan of K counters over the CTA (thread order); totals returned through tot[K] (valid in all threads)
+template <int K>
+__device__ __forceinline__ void block_scan(uint32_t (&v)[K], uint32_t (&tot)[K])
 {
-	__shared__ uint32_t s_w[3][CTA / 32];
-	__shared__ uint32_t s_t[3];
+	__shared__ uint32_t s_w[K][CTA / 32];
+	__shared__ uint32_t s_t[K];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t ia = a, ib = b, ic = c;
+	uint32_t in[K];
+#pragma unroll
+	for (int q = 0; q < K; q++) in[q] = v[q];
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
-		uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
-		if (lane >= o) { ia += ta; ib += tb; ic += tc; }
+#pragma unroll
+		for (int q = 0; q < K; q++)
+		{
+			const uint32_t t = __shfl_up_sync(0xffffffffu, in[q], o);
+			if (lane >= o) in[q] += t;
+		}
 	}
-	if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
+	if (lane == 31)
+	{
+#pragma unroll
+		for (int q = 0; q < K; q++) s_w[q][warp] = in[q];
+	}
 	__syncthreads();
 	if (warp == 0)
 	{
-		uint32_t va = lane < CTA / 32 ? s_w[0][lane] : 0, vb = lane < CTA / 32 ? s_w[1][lane] : 0, vc = lane < CTA / 32 ? s_w[2][lane] : 0;
-		uint32_t ja = va, jb = vb, jc = vc;
 #pragma unroll
-		for (int o = 1; o < CTA / 32; o <<= 1)
+		for (int q = 0; q < K; q++)
 		{
-			uint32_t ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
-			if (lane >= o) { ja += ta; jb += tb; jc += tc; }
+			const uint32_t w = lane < CTA / 32 ? s_w[q][lane] : 0;
+			uint32_t j = w;
+#pragma unroll
+			for (int o = 1; o < CTA / 32; o <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(0xffffffffu, j, o);
+				if (lane >= o) j += t;
+			}
+			if (lane < CTA / 32) s_w[q][lane] = j - w;
+			if (lane == CTA / 32 - 1) s_t[q] = j;
 		}
-		if (lane < CTA / 32) { s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc; }
-		if (lane == CTA / 32 - 1) { s_t[0] = ja; s_t[1] = jb; s_t[2] = jc; }
 	}
 	__syncthreads();
-	a = ia - a + s_w[0][warp];
-	b = ib - b + s_w[1][warp];
-	c = ic - c + s_w[2][warp];
-	tot[0] = s_t[0]; tot[1] = s_t[1]; tot[2] = s_t[2];
+#pragma unroll
+	for (int q = 0; q < K; q++)
+	{
+		v[q] = in[q] - v[q] + s_w[q][warp];
+		tot[q] = s_t[q];
+	}
 	__syncthreads();
+}
+
+__device__ __forceinline__ void block_scan3(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t tot[3])
+{
+	uint32_t v[3] = { a, b, c }, t[3];
+	block_scan<3>(v, t);
+	a = v[0]; b = v[1]; c = v[2];
+	tot[0] = t[0]; tot[1] = t[1]; tot[2] = t[2];
 }
 
 // ---- K3: cell-mask build + counts.  One CTA per segment (P whole x-planes); each thread owns wpt
@@ -551,22 +607,27 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __re
 	}
 }
 
-// ---- K4a: per-word output bases + compaction of the words that emit anything.  One CTA per segment with
-// active cells (everything else leaves at once).  wvb[word] = chunk-local id of the word's first vertex,
-// wib[word] = batch-wide position of its first index.  Words with vertices / indices are appended to two
-// lists (a range per CTA reserved with one atomic; list order does not matter, every entry carries its own
-// output position), so the emitters below only ever touch words on the surface.
+// ---- K4a: per-word output bases + compaction of the CELLS that emit anything.  One CTA per segment with
+// active cells (everything else leaves at once); the segment's sign planes are staged like in k_count.
+// wvb[word] = chunk-local id of the word's first vertex, wib[word] = batch-wide position of its first index.
+// Every cell that owns iso-vertices and every cell that polygonizes is appended to a compact list (a range per
+// CTA reserved with one atomic; list order does not matter, each record carries its own output position):
+//   vertex cell : {word, bit | edge flags << 5 | rank of its first vertex inside the word << 8}
+//   index cell  : {word, bit | offset of its first index inside the word << 5 | mask8 << 16}
+// so the emitters run one THREAD per surface cell, whatever the orientation of the surface inside the words.
 template <int WPT>
-__global__ void __launch_bounds__(CTA) k_bases(Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
+__global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
                                                 const uint32_t* __restrict__ seg_base, const ChunkCounts* __restrict__ chunks,
-                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib, uint32_t* __restrict__ vlist,
-                                                uint32_t* __restrict__ ilist, unsigned long long* __restrict__ list_count /* [2] */)
+                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib, uint2* __restrict__ vcells,
+                                                uint2* __restrict__ icells, unsigned long long* __restrict__ list_count /* [2] */)
 {
+	extern __shared__ uint32_t sb[];
 	__shared__ uint32_t s_base[2];
 	const int seg = blockIdx.x;
-	const int chunk = seg >> L.lS;
+	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	const ChunkCounts cc = chunks[chunk];
 	if (!cc.contains_mesh || seg_tot[3 * (size_t)seg] == 0) return;
+	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
 	uint32_t cnt[WPT];
 	{
 		const uint32_t* in = wcnt + (size_t)seg * L.ws + threadIdx.x * WPT;
@@ -577,35 +638,64 @@ __global__ void __launch_bounds__(CTA) k_bases(Layout L, const uint32_t* __restr
 			cnt[k] = v.x; cnt[k + 1] = v.y; cnt[k + 2] = v.z; cnt[k + 3] = v.w;
 		}
 	}
-	uint32_t tv = 0, ti = 0, tw = 0; // tw: words with vertices (low 16 bits) and words with indices (high 16 bits)
+	__syncthreads();
+	uint32_t sc[4] = { 0, 0, 0, 0 }; // verts, indices, vertex cells, index cells
 #pragma unroll
 	for (int k = 0; k < WPT; k++)
 	{
-		const uint32_t nv = (cnt[k] >> 8) & 0xFF, ni = cnt[k] >> 16;
-		tv += nv; ti += ni;
-		tw += (nv ? 1u : 0u) + (ni ? 0x10000u : 0u);
+		if (cnt[k] == 0) continue;
+		const int lw = threadIdx.x * WPT + k;
+		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
+		const WordBits b = load_word_bits(sb, L, lx, y, zb);
+		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		sc[0] += (cnt[k] >> 8) & 0xFF;
+		sc[1] += cnt[k] >> 16;
+		sc[2] += __popc(c.ex | c.ey | c.ez);
+		sc[3] += __popc(c.active & c.interior);
 	}
-	uint32_t tot[3];
-	block_scan3(tv, ti, tw, tot);
+	uint32_t tot[4];
+	block_scan<4>(sc, tot);
 	if (threadIdx.x == 0)
 	{
-		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)(tot[2] & 0xFFFF));
-		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)(tot[2] >> 16));
+		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)tot[2]);
+		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)tot[3]);
 	}
 	__syncthreads();
-	uint32_t rv = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base + tv;
-	uint32_t ri = seg_base[3 * (size_t)seg + 2] + ti;
-	uint32_t ov = s_base[0] + (tw & 0xFFFF), oi = s_base[1] + (tw >> 16);
+	uint32_t rv = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base + sc[0];
+	uint32_t ri = seg_base[3 * (size_t)seg + 2] + sc[1];
+	uint32_t ov = s_base[0] + sc[2], oi = s_base[1] + sc[3];
 	const uint32_t gw0 = (uint32_t)((size_t)seg * L.ws + threadIdx.x * WPT);
 	uint32_t ob[WPT], oix[WPT];
 #pragma unroll
 	for (int k = 0; k < WPT; k++)
 	{
-		const uint32_t nv = (cnt[k] >> 8) & 0xFF, ni = cnt[k] >> 16;
 		ob[k] = rv; oix[k] = ri;
-		if (nv) vlist[ov++] = gw0 + k;
-		if (ni) ilist[oi++] = gw0 + k;
-		rv += nv; ri += ni;
+		if (cnt[k] == 0) continue;
+		rv += (cnt[k] >> 8) & 0xFF;
+		ri += cnt[k] >> 16;
+		const int lw = threadIdx.x * WPT + k;
+		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
+		const WordBits b = load_word_bits(sb, L, lx, y, zb);
+		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		uint32_t m = c.ex | c.ey | c.ez, rank = 0;
+		while (m)
+		{
+			const int bit = __ffs(m) - 1;
+			m &= m - 1;
+			const uint32_t fl = ((c.ex >> bit) & 1u) | (((c.ey >> bit) & 1u) << 1) | (((c.ez >> bit) & 1u) << 2);
+			vcells[ov++] = make_uint2(gw0 + k, (uint32_t)bit | (fl << 5) | (rank << 8));
+			rank += __popc(fl);
+		}
+		m = c.active & c.interior;
+		uint32_t ofs = 0;
+		while (m)
+		{
+			const int bit = __ffs(m) - 1;
+			m &= m - 1;
+			const uint32_t m8 = mask8_of(b, bit);
+			icells[oi++] = make_uint2(gw0 + k, (uint32_t)bit | (ofs << 5) | (m8 << 16));
+			ofs += (uint32_t)(c_tri_pack[m8] >> 60);
+		}
 	}
 	uint32_t* o1 = wvb + gw0;
 	uint32_t* o2 = wib + gw0;
@@ -617,45 +707,32 @@ __global__ void __launch_bounds__(CTA) k_bases(Layout L, const uint32_t* __restr
 	}
 }
 
-// ---- K4b: vertex emission, one WARP per word that owns vertices, one LANE per cell (z).
-// calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674): X, Y, Z edge of a cell in that
-// order; the id of a lane's first vertex is the word base plus the popcounts of the edge flags below the lane.
-// Neighbour samples along z are consecutive floats of one row, so the crossing-edge reads are coalesced.
-__global__ void __launch_bounds__(CTA) k_verts2(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb,
-                                                 const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
-                                                 const ChunkGeom* __restrict__ geom, const uint32_t* __restrict__ vlist,
+// ---- K4b: vertex emission, one THREAD per cell that owns iso-vertices.
+// calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674): X, Y, Z edge of a cell in that order.
+__global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint32_t* __restrict__ wvb, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
+                                                 const ChunkGeom* __restrict__ geom, const uint2* __restrict__ vcells,
                                                  const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary)
 {
-	const int lane = threadIdx.x & 31;
-	const uint32_t n_words = (uint32_t)list_count[0];
-	const uint32_t stride = gridDim.x * (CTA / 32);
+	const uint32_t n_cells = (uint32_t)list_count[0];
+	const uint32_t stride = gridDim.x * CTA;
 	const int d = L.d;
-	for (uint32_t i = blockIdx.x * (CTA / 32) + (threadIdx.x >> 5); i < n_words; i += stride)
+	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
 	{
-		const uint32_t gw = vlist[i];
+		const uint2 rec = vcells[i];
+		const uint32_t gw = rec.x;
+		const int bit = rec.y & 31, fl = (rec.y >> 5) & 7, rank = rec.y >> 8;
 		const int chunk = (int)(gw >> L.lwc);
 		const int w = (int)(gw & (uint32_t)(L.wc - 1));
 		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
-		const uint32_t* cb = bits + (size_t)chunk * L.wc;
-		const bool zn = zb + 1 < L.zc, yn = y + 1 < d, xn = x + 1 < d;
-		const uint32_t A = cb[w];
-		const uint32_t A1 = __funnelshift_r(A, zn ? cb[w + 1] : 0u, 1);
-		const uint32_t ex = xn ? (A ^ cb[w + L.wp]) : 0u;
-		const uint32_t ey = yn ? (A ^ cb[w + L.zc]) : 0u;
-		const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
-		const uint32_t any = ex | ey | ez;
-		if (!((any >> lane) & 1u)) continue;
-		const uint32_t lt = (1u << lane) - 1u;
+		const int z = zb * 32 + bit;
 		const ChunkGeom g = geom[chunk];
-		const int z = zb * 32 + lane;
-		size_t v = (size_t)chunks[chunk].vert_base + wvb[gw] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
+		size_t v = (size_t)chunks[chunk].vert_base + wvb[gw] + rank;
 		const float s0 = density_at(s, src, g, d, chunk, x, y, z);
 		const bool b0 = x == 0 || y == 0 || z == 0 || x == d - 1 || y == d - 1 || z == d - 1;
 #pragma unroll
 		for (int axis = 0; axis < 3; axis++)
 		{
-			const uint32_t e = axis == 0 ? ex : axis == 1 ? ey : ez;
-			if (!((e >> lane) & 1u)) continue;
+			if (!((fl >> axis) & 1)) continue;
 			const int x1 = x + (axis == 0), y1 = y + (axis == 1), z1 = z + (axis == 2);
 			const float s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
 			const float mu = (0.0f - s0) / (s1 - s0);
@@ -669,79 +746,54 @@ __global__ void __launch_bounds__(CTA) k_verts2(const uint32_t* __restrict__ bit
 	}
 }
 
-// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence, one WARP per
-// word that emits indices, one LANE per cell.  The 16 sign words of the 8 neighbouring rows (x..x+2, y..y+2) x
-// (zb, zb+1) and the 8 vertex bases of rows (x..x+1, y..y+1) are fetched by 24 lanes in one load and broadcast by
-// shuffle; every lane then derives its cell mask and the ids of its 12 edge vertices with popcounts
-// (EDGE_V, DMCChunk.cpp:32, 543-565), the warp scans the per-cell index counts and the word's indices leave
-// shared memory as one coalesced run.
-__global__ void __launch_bounds__(CTA) k_inds2(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb,
-                                                const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
-                                                const uint32_t* __restrict__ ilist, const unsigned long long* __restrict__ list_count,
-                                                uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
+// chunk-local id of the vertex on `axis` of cell (x,y,z): base of its word + popcounts of the edge-owner words below it
+__device__ __forceinline__ uint32_t vertex_id_global(const uint32_t* __restrict__ cb, const uint32_t* __restrict__ vb, const Layout& L, int x, int y, int z, int axis)
+{
+	const int zb = z >> 5, bit = z & 31;
+	const int w = (((x << L.ld) + y) << L.lzc) + zb;
+	const uint32_t A = cb[w];
+	const uint32_t A1 = __funnelshift_r(A, (zb + 1 < L.zc) ? cb[w + 1] : 0u, 1);
+	const uint32_t ex = (x + 1 < L.d) ? (A ^ cb[w + L.wp]) : 0u;
+	const uint32_t ey = (y + 1 < L.d) ? (A ^ cb[w + L.zc]) : 0u;
+	const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+	const uint32_t lt = (1u << bit) - 1u;
+	uint32_t id = vb[w] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
+	if (axis >= 1) id += (ex >> bit) & 1u;
+	if (axis >= 2) id += (ey >> bit) & 1u;
+	return id;
+}
+
+// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence, one THREAD per
+// polygonizing cell.  The cell's corner mask travels in its record; the ids of the edge vertices the triangle table
+// names (EDGE_V, DMCChunk.cpp:32, 543-565) are recomputed from the neighbouring sign words and per-word vertex bases.
+__global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb, const uint32_t* __restrict__ wib,
+                                                const ChunkCounts* __restrict__ chunks, const uint2* __restrict__ icells,
+                                                const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
 {
 	__shared__ uint64_t s_tri[256];
-	__shared__ uint32_t s_id[CTA / 32][12][32];
-	__shared__ uint32_t s_out[CTA / 32][480];
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t n_words = (uint32_t)list_count[1];
-	const uint32_t stride = gridDim.x * (CTA / 32);
+	const uint32_t n_cells = (uint32_t)list_count[1];
+	const uint32_t stride = gridDim.x * CTA;
 	const int d = L.d;
-	for (uint32_t i = blockIdx.x * (CTA / 32) + warp; i < n_words; i += stride)
+	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
 	{
-		const uint32_t gw = ilist[i];
+		const uint2 rec = icells[i];
+		const uint32_t gw = rec.x;
+		const int bit = rec.y & 31;
+		const uint32_t ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
 		const int chunk = (int)(gw >> L.lwc);
 		const int w = (int)(gw & (uint32_t)(L.wc - 1));
 		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
-		// lanes 0..15: sign word of row r = lane>>1 in {(0,0),(0,1),(0,2),(1,0),(1,1),(1,2),(2,0),(2,1)}, z-word zb + (lane&1)
-		// lanes 16..23: vertex base of row (dx,dy) in {0,1}^2, z-word zb + (lane&1)
-		uint32_t mine = 0;
-		{
-			const int k = lane & 1;
-			int dx, dy;
-			const uint32_t* base;
-			if (lane < 16) { const int r = lane >> 1; dx = r / 3; dy = r - 3 * dx; base = bits; }
-			else { const int r = (lane - 16) >> 1; dx = r >> 1; dy = r & 1; base = wvb; }
-			if (lane < 24 && x + dx < d && y + dy < d && zb + k < L.zc) mine = base[(size_t)chunk * L.wc + w + dx * L.wp + dy * L.zc + k];
-		}
-#define BMF_ROW(dx, dy, k) __shfl_sync(0xffffffffu, mine, ((dx) * 3 + (dy)) * 2 + (k))
-#define BMF_VB(dx, dy, k) __shfl_sync(0xffffffffu, mine, 16 + ((dx) * 2 + (dy)) * 2 + (k))
-		const uint32_t zvalid = (zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu;
-		// per row (dx,dy) in {0,1}^2 and z-word k: the sign word, the edge-owner words and the vertex base
-		uint32_t rb[2][2][2], rex[2][2][2], rey[2][2][2], rez[2][2], rvb[2][2][2];
-#pragma unroll
-		for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-			for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-				for (int k = 0; k < 2; k++)
-				{
-					const uint32_t b = BMF_ROW(dx, dy, k);
-					rb[dx][dy][k] = b;
-					rex[dx][dy][k] = (x + dx + 1 < d) ? (b ^ BMF_ROW(dx + 1, dy, k)) : 0u;
-					rey[dx][dy][k] = (y + dy + 1 < d) ? (b ^ BMF_ROW(dx, dy + 1, k)) : 0u;
-					rvb[dx][dy][k] = BMF_VB(dx, dy, k);
-				}
-#pragma unroll
-		for (int dx = 0; dx < 2; dx++)
-#pragma unroll
-			for (int dy = 0; dy < 2; dy++)
-				rez[dx][dy] = (rb[dx][dy][0] ^ __funnelshift_r(rb[dx][dy][0], rb[dx][dy][1], 1)) & zvalid;
-#undef BMF_ROW
-#undef BMF_VB
-		// this lane's cell: corner mask (x high bit, z low bit) and whether it polygonizes
-		WordBits wb;
-		wb.A = rb[0][0][0]; wb.A1 = __funnelshift_r(rb[0][0][0], rb[0][0][1], 1);
-		wb.B = rb[0][1][0]; wb.B1 = __funnelshift_r(rb[0][1][0], rb[0][1][1], 1);
-		wb.C = rb[1][0][0]; wb.C1 = __funnelshift_r(rb[1][0][0], rb[1][0][1], 1);
-		wb.D = rb[1][1][0]; wb.D1 = __funnelshift_r(rb[1][1][0], rb[1][1][1], 1);
-		const WordClass c = classify(wb, L, x, y, zb);
-		const bool emits = ((c.active & c.interior) >> lane) & 1u;
-		const uint64_t tp = emits ? s_tri[mask8_of(wb, lane)] : 0ull;
-		const uint32_t n_l = (uint32_t)(tp >> 60);
-		// ids of the 12 edge vertices of this cell (only meaningful where the table uses them)
+		const int z = zb * 32 + bit;
+		const uint32_t* cb = bits + (size_t)chunk * L.wc;
+		const uint32_t* vb = wvb + (size_t)chunk * L.wc;
+		const uint64_t tp = s_tri[m8];
+		const int n = (int)(tp >> 60);
+		// which of the 12 edges the table uses: compute each id once
+		uint32_t used = 0;
+		for (int t = 0; t < n; t++) used |= 1u << ((tp >> (4 * t)) & 15);
+		uint32_t id[12];
 #pragma unroll
 		for (int e = 0; e < 12; e++)
 		{
@@ -749,41 +801,21 @@ __global__ void __launch_bounds__(CTA) k_inds2(const uint32_t* __restrict__ bits
 			const int dx = axis == 0 ? 0 : hi;
 			const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
 			const int dz = axis == 2 ? 0 : lo;
-			const int zz = lane + dz;          // 0..32: bit 32 is bit 0 of the next z-word
-			const int k = zz >> 5, bit = zz & 31;
-			const uint32_t exw = k ? rex[dx][dy][1] : rex[dx][dy][0];
-			const uint32_t eyw = k ? rey[dx][dy][1] : rey[dx][dy][0];
-			const uint32_t ezw = k ? 0u : rez[dx][dy]; // k == 1 only with bit == 0: nothing below it
-			const uint32_t lt = (1u << bit) - 1u;
-			uint32_t id = (k ? rvb[dx][dy][1] : rvb[dx][dy][0]) + __popc(exw & lt) + __popc(eyw & lt) + __popc(ezw & lt);
-			if (axis >= 1) id += (exw >> bit) & 1u;
-			if (axis >= 2) id += (eyw >> bit) & 1u;
-			s_id[warp][e][lane] = id;
+			id[e] = ((used >> e) & 1u) ? vertex_id_global(cb, vb, L, x + dx, y + dy, z + dz, axis) : 0u;
 		}
-		// exclusive scan of the per-cell index counts across the warp
-		uint32_t incl = n_l;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o) incl += t;
-		}
-		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		uint32_t o = incl - n_l;
-		__syncwarp();
-		for (uint32_t t = 0; t < n_l; t++) s_out[warp][o + t] = s_id[warp][(tp >> (4 * t)) & 15][lane];
-		__syncwarp();
-		const size_t out0 = wib[gw];
+		const size_t out0 = (size_t)wib[gw] + ofs;
 		const size_t vbase = (size_t)chunks[chunk].vert_base;
-		for (uint32_t j = lane; j < total; j += 32)
+		for (int t = 0; t < n; t++)
 		{
-			const uint32_t vid = s_out[warp][j];
-			inds[out0 + j] = vid;
+			const int e = (int)(tp >> (4 * t)) & 15;
+			uint32_t vid = 0;
+#pragma unroll
+			for (int q = 0; q < 12; q++) vid = (e == q) ? id[q] : vid;
+			inds[out0 + t] = vid;
 			// init_valence++ (DMCChunk.cpp:573): byte-wise add through the aligned 32-bit word
 			const size_t gv = vbase + vid;
 			atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
 		}
-		__syncwarp();
 	}
 }
 
