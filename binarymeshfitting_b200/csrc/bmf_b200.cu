@@ -235,8 +235,10 @@ inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1
 // MeshProcessor<N> on device arrays (all batch-wide); chunks_dev maps index positions to vertex bases.
 template <int N>
 int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* color, float* normal, const uint8_t* boundary,
-               const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef, int final_primal = 1)
+               const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef, int final_primal = 1,
+               bool grid_path = false)
 {
+	// grid_path: the mesh comes from the resident batch (cell lists + per-word bases are valid and every colour is exactly 1)
 	if (n_verts == 0 || n_inds < (size_t)N || iters <= 0) return BMF_OK;
 	const size_t n_prims = n_inds / N;
 	BMF_CUDA(ctx->adj_off.reserve(n_verts));
@@ -244,7 +246,8 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	BMF_CUDA(ctx->adj.reserve(n_inds));
 	BMF_CUDA(ctx->prim_vbase.reserve(n_prims));
 	BMF_CUDA(ctx->dp.reserve(3 * n_prims));
-	BMF_CUDA(ctx->dc.reserve(3 * n_prims));
+	if (!grid_path) BMF_CUDA(ctx->dc.reserve(3 * n_prims));
+	float* dcp = grid_path ? nullptr : ctx->dc.p;
 	const bool need_dn = smooth || qef;
 	if (need_dn) BMF_CUDA(ctx->dn.reserve(3 * n_prims));
 	const size_t per_block = (size_t)CTA * SCAN_ITEMS;
@@ -256,8 +259,17 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
 	BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
 	BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, n_verts * sizeof(uint32_t), ctx->stream));
-	BMF_LAUNCH(k_csr_fill<N>, grid_for(n_prims, CTA), CTA, 0, inds, n_prims, chunks_dev, n_chunks, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
-	BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
+	if (grid_path)
+	{
+		for (int pass = 0; pass < 4; pass++)
+			BMF_LAUNCH(k_adj_pass, ctx->sm_count * 8, CTA, 0, pass, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->adj_off.p, ctx->cursor.p,
+			           ctx->adj.p, ctx->prim_vbase.p);
+	}
+	else
+	{
+		BMF_LAUNCH(k_csr_fill<N>, grid_for(n_prims, CTA), CTA, 0, inds, n_prims, chunks_dev, n_chunks, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
+		BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
+	}
 
 	// optimize_dual_grid (MeshProcessor.cpp:130-236)
 	const int hard_norm_max = 10;
@@ -265,23 +277,23 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	for (int m = 0; m < iters; m++)
 	{
 		const int face = (m == 0 || m < max_norms || m < 3) ? 1 : 0;
-		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, ctx->dc.p,
+		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp,
 		           need_dn ? ctx->dn.p : nullptr, smooth, face);
 		if (m < iters - 1)
 		{
 			const int set_colors = (m == 3) || (m == 0 && iters <= 3);
-			BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p,
+			BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp,
 			           ctx->dn.p, pos, color, normal, smooth, set_colors, pb);
 		}
 	}
 	// the driver's extra primal call (ChunkGenerator.cpp:120)
 	if (final_primal)
-		BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dc.p, ctx->dn.p, pos,
+		BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp, ctx->dn.p, pos,
 		           color, normal, smooth, 0, pb);
 	if (qef)
 	{
 		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
-		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, ctx->dc.p, ctx->dn.p, 1, 1);
+		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1);
 		BMF_LAUNCH(k_qef_place, grid_for(n_verts, 128), 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb);
 	}
 	return BMF_OK;
@@ -595,7 +607,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (params->iters > 0 && V && I)
 	{
 		int rc = run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
-		                       params->iters, params->process_boundary, params->smooth_normals, params->qef);
+		                       params->iters, params->process_boundary, params->smooth_normals, params->qef, 1, true);
 		if (rc) return rc;
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));

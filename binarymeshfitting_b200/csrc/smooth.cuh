@@ -146,6 +146,46 @@ __global__ void __launch_bounds__(CTA) k_csr_sort(const uint32_t* __restrict__ a
 	}
 }
 
+// ---- CSR build for the batch path WITHOUT a sort: a vertex is shared by at most the four cells around its grid
+// edge, and the place of a cell among them in scan order is a function of the local edge id alone
+// (class = 3 - (e & 3): edge 3/7/11 of the first cell ... edge 0/4/8 of the owner, the last one).  Filling in
+// four passes by class therefore appends, per vertex, one cell per pass in ascending cell order, and inside a
+// pass all uses of a vertex come from ONE thread (its cell) in table order -- the cursor atomics of a single
+// thread are ordered, so every list comes out ascending in primitive id (init_primitives :114-127).
+__global__ void __launch_bounds__(CTA) k_adj_pass(int pass, Layout L, const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
+                                                   const uint2* __restrict__ icells, const unsigned long long* __restrict__ list_count,
+                                                   const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off, uint32_t* __restrict__ cursor,
+                                                   uint32_t* __restrict__ adj, uint32_t* __restrict__ prim_vbase)
+{
+	__shared__ uint64_t s_tri[256];
+	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
+	__syncthreads();
+	const uint32_t n_cells = (uint32_t)list_count[1];
+	const uint32_t stride = gridDim.x * CTA;
+	const uint32_t want = 3u - (uint32_t)pass;
+	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
+	{
+		const uint2 rec = icells[i];
+		const uint32_t gw = rec.x;
+		const uint32_t ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
+		const int chunk = (int)(gw >> L.lwc);
+		const uint64_t tp = s_tri[m8];
+		const int n = (int)(tp >> 60);
+		const size_t out0 = (size_t)wib[gw] + ofs;
+		const uint32_t vbase = (uint32_t)chunks[chunk].vert_base;
+		for (int t = 0; t < n; t++)
+		{
+			const uint32_t e = (uint32_t)(tp >> (4 * t)) & 15u;
+			const uint32_t prim = (uint32_t)((out0 + t) / 3);
+			if (pass == 0 && (t % 3) == 0) prim_vbase[prim] = vbase;
+			if ((e & 3u) != want) continue;
+			const uint32_t v = vbase + inds[out0 + t];
+			const uint32_t slot = atomicAdd(cursor + v, 1u);
+			adj[adj_off[v] + slot] = prim;
+		}
+	}
+}
+
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 ld3(const float* p, size_t i) { return { p[3 * i], p[3 * i + 1], p[3 * i + 2] }; }
 __device__ __forceinline__ void st3(float* p, size_t i, f3 v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
@@ -176,10 +216,10 @@ __global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds,
 	{
 		p[k] = ld3(pos, v[k]);
 		sp = add3(sp, p[k]);
-		sc = add3(sc, ld3(color, v[k]));
+		if (dc) sc = add3(sc, ld3(color, v[k]));
 	}
 	st3(dp, t, div3(sp, (float)N));
-	st3(dc, t, div3(sc, (float)N));
+	if (dc) st3(dc, t, div3(sc, (float)N)); // dc == null: all colours are exactly (1,1,1) and stay so ((1+1+1)/3 == 1, k/k == 1)
 	if (!smooth) return;
 	if (face_normals)
 	{
@@ -228,16 +268,16 @@ __global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj
 	{
 		const size_t t = a[k];
 		p = add3(p, ld3(dp, t));
-		c = add3(c, ld3(dc, t));
+		if (dc) c = add3(c, ld3(dc, t));
 		if (smooth) n = add3(n, ld3(dn, t));
 	}
 	const float fc = (float)cnt;
 	p = div3(p, fc);
-	c = div3(c, fc);
+	if (dc) c = div3(c, fc);
 	if (smooth) n = div3(n, fc);
 	if (set_colors) n = normalize3(n);
 	st3(pos, v, p);
-	st3(color, v, c);
+	if (dc) st3(color, v, c);
 	if (n.y != 0 && normal) st3(normal, v, n);
 }
 
