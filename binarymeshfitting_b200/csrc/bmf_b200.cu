@@ -88,7 +88,7 @@ struct bmf_ctx
 	DevBuf<uint8_t> boundary, valence;
 	DevBuf<uint32_t> inds;
 	// smoothing temporaries
-	DevBuf<uint32_t> adj_off, cursor, adj, prim_vbase, block_sums;
+	DevBuf<uint32_t> adj_off, cursor, adj, prim_vbase, block_sums, cls;
 	DevBuf<float> dp, dc, dn;
 	// qef scratch
 	DevBuf<float> qp, qn, qo, qe;
@@ -242,7 +242,7 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	if (n_verts == 0 || n_inds < (size_t)N || iters <= 0) return BMF_OK;
 	const size_t n_prims = n_inds / N;
 	BMF_CUDA(ctx->adj_off.reserve(n_verts));
-	BMF_CUDA(ctx->cursor.reserve(n_verts));
+	if (!grid_path) BMF_CUDA(ctx->cursor.reserve(n_verts));
 	BMF_CUDA(ctx->adj.reserve(n_inds));
 	BMF_CUDA(ctx->prim_vbase.reserve(n_prims));
 	BMF_CUDA(ctx->dp.reserve(3 * n_prims));
@@ -258,15 +258,14 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	BMF_LAUNCH(k_scan8_partial, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p);
 	BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
 	BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
-	BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, n_verts * sizeof(uint32_t), ctx->stream));
 	if (grid_path)
 	{
-		for (int pass = 0; pass < 4; pass++)
-			BMF_LAUNCH(k_adj_pass, ctx->sm_count * 8, CTA, 0, pass, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->adj_off.p, ctx->cursor.p,
-			           ctx->adj.p, ctx->prim_vbase.p);
+		BMF_LAUNCH(k_adj_fill, ctx->sm_count * 8, CTA, 0, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->cls.p, ctx->adj_off.p, ctx->adj.p,
+		           ctx->prim_vbase.p);
 	}
 	else
 	{
+		BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, n_verts * sizeof(uint32_t), ctx->stream));
 		BMF_LAUNCH(k_csr_fill<N>, grid_for(n_prims, CTA), CTA, 0, inds, n_prims, chunks_dev, n_chunks, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
 		BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
 	}
@@ -357,7 +356,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
 	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
-	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cursor.release();
+	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cls.release(); ctx->cursor.release();
 	ctx->adj.release(); ctx->prim_vbase.release(); ctx->block_sums.release(); ctx->dp.release(); ctx->dc.release(); ctx->dn.release();
 	ctx->qp.release(); ctx->qn.release(); ctx->qo.release(); ctx->qe.release(); ctx->qc.release();
 	if (ctx->totals_pinned) cudaFreeHost(ctx->totals_pinned);
@@ -571,6 +570,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->normal.reserve(3 * V + 4));
 	BMF_CUDA(ctx->boundary.reserve(V + 16));
 	BMF_CUDA(ctx->valence.reserve(V + 16));
+	BMF_CUDA(ctx->cls.reserve(V + 16));
 	BMF_CUDA(ctx->inds.reserve(I + 4));
 
 	// ---- K4
@@ -593,14 +593,15 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 	if (V)
 	{
-		BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, V + 16, st));
+		BMF_CUDA(cudaMemsetAsync(ctx->cls.p, 0, sizeof(uint32_t) * V, st));
 		BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
 		BMF_LAUNCH(k_fill_f32, grid_for(3 * V, CTA), CTA, 0, ctx->color.p, 3 * V, 1.0f); // calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681)
 	}
 	if (I)
 	{
-		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->valence.p);
+		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p);
 	}
+	if (V) BMF_LAUNCH(k_cls_to_valence, grid_for(V, CTA), CTA, 0, ctx->cls.p, V, ctx->valence.p);
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 
 	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it

@@ -763,12 +763,12 @@ __device__ __forceinline__ uint32_t vertex_id_global(const uint32_t* __restrict_
 	return id;
 }
 
-// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + init_valence, one THREAD per
+// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + per-class use counts, one THREAD per
 // polygonizing cell.  The cell's corner mask travels in its record; the ids of the edge vertices the triangle table
 // names (EDGE_V, DMCChunk.cpp:32, 543-565) are recomputed from the neighbouring sign words and per-word vertex bases.
 __global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb, const uint32_t* __restrict__ wib,
                                                 const ChunkCounts* __restrict__ chunks, const uint2* __restrict__ icells,
-                                                const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint8_t* __restrict__ valence)
+                                                const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint32_t* __restrict__ cls)
 {
 	__shared__ uint64_t s_tri[256];
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
@@ -812,11 +812,21 @@ __global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits
 #pragma unroll
 			for (int q = 0; q < 12; q++) vid = (e == q) ? id[q] : vid;
 			inds[out0 + t] = vid;
-			// init_valence++ (DMCChunk.cpp:573): byte-wise add through the aligned 32-bit word
-			const size_t gv = vbase + vid;
-			atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
+			// init_valence++ (DMCChunk.cpp:573), kept per "cell class": a vertex is shared by at most the four cells
+			// around its grid edge and class = 3 - (e & 3) is this cell's place among them in scan order; byte c of
+			// cls[v] counts the uses by the class-c cell (the sort-free CSR build in smooth.cuh needs the split)
+			atomicAdd(cls + vbase + vid, 1u << (8 * (3 - (e & 3))));
 		}
 	}
+}
+
+// init_valence of every vertex = sum of its four per-class use counts
+__global__ void __launch_bounds__(CTA) k_cls_to_valence(const uint32_t* __restrict__ cls, size_t n_verts, uint8_t* __restrict__ valence)
+{
+	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
+	if (v >= n_verts) return;
+	const uint32_t w = cls[v];
+	valence[v] = (uint8_t)((w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24));
 }
 
 } // namespace bmf

@@ -146,15 +146,15 @@ __global__ void __launch_bounds__(CTA) k_csr_sort(const uint32_t* __restrict__ a
 	}
 }
 
-// ---- CSR build for the batch path WITHOUT a sort: a vertex is shared by at most the four cells around its grid
-// edge, and the place of a cell among them in scan order is a function of the local edge id alone
-// (class = 3 - (e & 3): edge 3/7/11 of the first cell ... edge 0/4/8 of the owner, the last one).  Filling in
-// four passes by class therefore appends, per vertex, one cell per pass in ascending cell order, and inside a
-// pass all uses of a vertex come from ONE thread (its cell) in table order -- the cursor atomics of a single
-// thread are ordered, so every list comes out ascending in primitive id (init_primitives :114-127).
-__global__ void __launch_bounds__(CTA) k_adj_pass(int pass, Layout L, const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
+// ---- CSR build for the batch path WITHOUT a sort and WITHOUT atomics: a vertex is shared by at most the four
+// cells around its grid edge, and the place of a cell among them in scan order is a function of the local edge
+// id alone (class = 3 - (e & 3): edge 3/7/11 of the first cell ... edge 0/4/8 of the owner, the last one).
+// k_inds3 counted the uses of every vertex per class (4 bytes of cls[v]); the slot of use (cell, t) in the
+// vertex's list is therefore (uses by lower classes) + (earlier uses of the same edge inside this cell's table
+// row): every list comes out ascending in primitive id, exactly init_primitives' order (:114-127).
+__global__ void __launch_bounds__(CTA) k_adj_fill(Layout L, const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
                                                    const uint2* __restrict__ icells, const unsigned long long* __restrict__ list_count,
-                                                   const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off, uint32_t* __restrict__ cursor,
+                                                   const uint32_t* __restrict__ inds, const uint32_t* __restrict__ cls, const uint32_t* __restrict__ adj_off,
                                                    uint32_t* __restrict__ adj, uint32_t* __restrict__ prim_vbase)
 {
 	__shared__ uint64_t s_tri[256];
@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(CTA) k_adj_pass(int pass, Layout L, const uint
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
 	const uint32_t stride = gridDim.x * CTA;
-	const uint32_t want = 3u - (uint32_t)pass;
 	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
 	{
 		const uint2 rec = icells[i];
@@ -173,15 +172,19 @@ __global__ void __launch_bounds__(CTA) k_adj_pass(int pass, Layout L, const uint
 		const int n = (int)(tp >> 60);
 		const size_t out0 = (size_t)wib[gw] + ofs;
 		const uint32_t vbase = (uint32_t)chunks[chunk].vert_base;
+		uint64_t seen = 0; // 4-bit use counter per local edge id
 		for (int t = 0; t < n; t++)
 		{
 			const uint32_t e = (uint32_t)(tp >> (4 * t)) & 15u;
 			const uint32_t prim = (uint32_t)((out0 + t) / 3);
-			if (pass == 0 && (t % 3) == 0) prim_vbase[prim] = vbase;
-			if ((e & 3u) != want) continue;
+			if ((t % 3) == 0) prim_vbase[prim] = vbase;
+			const uint32_t local = (uint32_t)(seen >> (4 * e)) & 15u;
+			seen += 1ull << (4 * e);
 			const uint32_t v = vbase + inds[out0 + t];
-			const uint32_t slot = atomicAdd(cursor + v, 1u);
-			adj[adj_off[v] + slot] = prim;
+			const uint32_t c = 3u - (e & 3u);
+			const uint32_t below = cls[v] & ((1u << (8 * c)) - 1u); // c <= 3: the shift stays below 32
+			const uint32_t pre = (below & 0xFF) + ((below >> 8) & 0xFF) + ((below >> 16) & 0xFF);
+			adj[adj_off[v] + pre + local] = prim;
 		}
 	}
 }
