@@ -21,7 +21,7 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 # symbols include/bmf_b200.h declares (tests check that the library exports every one of them)
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
-           "bmf_batch_download", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
+           "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve")
 
 
@@ -85,6 +85,7 @@ def load_library(path=SO):
     lib.bmf_batch_chunk_info.argtypes = [vp, C.c_int, C.POINTER(ChunkInfo)]
     lib.bmf_batch_chunk_infos.argtypes = [vp, vp]
     lib.bmf_batch_download.argtypes = [vp] * 7
+    lib.bmf_batch_download_async.argtypes = [vp] * 7
     lib.bmf_batch_copy_chunk.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     lib.bmf_batch_stage_ms.argtypes = [vp, vp]
     lib.bmf_ctx_launch_count.argtypes = [vp]
@@ -184,7 +185,7 @@ class Context:
         self._check(self.lib.bmf_batch_chunk_infos(self.h, _p(out)))
         return out
 
-    def download(self, want=("pos", "normal", "color", "boundary", "valence", "inds"), out=None):
+    def download(self, want=("pos", "normal", "color", "boundary", "valence", "inds"), out=None, wait=True):
         _, V, I = self.totals()
         out = out or {}
         def buf(name, shape, dt):
@@ -199,7 +200,8 @@ class Context:
         bnd = buf("boundary", (V,), np.uint8)
         val = buf("valence", (V,), np.uint8)
         ind = buf("inds", (I,), np.uint32)
-        self._check(self.lib.bmf_batch_download(self.h, _p(pos), _p(nrm), _p(col), _p(bnd), _p(val), _p(ind)))
+        fn = self.lib.bmf_batch_download if wait else self.lib.bmf_batch_download_async
+        self._check(fn(self.h, _p(pos), _p(nrm), _p(col), _p(bnd), _p(val), _p(ind)))
         return out
 
     def copy_chunk(self, i, want=("verts", "inds", "bits")):

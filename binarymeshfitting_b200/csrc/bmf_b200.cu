@@ -77,7 +77,7 @@ struct bmf_ctx
 	DevBuf<int> sheet_of;
 	std::vector<ChunkGeom> sheet_geom_host;
 	std::vector<int> sheet_of_host;
-	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, seg_base;
+	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, chunk_tot;
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	int sm_count = 148;
 	DevBuf<float> density, hmap;
@@ -317,6 +317,8 @@ int elapsed(bmf_ctx* ctx, int a, int b, float* out)
 
 extern "C" {
 
+int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices);
+
 const char* bmf_version(void) { return "bmf_b200 0.1 (sm_100a)"; }
 
 const char* bmf_last_error(const bmf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -354,7 +356,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
-	ctx->seg_tot.release(); ctx->seg_base.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
+	ctx->seg_tot.release(); ctx->chunk_tot.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cls.release(); ctx->cursor.release();
 	ctx->adj.release(); ctx->prim_vbase.release(); ctx->block_sums.release(); ctx->dp.release(); ctx->dc.release(); ctx->dn.release();
@@ -447,7 +449,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->wvb.reserve(n_words));
 	BMF_CUDA(ctx->wib.reserve(n_words));
 	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
-	BMF_CUDA(ctx->seg_base.reserve(3 * ((size_t)nseg + 1)));
+	BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
 	BMF_CUDA(ctx->counts.reserve(n));
 	BMF_CUDA(ctx->totals_dev.reserve(8));
 	if ((size_t)n > ctx->counts_pinned_cap)
@@ -506,6 +508,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (host_density && !params->density_on_device)
 		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st));
 	if (n_sheets)
 	{
 		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_geom.p, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * n_sheets, cudaMemcpyHostToDevice, st));
@@ -547,13 +550,13 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
 	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->chunk_tot.p, masks_w);
 	else
-		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, masks_w);
+		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->chunk_tot.p, masks_w);
 	BMF_CUDA(cudaEventRecord(ctx->ev[2], st));
 
 	// ---- scan + the one host round trip (output sizes)
-	BMF_LAUNCH(k_scan_segments, 1, SCAN_CTA, 0, ctx->seg_tot.p, ctx->flags.p, nseg, L.lS, ctx->seg_base.p, ctx->counts.p, n, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
 	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, ctx->totals_dev.p, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -583,10 +586,10 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->vcells.reserve(ctx->totals[0] + 1));
 	BMF_CUDA(ctx->icells.reserve(ctx->totals[0] + 1));
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count);
 	else
-		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->seg_base.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count);
 	if (V)
 		BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wvb.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p);
@@ -673,6 +676,12 @@ int bmf_batch_chunk_infos(bmf_ctx* ctx, bmf_chunk_info* out)
 
 int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices)
 {
+	int rc = bmf_batch_download_async(ctx, pos, normal, color, boundary, valence, indices);
+	return rc ? rc : bmf_batch_wait(ctx);
+}
+
+int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices)
+{
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download: no batch submitted");
 	BMF_CUDA(cudaSetDevice(ctx->device));
@@ -687,7 +696,7 @@ int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, ui
 		if (valence) BMF_CUDA(cudaMemcpyAsync(valence, ctx->valence.p, V, cudaMemcpyDeviceToHost, st));
 	}
 	if (I && indices) BMF_CUDA(cudaMemcpyAsync(indices, ctx->inds.p, sizeof(uint32_t) * I, cudaMemcpyDeviceToHost, st));
-	return bmf_batch_wait(ctx);
+	return BMF_OK;
 }
 
 int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* indices, uint32_t* bits, uint8_t* masks, float* density)

@@ -462,7 +462,7 @@ __device__ __forceinline__ void block_scan3(uint32_t& a, uint32_t& b, uint32_t& 
 // optionally the 8-bit mask image (MasksBlock, DMCChunk.cpp:184-438) when the caller wants it back.
 template <int WPT>
 __global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, uint32_t* __restrict__ wcnt,
-                                                uint32_t* __restrict__ seg_tot, uint8_t* __restrict__ masks)
+                                                uint32_t* __restrict__ seg_tot, uint32_t* __restrict__ chunk_tot, uint8_t* __restrict__ masks)
 {
 	extern __shared__ uint32_t sb[];
 	const int seg = blockIdx.x;
@@ -519,17 +519,17 @@ __global__ void __launch_bounds__(CTA) k_count(const uint32_t* __restrict__ bits
 	// CTA totals
 	uint32_t tot[3];
 	block_scan3(tc, tv, ti, tot);
-	if (threadIdx.x == 0)
+	if (threadIdx.x < 3)
 	{
-		seg_tot[3 * (size_t)seg + 0] = tot[0];
-		seg_tot[3 * (size_t)seg + 1] = tot[1];
-		seg_tot[3 * (size_t)seg + 2] = tot[2];
+		seg_tot[3 * (size_t)seg + threadIdx.x] = tot[threadIdx.x];
+		if (tot[threadIdx.x]) atomicAdd(chunk_tot + 3 * (size_t)chunk + threadIdx.x, tot[threadIdx.x]); // integer adds commute: deterministic
 	}
 }
 
-// ---- segment scan: one CTA walks the segment totals in coalesced tiles of SCAN_CTA with a running carry.
-// seg_base[3*(nseg+1)] = exclusive prefix of seg_tot; segments of chunks that do not contain a mesh
-// (DMCChunk.cpp:159-162, label_edges :170-171) count as zero.
+// ---- chunk scan: one CTA walks the per-chunk totals (accumulated by k_count) in coalesced tiles of SCAN_CTA
+// with a running carry and writes the chunk table.  A chunk that does not contain a mesh (DMCChunk.cpp:159-162,
+// label_edges :170-171) has zero totals because k_count skipped it.  Segment bases inside a chunk are a <= S-term
+// sum that k_bases forms itself, so the scan length is the number of chunks, not of segments.
 struct ChunkCounts
 {
 	uint32_t contains_mesh;
@@ -539,21 +539,21 @@ struct ChunkCounts
 
 static constexpr int SCAN_CTA = 1024;
 
-__global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __restrict__ seg_tot, const uint32_t* __restrict__ flags, int nseg, int lS,
-                                                             uint32_t* __restrict__ seg_base, ChunkCounts* __restrict__ chunks, int n_chunks,
-                                                             unsigned long long* __restrict__ totals /* cells, verts, inds, overflow */)
+__global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __restrict__ chunk_tot, const uint32_t* __restrict__ flags, int n_chunks,
+                                                           ChunkCounts* __restrict__ chunks, unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
 {
 	__shared__ uint32_t s_w[3][SCAN_CTA / 32];
 	__shared__ uint32_t s_tot[3];
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	unsigned long long carry0 = 0, carry1 = 0, carry2 = 0;
-	for (int base = 0; base < nseg; base += SCAN_CTA)
+	for (int base = 0; base < n_chunks; base += SCAN_CTA)
 	{
 		const int i = base + t;
-		uint32_t a = 0, b = 0, c = 0;
-		if (i < nseg && flags_contain_mesh(flags[i >> lS]))
+		uint32_t a = 0, b = 0, c = 0, f = 0;
+		if (i < n_chunks)
 		{
-			a = seg_tot[3 * (size_t)i]; b = seg_tot[3 * (size_t)i + 1]; c = seg_tot[3 * (size_t)i + 2];
+			f = flags_contain_mesh(flags[i]) ? 1u : 0u;
+			if (f) { a = chunk_tot[3 * (size_t)i]; b = chunk_tot[3 * (size_t)i + 1]; c = chunk_tot[3 * (size_t)i + 2]; }
 		}
 		uint32_t ia = a, ib = b, ic = c;
 #pragma unroll
@@ -578,32 +578,24 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __re
 			if (lane == 31) { s_tot[0] = ja; s_tot[1] = jb; s_tot[2] = jc; }
 		}
 		__syncthreads();
-		if (i < nseg)
+		if (i < n_chunks)
 		{
-			seg_base[3 * (size_t)i] = (uint32_t)(carry0 + (ia - a + s_w[0][warp]));
-			seg_base[3 * (size_t)i + 1] = (uint32_t)(carry1 + (ib - b + s_w[1][warp]));
-			seg_base[3 * (size_t)i + 2] = (uint32_t)(carry2 + (ic - c + s_w[2][warp]));
+			ChunkCounts cc;
+			cc.contains_mesh = f;
+			cc.n_cells = a; cc.n_verts = b; cc.n_inds = c;
+			cc.cell_base = carry0 + (ia - a + s_w[0][warp]);
+			cc.vert_base = carry1 + (ib - b + s_w[1][warp]);
+			cc.ind_base = carry2 + (ic - c + s_w[2][warp]);
+			chunks[i] = cc;
 		}
 		carry0 += s_tot[0]; carry1 += s_tot[1]; carry2 += s_tot[2];
 		__syncthreads();
 	}
 	if (t == 0)
 	{
-		seg_base[3 * (size_t)nseg] = (uint32_t)carry0; seg_base[3 * (size_t)nseg + 1] = (uint32_t)carry1; seg_base[3 * (size_t)nseg + 2] = (uint32_t)carry2;
 		const bool overflow = carry0 >= 0xFFFFFFFFull || carry1 >= 0xFFFFFFFFull || carry2 >= 0xFFFFFFFFull;
 		totals[0] = carry0; totals[1] = carry1; totals[2] = carry2; totals[3] = overflow ? 1ull : 0ull;
-		totals[4] = 0; totals[5] = 0; // active-word list counters (k_bases)
-	}
-	__syncthreads(); // seg_base complete (single CTA)
-	for (int ch = t; ch < n_chunks; ch += SCAN_CTA)
-	{
-		ChunkCounts cc;
-		const uint32_t* b0 = seg_base + 3 * ((size_t)ch << lS);
-		const uint32_t* b1 = seg_base + 3 * ((size_t)(ch + 1) << lS);
-		cc.contains_mesh = flags_contain_mesh(flags[ch]) ? 1u : 0u;
-		cc.cell_base = b0[0]; cc.vert_base = b0[1]; cc.ind_base = b0[2];
-		cc.n_cells = b1[0] - b0[0]; cc.n_verts = b1[1] - b0[1]; cc.n_inds = b1[2] - b0[2];
-		chunks[ch] = cc;
+		totals[4] = 0; totals[5] = 0; // surface-cell list counters (k_bases)
 	}
 }
 
@@ -617,16 +609,25 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_segments(const uint32_t* __re
 // so the emitters run one THREAD per surface cell, whatever the orientation of the surface inside the words.
 template <int WPT>
 __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
-                                                const uint32_t* __restrict__ seg_base, const ChunkCounts* __restrict__ chunks,
+                                                const ChunkCounts* __restrict__ chunks,
                                                 uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib, uint2* __restrict__ vcells,
                                                 uint2* __restrict__ icells, unsigned long long* __restrict__ list_count /* [2] */)
 {
 	extern __shared__ uint32_t sb[];
-	__shared__ uint32_t s_base[2];
+	__shared__ uint32_t s_base[2], s_pre[2];
 	const int seg = blockIdx.x;
 	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	const ChunkCounts cc = chunks[chunk];
 	if (!cc.contains_mesh || seg_tot[3 * (size_t)seg] == 0) return;
+	// vertices / indices of the chunk's earlier segments (S <= 256 = CTA terms)
+	if (threadIdx.x < 2) s_pre[threadIdx.x] = 0;
+	__syncthreads();
+	if ((int)threadIdx.x < (seg & (L.S - 1)))
+	{
+		const uint32_t* st = seg_tot + 3 * (((size_t)chunk << L.lS) + threadIdx.x);
+		if (st[1]) atomicAdd(&s_pre[0], st[1]);
+		if (st[2]) atomicAdd(&s_pre[1], st[2]);
+	}
 	stage_planes(sb, bits + (size_t)chunk * L.wc, L, x0, L.P + 1);
 	uint32_t cnt[WPT];
 	{
@@ -661,8 +662,8 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)tot[3]);
 	}
 	__syncthreads();
-	uint32_t rv = seg_base[3 * (size_t)seg + 1] - (uint32_t)cc.vert_base + sc[0];
-	uint32_t ri = seg_base[3 * (size_t)seg + 2] + sc[1];
+	uint32_t rv = s_pre[0] + sc[0];                          // chunk-local vertex id
+	uint32_t ri = (uint32_t)cc.ind_base + s_pre[1] + sc[1];  // batch-wide index position
 	uint32_t ov = s_base[0] + sc[2], oi = s_base[1] + sc[3];
 	const uint32_t gw0 = (uint32_t)((size_t)seg * L.ws + threadIdx.x * WPT);
 	uint32_t ob[WPT], oix[WPT];

@@ -138,6 +138,9 @@ int bmf_batch_chunk_infos(bmf_ctx* ctx, bmf_chunk_info* out /* [n] */);
  * p_data / n_data / c_data + the index buffer), chunk i at [vert_offset, +n_verts) / [ind_offset, +n_inds).
  * Indices are chunk-local like DMCChunk::vi->mesh_indexes.  Any pointer may be NULL. */
 int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices);
+/* same, but only enqueues the copies on the ctx stream (use pinned host buffers); bmf_batch_wait completes them.
+ * Two contexts on one GPU ping-pong this way: the copies of batch i overlap the kernels of batch i+1. */
+int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices);
 
 /* One chunk in the reference's own layouts: DualVertex[n_verts] (84-byte records, Vertices.hpp:5-24),
  * mesh_indexes, BinaryBlock words (dim^3/32), MasksBlock byte image (dim^3, needs keep_masks),
