@@ -72,6 +72,7 @@ struct bmf_ctx
 	unsigned long long totals[3] = { 0, 0, 0 };
 	const float* ext_density = nullptr; // caller-owned device density (density_on_device)
 	bool density_valid = false, masks_valid = false;
+	size_t color_ones = 0; // the first color_ones floats of the colour arena are known to be exactly 1.0f
 
 	DevBuf<ChunkGeom> geom, sheet_geom;
 	DevBuf<int> sheet_of;
@@ -569,6 +570,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	const size_t V = ctx->totals[1], I = ctx->totals[2];
 
 	BMF_CUDA(ctx->pos.reserve(3 * V + 4));
+	if (3 * V + 4 > ctx->color.cap) ctx->color_ones = 0;
 	BMF_CUDA(ctx->color.reserve(3 * V + 4));
 	BMF_CUDA(ctx->normal.reserve(3 * V + 4));
 	BMF_CUDA(ctx->boundary.reserve(V + 16));
@@ -598,7 +600,13 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	{
 		BMF_CUDA(cudaMemsetAsync(ctx->cls.p, 0, sizeof(uint32_t) * V, st));
 		BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
-		BMF_LAUNCH(k_fill_f32, grid_for(3 * V, CTA), CTA, 0, ctx->color.p, 3 * V, 1.0f); // calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681)
+		if (ctx->color_ones < 3 * V)
+		{
+			// calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681).  The batch path never writes another colour
+			// (see run_smooth), so the arena is filled once to its capacity and reused.
+			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
+			ctx->color_ones = ctx->color.cap;
+		}
 	}
 	if (I)
 	{
@@ -834,6 +842,7 @@ int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal
 		if (indices[i] >= (uint32_t)n_verts) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: index out of range");
 	BMF_CUDA(cudaSetDevice(ctx->device));
 	ctx->have_batch = false; // the arenas are reused
+	ctx->color_ones = 0;
 	const size_t V = n_verts, I = (size_t)(n_inds / prim_n) * prim_n;
 	cudaStream_t st = ctx->stream;
 	BMF_CUDA(ctx->pos.reserve(3 * V + 4));

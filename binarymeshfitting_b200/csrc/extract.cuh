@@ -234,7 +234,12 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const Chun
 	uint32_t mine;
 	const float nxt = __shfl_down_sync(0xffffffffu, ndy, 1);
 	const bool monotone = __all_sync(0xffffffffu, lane == 31 || ndy >= nxt); // false if any NaN
-	if (monotone)
+	const float top = __shfl_sync(0xffffffffu, ndy, 0), bot = __shfl_sync(0xffffffffu, ndy, 31); // largest / smallest -dy of the tile
+	if (monotone && __all_sync(0xffffffffu, top < t))
+		mine = 0xFFFFFFFFu; // the whole tile is above the surface: every row word is all air
+	else if (monotone && __all_sync(0xffffffffu, !(bot < t)))
+		mine = 0u; // the whole tile is below the surface (NaN columns are never air)
+	else if (monotone)
 	{
 		// number of rows y (from the bottom of the tile) whose bit is still 0 in this lane's column
 		int cnt = 0;

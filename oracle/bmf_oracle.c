@@ -698,6 +698,59 @@ float orc_qef_solve(const float* positions, const float* normals, int count, flo
 	return err;
 }
 
+/* Build-defined QEF placement (bmf_params.qef, config 5; UNPINNED: the reference never calls its solver,
+ * MeshProcessor.cpp:239).  Restated here only so the GPU policy has a CPU twin: after smoothing, every processed
+ * vertex with >= 2 adjacent triangles is moved to the QEF minimiser of the planes (centroid, face normal) of its
+ * first <= 12 adjacent triangles (ascending triangle id), clamped to the bounding box of those centroids. */
+void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int pb)
+{
+	const int np = n_inds / 3;
+	if (n_verts == 0 || np == 0) return;
+	uint32_t* off = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_verts);
+	uint8_t* cnt = (uint8_t*)calloc((size_t)n_verts, 1);
+	uint32_t a = 0;
+	for (int i = 0; i < n_verts; i++) { off[i] = a; a += valence[i]; }
+	uint32_t* adj = (uint32_t*)malloc(sizeof(uint32_t) * (a ? a : 1));
+	for (int t = 0; t < np; t++)
+		for (int k = 0; k < 3; k++) { uint32_t v = inds[3 * (size_t)t + k]; adj[off[v] + cnt[v]++] = (uint32_t)t; }
+	float* dp = (float*)malloc(sizeof(float) * 3 * (size_t)np);
+	float* dn = (float*)malloc(sizeof(float) * 3 * (size_t)np);
+	for (int t = 0; t < np; t++)
+	{
+		const float *p0 = pos + 3 * (size_t)inds[3 * (size_t)t], *p1 = pos + 3 * (size_t)inds[3 * (size_t)t + 1], *p2 = pos + 3 * (size_t)inds[3 * (size_t)t + 2];
+		for (int c = 0; c < 3; c++) dp[3 * (size_t)t + c] = (((0.0f + p0[c]) + p1[c]) + p2[c]) / 3.0f;
+		float u[3] = { p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2] }, w[3] = { p0[0] - p2[0], p0[1] - p2[1], p0[2] - p2[2] }, cr[3];
+		v3_normalize(u); v3_normalize(w);
+		v3_cross(u, w, cr);
+		dn[3 * (size_t)t] = -cr[0]; dn[3 * (size_t)t + 1] = -cr[1]; dn[3 * (size_t)t + 2] = -cr[2];
+	}
+	float* out = (float*)malloc(sizeof(float) * 3 * (size_t)n_verts);
+	memcpy(out, pos, sizeof(float) * 3 * (size_t)n_verts);
+	for (int v = 0; v < n_verts; v++)
+	{
+		int c = valence[v];
+		if (c < 2 || (!pb && boundary[v])) continue;
+		if (c > 12) c = 12;
+		float P[36], Nn[36], lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f }, x[3];
+		for (int k = 0; k < c; k++)
+		{
+			uint32_t t = adj[off[v] + k];
+			for (int q = 0; q < 3; q++)
+			{
+				P[3 * k + q] = dp[3 * (size_t)t + q];
+				Nn[3 * k + q] = dn[3 * (size_t)t + q];
+				lo[q] = fminf(lo[q], P[3 * k + q]);
+				hi[q] = fmaxf(hi[q], P[3 * k + q]);
+			}
+		}
+		orc_qef_solve(P, Nn, c, x);
+		if (isnan(x[0]) || isnan(x[1]) || isnan(x[2])) continue;
+		for (int q = 0; q < 3; q++) out[3 * (size_t)v + q] = fminf(fmaxf(x[q], lo[q]), hi[q]);
+	}
+	memcpy(pos, out, sizeof(float) * 3 * (size_t)n_verts);
+	free(off); free(cnt); free(adj); free(dp); free(dn); free(out);
+}
+
 /* ---- whole chunk / batch --------------------------------------------------------------------------- */
 
 int orc_chunk(const orc_sampler* s, const float pos[3], float size, int dim, float overlap, int iters, int pb, int smooth,

@@ -85,6 +85,9 @@ void orc_smooth(float* pos, float* color, float* normal, const uint8_t* boundary
 /* qef_solve_from_points_3d (qef_simd.h:550-579), exact 1/sqrt in givens_coeffs_sym */
 float orc_qef_solve(const float* positions, const float* normals, int count, float solved[3]);
 
+/* build-defined QEF placement after smoothing (UNPINNED policy; N = 3) */
+void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int process_boundary);
+
 /* whole chunk: geometry -> sample -> bits -> masks -> extract -> smooth; returns contains_mesh.
  * density_io: if kind == ORC_HOST_DENSITY it is the input, else (if non-null) receives the samples. */
 int orc_chunk(const orc_sampler* s, const float pos[3], float size, int dim, float overlap, int iters, int process_boundary,

@@ -68,6 +68,7 @@ class Oracle:
         lib.orc_smooth.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p] + [C.c_int] * 5
         lib.orc_qef_solve.restype = C.c_float
         lib.orc_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.orc_qef_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
         lib.orc_batch.restype = C.c_int64
         lib.orc_batch.argtypes = [C.POINTER(Sampler), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 
@@ -149,7 +150,7 @@ class Oracle:
         err = self.lib.orc_qef_solve(_p(p), _p(n), len(p), _p(out))
         return out[:3].copy(), float(err)
 
-    def chunk(self, sampler, pos, size, dim, overlap=0.0, iters=0, process_boundary=False, smooth_normals=False, host_density=None):
+    def chunk(self, sampler, pos, size, dim, overlap=0.0, iters=0, process_boundary=False, smooth_normals=False, host_density=None, qef=False):
         """Full pipeline for one chunk through the stage functions (python-level composition)."""
         op, delta = self.geometry(pos, size, dim, overlap)
         if sampler.kind == HOST_DENSITY:
@@ -170,6 +171,10 @@ class Oracle:
         if iters > 0 and nv and out["n_inds"]:
             out["pos"], out["color"], out["normal"] = self.smooth(out["pos"], out["color"], out["normal"], out["boundary"], out["valence"],
                                                                   out["inds"], 3, iters, process_boundary, smooth_normals)
+            if qef:
+                p = np.ascontiguousarray(out["pos"], np.float32)
+                self.lib.orc_qef_place(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary))
+                out["pos"] = p
         return out
 
     def batch(self, sampler, pos_size, dim, overlaps=None, iters=0, process_boundary=False, threads=0):

@@ -243,3 +243,29 @@ def test_errors_are_reported(gpu):
     gpu.set_sampler(ob.HOST_DENSITY)
     with pytest.raises(capi.BmfError):
         gpu.submit(descs, 32)  # HOST_DENSITY without a density block
+
+
+@pytest.mark.parametrize("op,ka,kb", [(ob.CSG_UNION, ob.SPHERE, ob.TORUS_Z), (ob.CSG_SUBTRACT, ob.SPHERE, ob.CUBOID), (ob.CSG_INTERSECT, ob.CUBOID, ob.SPHERE)])
+def test_csg_with_smooth_normals_and_qef(gpu, oracle, op, ka, kb):
+    """config 5: 128^3 CSG of two reference primitives, smoothed normals + colour blend + QEF vertex placement, triangles.
+    CSG combinators and the QEF placement policy are build-defined (no reference producer): parity is against the oracle's twin."""
+    kw = dict(csg_op=op, csg_kind_a=ka, csg_kind_b=kb, csg_world_size_a=256.0, csg_world_size_b=300.0, csg_offset_a=(0.0, 0.0, 0.0), csg_offset_b=(20.0, -10.0, 5.0))
+    pos, size, dim, overlap = (-128.0, -128.0, -128.0), 256.0, 128, 0.055
+    gpu.set_sampler(ob.CSG, **kw)
+    descs = capi.make_chunk_descs([[pos[0], pos[1], pos[2], size]], overlaps=overlap)
+    gpu.submit(descs, dim, iters=4, smooth_normals=True, qef=True, keep_density=True, keep_masks=True)
+    gpu.wait()
+    g = gpu.copy_chunk(0, want=("verts", "inds", "bits", "masks", "density"))
+    o = oracle.chunk(oracle.sampler(ob.CSG, **kw), pos, size, dim, overlap, iters=4, smooth_normals=True, qef=True)
+    np.testing.assert_array_equal(g["density"].view(np.uint32), o["density"].view(np.uint32))
+    assert_same_topology(g, o)
+    assert o["n_verts"] > 10000
+    d = np.abs(g["verts"]["p"] - o["pos"])
+    assert d.max() <= 1e-4 * (dim - 1), "QEF-placed positions differ by %g grid units" % d.max()  # bar: 1e-4 of chunk extent
+    moved = np.abs(o["pos"] - oracle.chunk(oracle.sampler(ob.CSG, **kw), pos, size, dim, overlap, iters=4, smooth_normals=True)["pos"]).max()
+    assert moved > 1e-3  # the QEF step really moves vertices
+    gn, on = g["verts"]["n"], o["normal"]
+    m = ~np.isnan(on)
+    np.testing.assert_array_equal(np.isnan(gn), np.isnan(on))
+    assert np.abs(gn[m] - on[m]).max() <= 1e-5
+    np.testing.assert_array_equal(g["verts"]["color"].view(np.uint32), o["color"].view(np.uint32))
