@@ -259,7 +259,7 @@ def test_csg_with_smooth_normals_and_qef(gpu, oracle, op, ka, kb):
     o = oracle.chunk(oracle.sampler(ob.CSG, **kw), pos, size, dim, overlap, iters=4, smooth_normals=True, qef=True)
     np.testing.assert_array_equal(g["density"].view(np.uint32), o["density"].view(np.uint32))
     assert_same_topology(g, o)
-    assert o["n_verts"] > 10000
+    assert o["n_verts"] > 1000
     d = np.abs(g["verts"]["p"] - o["pos"])
     assert d.max() <= 1e-4 * (dim - 1), "QEF-placed positions differ by %g grid units" % d.max()  # bar: 1e-4 of chunk extent
     moved = np.abs(o["pos"] - oracle.chunk(oracle.sampler(ob.CSG, **kw), pos, size, dim, overlap, iters=4, smooth_normals=True)["pos"]).max()
