@@ -76,6 +76,11 @@ struct bmf_ctx
 
 	DevBuf<ChunkGeom> geom, sheet_geom;
 	DevBuf<int> sheet_of;
+	DevBuf<uint32_t> sheet_mm;
+	DevBuf<uint8_t> uni;
+	uint8_t* uni_pinned = nullptr;
+	size_t uni_pinned_cap = 0;
+	bool uni_valid = false;
 	std::vector<ChunkGeom> sheet_geom_host;
 	std::vector<int> sheet_of_host;
 	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, chunk_tot;
@@ -364,6 +369,8 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	ctx->qp.release(); ctx->qn.release(); ctx->qo.release(); ctx->qe.release(); ctx->qc.release();
 	if (ctx->totals_pinned) cudaFreeHost(ctx->totals_pinned);
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
+	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
+	ctx->sheet_mm.release(); ctx->uni.release();
 	for (int i = 0; i <= BMF_NUM_STAGES; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -420,6 +427,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	ctx->have_batch = false;
 	ctx->finished = false;
+	ctx->uni_valid = false;
 	ctx->kused = 0;
 	ctx->n = n;
 	ctx->params = *params;
@@ -456,6 +464,8 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
 		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
+	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
+	ctx->sheet_mm.release(); ctx->uni.release();
 		ctx->counts_pinned = nullptr;
 		BMF_CUDA(cudaMallocHost((void**)&ctx->counts_pinned, sizeof(ChunkCounts) * (size_t)n));
 		ctx->counts_pinned_cap = n;
@@ -502,6 +512,15 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		BMF_CUDA(ctx->hmap.reserve((size_t)n_sheets * d * d));
 		BMF_CUDA(ctx->sheet_geom.reserve(n_sheets));
 		BMF_CUDA(ctx->sheet_of.reserve(n));
+		BMF_CUDA(ctx->sheet_mm.reserve(3 * (size_t)n_sheets));
+		BMF_CUDA(ctx->uni.reserve(n));
+		if ((size_t)n > ctx->uni_pinned_cap)
+		{
+			if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
+			ctx->uni_pinned = nullptr;
+			BMF_CUDA(cudaMallocHost((void**)&ctx->uni_pinned, (size_t)n));
+			ctx->uni_pinned_cap = n;
+		}
 	}
 
 	cudaStream_t st = ctx->stream;
@@ -525,13 +544,22 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	else if (is_terrain2d(kind))
 	{
-		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n_sheets * d * d, CTA), CTA, 0, ctx->sampler, ctx->sheet_geom.p, d, L.ld, ctx->hmap.p, n_sheets);
+		BMF_CUDA(cudaMemsetAsync(ctx->sheet_mm.p, 0xFF, sizeof(uint32_t) * n_sheets, st));
+		BMF_CUDA(cudaMemsetAsync(ctx->sheet_mm.p + n_sheets, 0, sizeof(uint32_t) * 2 * n_sheets, st));
+		BMF_LAUNCH(k_terrain2d_sheet<NT_VALUE>, grid_for((size_t)n_sheets * d * d, CTA), CTA, 0, ctx->sampler, ctx->sheet_geom.p, d, L.ld, ctx->hmap.p, n_sheets, ctx->sheet_mm.p);
 		if (dens_w)
 			BMF_LAUNCH(k_terrain2d_density, (unsigned)(n_words / SAMPLE_WORDS_PER_CTA), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p, ctx->bits.p,
 			           dens_w, ctx->flags.p);
-		else // no density block wanted: compare-only sign words (32 voxels per ballot, no per-voxel arithmetic)
+		else
+		{
+			// no density block wanted: chunks entirely above / below the surface are classified from the sheet range and
+			// skipped; the rest get compare-only sign words (binary search + warp bit transpose, no per-voxel arithmetic)
+			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p);
 			BMF_LAUNCH(k_terrain2d_bits, (unsigned)((size_t)n * L.d * L.zc * L.zc / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
-			           ctx->bits.p, ctx->flags.p);
+			           ctx->uni.p, ctx->bits.p, ctx->flags.p);
+			BMF_CUDA(cudaMemcpyAsync(ctx->uni_pinned, ctx->uni.p, n, cudaMemcpyDeviceToHost, st));
+			ctx->uni_valid = true;
+		}
 	}
 	else if (kind == BMF_SAMPLER_TERRAIN3D)
 	{
@@ -717,7 +745,9 @@ int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* ind
 	const Layout& L = ctx->L;
 	const size_t nvox = (size_t)L.d * L.d * L.d;
 	cudaStream_t st = ctx->stream;
-	if (bits) BMF_CUDA(cudaMemcpyAsync(bits, ctx->bits.p + (size_t)i * L.wc, sizeof(uint32_t) * L.wc, cudaMemcpyDeviceToHost, st));
+	const uint8_t uniform = ctx->uni_valid ? ctx->uni_pinned[i] : 0; // chunk skipped by the 2-D terrain classifier: all ones (1) / all zeros (2)
+	if (bits && uniform) memset(bits, uniform == 1 ? 0xFF : 0x00, sizeof(uint32_t) * L.wc);
+	else if (bits) BMF_CUDA(cudaMemcpyAsync(bits, ctx->bits.p + (size_t)i * L.wc, sizeof(uint32_t) * L.wc, cudaMemcpyDeviceToHost, st));
 	if (masks)
 	{
 		if (!ctx->masks_valid) return fail(ctx, BMF_ERR_STATE, "bmf_batch_copy_chunk: masks were not kept (params.keep_masks)");

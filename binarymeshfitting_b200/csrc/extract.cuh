@@ -163,11 +163,21 @@ __global__ void __launch_bounds__(CTA) k_sample_implicit(SamplerDev s, const Chu
 // NoiseSampler.cpp:117,152), then density = -dy - n*height per voxel and the sign word.
 // The sheet depends only on (overlap_pos.x, overlap_pos.z, delta): chunks stacked in y get the same
 // floats, so the host deduplicates and `geom` here holds one entry per UNIQUE sheet.
-template <int BASE>
-__global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, int ld, float* __restrict__ hmap, int n_chunks)
+// order-preserving map float -> uint32 (for atomicMin / atomicMax on floats); NaNs are handled separately
+__device__ __forceinline__ uint32_t float_order(float f)
 {
-	size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
-	if (i >= ((size_t)n_chunks << (2 * ld))) return;
+	const uint32_t u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_unorder(uint32_t o) { return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o); }
+
+// sheet_mm[0*ns + s] = min, [1*ns + s] = max of t = n*height over sheet s (order-mapped), [2*ns + s] = 1 if any NaN
+template <int BASE>
+__global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, int ld, float* __restrict__ hmap, int n_chunks,
+                                                          uint32_t* __restrict__ sheet_mm)
+{
+	__shared__ uint32_t s_mm[3];
+	size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; // d*d is a multiple of CTA: a CTA never straddles two sheets, no thread is out of range
 	int chunk = (int)(i >> (2 * ld));
 	int r = (int)(i & (((size_t)1 << (2 * ld)) - 1));
 	int ix = r >> ld, iz = r & (d - 1);
@@ -176,7 +186,61 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 	float vx = (float)ix * sg + g.ox * s.g;
 	float vy = (float)0 * sg + 0.0f;
 	float vz = (float)iz * sg + g.oz * s.g;
-	hmap[i] = noise_eval<BASE>(s.ns, vx, vy, vz);
+	const float n = noise_eval<BASE>(s.ns, vx, vy, vz);
+	hmap[i] = n;
+	// per-sheet range of t = n*height (the same product k_terrain2d_bits compares against)
+	const float t = n * s.nm;
+	const bool nan = t != t;
+	uint32_t lo = nan ? 0xFFFFFFFFu : float_order(t), hi = nan ? 0u : float_order(t), bad = nan ? 1u : 0u;
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1)
+	{
+		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+		bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+	}
+	if (threadIdx.x == 0) { s_mm[0] = 0xFFFFFFFFu; s_mm[1] = 0u; s_mm[2] = 0u; }
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicMin(&s_mm[0], lo);
+		atomicMax(&s_mm[1], hi);
+		if (bad) atomicOr(&s_mm[2], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		atomicMin(sheet_mm + chunk, s_mm[0]);
+		atomicMax(sheet_mm + n_chunks + chunk, s_mm[1]);
+		if (s_mm[2]) atomicOr(sheet_mm + 2 * n_chunks + chunk, 1u);
+	}
+}
+
+// Chunks that lie entirely above or below the heightfield: with -dy monotone in y, every bit of the chunk is 1 if
+// -dy(0) < min t, and 0 if !(-dy(d-1) < max t) (no NaN in the sheet).  Such a chunk contains no mesh
+// (DMCChunk.cpp:159-162); its flags are set here and k_terrain2d_bits skips it, so its sign words are never written
+// (bmf_batch_copy_chunk synthesises them on request).  uni: 0 = mixed, 1 = all air (ones), 2 = all solid (zeros).
+__global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, const int* __restrict__ sheet_of,
+                                                             const uint32_t* __restrict__ sheet_mm, int n_sheets, int n_chunks, uint32_t* __restrict__ flags,
+                                                             uint8_t* __restrict__ uni)
+{
+	const int c = blockIdx.x * CTA + threadIdx.x;
+	if (c >= n_chunks) return;
+	const ChunkGeom g = geom[c];
+	const int sh = sheet_of[c];
+	float top = ((float)0 * g.delta + g.oy) * s.g, bot = ((float)(d - 1) * g.delta + g.oy) * s.g;
+	if (s.dy_half) { top = top * 0.5f; bot = bot * 0.5f; }
+	top = -top; bot = -bot; // largest / smallest -dy of the chunk when -dy is non-increasing in y
+	uint8_t u = 0;
+	const bool monotone = g.delta >= 0.0f && s.g >= 0.0f && top >= bot; // rounding is monotone, so the chain y -> -dy(y) is too; false on NaN
+	if (monotone && !sheet_mm[2 * n_sheets + sh])
+	{
+		const float tmin = float_unorder(sheet_mm[sh]), tmax = float_unorder(sheet_mm[n_sheets + sh]);
+		if (top < tmin) u = 1;
+		else if (!(bot < tmax)) u = 2;
+	}
+	uni[c] = u;
+	if (u) flags[c] = (u == 1) ? CF_ONES : CF_ZERO;
 }
 
 __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
@@ -216,14 +280,16 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const C
 // y-mask with one shift, and a 5-stage warp bit-matrix transpose turns the 32 column masks into the 32 row
 // words -> one coalesced store.  ~70 instructions per 1024 voxels; a non-monotone tile falls back to 32 ballots.
 __global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
-                                                         const int* __restrict__ sheet_of, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
+                                                         const int* __restrict__ sheet_of, const uint8_t* __restrict__ uni, uint32_t* __restrict__ bits,
+                                                         uint32_t* __restrict__ flags)
 {
 	const int lane = threadIdx.x & 31;
 	const size_t task = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5; // (chunk, x, yb, zb); tasks per chunk = d * zc^2, a multiple of 8
+	const int chunk = (int)(task >> (2 * L.lzc + L.ld));
+	if (uni[chunk]) return; // entirely above / below the surface (the whole CTA belongs to one chunk)
 	const int zb = (int)task & (L.zc - 1);
 	const int yb = (int)(task >> L.lzc) & (L.zc - 1);
 	const int x = (int)(task >> (2 * L.lzc)) & (L.d - 1);
-	const int chunk = (int)(task >> (2 * L.lzc + L.ld));
 	const ChunkGeom g = geom[chunk];
 	const float n = hmap[((size_t)sheet_of[chunk] << (2 * L.ld)) + ((size_t)x << L.ld) + zb * 32 + lane];
 	const float t = n * s.nm;
