@@ -141,6 +141,15 @@ def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
     return None
 
 
+def load_kernel_profile(workload):
+    p = os.path.join(ROOT, "profiles", "r1_kernel_profile.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d["kernels"] if d.get("workload") == workload else None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -214,7 +223,6 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - t0
     dev_s = e0.elapsed_time(e1) * 1e-3
-    clk = clocks.stop()
     launches = ctx.launch_count() - launches0
     t_max = max_over_ranks(dev_s)
     total_vox = sum_over_ranks(float(nvox)) * K
@@ -254,6 +262,7 @@ def run_ours(args):
     e2e_run(K)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()  # sampled across both timed regions (device-timed steps and the end-to-end steps)
     e2e_val = total_vox / e2e_s
     out = bufs[(K - 1) & 1]
     h2d = int(descs.nbytes + 16 * n_chunks)          # descriptors (host ABI) + the geometry records the library uploads
@@ -282,18 +291,41 @@ def run_ours(args):
     dominant = max(per_kernel, key=per_kernel.get)
     peaks = load_peaks()
     n_launch_dom = len(agg[dominant]) / reps
-    roof = kernel_roofline(dominant, per_kernel[dominant] / n_launch_dom, nvox, V, I, n_chunks, dim, peaks)
+    launch_ms = per_kernel[dominant] / n_launch_dom
+    roof = kernel_roofline(dominant, launch_ms, nvox, V, I, n_chunks, dim, peaks)
     if roof is None:
-        roof = {"kernel": dominant, "bound": "issue", "achieved": None, "peak": None, "unit": "Tinst/s", "frac": None, "traffic": None,
-                "note": "dominant kernel is FP32/INT issue bound (noise); see DESIGN.md and profiles/ for the ncu pipe utilisation"}
+        roof = {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
+                "peak_source": peaks["source"], "note": "no HBM model for this kernel (FP32/INT issue bound): see the `issue` view"}
     roof["share_of_step"] = round(per_kernel[dominant] / ktot, 4)
-    roof["launch_ms"] = round(per_kernel[dominant] / n_launch_dom, 4)
-    # the HBM-bound kernels of the step, each against the measured copy peak
+    roof["launch_ms"] = round(launch_ms, 4)
+    # The kernels of this path are integer / FP32 ISSUE bound, not HBM bound (north_star: "FP32/INT pipe utilisation for
+    # the noise ... stages").  Issue view of the dominant kernel: warp instructions per launch (counted by ncu on this very
+    # workload, profiles/r1_kernel_profile.json) / live CUDA-event time, against 4 schedulers x SMs x the SM clock sampled
+    # during the timed region.
+    prof = load_kernel_profile(workload_name(args))
+    base = dominant.split("<")[0]
+    if prof and base in prof and prof[base].get("warp_inst") and clk.get("sm_mhz"):
+        kp = prof[base]
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        peak_inst = sms * 4 * clk["sm_mhz"] * 1e6
+        ach_inst = kp["warp_inst"] / (launch_ms * 1e-3)
+        roof["issue"] = {"bound": "issue", "achieved": round(ach_inst / 1e9, 1), "peak": round(peak_inst / 1e9, 1), "unit": "Gwarp-inst/s",
+                         "frac": round(ach_inst / peak_inst, 4), "warp_inst_per_launch": int(kp["warp_inst"]),
+                         "ncu_issue_active_pct": kp.get("issue_active_pct"), "ncu_alu_pipe_pct": kp.get("alu_pipe_pct"), "ncu_fma_pipe_pct": kp.get("fma_pipe_pct"),
+                         "source": "profiles/r1_kernel_profile.json (ncu) + live event time + live SM clock"}
+        if kp.get("dram_read_bytes") is not None:
+            roof["traffic"] = int(kp["dram_read_bytes"] + kp["dram_write_bytes"])  # dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu)
+    # the HBM view of every kernel of the step that has a byte model, each against the measured copy peak
     hbm_lines = {}
     for name, ms in per_kernel.items():
         r = kernel_roofline(name, ms / (len(agg[name]) / reps), nvox, V, I, n_chunks, dim, peaks)
         if r:
             hbm_lines[name] = {"ms": round(ms, 4), "GB/s": r["achieved"], "frac": r["frac"]}
+    # whole step against SURVEY 8(d)'s fused sample->mesh figure: N/8 (sign words) + N (cell masks) + 14 V + 4 I bytes
+    step_bytes = nvox / 8 + nvox + 14.0 * V + 4.0 * I
+    step_roof = {"algorithmic_bytes": int(step_bytes), "achieved": round(step_bytes / (t_max / K) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": round(step_bytes / (t_max / K) / 1e9 / peaks["hbm_gbs"], 4),
+                 "note": "SURVEY 8(d) fused figure (counts N bytes of cell masks the device path never writes)"}
 
     result = {
         "metric": "voxels/sec sampled+meshed", "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
@@ -309,6 +341,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roof,
+        "step_roofline": step_roof,
         "kernels_ms": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
         "hbm_kernels": hbm_lines,
         "stage_ms": {k: round(v, 4) for k, v in stage.items()},

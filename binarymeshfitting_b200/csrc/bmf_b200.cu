@@ -83,7 +83,8 @@ struct bmf_ctx
 	bool uni_valid = false;
 	std::vector<ChunkGeom> sheet_geom_host;
 	std::vector<int> sheet_of_host;
-	DevBuf<uint32_t> flags, bits, wcnt, wvb, wib, seg_tot, chunk_tot;
+	DevBuf<uint32_t> flags, bits, wcnt, wib, seg_tot, chunk_tot;
+	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	int sm_count = 148;
 	DevBuf<float> density, hmap;
@@ -361,7 +362,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wvb.release(); ctx->wib.release();
+	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wv4.release(); ctx->wib.release();
 	ctx->seg_tot.release(); ctx->chunk_tot.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cls.release(); ctx->cursor.release();
@@ -455,7 +456,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
 	BMF_CUDA(ctx->wcnt.reserve(n_words));
-	BMF_CUDA(ctx->wvb.reserve(n_words));
+	BMF_CUDA(ctx->wv4.reserve(n_words));
 	BMF_CUDA(ctx->wib.reserve(n_words));
 	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
 	BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
@@ -616,13 +617,13 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->vcells.reserve(ctx->totals[0] + 1));
 	BMF_CUDA(ctx->icells.reserve(ctx->totals[0] + 1));
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count);
 	else
-		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wvb.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count);
 	if (V)
-		BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wvb.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p);
+		BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 	if (V)
 	{
@@ -638,7 +639,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	if (I)
 	{
-		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, ctx->bits.p, L, ctx->wvb.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p);
+		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p);
 	}
 	if (V) BMF_LAUNCH(k_cls_to_valence, grid_for(V, CTA), CTA, 0, ctx->cls.p, V, ctx->valence.p);
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));

@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 
 // ---- K4a: per-word output bases + compaction of the CELLS that emit anything.  One CTA per segment with
 // active cells (everything else leaves at once); the segment's sign planes are staged like in k_count.
-// wvb[word] = chunk-local id of the word's first vertex, wib[word] = batch-wide position of its first index.
+// wv4[word] = {chunk-local id of the word's first vertex, X/Y/Z edge-owner masks}, wib[word] = batch-wide position of
+// its first index (wv4 is only written -- and only ever read -- for words with active cells).
 // Every cell that owns iso-vertices and every cell that polygonizes is appended to a compact list (a range per
 // CTA reserved with one atomic; list order does not matter, each record carries its own output position):
 //   vertex cell : {word, bit | edge flags << 5 | rank of its first vertex inside the word << 8}
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 template <int WPT>
 __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
                                                 const ChunkCounts* __restrict__ chunks,
-                                                uint32_t* __restrict__ wvb, uint32_t* __restrict__ wib, uint2* __restrict__ vcells,
+                                                uint4* __restrict__ wv4, uint32_t* __restrict__ wib, uint2* __restrict__ vcells,
                                                 uint2* __restrict__ icells, unsigned long long* __restrict__ list_count /* [2] */)
 {
 	extern __shared__ uint32_t sb[];
@@ -737,18 +738,20 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 	uint32_t ri = (uint32_t)cc.ind_base + s_pre[1] + sc[1];  // batch-wide index position
 	uint32_t ov = s_base[0] + sc[2], oi = s_base[1] + sc[3];
 	const uint32_t gw0 = (uint32_t)((size_t)seg * L.ws + threadIdx.x * WPT);
-	uint32_t ob[WPT], oix[WPT];
+	uint32_t oix[WPT];
 #pragma unroll
 	for (int k = 0; k < WPT; k++)
 	{
-		ob[k] = rv; oix[k] = ri;
-		if (cnt[k] == 0) continue;
-		rv += (cnt[k] >> 8) & 0xFF;
-		ri += cnt[k] >> 16;
+		oix[k] = ri;
+		if (cnt[k] == 0) continue; // nothing references a word without active cells
 		const int lw = threadIdx.x * WPT + k;
 		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		// vertex record of the word: first vertex id + the three edge-owner masks (everything a vertex id needs)
+		wv4[gw0 + k] = make_uint4(rv, c.ex, c.ey, c.ez);
+		rv += (cnt[k] >> 8) & 0xFF;
+		ri += cnt[k] >> 16;
 		uint32_t m = c.ex | c.ey | c.ez, rank = 0;
 		while (m)
 		{
@@ -769,19 +772,15 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 			ofs += (uint32_t)(c_tri_pack[m8] >> 60);
 		}
 	}
-	uint32_t* o1 = wvb + gw0;
 	uint32_t* o2 = wib + gw0;
 #pragma unroll
 	for (int k = 0; k < WPT; k += 4)
-	{
-		*reinterpret_cast<uint4*>(o1 + k) = make_uint4(ob[k], ob[k + 1], ob[k + 2], ob[k + 3]);
 		*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oix[k], oix[k + 1], oix[k + 2], oix[k + 3]);
-	}
 }
 
 // ---- K4b: vertex emission, one THREAD per cell that owns iso-vertices.
 // calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674): X, Y, Z edge of a cell in that order.
-__global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint32_t* __restrict__ wvb, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
+__global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint4* __restrict__ wv4, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
                                                  const ChunkGeom* __restrict__ geom, const uint2* __restrict__ vcells,
                                                  const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary)
 {
@@ -798,7 +797,7 @@ __global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint32_t* __rest
 		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
 		const int z = zb * 32 + bit;
 		const ChunkGeom g = geom[chunk];
-		size_t v = (size_t)chunks[chunk].vert_base + wvb[gw] + rank;
+		size_t v = (size_t)chunks[chunk].vert_base + wv4[gw].x + rank;
 		const float s0 = density_at(s, src, g, d, chunk, x, y, z);
 		const bool b0 = x == 0 || y == 0 || z == 0 || x == d - 1 || y == d - 1 || z == d - 1;
 #pragma unroll
@@ -818,27 +817,22 @@ __global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint32_t* __rest
 	}
 }
 
-// chunk-local id of the vertex on `axis` of cell (x,y,z): base of its word + popcounts of the edge-owner words below it
-__device__ __forceinline__ uint32_t vertex_id_global(const uint32_t* __restrict__ cb, const uint32_t* __restrict__ vb, const Layout& L, int x, int y, int z, int axis)
+// chunk-local id of the vertex on `axis` of cell (x,y,z): one 16-byte record of its word + popcounts below the cell
+__device__ __forceinline__ uint32_t vertex_id_rec(const uint4* __restrict__ rec4, const Layout& L, int x, int y, int z, int axis)
 {
-	const int zb = z >> 5, bit = z & 31;
-	const int w = (((x << L.ld) + y) << L.lzc) + zb;
-	const uint32_t A = cb[w];
-	const uint32_t A1 = __funnelshift_r(A, (zb + 1 < L.zc) ? cb[w + 1] : 0u, 1);
-	const uint32_t ex = (x + 1 < L.d) ? (A ^ cb[w + L.wp]) : 0u;
-	const uint32_t ey = (y + 1 < L.d) ? (A ^ cb[w + L.zc]) : 0u;
-	const uint32_t ez = (A ^ A1) & ((zb == L.zc - 1) ? 0x7FFFFFFFu : 0xFFFFFFFFu);
+	const int bit = z & 31;
+	const uint4 r = rec4[(((x << L.ld) + y) << L.lzc) + (z >> 5)];
 	const uint32_t lt = (1u << bit) - 1u;
-	uint32_t id = vb[w] + __popc(ex & lt) + __popc(ey & lt) + __popc(ez & lt);
-	if (axis >= 1) id += (ex >> bit) & 1u;
-	if (axis >= 2) id += (ey >> bit) & 1u;
+	uint32_t id = r.x + __popc(r.y & lt) + __popc(r.z & lt) + __popc(r.w & lt);
+	if (axis >= 1) id += (r.y >> bit) & 1u;
+	if (axis >= 2) id += (r.z >> bit) & 1u;
 	return id;
 }
 
 // ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + per-class use counts, one THREAD per
 // polygonizing cell.  The cell's corner mask travels in its record; the ids of the edge vertices the triangle table
-// names (EDGE_V, DMCChunk.cpp:32, 543-565) are recomputed from the neighbouring sign words and per-word vertex bases.
-__global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wvb, const uint32_t* __restrict__ wib,
+// names (EDGE_V, DMCChunk.cpp:32, 543-565) come from the 16-byte vertex records of the neighbouring words.
+__global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict__ wv4, const uint32_t* __restrict__ wib,
                                                 const ChunkCounts* __restrict__ chunks, const uint2* __restrict__ icells,
                                                 const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint32_t* __restrict__ cls)
 {
@@ -858,8 +852,7 @@ __global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits
 		const int w = (int)(gw & (uint32_t)(L.wc - 1));
 		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
 		const int z = zb * 32 + bit;
-		const uint32_t* cb = bits + (size_t)chunk * L.wc;
-		const uint32_t* vb = wvb + (size_t)chunk * L.wc;
+		const uint4* rec4 = wv4 + (size_t)chunk * L.wc;
 		const uint64_t tp = s_tri[m8];
 		const int n = (int)(tp >> 60);
 		// which of the 12 edges the table uses: compute each id once
@@ -873,7 +866,7 @@ __global__ void __launch_bounds__(CTA) k_inds3(const uint32_t* __restrict__ bits
 			const int dx = axis == 0 ? 0 : hi;
 			const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
 			const int dz = axis == 2 ? 0 : lo;
-			id[e] = ((used >> e) & 1u) ? vertex_id_global(cb, vb, L, x + dx, y + dy, z + dz, axis) : 0u;
+			id[e] = ((used >> e) & 1u) ? vertex_id_rec(rec4, L, x + dx, y + dy, z + dz, axis) : 0u;
 		}
 		const size_t out0 = (size_t)wib[gw] + ofs;
 		const size_t vbase = (size_t)chunks[chunk].vert_base;
