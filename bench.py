@@ -131,8 +131,15 @@ def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
         "k_bases<4>": words * 12, "k_bases<8>": words * 12,
         # 13 B per vertex out (position + boundary flag), two crossing-edge samples in
         "k_verts3": 13.0 * V + 8.0 * V,
-        # 4 B per index out, 1 B valence per vertex
-        "k_inds3": 4.0 * I + V,
+        # 4 B per index out + 4 B per-class use counter per vertex; one 8-byte cell record in per ~3 indices
+        "k_inds3": 4.0 * I + 4.0 * V + 8.0 * I / 9.0,
+        # smoothing, per launch (gathers counted at their algorithmic size, wherever the cache serves them from):
+        # dual: 3 indices + vertex base + 3 positions in, 1 centroid out per triangle
+        "k_dual<N>": (12 + 4 + 36 + 12) * (I / 3.0),
+        # primal: offset + valence + boundary + 12 B out per vertex; 4 B adjacency + 12 B centroid per (vertex, triangle) incidence
+        "k_primal": 18.0 * V + 16.0 * I,
+        # CSR fill: index + class counters + offset in, adjacency entry out per incidence; cell record + vertex base per cell / triangle
+        "k_adj_fill": 16.0 * I + 4.0 * I / 3.0 + 8.0 * I / 9.0,
     }
     if name in algo:
         ach = algo[name] / (ms * 1e-3) / 1e9
