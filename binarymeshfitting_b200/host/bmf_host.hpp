@@ -34,7 +34,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <algorithm>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/bmf_b200.h"
@@ -325,19 +327,27 @@ private:
 class BmfDevice
 {
 public:
-	static BmfDevice& get(int device = 0)
+	// slot 0 = the default context on `device`; further slots are the extra contexts of the multi-GPU generator
+	// (one per GPU, or several on one GPU for testing)
+	static BmfDevice& get(int device = 0) { return slot(0, device); }
+	static BmfDevice& slot(int index, int device)
 	{
-		static BmfDevice d(device);
-		return d;
+		static std::mutex m;
+		static std::vector<BmfDevice*> slots;
+		std::lock_guard<std::mutex> lock(m);
+		if ((int)slots.size() <= index) slots.resize(index + 1, nullptr);
+		if (!slots[index]) slots[index] = new BmfDevice(device); // lives for the process (contexts are cheap to keep)
+		return *slots[index];
 	}
 	bmf_ctx* ctx = nullptr;
+	int device = 0;
 	bool ok() const { return ctx != nullptr; }
 	const char* error() const { return ctx ? bmf_last_error(ctx) : "no CUDA device / libbmf_b200 context (no CPU fallback)"; }
 
 private:
-	explicit BmfDevice(int device)
+	explicit BmfDevice(int dev) : device(dev)
 	{
-		if (bmf_ctx_create(device, &ctx) != BMF_OK) ctx = nullptr;
+		if (bmf_ctx_create(dev, &ctx) != BMF_OK) ctx = nullptr;
 	}
 	~BmfDevice() { bmf_ctx_destroy(ctx); }
 };
@@ -550,10 +560,68 @@ public:
 	std::mutex chunk_mutex;
 	int next_chunk_id = 0;
 	std::vector<DMCChunk*> chunks;
+	std::vector<WorldOctreeNode*> leaves; // split_leaves() result, in the reference's order (LIFO DFS, not Morton order)
+	glm::vec3 focus_point;
+	WorldOctreeNode octree; // root
+
 	~WorldOctree()
 	{
 		for (DMCChunk* c : chunks) delete c;
+		for (WorldOctreeNode* n : owned) delete n;
 	}
+
+	// WorldOctree::init (WorldOctree.cpp:117-127): root cube of twice the world size centred on the origin, code 1
+	void init(uint32_t size)
+	{
+		size *= 2;
+		const float p = 1.0f * (float)size * -0.5f;
+		octree = WorldOctreeNode((float)size, glm::vec3(p, p, p), 0, 1);
+	}
+
+	// WorldOctree::node_needs_split (WorldOctree.cpp:239-249); middle = pos + size*0.5 (WorldOctreeNode.cpp:26)
+	bool node_needs_split(const glm::vec3& center, const WorldOctreeNode* n) const
+	{
+		if (n->level >= properties.max_level) return false;
+		if (n->level < properties.min_level) return true;
+		const float half = n->size * 0.5f;
+		const float mx = n->pos.x + half, my = n->pos.y + half, mz = n->pos.z + half;
+		const float dx = center.x - mx, dy = center.y - my, dz = center.z - mz;
+		const float t0 = dx * dx, t1 = dy * dy, t2 = dz * dz;
+		const float d = std::sqrt(t0 + t1 + t2);
+		return d < n->size * properties.split_multiplier + properties.size_modifier + n->size * 0.5f;
+	}
+
+	// WorldOctree::split_leaves (WorldOctree.cpp:129-173) + split_node (:175-210): static LOD build; children in
+	// MC-corner order (Tables.hpp:7-9), Morton digit x | y<<1 | z<<2, chunk created for every leaf
+	void split_leaves()
+	{
+		static const int MCDX[8] = { 0, 1, 1, 0, 0, 1, 1, 0 }, MCDY[8] = { 0, 0, 0, 0, 1, 1, 1, 1 }, MCDZ[8] = { 0, 0, 1, 1, 0, 0, 1, 1 };
+		leaves.clear();
+		std::vector<WorldOctreeNode*> stack;
+		stack.push_back(&octree);
+		while (!stack.empty())
+		{
+			WorldOctreeNode* n = stack.back();
+			stack.pop_back();
+			if (!node_needs_split(focus_point, n))
+			{
+				leaves.push_back(n);
+				continue;
+			}
+			const float c_size = n->size * 0.5f;
+			for (int i = 0; i < 8; i++)
+			{
+				glm::vec3 c_pos(n->pos.x + (float)MCDX[i] * c_size, n->pos.y + (float)MCDY[i] * c_size, n->pos.z + (float)MCDZ[i] * c_size);
+				const uint64_t code = (n->morton_code << 3) | (uint64_t)(MCDX[i] | (MCDY[i] << 1) | (MCDZ[i] << 2));
+				WorldOctreeNode* c = new WorldOctreeNode(c_size, c_pos, (uint8_t)(n->level + 1), code);
+				owned.push_back(c);
+				stack.push_back(c);
+			}
+		}
+		next_chunk_id = 0;
+		for (WorldOctreeNode* n : leaves) create_chunk(n);
+	}
+
 	void create_chunk(WorldOctreeNode* n)
 	{
 		n->chunk = new DMCChunk();
@@ -562,6 +630,9 @@ public:
 		n->chunk->dim = (uint32_t)properties.chunk_resolution;
 		n->chunk->id = next_chunk_id++;
 	}
+
+private:
+	std::vector<WorldOctreeNode*> owned;
 };
 
 // ---- ChunkGenerator ---------------------------------------------------------------------------------------------
@@ -579,91 +650,120 @@ public:
 
 	void init(WorldOctree* w) { world = w; }
 
-	// ChunkGenerator.cpp:27-60 + extract_chunk :80-147, the whole batch as one device submission
+	// Multi-GPU: chunks are independent, so a batch is dealt to the devices in contiguous
+	// Morton-ordered, equal-count ranges (one context + one host thread per entry; the same GPU may be listed twice),
+	// with no collective: each device fills the chunks of its own range and the host just joins the threads.
+	void set_devices(const std::vector<int>& device_ids) { devices = device_ids; }
+
+	// ChunkGenerator.cpp:27-60 + extract_chunk :80-147, the whole batch as one device submission per GPU
 	bool process_queue(SmartContainer<WorldOctreeNode*>& batch)
 	{
-		BmfDevice& dev = BmfDevice::get();
-		if (!dev.ok() || !world) return false;
+		if (!world) return false;
 		const int count = (int)batch.count;
 		{
 			std::unique_lock<std::mutex> lock(world->chunk_mutex);
 			for (int i = 0; i < count; i++)
 				if (!batch[i]->chunk) world->create_chunk(batch[i]);
 		}
-		const int iters = world->properties.process_iters, max_level = world->properties.max_level;
-		const bool pb = world->properties.boundary_processing;
-		const float base_overlap = world->properties.overlap;
-		std::vector<bmf_chunk_desc> descs;
 		std::vector<int> who;
 		for (int i = 0; i < count; i++)
+			if (batch[i]->generation_stage == GENERATION_STAGES_GENERATING) who.push_back(i);
+		bool ok = true;
+		if (!who.empty())
 		{
-			WorldOctreeNode* n = batch[i];
-			if (n->generation_stage != GENERATION_STAGES_GENERATING) continue;
-			bmf_chunk_desc c;
-			c.pos[0] = n->pos.x; c.pos[1] = n->pos.y; c.pos[2] = n->pos.z; c.size = n->size; c.level = n->level; c.morton = n->morton_code;
-			c.overlap = (n->level == max_level && (!pb || iters == 0)) ? 0.0f : base_overlap + 0.005f * (float)iters; // ChunkGenerator.cpp:98
-			descs.push_back(c);
-			who.push_back(i);
-		}
-		if (!descs.empty())
-		{
-			bmf_sampler_desc d = world->sampler.device;
-			d.world_size = world->sampler.world_size;
-			if (d.kind == BMF_SAMPLER_TERRAIN2D_PERT)
+			if (world->sampler.device.kind == BMF_SAMPLER_HOST_DENSITY) return false; // host callbacks go through DMCChunk::label_grid one chunk at a time
+			const int n_dev = devices.empty() ? 1 : (int)devices.size();
+			if (n_dev == 1)
+				ok = run_range(BmfDevice::slot(0, devices.empty() ? 0 : devices[0]), batch, who);
+			else
 			{
-				const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
-				d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
-			}
-			if (d.kind == BMF_SAMPLER_HOST_DENSITY) return false; // host callbacks go through DMCChunk::label_grid one chunk at a time
-			if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
-			bmf_params p;
-			std::memset(&p, 0, sizeof(p));
-			p.dim = world->properties.chunk_resolution;
-			p.iters = iters;
-			p.process_boundary = pb ? 1 : 0;
-			p.smooth_normals = 0; // SMOOTH_NORMALS 0 (DefaultOptions.h:8)
-			if (bmf_batch_submit(dev.ctx, descs.data(), (int)descs.size(), &p, nullptr) != BMF_OK) return false;
-			int64_t nc = 0, nv = 0, ni = 0;
-			bmf_batch_totals(dev.ctx, &nc, &nv, &ni);
-			std::vector<float> pos(3 * (size_t)nv + 3), col(3 * (size_t)nv + 3), nrm(3 * (size_t)nv + 3);
-			std::vector<uint8_t> bnd((size_t)nv + 1), val((size_t)nv + 1);
-			std::vector<uint32_t> idx((size_t)ni + 1);
-			if (bmf_batch_download(dev.ctx, pos.data(), nrm.data(), col.data(), bnd.data(), val.data(), idx.data()) != BMF_OK) return false;
-			std::vector<bmf_chunk_info> infos(descs.size());
-			bmf_batch_chunk_infos(dev.ctx, infos.data());
-			for (size_t k = 0; k < descs.size(); k++)
-			{
-				WorldOctreeNode* n = batch[who[k]];
-				DMCChunk* c = n->chunk;
-				const bmf_chunk_info& inf = infos[k];
-				c->contains_mesh = inf.contains_mesh != 0;
-				c->overlap_pos = glm::vec3(inf.overlap_pos[0], inf.overlap_pos[1], inf.overlap_pos[2]);
-				c->scale = inf.scale;
-				c->bound_size = c->size * (1.0f + descs[k].overlap * 2.0f) * 0.5f;
-				c->bound_start = c->overlap_pos + c->bound_size;
-				if (!c->contains_mesh) continue;
-				if (!c->vi) { c->vi = vi_allocator.new_element(); c->vi->init(); }
-				const size_t v0 = (size_t)inf.vert_offset, i0 = (size_t)inf.ind_offset;
-				const bool processed = iters > 0 && inf.n_verts > 0 && inf.n_inds > 0;
-				bmf_detail::fill_dual_vertices(c->vi->vertices, &pos[3 * v0], &nrm[3 * v0], &col[3 * v0], &bnd[v0], &val[v0], (size_t)inf.n_verts, true, processed);
-				c->vi->mesh_indexes.count = 0;
-				c->vi->mesh_indexes.push_back(&idx[i0], (size_t)inf.n_inds);
-				// WorldOctreeNode::format -> GLChunk::format_data(vertices, indexes, false, false) (WorldOctreeNode.cpp:72-88)
-				if (!n->gl_chunk) n->gl_chunk = gl_allocator.new_element();
-				GLChunk* g = n->gl_chunk;
-				g->p_data.count = g->n_data.count = g->c_data.count = 0;
-				g->p_data.push_back((const glm::vec3*)&pos[3 * v0], (size_t)inf.n_verts);
-				g->n_data.push_back((const glm::vec3*)&nrm[3 * v0], (size_t)inf.n_verts);
-				g->c_data.push_back((const glm::vec3*)&col[3 * v0], (size_t)inf.n_verts);
+				std::vector<int> order(who);
+				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return batch[a]->morton_code < batch[b]->morton_code; });
+				std::vector<std::vector<int>> parts(n_dev);
+				for (int k = 0; k < n_dev; k++)
+					parts[k].assign(order.begin() + (size_t)order.size() * k / n_dev, order.begin() + (size_t)order.size() * (k + 1) / n_dev);
+				std::vector<char> res(n_dev, 1);
+				std::vector<std::thread> th;
+				for (int k = 0; k < n_dev; k++)
+					th.emplace_back([&, k] { res[k] = parts[k].empty() ? 1 : (run_range(BmfDevice::slot(k, devices[k]), batch, parts[k]) ? 1 : 0); });
+				for (std::thread& t : th) t.join();
+				for (char r : res) ok = ok && r;
 			}
 		}
 		for (int i = 0; i < count; i++)
 			batch[i]->generation_stage = (batch[i]->chunk && batch[i]->chunk->vi) ? GENERATION_STAGES_NEEDS_UPLOAD : GENERATION_STAGES_DONE; // ChunkGenerator.cpp:137-143
-		return true;
+		return ok;
 	}
 
 private:
+	// one device, one submission: the chunks batch[who[k]]
+	bool run_range(BmfDevice& dev, SmartContainer<WorldOctreeNode*>& batch, const std::vector<int>& who)
+	{
+		if (!dev.ok()) return false;
+		const int iters = world->properties.process_iters, max_level = world->properties.max_level;
+		const bool pb = world->properties.boundary_processing;
+		const float base_overlap = world->properties.overlap;
+		std::vector<bmf_chunk_desc> descs(who.size());
+		for (size_t k = 0; k < who.size(); k++)
+		{
+			WorldOctreeNode* n = batch[who[k]];
+			bmf_chunk_desc& c = descs[k];
+			c.pos[0] = n->pos.x; c.pos[1] = n->pos.y; c.pos[2] = n->pos.z; c.size = n->size; c.level = n->level; c.morton = n->morton_code;
+			c.overlap = (n->level == max_level && (!pb || iters == 0)) ? 0.0f : base_overlap + 0.005f * (float)iters; // ChunkGenerator.cpp:98
+		}
+		bmf_sampler_desc d = world->sampler.device;
+		d.world_size = world->sampler.world_size;
+		if (d.kind == BMF_SAMPLER_TERRAIN2D_PERT)
+		{
+			const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
+			d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
+		}
+		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
+		bmf_params p;
+		std::memset(&p, 0, sizeof(p));
+		p.dim = world->properties.chunk_resolution;
+		p.iters = iters;
+		p.process_boundary = pb ? 1 : 0;
+		p.smooth_normals = 0; // SMOOTH_NORMALS 0 (DefaultOptions.h:8)
+		if (bmf_batch_submit(dev.ctx, descs.data(), (int)descs.size(), &p, nullptr) != BMF_OK) return false;
+		int64_t nc = 0, nv = 0, ni = 0;
+		bmf_batch_totals(dev.ctx, &nc, &nv, &ni);
+		std::vector<float> pos(3 * (size_t)nv + 3), col(3 * (size_t)nv + 3), nrm(3 * (size_t)nv + 3);
+		std::vector<uint8_t> bnd((size_t)nv + 1), val((size_t)nv + 1);
+		std::vector<uint32_t> idx((size_t)ni + 1);
+		if (bmf_batch_download(dev.ctx, pos.data(), nrm.data(), col.data(), bnd.data(), val.data(), idx.data()) != BMF_OK) return false;
+		std::vector<bmf_chunk_info> infos(descs.size());
+		bmf_batch_chunk_infos(dev.ctx, infos.data());
+		for (size_t k = 0; k < descs.size(); k++)
+		{
+			WorldOctreeNode* n = batch[who[k]];
+			DMCChunk* c = n->chunk;
+			const bmf_chunk_info& inf = infos[k];
+			c->contains_mesh = inf.contains_mesh != 0;
+			c->overlap_pos = glm::vec3(inf.overlap_pos[0], inf.overlap_pos[1], inf.overlap_pos[2]);
+			c->scale = inf.scale;
+			c->bound_size = c->size * (1.0f + descs[k].overlap * 2.0f) * 0.5f;
+			c->bound_start = c->overlap_pos + c->bound_size;
+			if (!c->contains_mesh) continue;
+			if (!c->vi) { c->vi = vi_allocator.new_element(); c->vi->init(); }
+			const size_t v0 = (size_t)inf.vert_offset, i0 = (size_t)inf.ind_offset;
+			const bool processed = iters > 0 && inf.n_verts > 0 && inf.n_inds > 0;
+			bmf_detail::fill_dual_vertices(c->vi->vertices, &pos[3 * v0], &nrm[3 * v0], &col[3 * v0], &bnd[v0], &val[v0], (size_t)inf.n_verts, true, processed);
+			c->vi->mesh_indexes.count = 0;
+			c->vi->mesh_indexes.push_back(&idx[i0], (size_t)inf.n_inds);
+			// WorldOctreeNode::format -> GLChunk::format_data(vertices, indexes, false, false) (WorldOctreeNode.cpp:72-88)
+			if (!n->gl_chunk) n->gl_chunk = gl_allocator.new_element();
+			GLChunk* g = n->gl_chunk;
+			g->p_data.count = g->n_data.count = g->c_data.count = 0;
+			g->p_data.push_back((const glm::vec3*)&pos[3 * v0], (size_t)inf.n_verts);
+			g->n_data.push_back((const glm::vec3*)&nrm[3 * v0], (size_t)inf.n_verts);
+			g->c_data.push_back((const glm::vec3*)&col[3 * v0], (size_t)inf.n_verts);
+		}
+		return true;
+	}
+
 	WorldOctree* world = nullptr;
+	std::vector<int> devices;
 };
 
 // ---- MeshProcessor -------------------------------------------------------------------------------------------------

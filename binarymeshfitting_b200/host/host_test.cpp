@@ -134,6 +134,53 @@ int main(int argc, char** argv)
 		}
 		return 0;
 	}
+	if (!strcmp(argv[1], "lod") && argc >= 6)
+	{
+		// SURVEY call stack B, all in C++: WorldOctree::init -> split_leaves -> ChunkGenerator::process_queue;
+		// optional 6th argument: comma-separated device list for the multi-GPU partition, e.g. 0,1 or 0,0,0
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), iters = atoi(argv[5]);
+		WorldOctree world;
+		world.sampler = make_sampler(kind);
+		world.properties.chunk_resolution = dim;
+		world.properties.max_level = max_level;
+		world.properties.process_iters = iters;
+		world.init(256);
+		world.split_leaves();
+		ChunkGenerator gen;
+		gen.init(&world);
+		if (argc >= 7)
+		{
+			std::vector<int> devs;
+			for (char* tok = strtok(argv[6], ","); tok; tok = strtok(nullptr, ",")) devs.push_back(atoi(tok));
+			gen.set_devices(devs);
+		}
+		SmartContainer<WorldOctreeNode*> batch;
+		for (WorldOctreeNode* n : world.leaves)
+		{
+			n->generation_stage = GENERATION_STAGES_GENERATING;
+			batch.push_back(n);
+		}
+		if (!gen.process_queue(batch))
+		{
+			fprintf(stderr, "process_queue failed: %s\n", BmfDevice::get().error());
+			return 5;
+		}
+		size_t nm = 0, nv = 0, ni = 0;
+		uint32_t hi = 0, hl = 0;
+		for (WorldOctreeNode* n : world.leaves)
+		{
+			float rec[4] = { n->pos.x, n->pos.y, n->pos.z, n->size };
+			hl = crc32_of(rec, sizeof(rec), hl);
+			DMCChunk* c = n->chunk;
+			if (!(c->contains_mesh && c->vi)) continue;
+			nm += c->vi->vertices.count ? 1 : 0;
+			nv += c->vi->vertices.count;
+			ni += c->vi->mesh_indexes.count;
+			hi = crc32_of(c->vi->mesh_indexes.elements, c->vi->mesh_indexes.count * 4, hi);
+		}
+		printf("lod chunks=%zu with_mesh=%zu verts=%zu inds=%zu inds_crc=%u leaves_crc=%u\n", world.leaves.size(), nm, nv, ni, hi, hl);
+		return 0;
+	}
 	if (!strcmp(argv[1], "world") && argc >= 7)
 	{
 		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), iters = atoi(argv[5]);

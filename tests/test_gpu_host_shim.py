@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "binarymeshfitting_b200", "host", "host_test")
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+ARR = np.load(os.path.join(ROOT, "tests", "golden", "golden_arrays.npz"))
 
 
 def crc(a):
@@ -82,3 +83,16 @@ def test_chunkgenerator_process_queue(tmp_path, w):
     assert (int(out["chunks"]), int(out["with_mesh"]), int(out["verts"]), int(out["inds"])) == (w["leaves"], w["chunks_with_mesh"], w["verts"], w["inds"])
     assert int(out["inds_crc"]) == w["inds_crc"]  # golden: the compiled reference's ChunkGenerator::process_queue
     assert int(out["needs_upload"]) == w["chunks_with_mesh"]
+
+
+@pytest.mark.parametrize("devices", [None, "0,0", "0,0,0"])
+@pytest.mark.parametrize("w", [g for g in GOLD["worlds"] if g["dim"] == 32 and g["focus"] == [0, 0, 0]], ids=lambda w: w["key"])
+def test_cpp_split_leaves_and_multi_context_partition(w, devices):
+    """all in C++: WorldOctree::init -> split_leaves -> process_queue, optionally dealt to several contexts (the
+    multi-GPU partition; here several contexts on GPU 0) -- same leaves and the same per-chunk meshes as the reference"""
+    args = ["lod", w["kind"], w["dim"], w["max_level"], w["iters"]] + ([devices] if devices else [])
+    out = run(*args)["lod"]
+    assert (int(out["chunks"]), int(out["with_mesh"]), int(out["verts"]), int(out["inds"])) == (w["leaves"], w["chunks_with_mesh"], w["verts"], w["inds"])
+    assert int(out["inds_crc"]) == w["inds_crc"]
+    leaves = ARR[w["key"] + "_leaves"][:, :4].astype(np.float32)
+    assert int(out["leaves_crc"]) == crc(leaves)
