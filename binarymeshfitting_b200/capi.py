@@ -235,6 +235,12 @@ class Context:
             self._check(n)
         return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
 
+    def device_ptrs(self):
+        """device pointers (ints) of the resident batch: pos, indices, bits, density (0 if not materialised)"""
+        p = [C.c_void_p() for _ in range(4)]
+        self._check(self.lib.bmf_batch_device_ptrs(self.h, *[C.byref(x) for x in p]))
+        return {k: int(v.value or 0) for k, v in zip(("pos", "indices", "bits", "density"), p)}
+
     def stream_ptr(self):
         return int(self.lib.bmf_ctx_stream(self.h) or 0)
 

@@ -261,10 +261,13 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	const unsigned nblk = grid_for(n_verts, (int)per_block);
 	BMF_CUDA(ctx->block_sums.reserve(nblk));
 
-	// init: adj_offset = exclusive prefix of init_valence (MeshProcessor.cpp:33-39)
-	BMF_LAUNCH(k_scan8_partial, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p);
-	BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
-	BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
+	// init: adj_offset = exclusive prefix of init_valence (MeshProcessor.cpp:33-39); on the batch path k_valence_offsets did it already
+	if (!grid_path)
+	{
+		BMF_LAUNCH(k_scan8_partial, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p);
+		BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
+		BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
+	}
 	if (grid_path)
 	{
 		BMF_LAUNCH(k_adj_fill, ctx->sm_count * 8, CTA, 0, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->cls.p, ctx->adj_off.p, ctx->adj.p,
@@ -641,7 +644,11 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	{
 		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p);
 	}
-	if (V) BMF_LAUNCH(k_cls_to_valence, grid_for(V, CTA), CTA, 0, ctx->cls.p, V, ctx->valence.p);
+	if (V)
+	{
+		BMF_CUDA(ctx->adj_off.reserve(V));
+		BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p);
+	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 
 	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it

@@ -885,13 +885,45 @@ __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict
 	}
 }
 
-// init_valence of every vertex = sum of its four per-class use counts
-__global__ void __launch_bounds__(CTA) k_cls_to_valence(const uint32_t* __restrict__ cls, size_t n_verts, uint8_t* __restrict__ valence)
+// init_valence of every vertex (= sum of its four per-class use counts) and, in the same pass, adj_offset = exclusive
+// prefix of init_valence (MeshProcessor.cpp:33-39).  The valences of a chunk add up to its index count, so the
+// batch-wide prefix at the chunk's first vertex is simply its ind_base: one CTA per chunk scans its own vertices
+// in tiles with a running carry -- no device-wide scan, one launch.
+static constexpr int VAL_ITEMS = 8;
+
+__global__ void __launch_bounds__(CTA) k_valence_offsets(const uint32_t* __restrict__ cls, const ChunkCounts* __restrict__ chunks, uint8_t* __restrict__ valence,
+                                                          uint32_t* __restrict__ adj_off)
 {
-	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
-	if (v >= n_verts) return;
-	const uint32_t w = cls[v];
-	valence[v] = (uint8_t)((w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24));
+	const ChunkCounts cc = chunks[blockIdx.x];
+	if (cc.n_verts == 0) return;
+	const size_t v0 = (size_t)cc.vert_base;
+	uint32_t carry = (uint32_t)cc.ind_base;
+	for (uint32_t base = 0; base < cc.n_verts; base += CTA * VAL_ITEMS)
+	{
+		const uint32_t i0 = base + threadIdx.x * VAL_ITEMS;
+		uint32_t val[VAL_ITEMS], sum = 0;
+#pragma unroll
+		for (int k = 0; k < VAL_ITEMS; k++)
+		{
+			uint32_t w = (i0 + k < cc.n_verts) ? cls[v0 + i0 + k] : 0u;
+			val[k] = (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
+			sum += val[k];
+		}
+		uint32_t sc[1] = { sum }, tot[1];
+		block_scan<1>(sc, tot);
+		uint32_t run = carry + sc[0];
+#pragma unroll
+		for (int k = 0; k < VAL_ITEMS; k++)
+		{
+			if (i0 + k < cc.n_verts)
+			{
+				valence[v0 + i0 + k] = (uint8_t)val[k];
+				adj_off[v0 + i0 + k] = run;
+			}
+			run += val[k];
+		}
+		carry += tot[0];
+	}
 }
 
 } // namespace bmf
