@@ -575,7 +575,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	else
 	{
-		BMF_LAUNCH(k_pack_density, (unsigned)(n_words / (PACK_UNROLL * (CTA / 32))), CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.lwc);
+		BMF_LAUNCH(k_pack_density, ctx->sm_count * 8, CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.lwc);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[1], st));
 
