@@ -112,20 +112,21 @@ __device__ __forceinline__ float density_at(const SamplerDev& s, const DensitySo
 	return implicit_point(s, g, x, y, z);
 }
 
-// warp-level flag merge: the flags of a chunk saturate after a few words, so a warp first looks at the current value and
-// only issues the atomicOr when it would add a bit (no block barrier, almost no atomics in steady state)
+// block-level flag merge: one atomicOr per CTA (a per-warp "read first, add only new bits" variant was 7x slower:
+// millions of same-address volatile reads serialise in L2)
 __device__ __forceinline__ void merge_flags(uint32_t f, uint32_t* chunk_flags)
 {
+	__shared__ uint32_t s_f;
+	if (threadIdx.x == 0) s_f = 0;
+	__syncthreads();
 	f |= __shfl_xor_sync(0xffffffffu, f, 16);
 	f |= __shfl_xor_sync(0xffffffffu, f, 8);
 	f |= __shfl_xor_sync(0xffffffffu, f, 4);
 	f |= __shfl_xor_sync(0xffffffffu, f, 2);
 	f |= __shfl_xor_sync(0xffffffffu, f, 1);
-	if ((threadIdx.x & 31) == 0 && f)
-	{
-		const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(chunk_flags);
-		if (f & ~cur) atomicOr(chunk_flags, f);
-	}
+	if ((threadIdx.x & 31) == 0 && f) atomicOr(&s_f, f);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_f) atomicOr(chunk_flags, s_f);
 }
 
 __device__ __forceinline__ uint32_t word_flags(uint32_t w) { return w == 0 ? CF_ZERO : (w == 0xFFFFFFFFu ? CF_ONES : CF_MIXED); }
