@@ -26,9 +26,13 @@ struct DevBuf
 	cudaError_t reserve(size_t n)
 	{
 		if (n <= cap) return cudaSuccess;
-		if (p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
+		if (p)
+		{
+			cudaError_t fe = cudaFree(p);
+			p = nullptr;
+			cap = 0;
+			if (fe != cudaSuccess) return fe;
+		}
 		size_t want = n + n / 8 + 64;
 		cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
 		if (e == cudaSuccess) cap = want;
@@ -468,8 +472,6 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
 		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
-	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
-	ctx->sheet_mm.release(); ctx->uni.release();
 		ctx->counts_pinned = nullptr;
 		BMF_CUDA(cudaMallocHost((void**)&ctx->counts_pinned, sizeof(ChunkCounts) * (size_t)n));
 		ctx->counts_pinned_cap = n;

@@ -74,3 +74,20 @@ def test_idempotent_resubmit_and_arena_reuse(gpu):
         o = gpu.download()
         crcs.append((zlib.crc32(o["inds"].tobytes()), zlib.crc32(o["pos"].tobytes()), gpu.totals()))
     assert crcs[0] == crcs[2] and crcs[1][2][1] > crcs[0][2][1]
+
+
+def test_growing_batches_all_samplers(gpu):
+    """arenas (device and pinned) grow across submits of increasing size for every sampler family; results of the
+    small batch are reproduced afterwards"""
+    for kind in (capi.TERRAIN2D_PERT, capi.SPHERE, capi.TERRAIN3D):
+        gpu.set_sampler(kind)
+        first = None
+        for n in (2, 5, 9, 2):
+            d = capi.make_chunk_descs(W.grid_chunks(n, 256.0 / n), overlaps=0.045)
+            gpu.submit(d, 32, iters=2)
+            gpu.wait()
+            o = gpu.download()
+            sig = (gpu.totals(), zlib.crc32(o["inds"].tobytes()), zlib.crc32(o["pos"].tobytes()))
+            if n == 2 and first is None:
+                first = sig
+        assert sig == first
