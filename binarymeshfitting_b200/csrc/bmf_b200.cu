@@ -81,7 +81,7 @@ struct bmf_ctx
 	DevBuf<ChunkGeom> geom, sheet_geom;
 	DevBuf<int> sheet_of;
 	DevBuf<uint32_t> sheet_mm;
-	DevBuf<uint8_t> uni;
+	DevBuf<uint8_t> uni, gflags;
 	uint8_t* uni_pinned = nullptr;
 	size_t uni_pinned_cap = 0;
 	bool uni_valid = false;
@@ -378,7 +378,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->totals_pinned) cudaFreeHost(ctx->totals_pinned);
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
-	ctx->sheet_mm.release(); ctx->uni.release();
+	ctx->sheet_mm.release(); ctx->uni.release(); ctx->gflags.release();
 	for (int i = 0; i <= BMF_NUM_STAGES; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for (cudaEvent_t e : ctx->kev) cudaEventDestroy(e);
@@ -577,7 +577,9 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	else
 	{
-		BMF_LAUNCH(k_pack_density, ctx->sm_count * 8, CTA, 0, density_dev, ctx->bits.p, ctx->flags.p, n_words, L.lwc);
+		BMF_CUDA(ctx->gflags.reserve(n_words / PACK_UNROLL));
+		BMF_LAUNCH(k_pack_density, (unsigned)(n_words / (PACK_UNROLL * (CTA / 32))), CTA, 0, density_dev, ctx->bits.p, ctx->gflags.p, n_words);
+		BMF_LAUNCH(k_reduce_flags, n, CTA, 0, ctx->gflags.p, L.wc / PACK_UNROLL, ctx->flags.p);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[1], st));
 

@@ -375,46 +375,54 @@ __global__ void __launch_bounds__(CTA) k_terrain3d(SamplerDev s, const ChunkGeom
 }
 
 // ---- K2: density block -> sign words (label_grid's pack, DMCChunk.cpp:118-157).  Pure streaming:
-// the density of a batch is one flat array of 32-float groups, each group is one word.  A persistent grid; every warp
-// owns one contiguous run of words, issues PACK_UNROLL independent coalesced 4-byte loads before the first ballot so
-// enough bytes are in flight, and keeps the chunk flags in registers -- one atomicOr per (warp, chunk), no barrier.
+// the density of a batch is one flat array of 32-float groups, each group is one word.  Every lane issues
+// PACK_UNROLL independent coalesced 4-byte loads before the first ballot so enough bytes are in flight; consecutive
+// warps read consecutive kilobytes (DRAM-page friendly).  No barrier, no atomic: the chunk-flag contribution of a
+// warp's PACK_UNROLL words goes to one byte of `gflags`, which k_reduce_flags ORs per chunk afterwards.
 static constexpr int PACK_UNROLL = 8;
 
-__global__ void __launch_bounds__(CTA) k_pack_density(const float* __restrict__ density, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags,
-                                                       size_t n_words, int lwc)
+__global__ void __launch_bounds__(CTA) k_pack_density(const float* __restrict__ density, uint32_t* __restrict__ bits, uint8_t* __restrict__ gflags,
+                                                       size_t n_words)
 {
 	const int lane = threadIdx.x & 31;
-	const size_t n_groups = n_words / PACK_UNROLL; // n_words is a multiple of 1024
-	const size_t warps = (size_t)gridDim.x * (CTA / 32);
-	const size_t per = (n_groups + warps - 1) / warps;
 	const size_t warp_global = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5;
-	const size_t g0 = warp_global * per, g1 = (g0 + per < n_groups) ? g0 + per : n_groups;
-	long long cur = -1;
-	uint32_t f = 0;
-	for (size_t g = g0; g < g1; g++)
+	const size_t w0 = warp_global * PACK_UNROLL;
+	if (w0 >= n_words) return; // n_words is a multiple of PACK_UNROLL * (CTA/32)
+	float v[PACK_UNROLL];
+#pragma unroll
+	for (int k = 0; k < PACK_UNROLL; k++) v[k] = __ldcs(density + (w0 + k) * 32 + lane);
+	uint32_t f = 0, mine = 0;
+#pragma unroll
+	for (int k = 0; k < PACK_UNROLL; k++)
 	{
-		const size_t w0 = g * PACK_UNROLL;
-		float v[PACK_UNROLL];
-#pragma unroll
-		for (int k = 0; k < PACK_UNROLL; k++) v[k] = __ldcs(density + (w0 + k) * 32 + lane);
-		const long long chunk = (long long)(w0 >> lwc); // the PACK_UNROLL words of a group lie in one chunk
-		if (chunk != cur)
-		{
-			if (lane == 0 && f) atomicOr(flags + cur, f);
-			cur = chunk;
-			f = 0;
-		}
-		uint32_t mine = 0;
-#pragma unroll
-		for (int k = 0; k < PACK_UNROLL; k++)
-		{
-			const uint32_t word = __ballot_sync(0xffffffffu, v[k] < 0.0f);
-			if (lane == k) mine = word;
-			f |= word_flags(word);
-		}
-		if (lane < PACK_UNROLL) bits[w0 + lane] = mine;
+		const uint32_t word = __ballot_sync(0xffffffffu, v[k] < 0.0f);
+		if (lane == k) mine = word;
+		f |= word_flags(word);
 	}
-	if (lane == 0 && f) atomicOr(flags + cur, f);
+	if (lane < PACK_UNROLL) bits[w0 + lane] = mine;
+	if (lane == 0) gflags[warp_global] = (uint8_t)f;
+}
+
+// chunk flags = OR of the chunk's group flags (words_per_chunk / PACK_UNROLL bytes, a multiple of 128); one CTA per chunk
+__global__ void __launch_bounds__(CTA) k_reduce_flags(const uint8_t* __restrict__ gflags, int groups_per_chunk, uint32_t* __restrict__ flags)
+{
+	__shared__ uint32_t s_f;
+	if (threadIdx.x == 0) s_f = 0;
+	__syncthreads();
+	const uint32_t* g = reinterpret_cast<const uint32_t*>(gflags + (size_t)blockIdx.x * groups_per_chunk);
+	uint32_t f = 0;
+	for (int i = threadIdx.x; i < groups_per_chunk / 4; i += CTA) f |= g[i];
+	f |= f >> 16;
+	f |= f >> 8;
+	f &= 0xFF;
+	f |= __shfl_xor_sync(0xffffffffu, f, 16);
+	f |= __shfl_xor_sync(0xffffffffu, f, 8);
+	f |= __shfl_xor_sync(0xffffffffu, f, 4);
+	f |= __shfl_xor_sync(0xffffffffu, f, 2);
+	f |= __shfl_xor_sync(0xffffffffu, f, 1);
+	if ((threadIdx.x & 31) == 0 && f) atomicOr(&s_f, f);
+	__syncthreads();
+	if (threadIdx.x == 0) flags[blockIdx.x] = s_f;
 }
 
 // ---- shared-memory staging of sign planes ----------------------------------------------------------------
