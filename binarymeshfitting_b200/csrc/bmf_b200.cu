@@ -6,6 +6,7 @@
 #include "extract.cuh"
 #include "smooth.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <array>
 #include <cstring>
@@ -48,7 +49,7 @@ struct DevBuf
 
 struct HostTotals
 {
-	unsigned long long v[4];
+	unsigned long long v[8]; // cells, verts, indices, >2^32 flag, list counters x2, -, arena-too-small flag
 };
 
 } // namespace
@@ -75,6 +76,8 @@ struct bmf_ctx
 	std::vector<ChunkCounts> counts_host;
 	unsigned long long totals[3] = { 0, 0, 0 };
 	const float* ext_density = nullptr; // caller-owned device density (density_on_device)
+	const float* density_cur = nullptr; // density block the emitters read crossing-edge samples from (or null)
+	int relaunches = 0;                 // batches whose emitters had to be re-launched after growing an arena
 	bool density_valid = false, masks_valid = false;
 	size_t color_ones = 0; // the first color_ones floats of the colour arena are known to be exactly 1.0f
 
@@ -247,8 +250,10 @@ inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1
 template <int N>
 int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* color, float* normal, const uint8_t* boundary,
                const uint8_t* valence, const uint32_t* inds, const ChunkCounts* chunks_dev, int n_chunks, int iters, int pb, int smooth, int qef, int final_primal = 1,
-               bool grid_path = false)
+               bool grid_path = false, const unsigned long long* tot = nullptr)
 {
+	// tot != null (batch path): n_verts / n_inds are arena capacities used to size the launches; the kernels read the
+	// real counts of the batch from tot[] on the device, so nothing here waits for the host
 	// grid_path: the mesh comes from the resident batch (cell lists + per-word bases are valid and every colour is exactly 1)
 	if (n_verts == 0 || n_inds < (size_t)N || iters <= 0) return BMF_OK;
 	const size_t n_prims = n_inds / N;
@@ -275,7 +280,7 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	if (grid_path)
 	{
 		BMF_LAUNCH(k_adj_fill, ctx->sm_count * 8, CTA, 0, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->cls.p, ctx->adj_off.p, ctx->adj.p,
-		           ctx->prim_vbase.p);
+		           ctx->prim_vbase.p, tot);
 	}
 	else
 	{
@@ -291,23 +296,23 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	{
 		const int face = (m == 0 || m < max_norms || m < 3) ? 1 : 0;
 		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp,
-		           need_dn ? ctx->dn.p : nullptr, smooth, face);
+		           need_dn ? ctx->dn.p : nullptr, smooth, face, tot);
 		if (m < iters - 1)
 		{
 			const int set_colors = (m == 3) || (m == 0 && iters <= 3);
 			BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp,
-			           ctx->dn.p, pos, color, normal, smooth, set_colors, pb);
+			           ctx->dn.p, pos, color, normal, smooth, set_colors, pb, tot);
 		}
 	}
 	// the driver's extra primal call (ChunkGenerator.cpp:120)
 	if (final_primal)
 		BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp, ctx->dn.p, pos,
-		           color, normal, smooth, 0, pb);
+		           color, normal, smooth, 0, pb, tot);
 	if (qef)
 	{
 		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
-		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1);
-		BMF_LAUNCH(k_qef_place, grid_for(n_verts, 128), 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb);
+		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1, tot);
+		BMF_LAUNCH(k_qef_place, grid_for(n_verts, 128), 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb, tot);
 	}
 	return BMF_OK;
 }
@@ -318,6 +323,148 @@ __global__ void __launch_bounds__(CTA) k_valence_from_inds(const uint32_t* __res
 	if (i >= n) return;
 	const size_t gv = inds[i];
 	atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3)));
+}
+
+int elapsed(bmf_ctx* ctx, int a, int b, float* out);
+
+struct MeshCaps
+{
+	size_t cells, verts, inds;
+};
+
+// what the output / smoothing arenas can hold right now (0 = something is not allocated yet)
+MeshCaps mesh_caps(const bmf_ctx* ctx)
+{
+	const bmf_params& p = ctx->params;
+	const bool smoothing = p.iters > 0, need_dn = smoothing && (p.smooth_normals || p.qef);
+	MeshCaps c;
+	c.cells = std::min(ctx->vcells.cap, ctx->icells.cap);
+	size_t v = std::min({ ctx->pos.cap / 3, ctx->color.cap / 3, ctx->normal.cap / 3, ctx->boundary.cap, ctx->valence.cap, ctx->cls.cap, ctx->adj_off.cap });
+	size_t i = ctx->inds.cap;
+	if (smoothing) i = std::min({ i, ctx->adj.cap, ctx->prim_vbase.cap * 3, ctx->dp.cap, need_dn ? ctx->dn.cap : (size_t)-1 });
+	c.verts = v > 32 ? v - 32 : 0; // the emitters touch up to 16 bytes past the last vertex (byte-packed words)
+	c.inds = i > 8 ? i - 8 : 0;
+	return c;
+}
+
+// grow the arenas to hold (cells, verts, inds) with headroom, so that the following batches of similar size fit
+int reserve_mesh(bmf_ctx* ctx, size_t cells, size_t verts, size_t inds)
+{
+	const bmf_params& p = ctx->params;
+	const bool smoothing = p.iters > 0, need_dn = smoothing && (p.smooth_normals || p.qef);
+	const size_t C = cells + cells / 4 + 64, V = verts + verts / 4 + 64, I = inds + inds / 4 + 64;
+	BMF_CUDA(ctx->vcells.reserve(C));
+	BMF_CUDA(ctx->icells.reserve(C));
+	BMF_CUDA(ctx->pos.reserve(3 * V));
+	if (3 * V > ctx->color.cap) ctx->color_ones = 0;
+	BMF_CUDA(ctx->color.reserve(3 * V));
+	BMF_CUDA(ctx->normal.reserve(3 * V));
+	BMF_CUDA(ctx->boundary.reserve(V));
+	BMF_CUDA(ctx->valence.reserve(V));
+	BMF_CUDA(ctx->cls.reserve(V));
+	BMF_CUDA(ctx->adj_off.reserve(V));
+	BMF_CUDA(ctx->inds.reserve(I));
+	if (smoothing)
+	{
+		BMF_CUDA(ctx->adj.reserve(I));
+		BMF_CUDA(ctx->prim_vbase.reserve(I / 3 + 1));
+		BMF_CUDA(ctx->dp.reserve(I));
+		if (need_dn) BMF_CUDA(ctx->dn.reserve(I));
+	}
+	return BMF_OK;
+}
+
+// K4 + K5 of the resident batch, sized by arena capacity and guarded on the device (k_check_caps): no host round trip
+int launch_mesh(bmf_ctx* ctx)
+{
+	const bmf_params* params = &ctx->params;
+	const Layout L = ctx->L;
+	const int n = ctx->n, nseg = n * L.S, kind = ctx->sampler.kind;
+	cudaStream_t st = ctx->stream;
+	const MeshCaps caps = mesh_caps(ctx);
+	unsigned long long* tot = ctx->totals_dev.p;
+	unsigned long long* list_count = tot + 4;
+	BMF_LAUNCH(k_check_caps, 1, 1, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
+	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, tot, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
+	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
+	{
+		// nothing allocated yet (first batch of this kind): k_check_caps has raised the flag unless the batch is empty;
+		// bmf_batch_wait sizes the arenas from the totals and calls this function again
+		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+		return BMF_OK;
+	}
+	const size_t V = caps.verts, I = caps.inds;
+	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
+
+	// ---- K4
+	DensitySource src;
+	src.density = ctx->density_cur;
+	src.hmap = (!ctx->density_cur && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
+	src.sheet_of = ctx->sheet_of.p;
+	if (L.wpt == 4)
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
+		           ctx->icells.p, list_count, tot);
+	else
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
+		           ctx->icells.p, list_count, tot);
+	BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p, tot);
+	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+	BMF_CUDA(cudaMemsetAsync(ctx->cls.p, 0, sizeof(uint32_t) * V, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
+	if (ctx->color_ones < 3 * V)
+	{
+		// calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681).  The batch path never writes another colour
+		// (see run_smooth), so the arena is filled once to its capacity and reused.
+		BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
+		ctx->color_ones = ctx->color.cap;
+	}
+	BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p, tot);
+	BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p, tot);
+	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+
+	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it
+	if (params->iters > 0)
+	{
+		int rc = run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
+		                       params->iters, params->process_boundary, params->smooth_normals, params->qef, 1, true, tot);
+		if (rc) return rc;
+	}
+	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+	return BMF_OK;
+}
+
+// completes the resident batch: waits for the stream, publishes totals / per-chunk counts to the host and, if an output
+// arena was too small for this batch, grows it and runs the emitters again (the front half of the pipeline is kept)
+int finish(bmf_ctx* ctx)
+{
+	if (ctx->finished) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+	const HostTotals t = *ctx->totals_pinned;
+	if (t.v[3]) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: batch exceeds 2^32 cells/vertices/indices; split it");
+	ctx->totals[0] = t.v[0];
+	ctx->totals[1] = t.v[1];
+	ctx->totals[2] = t.v[2];
+	ctx->counts_host.assign(ctx->counts_pinned, ctx->counts_pinned + ctx->n);
+	if (t.v[7])
+	{
+		int rc = reserve_mesh(ctx, (size_t)t.v[0], (size_t)t.v[1], (size_t)t.v[2]);
+		if (rc) return rc;
+		BMF_CUDA(cudaMemsetAsync(ctx->totals_dev.p + 4, 0, 2 * sizeof(unsigned long long), ctx->stream)); // list counters
+		rc = launch_mesh(ctx);
+		if (rc) return rc;
+		BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (ctx->totals_pinned->v[7]) return fail(ctx, BMF_ERR_NOMEM, "bmf_batch_wait: output arenas still too small after growing");
+		ctx->relaunches++;
+	}
+	for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
+	elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
+	ctx->finished = true;
+	return BMF_OK;
 }
 
 int elapsed(bmf_ctx* ctx, int a, int b, float* out)
@@ -471,6 +618,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->totals_dev.reserve(8));
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
+		BMF_CUDA(cudaStreamSynchronize(ctx->stream)); // an earlier batch may still be copying into the old buffer
 		if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 		ctx->counts_pinned = nullptr;
 		BMF_CUDA(cudaMallocHost((void**)&ctx->counts_pinned, sizeof(ChunkCounts) * (size_t)n));
@@ -522,6 +670,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		BMF_CUDA(ctx->uni.reserve(n));
 		if ((size_t)n > ctx->uni_pinned_cap)
 		{
+			BMF_CUDA(cudaStreamSynchronize(ctx->stream));
 			if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 			ctx->uni_pinned = nullptr;
 			BMF_CUDA(cudaMallocHost((void**)&ctx->uni_pinned, (size_t)n));
@@ -592,78 +741,17 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->chunk_tot.p, masks_w);
 	BMF_CUDA(cudaEventRecord(ctx->ev[2], st));
 
-	// ---- scan + the one host round trip (output sizes)
+	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
+	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
 	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
-	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, ctx->totals_dev.p, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
-	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
-	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
-	BMF_CUDA(cudaStreamSynchronize(st));
-	if (ctx->totals_pinned->v[3]) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: batch exceeds 2^32 cells/vertices/indices; split it");
-	ctx->totals[0] = ctx->totals_pinned->v[0];
-	ctx->totals[1] = ctx->totals_pinned->v[1];
-	ctx->totals[2] = ctx->totals_pinned->v[2];
-	ctx->counts_host.assign(ctx->counts_pinned, ctx->counts_pinned + n);
-	const size_t V = ctx->totals[1], I = ctx->totals[2];
-
-	BMF_CUDA(ctx->pos.reserve(3 * V + 4));
-	if (3 * V + 4 > ctx->color.cap) ctx->color_ones = 0;
-	BMF_CUDA(ctx->color.reserve(3 * V + 4));
-	BMF_CUDA(ctx->normal.reserve(3 * V + 4));
-	BMF_CUDA(ctx->boundary.reserve(V + 16));
-	BMF_CUDA(ctx->valence.reserve(V + 16));
-	BMF_CUDA(ctx->cls.reserve(V + 16));
-	BMF_CUDA(ctx->inds.reserve(I + 4));
-
-	// ---- K4
-	DensitySource src;
-	src.density = density_dev;
-	src.hmap = (!density_dev && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
-	src.sheet_of = ctx->sheet_of.p;
-	unsigned long long* list_count = ctx->totals_dev.p + 4;
-	// every vertex cell and every polygonizing cell is an active cell: totals[0] bounds both lists
-	BMF_CUDA(ctx->vcells.reserve(ctx->totals[0] + 1));
-	BMF_CUDA(ctx->icells.reserve(ctx->totals[0] + 1));
-	if (L.wpt == 4)
-		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
-		           ctx->icells.p, list_count);
-	else
-		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
-		           ctx->icells.p, list_count);
-	if (V)
-		BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p);
-	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
-	if (V)
-	{
-		BMF_CUDA(cudaMemsetAsync(ctx->cls.p, 0, sizeof(uint32_t) * V, st));
-		BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
-		if (ctx->color_ones < 3 * V)
-		{
-			// calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681).  The batch path never writes another colour
-			// (see run_smooth), so the arena is filled once to its capacity and reused.
-			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
-			ctx->color_ones = ctx->color.cap;
-		}
-	}
-	if (I)
-	{
-		BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p);
-	}
-	if (V)
-	{
-		BMF_CUDA(ctx->adj_off.reserve(V));
-		BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p);
-	}
-	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
-
-	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it
-	if (params->iters > 0 && V && I)
-	{
-		int rc = run_smooth<3>(ctx, V, I, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
-		                       params->iters, params->process_boundary, params->smooth_normals, params->qef, 1, true);
-		if (rc) return rc;
-	}
-	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
+	int rc = launch_mesh(ctx);
+	if (rc)
+	{
+		ctx->have_batch = false;
+		return rc;
+	}
 	return BMF_OK;
 }
 
@@ -671,14 +759,9 @@ int bmf_batch_wait(bmf_ctx* ctx)
 {
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_wait: no batch submitted");
-	BMF_CUDA(cudaSetDevice(ctx->device));
-	BMF_CUDA(cudaStreamSynchronize(ctx->stream));
-	if (!ctx->finished)
-	{
-		for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
-		elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
-		ctx->finished = true;
-	}
+	int rc = finish(ctx);
+	if (rc) return rc;
+	BMF_CUDA(cudaStreamSynchronize(ctx->stream)); // copies enqueued after the batch (bmf_batch_download_async)
 	return BMF_OK;
 }
 
@@ -686,6 +769,10 @@ int bmf_batch_totals(bmf_ctx* ctx, int64_t* n_cells, int64_t* n_verts, int64_t* 
 {
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_totals: no batch submitted");
+	{
+		int frc = finish(ctx);
+		if (frc) return frc;
+	}
 	if (n_cells) *n_cells = (int64_t)ctx->totals[0];
 	if (n_verts) *n_verts = (int64_t)ctx->totals[1];
 	if (n_inds) *n_inds = (int64_t)ctx->totals[2];
@@ -696,6 +783,10 @@ int bmf_batch_chunk_info(bmf_ctx* ctx, int i, bmf_chunk_info* out)
 {
 	if (!ctx || !out) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_chunk_info: no batch submitted");
+	{
+		int frc = finish(ctx);
+		if (frc) return frc;
+	}
 	if (i < 0 || i >= ctx->n) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_chunk_info: chunk index out of range");
 	const ChunkCounts& c = ctx->counts_host[i];
 	const ChunkGeom& g = ctx->geom_host[i];
@@ -732,6 +823,10 @@ int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* col
 {
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download: no batch submitted");
+	{
+		int frc = finish(ctx);
+		if (frc) return frc;
+	}
 	BMF_CUDA(cudaSetDevice(ctx->device));
 	const size_t V = ctx->totals[1], I = ctx->totals[2];
 	cudaStream_t st = ctx->stream;
@@ -751,6 +846,10 @@ int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* ind
 {
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_copy_chunk: no batch submitted");
+	{
+		int frc = finish(ctx);
+		if (frc) return frc;
+	}
 	if (i < 0 || i >= ctx->n) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_copy_chunk: chunk index out of range");
 	BMF_CUDA(cudaSetDevice(ctx->device));
 	const ChunkCounts& c = ctx->counts_host[i];
@@ -855,6 +954,10 @@ int bmf_batch_device_ptrs(bmf_ctx* ctx, void** pos, void** indices, void** bits,
 {
 	if (!ctx) return BMF_ERR_INVALID;
 	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_device_ptrs: no batch submitted");
+	{
+		int frc = finish(ctx);
+		if (frc) return frc;
+	}
 	if (pos) *pos = ctx->pos.p;
 	if (indices) *indices = ctx->inds.p;
 	if (bits) *bits = ctx->bits.p;

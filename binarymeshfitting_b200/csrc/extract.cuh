@@ -694,6 +694,15 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 	}
 }
 
+// Output arenas are sized from the previous batches so that a submission never has to wait for the host.  This
+// one-thread kernel compares the totals of THIS batch with the capacities the emitters were launched with; if
+// anything does not fit it raises tot[7] and every emitter below returns at once -- the host then grows the
+// arenas and re-launches them (bmf_batch_wait).  tot = {cells, verts, indices, >2^32, list counters x2, -, too small}
+__global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
+{
+	tot[7] = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
+}
+
 // ---- K4a: per-word output bases + compaction of the CELLS that emit anything.  One CTA per segment with
 // active cells (everything else leaves at once); the segment's sign planes are staged like in k_count.
 // wv4[word] = {chunk-local id of the word's first vertex, X/Y/Z edge-owner masks}, wib[word] = batch-wide position of
@@ -707,10 +716,12 @@ template <int WPT>
 __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wcnt, const uint32_t* __restrict__ seg_tot,
                                                 const ChunkCounts* __restrict__ chunks,
                                                 uint4* __restrict__ wv4, uint32_t* __restrict__ wib, uint2* __restrict__ vcells,
-                                                uint2* __restrict__ icells, unsigned long long* __restrict__ list_count /* [2] */)
+                                                uint2* __restrict__ icells, unsigned long long* __restrict__ list_count /* [2] */,
+                                                const unsigned long long* __restrict__ tot)
 {
 	extern __shared__ uint32_t sb[];
 	__shared__ uint32_t s_base[2], s_pre[2];
+	if (tot[7]) return; // an output arena is too small for this batch (k_check_caps): the host grows it and re-launches
 	const int seg = blockIdx.x;
 	const int chunk = seg >> L.lS, x0 = (seg & (L.S - 1)) * L.P;
 	const ChunkCounts cc = chunks[chunk];
@@ -750,12 +761,12 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 		sc[2] += __popc(c.ex | c.ey | c.ez);
 		sc[3] += __popc(c.active & c.interior);
 	}
-	uint32_t tot[4];
-	block_scan<4>(sc, tot);
+	uint32_t cta_tot[4];
+	block_scan<4>(sc, cta_tot);
 	if (threadIdx.x == 0)
 	{
-		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)tot[2]);
-		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)tot[3]);
+		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)cta_tot[2]);
+		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)cta_tot[3]);
 	}
 	__syncthreads();
 	uint32_t rv = s_pre[0] + sc[0];                          // chunk-local vertex id
@@ -806,8 +817,10 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 // calculate_cell / calculate_isovertex / _get_intersection (DMCChunk.cpp:593-674): X, Y, Z edge of a cell in that order.
 __global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint4* __restrict__ wv4, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
                                                  const ChunkGeom* __restrict__ geom, const uint2* __restrict__ vcells,
-                                                 const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary)
+                                                 const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary,
+                                                 const unsigned long long* __restrict__ tot)
 {
+	if (tot[7]) return;
 	const uint32_t n_cells = (uint32_t)list_count[0];
 	const uint32_t stride = gridDim.x * CTA;
 	const int d = L.d;
@@ -858,9 +871,11 @@ __device__ __forceinline__ uint32_t vertex_id_rec(const uint4* __restrict__ rec4
 // names (EDGE_V, DMCChunk.cpp:32, 543-565) come from the 16-byte vertex records of the neighbouring words.
 __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict__ wv4, const uint32_t* __restrict__ wib,
                                                 const ChunkCounts* __restrict__ chunks, const uint2* __restrict__ icells,
-                                                const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint32_t* __restrict__ cls)
+                                                const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint32_t* __restrict__ cls,
+                                                const unsigned long long* __restrict__ tot)
 {
 	__shared__ uint64_t s_tri[256];
+	if (tot[7]) return;
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
@@ -916,8 +931,9 @@ __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict
 static constexpr int VAL_ITEMS = 8;
 
 __global__ void __launch_bounds__(CTA) k_valence_offsets(const uint32_t* __restrict__ cls, const ChunkCounts* __restrict__ chunks, uint8_t* __restrict__ valence,
-                                                          uint32_t* __restrict__ adj_off)
+                                                          uint32_t* __restrict__ adj_off, const unsigned long long* __restrict__ tot)
 {
+	if (tot[7]) return;
 	const ChunkCounts cc = chunks[blockIdx.x];
 	if (cc.n_verts == 0) return;
 	const size_t v0 = (size_t)cc.vert_base;

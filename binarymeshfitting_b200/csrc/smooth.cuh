@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(CTA) k_csr_sort(const uint32_t* __restrict__ a
 __global__ void __launch_bounds__(CTA) k_adj_fill(Layout L, const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
                                                    const uint2* __restrict__ icells, const unsigned long long* __restrict__ list_count,
                                                    const uint32_t* __restrict__ inds, const uint32_t* __restrict__ cls, const uint32_t* __restrict__ adj_off,
-                                                   uint32_t* __restrict__ adj, uint32_t* __restrict__ prim_vbase)
+                                                   uint32_t* __restrict__ adj, uint32_t* __restrict__ prim_vbase, const unsigned long long* __restrict__ tot)
 {
 	__shared__ uint64_t s_tri[256];
+	if (tot[7]) return;
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
@@ -204,8 +205,15 @@ __device__ __forceinline__ f3 cross3(f3 x, f3 y) { return { x.y * y.z - y.y * x.
 template <int N>
 __global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds, const uint32_t* __restrict__ prim_vbase, size_t n_prims,
                                                const float* __restrict__ pos, const float* __restrict__ color, const float* __restrict__ normal,
-                                               float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals)
+                                               float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals,
+                                               const unsigned long long* __restrict__ tot)
 {
+	if (tot)
+	{
+		// batch path: the launch is sized by arena capacity, the real count lives on the device
+		if (tot[7]) return;
+		n_prims = (size_t)(tot[2] / N);
+	}
 	const size_t t = (size_t)blockIdx.x * CTA + threadIdx.x;
 	if (t >= n_prims) return;
 	const uint32_t vb = prim_vbase[t];
@@ -259,8 +267,13 @@ __global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds,
 __global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
                                                  const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dc,
                                                  const float* __restrict__ dn, float* __restrict__ pos, float* __restrict__ color, float* __restrict__ normal,
-                                                 int smooth, int set_colors, int process_boundary)
+                                                 int smooth, int set_colors, int process_boundary, const unsigned long long* __restrict__ tot)
 {
+	if (tot)
+	{
+		if (tot[7]) return;
+		n_verts = (size_t)tot[1];
+	}
 	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
 	if (v >= n_verts) return;
 	const int cnt = valence[v];
@@ -424,8 +437,13 @@ __global__ void __launch_bounds__(128) k_qef_batch(const float* __restrict__ pos
 // adjacent primitives, clamped to the bounding box of those dual points.
 __global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
                                                     const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dn,
-                                                    float* __restrict__ pos, int process_boundary)
+                                                    float* __restrict__ pos, int process_boundary, const unsigned long long* __restrict__ tot)
 {
+	if (tot)
+	{
+		if (tot[7]) return;
+		n_verts = (size_t)tot[1];
+	}
 	const size_t v = (size_t)blockIdx.x * 128 + threadIdx.x;
 	if (v >= n_verts) return;
 	int cnt = valence[v];
