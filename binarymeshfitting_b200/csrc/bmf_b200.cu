@@ -384,9 +384,9 @@ int launch_mesh(bmf_ctx* ctx)
 	const MeshCaps caps = mesh_caps(ctx);
 	unsigned long long* tot = ctx->totals_dev.p;
 	unsigned long long* list_count = tot + 4;
-	BMF_LAUNCH(k_check_caps, 1, 1, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
-	BMF_CUDA(cudaMemcpyAsync(ctx->totals_pinned, tot, sizeof(HostTotals), cudaMemcpyDeviceToHost, st));
-	BMF_CUDA(cudaMemcpyAsync(ctx->counts_pinned, ctx->counts.p, sizeof(ChunkCounts) * n, cudaMemcpyDeviceToHost, st));
+	// totals and the chunk table reach the host through mapped pinned memory written by the kernels themselves (UVA):
+	// no D2H transfer sits in this stream, so nothing here can queue behind another context's mesh download
+	BMF_LAUNCH(k_check_caps, 1, 1, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 	{
@@ -709,10 +709,9 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		{
 			// no density block wanted: chunks entirely above / below the surface are classified from the sheet range and
 			// skipped; the rest get compare-only sign words (binary search + warp bit transpose, no per-voxel arithmetic)
-			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p);
+			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p, ctx->uni_pinned);
 			BMF_LAUNCH(k_terrain2d_bits, (unsigned)((size_t)n * L.d * L.zc * L.zc / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
 			           ctx->uni.p, ctx->bits.p, ctx->flags.p);
-			BMF_CUDA(cudaMemcpyAsync(ctx->uni_pinned, ctx->uni.p, n, cudaMemcpyDeviceToHost, st));
 			ctx->uni_valid = true;
 		}
 	}
@@ -743,7 +742,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->counts_pinned, ctx->totals_dev.p);
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
 	int rc = launch_mesh(ctx);

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 // (bmf_batch_copy_chunk synthesises them on request).  uni: 0 = mixed, 1 = all air (ones), 2 = all solid (zeros).
 __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, const int* __restrict__ sheet_of,
                                                              const uint32_t* __restrict__ sheet_mm, int n_sheets, int n_chunks, uint32_t* __restrict__ flags,
-                                                             uint8_t* __restrict__ uni)
+                                                             uint8_t* __restrict__ uni, uint8_t* __restrict__ uni_host /* mapped pinned host copy */)
 {
 	const int c = blockIdx.x * CTA + threadIdx.x;
 	if (c >= n_chunks) return;
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const 
 		else if (!(bot < tmax)) u = 2;
 	}
 	uni[c] = u;
+	uni_host[c] = u;
 	if (u) flags[c] = (u == 1) ? CF_ONES : CF_ZERO;
 }
 
@@ -635,7 +636,8 @@ struct ChunkCounts
 static constexpr int SCAN_CTA = 1024;
 
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __restrict__ chunk_tot, const uint32_t* __restrict__ flags, int n_chunks,
-                                                           ChunkCounts* __restrict__ chunks, unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
+                                                           ChunkCounts* __restrict__ chunks, ChunkCounts* __restrict__ chunks_host /* mapped pinned host copy */,
+                                                           unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
 {
 	__shared__ uint32_t s_w[3][SCAN_CTA / 32];
 	__shared__ uint32_t s_tot[3];
@@ -682,6 +684,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 			cc.vert_base = carry1 + (ib - b + s_w[1][warp]);
 			cc.ind_base = carry2 + (ic - c + s_w[2][warp]);
 			chunks[i] = cc;
+			chunks_host[i] = cc; // straight to the host over PCIe: no copy-engine transfer that could queue behind another context's download
 		}
 		carry0 += s_tot[0]; carry1 += s_tot[1]; carry2 += s_tot[2];
 		__syncthreads();
@@ -698,9 +701,12 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 // one-thread kernel compares the totals of THIS batch with the capacities the emitters were launched with; if
 // anything does not fit it raises tot[7] and every emitter below returns at once -- the host then grows the
 // arenas and re-launches them (bmf_batch_wait).  tot = {cells, verts, indices, >2^32, list counters x2, -, too small}
-__global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
+__global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long long* __restrict__ tot_host /* mapped pinned host copy */,
+                             unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
 {
 	tot[7] = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
+	for (int k = 0; k < 8; k++) tot_host[k] = tot[k];
+	__threadfence_system();
 }
 
 // ---- K4a: per-word output bases + compaction of the CELLS that emit anything.  One CTA per segment with
