@@ -94,6 +94,7 @@ struct bmf_ctx
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	int sm_count = 148;
+	int smooth_ctas_per_sm = 8; // resident CTAs per SM of the grid-stride smoothing kernels (tuning knob: BMF_SMOOTH_CTAS_PER_SM)
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
 	DevBuf<ChunkCounts> counts;
@@ -268,6 +269,10 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	if (need_dn) BMF_CUDA(ctx->dn.reserve(3 * n_prims));
 	const size_t per_block = (size_t)CTA * SCAN_ITEMS;
 	const unsigned nblk = grid_for(n_verts, (int)per_block);
+	// the smoothing kernels are grid-stride: at most smooth_ctas_per_sm CTAs per SM stay resident for the whole launch
+	const unsigned gmax = (unsigned)(ctx->sm_count * ctx->smooth_ctas_per_sm);
+	const unsigned g_prims = std::min(grid_for(n_prims, CTA), gmax), g_verts = std::min(grid_for(n_verts, CTA), gmax);
+	const unsigned g_qef = std::min(grid_for(n_verts, 128), gmax * 2);
 	BMF_CUDA(ctx->block_sums.reserve(nblk));
 
 	// init: adj_offset = exclusive prefix of init_valence (MeshProcessor.cpp:33-39); on the batch path k_valence_offsets did it already
@@ -295,24 +300,24 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	for (int m = 0; m < iters; m++)
 	{
 		const int face = (m == 0 || m < max_norms || m < 3) ? 1 : 0;
-		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp,
+		BMF_LAUNCH(k_dual<N>, g_prims, CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp,
 		           need_dn ? ctx->dn.p : nullptr, smooth, face, tot);
 		if (m < iters - 1)
 		{
 			const int set_colors = (m == 3) || (m == 0 && iters <= 3);
-			BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp,
+			BMF_LAUNCH(k_primal, g_verts, CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp,
 			           ctx->dn.p, pos, color, normal, smooth, set_colors, pb, tot);
 		}
 	}
 	// the driver's extra primal call (ChunkGenerator.cpp:120)
 	if (final_primal)
-		BMF_LAUNCH(k_primal, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp, ctx->dn.p, pos,
+		BMF_LAUNCH(k_primal, g_verts, CTA, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, dcp, ctx->dn.p, pos,
 		           color, normal, smooth, 0, pb, tot);
 	if (qef)
 	{
 		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
-		BMF_LAUNCH(k_dual<N>, grid_for(n_prims, CTA), CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1, tot);
-		BMF_LAUNCH(k_qef_place, grid_for(n_verts, 128), 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb, tot);
+		BMF_LAUNCH(k_dual<N>, g_prims, CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1, tot);
+		BMF_LAUNCH(k_qef_place, g_qef, 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb, tot);
 	}
 	return BMF_OK;
 }
@@ -413,8 +418,9 @@ int launch_mesh(bmf_ctx* ctx)
 		           ctx->icells.p, list_count, tot);
 	BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p, tot);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
-	BMF_CUDA(cudaMemsetAsync(ctx->cls.p, 0, sizeof(uint32_t) * V, st));
-	BMF_CUDA(cudaMemsetAsync(ctx->normal.p, 0, sizeof(float) * 3 * V, st));
+	// only the part of the arenas this batch uses is cleared (the count is on the device)
+	BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, ctx->cls.p, V, tot, 1, 1);
+	BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, reinterpret_cast<uint32_t*>(ctx->normal.p), 3 * V, tot, 1, 3);
 	if (ctx->color_ones < 3 * V)
 	{
 		// calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681).  The batch path never writes another colour
@@ -506,6 +512,7 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 	for (int i = 0; i <= BMF_NUM_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
 	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
 	if (ctx->sm_count <= 0) ctx->sm_count = 148;
+	if (const char* e = getenv("BMF_SMOOTH_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v <= 4096) ctx->smooth_ctas_per_sm = v; }
 	cudaMallocHost((void**)&ctx->totals_pinned, sizeof(HostTotals));
 	*out = ctx;
 	return BMF_OK;

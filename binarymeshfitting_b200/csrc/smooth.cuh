@@ -203,19 +203,10 @@ __device__ __forceinline__ f3 cross3(f3 x, f3 y) { return { x.y * y.z - y.y * x.
 
 // ---- dual step (optimize_dual_grid :141-227): centroid, colour mean and (optionally) normal per primitive
 template <int N>
-__global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds, const uint32_t* __restrict__ prim_vbase, size_t n_prims,
-                                               const float* __restrict__ pos, const float* __restrict__ color, const float* __restrict__ normal,
-                                               float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals,
-                                               const unsigned long long* __restrict__ tot)
+__device__ __forceinline__ void dual_one(size_t t, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ prim_vbase,
+                                         const float* __restrict__ pos, const float* __restrict__ color, const float* __restrict__ normal,
+                                         float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals)
 {
-	if (tot)
-	{
-		// batch path: the launch is sized by arena capacity, the real count lives on the device
-		if (tot[7]) return;
-		n_prims = (size_t)(tot[2] / N);
-	}
-	const size_t t = (size_t)blockIdx.x * CTA + threadIdx.x;
-	if (t >= n_prims) return;
 	const uint32_t vb = prim_vbase[t];
 	size_t v[N];
 #pragma unroll
@@ -263,19 +254,28 @@ __global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds,
 	}
 }
 
-// ---- primal step (optimize_primal_grid :238-306)
-__global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
-                                                 const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dc,
-                                                 const float* __restrict__ dn, float* __restrict__ pos, float* __restrict__ color, float* __restrict__ normal,
-                                                 int smooth, int set_colors, int process_boundary, const unsigned long long* __restrict__ tot)
+// grid-stride: the grid is a fixed multiple of the SM count; on the batch path the primitive count is read from the device
+template <int N>
+__global__ void __launch_bounds__(CTA) k_dual(const uint32_t* __restrict__ inds, const uint32_t* __restrict__ prim_vbase, size_t n_prims,
+                                               const float* __restrict__ pos, const float* __restrict__ color, const float* __restrict__ normal,
+                                               float* __restrict__ dp, float* __restrict__ dc, float* __restrict__ dn, int smooth, int face_normals,
+                                               const unsigned long long* __restrict__ tot)
 {
 	if (tot)
 	{
 		if (tot[7]) return;
-		n_verts = (size_t)tot[1];
+		n_prims = (size_t)(tot[2] / N);
 	}
-	const size_t v = (size_t)blockIdx.x * CTA + threadIdx.x;
-	if (v >= n_verts) return;
+	for (size_t t = (size_t)blockIdx.x * CTA + threadIdx.x; t < n_prims; t += (size_t)gridDim.x * CTA)
+		dual_one<N>(t, inds, prim_vbase, pos, color, normal, dp, dc, dn, smooth, face_normals);
+}
+
+// ---- primal step (optimize_primal_grid :238-306)
+__device__ __forceinline__ void primal_one(size_t v, const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                           const uint8_t* __restrict__ boundary, const float* __restrict__ dp, const float* __restrict__ dc,
+                                           const float* __restrict__ dn, float* __restrict__ pos, float* __restrict__ color, float* __restrict__ normal,
+                                           int smooth, int set_colors, int process_boundary)
+{
 	const int cnt = valence[v];
 	if (cnt == 0 || (!process_boundary && boundary[v])) return;
 	const uint32_t* a = adj + adj_off[v];
@@ -295,6 +295,31 @@ __global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj
 	st3(pos, v, p);
 	if (dc) st3(color, v, c);
 	if (n.y != 0 && normal) st3(normal, v, n);
+}
+
+__global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                                 const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dc,
+                                                 const float* __restrict__ dn, float* __restrict__ pos, float* __restrict__ color, float* __restrict__ normal,
+                                                 int smooth, int set_colors, int process_boundary, const unsigned long long* __restrict__ tot)
+{
+	if (tot)
+	{
+		if (tot[7]) return;
+		n_verts = (size_t)tot[1];
+	}
+	for (size_t v = (size_t)blockIdx.x * CTA + threadIdx.x; v < n_verts; v += (size_t)gridDim.x * CTA)
+		primal_one(v, adj_off, adj, valence, boundary, dp, dc, dn, pos, color, normal, smooth, set_colors, process_boundary);
+}
+
+// zero the first n (batch path: tot[idx] * mul) 32-bit words of p
+__global__ void __launch_bounds__(CTA) k_zero_u32(uint32_t* __restrict__ p, size_t n, const unsigned long long* __restrict__ tot, int idx, int mul)
+{
+	if (tot)
+	{
+		if (tot[7]) return;
+		n = (size_t)tot[idx] * mul;
+	}
+	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n; i += (size_t)gridDim.x * CTA) p[i] = 0u;
 }
 
 __global__ void __launch_bounds__(CTA) k_fill_f32(float* __restrict__ p, size_t n, float v)
@@ -435,17 +460,10 @@ __global__ void __launch_bounds__(128) k_qef_batch(const float* __restrict__ pos
 // Build-defined QEF placement (config 5; the reference never calls its solver, MeshProcessor.cpp:239):
 // each processed vertex is re-placed at the QEF minimiser of the planes (dual_p, dual_n) of its first <= 12
 // adjacent primitives, clamped to the bounding box of those dual points.
-__global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
-                                                    const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dn,
-                                                    float* __restrict__ pos, int process_boundary, const unsigned long long* __restrict__ tot)
+__device__ __forceinline__ void qef_place_one(size_t v, const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                              const uint8_t* __restrict__ boundary, const float* __restrict__ dp, const float* __restrict__ dn,
+                                              float* __restrict__ pos, int process_boundary)
 {
-	if (tot)
-	{
-		if (tot[7]) return;
-		n_verts = (size_t)tot[1];
-	}
-	const size_t v = (size_t)blockIdx.x * 128 + threadIdx.x;
-	if (v >= n_verts) return;
 	int cnt = valence[v];
 	if (cnt < 2 || (!process_boundary && boundary[v])) return;
 	if (cnt > 12) cnt = 12;
@@ -467,6 +485,19 @@ __global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ 
 	pos[3 * v] = fminf(fmaxf(o[0], lo.x), hi.x);
 	pos[3 * v + 1] = fminf(fmaxf(o[1], lo.y), hi.y);
 	pos[3 * v + 2] = fminf(fmaxf(o[2], lo.z), hi.z);
+}
+
+__global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence,
+                                                    const uint8_t* __restrict__ boundary, size_t n_verts, const float* __restrict__ dp, const float* __restrict__ dn,
+                                                    float* __restrict__ pos, int process_boundary, const unsigned long long* __restrict__ tot)
+{
+	if (tot)
+	{
+		if (tot[7]) return;
+		n_verts = (size_t)tot[1];
+	}
+	for (size_t v = (size_t)blockIdx.x * 128 + threadIdx.x; v < n_verts; v += (size_t)gridDim.x * 128)
+		qef_place_one(v, adj_off, adj, valence, boundary, dp, dn, pos, process_boundary);
 }
 
 } // namespace bmf
