@@ -22,7 +22,8 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
-           "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve")
+           "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
+           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms")
 
 
 class SamplerDesc(C.Structure):
@@ -98,6 +99,11 @@ def load_library(path=SO):
     lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_mesh_process_steps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    lib.bmf_seam_overlap.argtypes = [C.c_int]
+    lib.bmf_seam_overlap.restype = C.c_float
+    lib.bmf_batch_stitch.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
+    lib.bmf_seam_download.argtypes = [vp, vp]
+    lib.bmf_seam_stage_ms.argtypes = [vp, vp]
     return lib
 
 
@@ -256,6 +262,26 @@ class Context:
         self._check(self.lib.bmf_mesh_process(self.h, _p(pos), _p(color), _p(normal), _p(boundary), None, len(pos), _p(inds), len(inds), prim_n, iters,
                                               int(process_boundary), int(smooth_normals)))
         return pos, color, normal
+
+    def seam_overlap(self, dim):
+        """the overlap that puts a chunk's samples at its voxel-node centres (what the seam pass expects)"""
+        return float(self.lib.bmf_seam_overlap(dim))
+
+    def stitch(self, group=None, cross_group_only=False, download=True):
+        """seam pass over the resident batch -> [n_tris, 3, 3] world-space triangle soup (or the count)"""
+        g = None if group is None else np.ascontiguousarray(group, np.int32)
+        n = C.c_int64()
+        self._check(self.lib.bmf_batch_stitch(self.h, _p(g), int(cross_group_only), C.byref(n)))
+        if not download:
+            return int(n.value)
+        tris = np.zeros((int(n.value), 3, 3), np.float32)
+        self._check(self.lib.bmf_seam_download(self.h, _p(tris)))
+        return tris
+
+    def seam_ms(self):
+        ms = np.zeros(2, np.float32)
+        self._check(self.lib.bmf_seam_stage_ms(self.h, _p(ms)))
+        return {"count": float(ms[0]), "emit": float(ms[1])}
 
     def qef_solve(self, positions, normals, counts):
         """positions/normals: [m,12,3]; counts: [m]."""

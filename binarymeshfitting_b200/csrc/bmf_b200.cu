@@ -5,8 +5,10 @@
 #include "../../include/bmf_b200.h"
 #include "extract.cuh"
 #include "smooth.cuh"
+#include "seam.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <array>
 #include <cstring>
@@ -108,6 +110,16 @@ struct bmf_ctx
 	// qef scratch
 	DevBuf<float> qp, qn, qo, qe;
 	DevBuf<int32_t> qc;
+	// seam pass (seam.cuh)
+	DevBuf<SeamChunk> seam_chunks;
+	DevBuf<int32_t> seam_map, seam_group;
+	DevBuf<uint32_t> seam_blk, seam_cnt;
+	DevBuf<unsigned long long> seam_base; // [n] chunk bases + [1] total
+	DevBuf<float> seam_tris;
+	unsigned long long* seam_total_pinned = nullptr;
+	int64_t seam_n_tris = -1; // -1: no seam pass run on the resident batch
+	cudaEvent_t seam_ev[3] = {};
+	float seam_ms[2] = { 0, 0 };
 
 	HostTotals* totals_pinned = nullptr;
 	ChunkCounts* counts_pinned = nullptr;
@@ -532,6 +544,11 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->totals_pinned) cudaFreeHost(ctx->totals_pinned);
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
+	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
+	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
+	ctx->seam_base.release(); ctx->seam_tris.release();
+	for (cudaEvent_t e : ctx->seam_ev)
+		if (e) cudaEventDestroy(e);
 	ctx->sheet_mm.release(); ctx->uni.release(); ctx->gflags.release();
 	for (int i = 0; i <= BMF_NUM_STAGES; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -590,6 +607,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	ctx->have_batch = false;
 	ctx->finished = false;
 	ctx->uni_valid = false;
+	ctx->seam_n_tris = -1;
 	ctx->kused = 0;
 	ctx->n = n;
 	ctx->params = *params;
@@ -1046,6 +1064,145 @@ int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, co
 	BMF_CUDA(cudaMemcpyAsync(out_pos, ctx->qo.p, sizeof(float) * 3 * M, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(out_err, ctx->qe.p, sizeof(float) * M, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+float bmf_seam_overlap(int dim) { return dim > 0 ? -0.5f / (float)dim : 0.0f; }
+
+int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, int64_t* n_tris)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_stitch: no batch submitted");
+	if (cross_group_only && !group) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: cross_group_only needs group ids");
+	int rc = finish(ctx);
+	if (rc) return rc;
+	const int n = ctx->n;
+	const Layout L = ctx->L;
+	const int d = L.d;
+
+	// the chunk lattice: one slot = the extent of the finest chunk; every chunk must be a power-of-two number of slots
+	// wide and sit at a multiple of its own extent (leaves of one octree do: WorldOctree.cpp:175-210)
+	float smin = ctx->descs[0].size, o[3] = { ctx->descs[0].pos[0], ctx->descs[0].pos[1], ctx->descs[0].pos[2] };
+	for (int i = 0; i < n; i++)
+	{
+		const bmf_chunk_desc& c = ctx->descs[i];
+		if (!(c.size > 0.0f)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunk size must be positive");
+		smin = std::min(smin, c.size);
+		for (int a = 0; a < 3; a++) o[a] = std::min(o[a], c.pos[a]);
+	}
+	std::vector<SeamChunk> sc(n);
+	int g[3] = { 0, 0, 0 };
+	for (int i = 0; i < n; i++)
+	{
+		const bmf_chunk_desc& c = ctx->descs[i];
+		const double e = (double)c.size / (double)smin;
+		const long long ei = llround(e);
+		if (ei < 1 || ei > (1 << 20) || std::fabs(e - (double)ei) > 1e-3 * e || (ei & (ei - 1)))
+			return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunk sizes must be power-of-two multiples of the smallest one");
+		int org[3];
+		for (int a = 0; a < 3; a++)
+		{
+			const double q = ((double)c.pos[a] - (double)o[a]) / (double)smin;
+			const long long qi = llround(q);
+			if (std::fabs(q - (double)qi) > 1e-3 || qi < 0 || qi > (1 << 20) || (qi % ei))
+				return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunks must be aligned leaves of one octree");
+			org[a] = (int)qi;
+			g[a] = std::max(g[a], (int)(qi + ei));
+		}
+		sc[i].ox = org[0]; sc[i].oy = org[1]; sc[i].oz = org[2];
+		sc[i].lg = ilog2((int)ei);
+	}
+	const size_t slots = (size_t)g[0] * g[1] * g[2];
+	if (slots > ((size_t)1 << 24)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: more than 2^24 finest-chunk slots");
+	std::vector<int32_t> map(slots, -1);
+	for (int i = 0; i < n; i++)
+	{
+		const int e = 1 << sc[i].lg;
+		for (int x = sc[i].ox; x < sc[i].ox + e; x++)
+			for (int y = sc[i].oy; y < sc[i].oy + e; y++)
+				for (int z = sc[i].oz; z < sc[i].oz + e; z++)
+				{
+					int32_t& m = map[((size_t)x * g[1] + y) * g[2] + z];
+					if (m >= 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunks overlap");
+					m = i;
+				}
+	}
+
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	SeamArgs A;
+	A.G.gx = g[0]; A.G.gy = g[1]; A.G.gz = g[2];
+	A.G.n = n;
+	A.G.npts = 6 * d * d + 2;
+	A.G.bpc = (A.G.npts + CTA - 1) / CTA;
+	if ((size_t)n * A.G.bpc > 0x7FFFFFFFull) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: batch too large");
+	const unsigned nblk = (unsigned)((size_t)n * A.G.bpc);
+	BMF_CUDA(ctx->seam_chunks.reserve(n));
+	BMF_CUDA(ctx->seam_map.reserve(slots));
+	BMF_CUDA(ctx->seam_blk.reserve(nblk));
+	BMF_CUDA(ctx->seam_cnt.reserve(n));
+	BMF_CUDA(ctx->seam_base.reserve((size_t)n + 1));
+	if (group) BMF_CUDA(ctx->seam_group.reserve(n));
+	if (!ctx->seam_total_pinned) BMF_CUDA(cudaMallocHost((void**)&ctx->seam_total_pinned, sizeof(unsigned long long)));
+	for (cudaEvent_t& e : ctx->seam_ev)
+		if (!e) BMF_CUDA(cudaEventCreate(&e));
+	// pageable sources: these copies are staged by the runtime before the call returns
+	BMF_CUDA(cudaMemcpyAsync(ctx->seam_chunks.p, sc.data(), sizeof(SeamChunk) * n, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->seam_map.p, map.data(), sizeof(int32_t) * slots, cudaMemcpyHostToDevice, st));
+	if (group) BMF_CUDA(cudaMemcpyAsync(ctx->seam_group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->seam_cnt.p, 0, sizeof(uint32_t) * n, st));
+	A.L = L;
+	A.chunks = ctx->seam_chunks.p;
+	A.slot_map = ctx->seam_map.p;
+	A.bits = ctx->bits.p;
+	A.uni = ctx->uni_valid ? ctx->uni.p : nullptr;
+	A.group = group ? ctx->seam_group.p : nullptr;
+	A.cross_group_only = cross_group_only ? 1 : 0;
+	A.geom = ctx->geom.p;
+	A.s = ctx->sampler;
+	A.src.density = ctx->density_cur;
+	A.src.hmap = (!ctx->density_cur && is_terrain2d(ctx->sampler.kind)) ? ctx->hmap.p : nullptr;
+	A.src.sheet_of = ctx->sheet_of.p;
+
+	BMF_CUDA(cudaEventRecord(ctx->seam_ev[0], st));
+	BMF_LAUNCH(k_seam_count, nblk, CTA, 0, A, ctx->seam_blk.p, ctx->seam_cnt.p);
+	BMF_LAUNCH(k_seam_scan, 1, SEAM_SCAN_CTA, 0, ctx->seam_cnt.p, n, ctx->seam_base.p, ctx->seam_base.p + n);
+	BMF_CUDA(cudaEventRecord(ctx->seam_ev[1], st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->seam_total_pinned, ctx->seam_base.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	const unsigned long long T = *ctx->seam_total_pinned;
+	if (T > 0x7FFFFFFFull) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: more than 2^31 seam triangles; split the batch");
+	if (T)
+	{
+		BMF_CUDA(ctx->seam_tris.reserve(9 * (size_t)T));
+		BMF_LAUNCH(k_seam_emit, nblk, CTA, 0, A, ctx->seam_blk.p, ctx->seam_base.p, ctx->seam_tris.p);
+	}
+	BMF_CUDA(cudaEventRecord(ctx->seam_ev[2], st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	cudaEventElapsedTime(&ctx->seam_ms[0], ctx->seam_ev[0], ctx->seam_ev[1]);
+	cudaEventElapsedTime(&ctx->seam_ms[1], ctx->seam_ev[1], ctx->seam_ev[2]);
+	ctx->seam_n_tris = (int64_t)T;
+	if (n_tris) *n_tris = (int64_t)T;
+	return BMF_OK;
+}
+
+int bmf_seam_download(bmf_ctx* ctx, float* positions)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (ctx->seam_n_tris < 0) return fail(ctx, BMF_ERR_STATE, "bmf_seam_download: no seam pass run on the resident batch");
+	if (!positions || ctx->seam_n_tris == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	BMF_CUDA(cudaMemcpyAsync(positions, ctx->seam_tris.p, sizeof(float) * 9 * (size_t)ctx->seam_n_tris, cudaMemcpyDeviceToHost, ctx->stream));
+	BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+	return BMF_OK;
+}
+
+int bmf_seam_stage_ms(bmf_ctx* ctx, float* ms)
+{
+	if (!ctx || !ms) return BMF_ERR_INVALID;
+	if (ctx->seam_n_tris < 0) return fail(ctx, BMF_ERR_STATE, "bmf_seam_stage_ms: no seam pass run on the resident batch");
+	ms[0] = ctx->seam_ms[0];
+	ms[1] = ctx->seam_ms[1];
 	return BMF_OK;
 }
 

@@ -175,6 +175,24 @@ int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal
  * (2..12) planes from positions/normals[j*12*3 ...]; writes out_pos[3*j..], out_err[j]. */
 int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err);
 
+/* WorldStitcher::stitch_all(root) (WorldStitcher.cpp:26-49 -> stitch_cell :184-239 -> stitch_indexes :491-572): the seam
+ * pass over the RESIDENT batch, whose chunks must be aligned leaves of one octree (any mix of levels; a missing
+ * neighbour simply gets no seam).  Every dual cell formed by 8 voxel nodes that do not all belong to one chunk is
+ * polygonised with the marching-cubes table from the nodes' sample positions and densities.  The reference's version is
+ * non-functional as committed, so the behaviour is defined by this build (UNPINNED; see csrc/seam.cuh): chunks are
+ * expected to be sampled at voxel-node centres, i.e. submitted with overlap = bmf_seam_overlap(dim) = -1/(2 dim), so
+ * that the chunk meshes and the seam tile space without gaps or overlaps.
+ * group / cross_group_only: with per-chunk group ids (e.g. the GPU that meshed the chunk) and cross_group_only = 1 only
+ * the cells whose nodes span more than one group are emitted -- the final pass after a multi-GPU gather.
+ * Output: a non-indexed triangle soup in world coordinates (stitch_indexes :568-570 pushes DualVertex triples),
+ * ordered by (chunk, lattice point, table order); zero-area triangles with two coincident corners are dropped. */
+float bmf_seam_overlap(int dim);
+int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group /* [n] or NULL */, int cross_group_only, int64_t* n_tris);
+/* positions: [n_tris][3 corners][xyz] floats.  The reference colours every seam vertex (0.85, 1, 0.85) (:484-487). */
+int bmf_seam_download(bmf_ctx* ctx, float* positions);
+/* device times of the last seam pass: ms[0] = count + scan, ms[1] = emit */
+int bmf_seam_stage_ms(bmf_ctx* ctx, float* ms /* [2] */);
+
 #ifdef __cplusplus
 }
 #endif

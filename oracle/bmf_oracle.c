@@ -818,3 +818,126 @@ int64_t orc_batch(const orc_sampler* s, const float* pos_size, int n, int dim, c
 	}
 	return total;
 }
+
+/* ---- seam pass (build-defined, UNPINNED: WorldStitcher.cpp:26-49, 184-239, 491-572 is non-functional as committed) ----
+ * Every chunk is d^3 voxel nodes; node (x,y,z) of a chunk sits at overlap_pos + (x,y,z)*delta and carries the chunk's
+ * density sample there.  Around every corner point P of the voxel lattice that lies on a chunk's boundary shell, the 8
+ * voxels (of whatever chunk / LOD) containing P's octants form a dual cell, polygonised like stitch_indexes does:
+ * corner o = 4*dx + 2*dy + dz, crossing points by _get_intersection (:476-481), triangles from the MC table.
+ * P is visited from the lowest-index chunk among the finest chunks touching it; cells reaching outside the chunk set
+ * are skipped; triangles with two coincident corners are dropped.  Order: chunk, shell point (x faces, y faces
+ * without x borders, z faces without x/y borders; low face first; row-major), table order. */
+typedef struct seam_lat { int o[3]; int lg; } seam_lat;
+
+static int seam_ilog2(long long v) { int l = 0; while ((1LL << l) < v) l++; return l; }
+
+int64_t orc_seam(const orc_seam_chunk* ch, int n, int dim, const int32_t* group, int cross_group_only, float** tris_out)
+{
+	const int d = dim, zc = d / 32;
+	*tris_out = 0;
+	if (n <= 0) return 0;
+	float smin = ch[0].size, org[3] = { ch[0].pos[0], ch[0].pos[1], ch[0].pos[2] };
+	for (int i = 0; i < n; i++)
+	{
+		if (ch[i].size < smin) smin = ch[i].size;
+		for (int a = 0; a < 3; a++) if (ch[i].pos[a] < org[a]) org[a] = ch[i].pos[a];
+	}
+	seam_lat* lat = (seam_lat*)malloc(sizeof(seam_lat) * (size_t)n);
+	float (*geo)[4] = (float (*)[4])malloc(sizeof(float) * 4 * (size_t)n);
+	int G[3] = { 0, 0, 0 };
+	for (int i = 0; i < n; i++)
+	{
+		long long e = llround((double)ch[i].size / (double)smin);
+		if (e < 1 || (e & (e - 1))) { free(lat); free(geo); return -1; }
+		lat[i].lg = seam_ilog2(e);
+		for (int a = 0; a < 3; a++)
+		{
+			long long q = llround(((double)ch[i].pos[a] - (double)org[a]) / (double)smin);
+			if (q % e) { free(lat); free(geo); return -1; }
+			lat[i].o[a] = (int)q;
+			if (q + e > G[a]) G[a] = (int)(q + e);
+		}
+		orc_chunk_geometry(ch[i].pos, ch[i].size, d, ch[i].overlap, geo[i], &geo[i][3]);
+	}
+	int32_t* map = (int32_t*)malloc(sizeof(int32_t) * (size_t)G[0] * G[1] * G[2]);
+	for (size_t i = 0; i < (size_t)G[0] * G[1] * G[2]; i++) map[i] = -1;
+	for (int i = 0; i < n; i++)
+	{
+		const int e = 1 << lat[i].lg;
+		for (int x = 0; x < e; x++)
+			for (int y = 0; y < e; y++)
+				for (int z = 0; z < e; z++)
+					map[((size_t)(lat[i].o[0] + x) * G[1] + lat[i].o[1] + y) * G[2] + lat[i].o[2] + z] = i;
+	}
+	size_t cap = 1024, cnt = 0;
+	float* out = (float*)malloc(sizeof(float) * 9 * cap);
+	const int npts = 6 * d * d + 2;
+	for (int c = 0; c < n; c++)
+	{
+		const int vs = 1 << lat[c].lg; /* voxel size of chunk c in finest-voxel units */
+		for (int t = 0; t < npts; t++)
+		{
+			/* shell point t -> (i,j,k) */
+			int i, j, k, r = t;
+			const int fa = (d + 1) * (d + 1), fb = (d - 1) * (d + 1), fc = (d - 1) * (d - 1);
+			if (r < 2 * fa) { i = r < fa ? 0 : d; r %= fa; j = r / (d + 1); k = r % (d + 1); }
+			else if ((r -= 2 * fa) < 2 * fb) { j = r < fb ? 0 : d; r %= fb; i = 1 + r / (d + 1); k = r % (d + 1); }
+			else { r -= 2 * fb; k = r < fc ? 0 : d; r %= fc; i = 1 + r / (d - 1); j = 1 + r % (d - 1); }
+			const long long P[3] = { (long long)lat[c].o[0] * d + (long long)i * vs, (long long)lat[c].o[1] * d + (long long)j * vs,
+			                         (long long)lat[c].o[2] * d + (long long)k * vs };
+			int node_c[8], node_v[8][3], mask = 0, ok = 1, owner = c, multi = 0;
+			for (int o = 0; o < 8 && ok; o++)
+			{
+				const int off[3] = { o >> 2, (o >> 1) & 1, o & 1 };
+				long long q[3];
+				int m;
+				for (int a = 0; a < 3; a++) q[a] = P[a] - 1 + off[a];
+				if (q[0] < 0 || q[1] < 0 || q[2] < 0 || q[0] >= (long long)G[0] * d || q[1] >= (long long)G[1] * d || q[2] >= (long long)G[2] * d) { ok = 0; break; }
+				m = map[((size_t)(q[0] / d) * G[1] + (size_t)(q[1] / d)) * G[2] + (size_t)(q[2] / d)];
+				if (m < 0 || lat[m].lg < lat[c].lg) { ok = 0; break; }
+				if (lat[m].lg == lat[c].lg && m < owner) owner = m;
+				if (group && group[m] != group[c]) multi = 1;
+				node_c[o] = m;
+				for (int a = 0; a < 3; a++) node_v[o][a] = (int)((q[a] - (long long)lat[m].o[a] * d) >> lat[m].lg);
+				const int bit = (ch[m].bits[((size_t)node_v[o][0] * d + node_v[o][1]) * zc + (node_v[o][2] >> 5)] >> (node_v[o][2] & 31)) & 1;
+				mask |= bit << o;
+			}
+			if (!ok || owner != c || mask == 0 || mask == 255) continue;
+			if (cross_group_only && !multi) continue;
+			float np[8][3], ns[8];
+			for (int o = 0; o < 8; o++)
+			{
+				const int m = node_c[o];
+				for (int a = 0; a < 3; a++) np[o][a] = geo[m][a] + (float)node_v[o][a] * geo[m][3];
+				ns[o] = ch[m].density[((size_t)node_v[o][0] * d + node_v[o][1]) * d + node_v[o][2]];
+			}
+			const uint64_t tp = TRI_PACK[mask];
+			const int ni = (int)(tp >> 60);
+			for (int q0 = 0; q0 < ni; q0 += 3)
+			{
+				float v[3][3];
+				for (int rr = 0; rr < 3; rr++)
+				{
+					const int e = (int)((tp >> (4 * (q0 + rr))) & 15);
+					int a, b;
+					if (e < 4) { a = (((e >> 1) & 1) << 1) | (e & 1); b = a | 4; }
+					else if (e < 8) { a = ((((e - 4) >> 1) & 1) << 2) | ((e - 4) & 1); b = a | 2; }
+					else { a = ((((e - 8) >> 1) & 1) << 2) | (((e - 8) & 1) << 1); b = a | 1; }
+					const float mu = (0.0f - ns[a]) / (ns[b] - ns[a]);
+					for (int x = 0; x < 3; x++) v[rr][x] = (np[b][x] - np[a][x]) * mu + np[a][x];
+				}
+				if ((v[0][0] == v[1][0] && v[0][1] == v[1][1] && v[0][2] == v[1][2]) || (v[1][0] == v[2][0] && v[1][1] == v[2][1] && v[1][2] == v[2][2]) ||
+				    (v[0][0] == v[2][0] && v[0][1] == v[2][1] && v[0][2] == v[2][2]))
+					continue;
+				if (cnt == cap) { cap *= 2; out = (float*)realloc(out, sizeof(float) * 9 * cap); }
+				memcpy(out + 9 * cnt, v, sizeof(float) * 9);
+				cnt++;
+			}
+		}
+	}
+	free(lat); free(geo); free(map);
+	*tris_out = out;
+	return (int64_t)cnt;
+}
+
+void orc_free(void* p) { free(p); }

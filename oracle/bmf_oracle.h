@@ -98,6 +98,21 @@ int orc_chunk(const orc_sampler* s, const float pos[3], float size, int dim, flo
 int64_t orc_batch(const orc_sampler* s, const float* pos_size /* n x 4 */, int n, int dim, const float* overlaps, int iters,
                   int process_boundary, int threads, int32_t* counts);
 
+/* seam pass between chunks (UNPINNED, build-defined: the reference's WorldStitcher is non-functional as committed).
+ * bits / density: the chunk's sign words and density block as orc_label_grid / orc_sample_block produce them.
+ * Returns the number of triangles (or -1 if the chunks are not aligned octree leaves); *tris_out = malloc'd
+ * [n_tris][3][3] world-space positions (orc_free). */
+typedef struct orc_seam_chunk
+{
+	float pos[3];
+	float size;
+	float overlap;
+	const uint32_t* bits;
+	const float* density;
+} orc_seam_chunk;
+int64_t orc_seam(const orc_seam_chunk* chunks, int n, int dim, const int32_t* group, int cross_group_only, float** tris_out);
+void orc_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,10 @@ class Mesh(C.Structure):
                 ("boundary", C.POINTER(C.c_uint8)), ("valence", C.POINTER(C.c_uint8)), ("inds", C.POINTER(C.c_uint32))]
 
 
+class SeamChunk(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("size", C.c_float), ("overlap", C.c_float), ("bits", C.c_void_p), ("density", C.c_void_p)]
+
+
 def build(force=False):
     srcs = [os.path.join(HERE, f) for f in ("bmf_oracle.c", "bmf_oracle.h", "fastnoise_ref.h", "mc_tables_oracle.h")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
@@ -69,6 +73,9 @@ class Oracle:
         lib.orc_qef_solve.restype = C.c_float
         lib.orc_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_qef_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_seam.restype = C.c_int64
+        lib.orc_seam.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float))]
+        lib.orc_free.argtypes = [C.c_void_p]
         lib.orc_batch.restype = C.c_int64
         lib.orc_batch.argtypes = [C.POINTER(Sampler), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
 
@@ -176,6 +183,30 @@ class Oracle:
                 self.lib.orc_qef_place(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary))
                 out["pos"] = p
         return out
+
+    def seam(self, chunks, pos_size, dim, overlaps, group=None, cross_group_only=False):
+        """seam pass over chunks = [self.chunk(...) dicts] (needs their "bits" and "density") -> [n_tris, 3, 3]"""
+        ps = np.ascontiguousarray(pos_size, np.float32).reshape(-1, 4)
+        ov = np.broadcast_to(np.asarray(overlaps, np.float32), (len(ps),))
+        arr = (SeamChunk * len(ps))()
+        keep = []
+        for i, ch in enumerate(chunks):
+            b = np.ascontiguousarray(ch["bits"], np.uint32)
+            dn = np.ascontiguousarray(ch["density"], np.float32)
+            keep += [b, dn]
+            arr[i].pos[:] = [float(v) for v in ps[i, :3]]
+            arr[i].size = float(ps[i, 3])
+            arr[i].overlap = float(ov[i])
+            arr[i].bits = b.ctypes.data_as(C.c_void_p)
+            arr[i].density = dn.ctypes.data_as(C.c_void_p)
+        g = None if group is None else np.ascontiguousarray(group, np.int32)
+        out = C.POINTER(C.c_float)()
+        n = self.lib.orc_seam(arr, len(ps), dim, _p(g), int(cross_group_only), C.byref(out))
+        if n < 0:
+            raise ValueError("orc_seam: chunks are not aligned octree leaves")
+        tris = _np(out, 9 * n, np.float32).reshape(-1, 3, 3)
+        self.lib.orc_free(out)
+        return tris
 
     def batch(self, sampler, pos_size, dim, overlaps=None, iters=0, process_boundary=False, threads=0):
         ps = np.ascontiguousarray(pos_size, np.float32).reshape(-1, 4)
