@@ -635,10 +635,91 @@ private:
 	std::vector<WorldOctreeNode*> owned;
 };
 
+// ---- WorldStitcher ----------------------------------------------------------------------------------------------
+// WorldStitcher.hpp:15-77.  stitch_all(root) (WorldStitcher.cpp:26-49) walks the world octree for dual cells between
+// leaves and polygonises them into `vertices`, a non-indexed DualVertex triangle soup (:568-570) that format() turns
+// into the SoA gl_chunk (GLChunk::format_data_tris).  Here the leaves go to the device as one batch and
+// bmf_batch_stitch does the work (csrc/seam.cuh); behaviour is build-defined (the reference's version is
+// non-functional as committed).  Runs on the first device of the generator; with several GPUs this is the pass after
+// the host gather.
+class WorldStitcher
+{
+public:
+	SmartContainer<DualVertex> vertices;
+	GLChunk gl_chunk;
+	int stage = 0; // STITCHING_STAGES_READY
+	float last_ms[2] = { 0, 0 }; // device time of the last pass: count+scan, emit
+
+	void init() {}
+
+	bool stitch_all(WorldOctree* world, int device_slot = 0, int device_id = 0)
+	{
+		vertices.count = 0;
+		if (!world || world->leaves.empty()) return true;
+		return stitch_batch_nodes(world, world->leaves.data(), world->leaves.size(), device_slot, device_id);
+	}
+
+	bool stitch_batch_nodes(WorldOctree* world, WorldOctreeNode* const* nodes, size_t count, int device_slot = 0, int device_id = 0)
+	{
+		vertices.count = 0;
+		BmfDevice& dev = BmfDevice::slot(device_slot, device_id);
+		if (!dev.ok()) return false;
+		std::vector<bmf_chunk_desc> descs(count);
+		const int dim = world->properties.chunk_resolution;
+		for (size_t k = 0; k < count; k++)
+		{
+			const WorldOctreeNode* n = nodes[k];
+			bmf_chunk_desc& c = descs[k];
+			c.pos[0] = n->pos.x; c.pos[1] = n->pos.y; c.pos[2] = n->pos.z; c.size = n->size; c.level = n->level; c.morton = n->morton_code;
+			c.overlap = bmf_seam_overlap(dim);
+		}
+		bmf_sampler_desc d = world->sampler.device;
+		if (d.kind == BMF_SAMPLER_HOST_DENSITY) return false;
+		d.world_size = world->sampler.world_size;
+		if (d.kind == BMF_SAMPLER_TERRAIN2D_PERT)
+		{
+			const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
+			d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
+		}
+		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
+		bmf_params p;
+		std::memset(&p, 0, sizeof(p));
+		p.dim = dim; // signs and border samples only: no smoothing
+		if (bmf_batch_submit(dev.ctx, descs.data(), (int)count, &p, nullptr) != BMF_OK) return false;
+		int64_t nt = 0;
+		if (bmf_batch_stitch(dev.ctx, nullptr, 0, &nt) != BMF_OK) return false;
+		bmf_seam_stage_ms(dev.ctx, last_ms);
+		std::vector<float> tris(9 * (size_t)nt + 9);
+		if (bmf_seam_download(dev.ctx, tris.data()) != BMF_OK) return false;
+		if (!vertices.prepare(3 * (size_t)nt)) return false;
+		vertices.count = 3 * (size_t)nt;
+		for (size_t v = 0; v < 3 * (size_t)nt; v++)
+		{
+			DualVertex& dv = vertices[v];
+			std::memset((void*)&dv, 0, sizeof(dv));
+			dv.p = glm::vec3(tris[3 * v], tris[3 * v + 1], tris[3 * v + 2]);
+			dv.color = glm::vec3(0.85f, 1.0f, 0.85f); // DUAL_VERTEX (WorldStitcher.cpp:484-487)
+		}
+		return true;
+	}
+
+	// GLChunk::format_data_tris(vertices): positions and colours of the soup, flat
+	void format()
+	{
+		gl_chunk.p_data.count = gl_chunk.c_data.count = gl_chunk.n_data.count = 0;
+		for (size_t v = 0; v < vertices.count; v++)
+		{
+			gl_chunk.p_data.push_back(vertices[v].p);
+			gl_chunk.c_data.push_back(vertices[v].color);
+		}
+	}
+};
+
 // ---- ChunkGenerator ---------------------------------------------------------------------------------------------
 class ChunkGenerator
 {
 public:
+	WorldStitcher stitcher; // ChunkGenerator.hpp:38
 	ResourceAllocator<GLChunk> gl_allocator;
 	ResourceAllocator<DensityBlock> density_allocator;
 	ResourceAllocator<BinaryBlock> binary_allocator;
@@ -710,6 +791,8 @@ private:
 			bmf_chunk_desc& c = descs[k];
 			c.pos[0] = n->pos.x; c.pos[1] = n->pos.y; c.pos[2] = n->pos.z; c.size = n->size; c.level = n->level; c.morton = n->morton_code;
 			c.overlap = (n->level == max_level && (!pb || iters == 0)) ? 0.0f : base_overlap + 0.005f * (float)iters; // ChunkGenerator.cpp:98
+			// with a working seam pass the chunks are sampled at voxel-node centres instead of being overlapped
+			if (world->properties.enable_stitching) c.overlap = bmf_seam_overlap(world->properties.chunk_resolution);
 		}
 		bmf_sampler_desc d = world->sampler.device;
 		d.world_size = world->sampler.world_size;

@@ -181,6 +181,40 @@ int main(int argc, char** argv)
 		printf("lod chunks=%zu with_mesh=%zu verts=%zu inds=%zu inds_crc=%u leaves_crc=%u\n", world.leaves.size(), nm, nv, ni, hi, hl);
 		return 0;
 	}
+	if (!strcmp(argv[1], "stitch") && argc >= 8)
+	{
+		// LOD world with enable_stitching: process_queue samples at voxel-node centres, stitcher.stitch_all closes the seams
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]);
+		WorldOctree world;
+		world.sampler = make_sampler(kind);
+		world.properties.chunk_resolution = dim;
+		world.properties.max_level = max_level;
+		world.properties.enable_stitching = true;
+		world.focus_point = glm::vec3((float)atof(argv[5]), (float)atof(argv[6]), (float)atof(argv[7]));
+		world.init(256);
+		world.split_leaves();
+		ChunkGenerator gen;
+		gen.init(&world);
+		SmartContainer<WorldOctreeNode*> batch;
+		for (WorldOctreeNode* n : world.leaves)
+		{
+			n->generation_stage = GENERATION_STAGES_GENERATING;
+			batch.push_back(n);
+		}
+		if (!gen.process_queue(batch) || !gen.stitcher.stitch_all(&world))
+		{
+			fprintf(stderr, "stitch failed: %s\n", BmfDevice::get().error());
+			return 5;
+		}
+		gen.stitcher.format();
+		size_t nv = 0, ni = 0;
+		for (WorldOctreeNode* n : world.leaves)
+			if (n->chunk->contains_mesh && n->chunk->vi) { nv += n->chunk->vi->vertices.count; ni += n->chunk->vi->mesh_indexes.count; }
+		const uint32_t hp = crc32_of(gen.stitcher.gl_chunk.p_data.elements, gen.stitcher.gl_chunk.p_data.count * 12, 0);
+		printf("stitch chunks=%zu verts=%zu inds=%zu seam_verts=%zu seam_crc=%u color_g=%g\n", world.leaves.size(), nv, ni, gen.stitcher.vertices.count, hp,
+		       gen.stitcher.vertices.count ? (double)gen.stitcher.vertices[0].color.y : 0.0);
+		return 0;
+	}
 	if (!strcmp(argv[1], "world") && argc >= 7)
 	{
 		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), iters = atoi(argv[5]);

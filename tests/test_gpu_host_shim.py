@@ -96,3 +96,20 @@ def test_cpp_split_leaves_and_multi_context_partition(w, devices):
     assert int(out["inds_crc"]) == w["inds_crc"]
     leaves = ARR[w["key"] + "_leaves"][:, :4].astype(np.float32)
     assert int(out["leaves_crc"]) == crc(leaves)
+
+
+def test_worldstitcher_mirror_closes_a_lod_world(oracle):
+    """C++: properties.enable_stitching -> process_queue samples at voxel-node centres, ChunkGenerator::stitcher
+    (WorldStitcher mirror) emits the seam soup; same triangles as the oracle's seam pass over the same leaves"""
+    focus, dim, max_level = (90.0, 20.0, -30.0), 32, 3
+    out = run("stitch", ob.TORUS_Z, dim, max_level, *focus)["stitch"]
+    props = W.WorldProperties(max_level=max_level, chunk_resolution=dim)
+    ps, lv, mc = W.split_leaves(props, 256, focus)
+    ov = np.float32(-0.5) / np.float32(dim)
+    s = oracle.sampler(ob.TORUS_Z)
+    chunks = [oracle.chunk(s, p[:3], p[3], dim, ov) for p in ps]
+    seam = oracle.seam(chunks, ps, dim, ov)
+    assert int(out["chunks"]) == len(ps) and len(seam) > 0
+    assert (int(out["verts"]), int(out["inds"])) == (sum(c["n_verts"] for c in chunks), sum(c["n_inds"] for c in chunks))
+    assert int(out["seam_verts"]) == 3 * len(seam) and int(out["seam_crc"]) == crc(seam)
+    assert abs(float(out["color_g"]) - 1.0) < 1e-6
