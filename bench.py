@@ -412,6 +412,32 @@ def extras(ctx, args, capi, world):
         ctx.set_sampler(kind)
         s = timed(ld, 64, 2, reps=10)
         ex["lod_rebuild_232x64_%s" % name] = {"ms": s * 1e3, "voxels_per_s": len(ld) * 64 ** 3 / s}
+    # config 4 as named ("multi-level chunks + WorldStitcher seams"): the same world sampled at voxel-node centres, chunk
+    # meshes + 2 smoothing iterations, then the seam pass (bmf_batch_stitch); wall time incl. its one host round trip
+    try:
+        sd = capi.make_chunk_descs(lps, overlaps=ctx.seam_overlap(64), levels=lv)
+        for name, kind in (("terrain2d_pert", capi.TERRAIN2D_PERT), ("terrain3d_pert", capi.TERRAIN3D_PERT)):
+            ctx.set_sampler(kind)
+            walls, nt = [], 0
+            for r in range(6):
+                t0 = _t.perf_counter()
+                ctx.submit(sd, 64, iters=2)
+                nt = ctx.stitch(download=False)
+                walls.append(_t.perf_counter() - t0)
+            ex["lod_rebuild_with_seams_232x64_%s" % name] = {"ms": min(walls[1:]) * 1e3, "seam_tris": nt, "seam_device_ms": ctx.seam_ms(),
+                                                            "mesh": dict(zip(("cells", "verts", "indices"), ctx.totals()))}
+        # seams of the uniform benchmark grid (every chunk border of the 16^3 grid)
+        ctx.set_sampler(SAMPLERS[args.sampler])
+        gd = capi.make_chunk_descs(ps, overlaps=ctx.seam_overlap(args.dim))
+        ctx.submit(gd, args.dim, iters=args.iters)
+        nt = ctx.stitch(download=False)
+        nt = ctx.stitch(download=False)
+        sm = ctx.seam_ms()
+        pts = len(gd) * (6 * args.dim ** 2 + 2)
+        ex["seam_pass_4096x64_%s" % args.sampler] = {"seam_tris": nt, "device_ms": sm, "lattice_points": pts,
+                                                     "lattice_points_per_s": pts / ((sm["count"] + sm["emit"]) * 1e-3)}
+    except Exception as e:  # noqa: BLE001
+        ex["lod_rebuild_with_seams"] = {"error": str(e)}
     # config 2: single 128^3 chunk, 2 smoothing iterations
     one = capi.make_chunk_descs([[-64, -64, -64, 128.0]], overlaps=0.045)
     for name, kind in (("terrain2d_pert", capi.TERRAIN2D_PERT), ("terrain3d_pert", capi.TERRAIN3D_PERT)):

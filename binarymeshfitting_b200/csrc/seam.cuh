@@ -26,6 +26,10 @@
 namespace bmf
 {
 
+// the triangle table again, in global memory: only the rare sign-changing cells read it (a threadIdx-indexed fill of
+// shared memory from __constant__ serialises 32 ways per warp and would cost more than the cells themselves)
+__device__ const uint64_t g_tri_pack[256] = BMF_TRI_PACK_INIT;
+
 struct SeamChunk
 {
 	int32_t ox, oy, oz; // origin in slots (one slot = the extent of the finest chunk of the batch)
@@ -81,6 +85,7 @@ struct SeamArgs
 	const int32_t* slot_map; // [gx][gy][gz] chunk index or -1
 	const uint32_t* bits;
 	const uint8_t* uni;      // per-chunk uniform flag (2-D terrains without a density block) or null
+	const uint8_t* clean;    // per-chunk, bit f: no dual cell in the interior of face f (x0,x1,y0,y1,z0,z1) changes sign
 	const int32_t* group;    // per-chunk group id or null
 	int cross_group_only;    // 1: only cells whose nodes span more than one group
 	const ChunkGeom* geom;
@@ -88,46 +93,97 @@ struct SeamArgs
 	DensitySource src;
 };
 
+// One entry per direction (dx,dy,dz) in {-1,0,1}^3 around a chunk: the chunk on that side if it is a single
+// same-or-coarser chunk (then it covers the whole face / edge / corner region), else invalid -- a finer or missing
+// neighbour means this chunk owns no dual cell touching that region.
+struct SeamNbr
+{
+	int32_t m;          // chunk index, < 0 = invalid
+	int32_t bx, by, bz; // origin in finest-voxel units
+	int32_t lg;
+	int32_t u;          // 0: read sign words, 1: uniformly air, 2: uniformly solid
+	int32_t grp;
+};
+
+// filled by the first 27 threads of the CTA for chunk c (direction index = 9 (dx+1) + 3 (dy+1) + (dz+1))
+__device__ __forceinline__ void seam_fill_nbrs(const SeamArgs& A, int c, SeamNbr* tab)
+{
+	if (threadIdx.x < 27)
+	{
+		const int q = threadIdx.x, dx = q / 9 - 1, dy = (q / 3) % 3 - 1, dz = q % 3 - 1;
+		const SeamChunk me = A.chunks[c];
+		const int e = 1 << me.lg;
+		const int sx = me.ox + (dx < 0 ? -1 : dx > 0 ? e : 0), sy = me.oy + (dy < 0 ? -1 : dy > 0 ? e : 0), sz = me.oz + (dz < 0 ? -1 : dz > 0 ? e : 0);
+		SeamNbr n;
+		n.m = -1;
+		n.bx = n.by = n.bz = n.lg = n.u = n.grp = 0;
+		if (sx >= 0 && sy >= 0 && sz >= 0 && sx < A.G.gx && sy < A.G.gy && sz < A.G.gz)
+		{
+			const int m = A.slot_map[((size_t)sx * A.G.gy + sy) * A.G.gz + sz];
+			if (m >= 0)
+			{
+				const SeamChunk o = A.chunks[m];
+				if (o.lg >= me.lg)
+				{
+					n.m = m;
+					n.bx = o.ox << A.L.ld; n.by = o.oy << A.L.ld; n.bz = o.oz << A.L.ld;
+					n.lg = o.lg;
+					n.u = A.uni ? (int32_t)A.uni[m] : 0;
+					n.grp = A.group ? A.group[m] : 0;
+				}
+			}
+		}
+		tab[q] = n;
+	}
+}
+
 // the dual cell at shell point t of chunk c: returns the number of triangles kept and (if tri) their 9 floats each
-__device__ __forceinline__ int seam_cell(const SeamArgs& A, const uint64_t* __restrict__ s_tri, int c, int t, float* tri)
+__device__ __forceinline__ int seam_cell(const SeamArgs& A, const SeamNbr* __restrict__ tab, int c, int t, float* tri)
 {
 	const int d = A.L.d, ld = A.L.ld;
 	int i, j, k;
 	seam_shell_point(t, d, i, j, k);
-	const SeamChunk me = A.chunks[c];
-	const int Px = (me.ox << ld) + (i << me.lg), Py = (me.oy << ld) + (j << me.lg), Pz = (me.oz << ld) + (k << me.lg);
-	int cm[8], vx[8], vy[8], vz[8];
-	uint32_t mask = 0;
+	{
+		// interior of a face whose two voxel layers (this chunk's and the neighbour's) are uniformly of one sign
+		const int fx = i == 0 ? 0 : i == d ? 1 : -1, fy = j == 0 ? 2 : j == d ? 3 : -1, fz = k == 0 ? 4 : k == d ? 5 : -1;
+		const int nf = (fx >= 0) + (fy >= 0) + (fz >= 0);
+		if (nf == 1 && ((A.clean[c] >> (fx >= 0 ? fx : fy >= 0 ? fy : fz)) & 1)) return 0;
+	}
+	const SeamNbr me = tab[13];
+	const int Px = me.bx + (i << me.lg), Py = me.by + (j << me.lg), Pz = me.bz + (k << me.lg);
+	const int hx = me.bx + (d << me.lg), hy = me.by + (d << me.lg), hz = me.bz + (d << me.lg);
+	int cm[8], vx[8], vy[8], vz[8], un[8];
 	int owner = c;
-	bool same_group = true;
-	const int g0 = A.group ? A.group[c] : 0;
+	bool same_group = true, ok = true;
 #pragma unroll
 	for (int o = 0; o < 8; o++)
 	{
 		const int qx = Px - 1 + (o >> 2), qy = Py - 1 + ((o >> 1) & 1), qz = Pz - 1 + (o & 1);
-		if (qx < 0 || qy < 0 || qz < 0) return 0;
-		const int sx = qx >> ld, sy = qy >> ld, sz = qz >> ld;
-		if (sx >= A.G.gx || sy >= A.G.gy || sz >= A.G.gz) return 0;
-		const int m = A.slot_map[((size_t)sx * A.G.gy + sy) * A.G.gz + sz];
-		if (m < 0) return 0; // outside the world (or a leaf that is not in the batch)
-		const SeamChunk cm_ = A.chunks[m];
-		if (cm_.lg < me.lg) return 0; // a finer chunk touches P: it owns the cell
-		if (cm_.lg == me.lg && m < owner) owner = m;
-		if (A.group && A.group[m] != g0) same_group = false;
-		cm[o] = m;
-		vx[o] = (qx - (cm_.ox << ld)) >> cm_.lg;
-		vy[o] = (qy - (cm_.oy << ld)) >> cm_.lg;
-		vz[o] = (qz - (cm_.oz << ld)) >> cm_.lg;
+		const int dirx = qx < me.bx ? 0 : qx >= hx ? 2 : 1, diry = qy < me.by ? 0 : qy >= hy ? 2 : 1, dirz = qz < me.bz ? 0 : qz >= hz ? 2 : 1;
+		const SeamNbr nb = tab[9 * dirx + 3 * diry + dirz];
+		ok = ok && nb.m >= 0; // outside the world, a leaf that is not in the batch, or a finer chunk (which owns the cell)
+		if (nb.lg == me.lg && nb.m >= 0 && nb.m < owner) owner = nb.m;
+		if (nb.grp != me.grp) same_group = false;
+		cm[o] = nb.m;
+		un[o] = nb.u;
+		vx[o] = (qx - nb.bx) >> nb.lg;
+		vy[o] = (qy - nb.by) >> nb.lg;
+		vz[o] = (qz - nb.bz) >> nb.lg;
+	}
+	if (!ok || owner != c) return 0;
+	if (A.cross_group_only && same_group) return 0;
+	uint32_t mask = 0;
+#pragma unroll
+	for (int o = 0; o < 8; o++)
+	{
 		uint32_t bit;
-		const uint8_t u = A.uni ? A.uni[m] : (uint8_t)0;
-		if (u) bit = (u == 1) ? 1u : 0u;
-		else bit = (A.bits[(size_t)m * A.L.wc + ((((size_t)vx[o] << ld) + vy[o]) << A.L.lzc) + (vz[o] >> 5)] >> (vz[o] & 31)) & 1u;
+		if (un[o]) bit = (un[o] == 1) ? 1u : 0u;
+		else bit = (A.bits[(size_t)cm[o] * A.L.wc + ((((size_t)vx[o] << ld) + vy[o]) << A.L.lzc) + (vz[o] >> 5)] >> (vz[o] & 31)) & 1u;
 		mask |= bit << o;
 	}
-	if (owner != c || mask == 0 || mask == 255) return 0;
-	if (A.cross_group_only && same_group) return 0;
+	if (mask == 0 || mask == 255) return 0;
 
-	const uint64_t tp = s_tri[mask];
+	const uint64_t tp = __ldg(g_tri_pack + mask);
 	const int n = (int)(tp >> 60);
 	// node positions (the chunk's own sample coordinates, ImplicitSampler.hpp:24-30) and samples of the 8 corners
 	float px[8], py[8], pz[8], sv[8];
@@ -180,26 +236,132 @@ __device__ __forceinline__ int seam_cell(const SeamArgs& A, const uint64_t* __re
 	return kept;
 }
 
-// pass 1: triangles per CTA and per chunk
-__global__ void __launch_bounds__(CTA) k_seam_count(SeamArgs A, uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ chunk_cnt)
+// pass 0a: which signs occur in each of the six boundary voxel layers of a chunk (bit 2f = some solid, bit 2f+1 = some
+// air; f = x0,x1,y0,y1,z0,z1).  One CTA per chunk; uniform chunks answer from their flags without reading sign words.
+__global__ void __launch_bounds__(CTA) k_seam_layers(Layout L, const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, int n,
+                                                      uint16_t* __restrict__ layers)
 {
-	__shared__ uint64_t s_tri[256];
-	__shared__ uint32_t s_sum;
-	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
-	if (threadIdx.x == 0) s_sum = 0;
-	__syncthreads();
-	const int c = blockIdx.x / A.G.bpc, b = blockIdx.x - c * A.G.bpc;
-	const int t = b * CTA + threadIdx.x;
-	uint32_t cnt = 0;
-	if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tri, c, t, nullptr);
-#pragma unroll
-	for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-	if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_sum, cnt);
-	__syncthreads();
-	if (threadIdx.x == 0)
+	__shared__ uint32_t s_f;
+	const int c = blockIdx.x;
+	const uint32_t f = flags[c];
+	if (f == CF_ONES || f == CF_ZERO)
 	{
-		blk_cnt[blockIdx.x] = s_sum;
-		if (s_sum) atomicAdd(chunk_cnt + c, s_sum);
+		if (threadIdx.x == 0) layers[c] = f == CF_ONES ? 0xAAA : 0x555;
+		return;
+	}
+	if (threadIdx.x == 0) s_f = 0;
+	__syncthreads();
+	const uint32_t* b = bits + (size_t)c * L.wc;
+	const int d = L.d, zc = L.zc;
+	uint32_t acc = 0;
+	auto see = [&](uint32_t w, int face) { acc |= ((w != 0xFFFFFFFFu) ? 1u : 0u) << (2 * face) | ((w != 0u) ? 2u : 0u) << (2 * face); };
+	for (int q = threadIdx.x; q < L.wp; q += CTA)
+	{
+		see(b[q], 0);
+		see(b[(size_t)(d - 1) * L.wp + q], 1);
+	}
+	for (int q = threadIdx.x; q < d * zc; q += CTA)
+	{
+		const int x = q >> L.lzc, zb = q & (zc - 1);
+		see(b[((size_t)x * d + 0) * zc + zb], 2);
+		see(b[((size_t)x * d + d - 1) * zc + zb], 3);
+	}
+	for (int q = threadIdx.x; q < d * d; q += CTA)
+	{
+		const uint32_t lo = b[(size_t)q * zc] & 1u, hi = b[(size_t)q * zc + zc - 1] >> 31;
+		acc |= (lo ? 2u : 1u) << 8;
+		acc |= (hi ? 2u : 1u) << 10;
+	}
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) atomicOr(&s_f, acc);
+	__syncthreads();
+	if (threadIdx.x == 0) layers[c] = (uint16_t)s_f;
+}
+
+// pass 0b, one warp per chunk:
+//  * a chunk whose whole neighbourhood (itself and every chunk sharing a face, edge or corner with it, at any LOD) is
+//    uniformly air or uniformly solid owns no sign-changing dual cell: it is left out of the active list;
+//  * per face: the cells in the face's interior only see this chunk's boundary layer and the layer of the one
+//    same-or-coarser neighbour across it (finer or missing neighbours: this chunk owns nothing there); if both
+//    layers are uniformly of the same sign the face is "clean".
+__global__ void __launch_bounds__(CTA) k_seam_cull(SeamGrid G, const SeamChunk* __restrict__ chunks, const int32_t* __restrict__ slot_map,
+                                                    const uint32_t* __restrict__ flags, const uint16_t* __restrict__ layers, uint8_t* __restrict__ clean,
+                                                    uint32_t* __restrict__ active, uint32_t* __restrict__ counters /* [0] active chunks, [1] emit tasks */)
+{
+	const int c = (int)(((size_t)blockIdx.x * CTA + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (c >= G.n) return;
+	const uint32_t f = flags[c];
+	const SeamChunk me = chunks[c];
+	const int e = 1 << me.lg;
+	bool same = f == CF_ONES || f == CF_ZERO;
+	if (same)
+	{
+		const int w = e + 2;
+		for (int q = lane; q < w * w * w && same; q += 32)
+		{
+			const int x = q / (w * w), r = q - x * w * w, y = r / w, z = r - y * w;
+			if (x > 0 && x < w - 1 && y > 0 && y < w - 1 && z > 0 && z < w - 1) continue; // inside the chunk itself
+			const int sx = me.ox + x - 1, sy = me.oy + y - 1, sz = me.oz + z - 1;
+			if (sx < 0 || sy < 0 || sz < 0 || sx >= G.gx || sy >= G.gy || sz >= G.gz) continue;
+			const int m = slot_map[((size_t)sx * G.gy + sy) * G.gz + sz];
+			if (m >= 0 && flags[m] != f) same = false;
+		}
+	}
+	same = __all_sync(0xffffffffu, same);
+	if (same) return;
+	uint32_t cl = 0;
+	if (lane < 6)
+	{
+		const int axis = lane >> 1, hi = lane & 1;
+		int s[3] = { me.ox, me.oy, me.oz };
+		s[axis] += hi ? e : -1;
+		int m = -1;
+		if (s[0] >= 0 && s[1] >= 0 && s[2] >= 0 && s[0] < G.gx && s[1] < G.gy && s[2] < G.gz) m = slot_map[((size_t)s[0] * G.gy + s[1]) * G.gz + s[2]];
+		if (m < 0 || chunks[m].lg < me.lg) cl = 1;
+		else
+		{
+			const uint32_t mine = (layers[c] >> (2 * lane)) & 3u, theirs = (layers[m] >> (2 * (lane ^ 1))) & 3u;
+			cl = (mine == theirs && (mine == 1u || mine == 2u)) ? 1u : 0u;
+		}
+	}
+	cl = __ballot_sync(0xffffffffu, cl != 0) & 0x3Fu;
+	if (lane == 0)
+	{
+		clean[c] = (uint8_t)cl;
+		active[atomicAdd(counters, 1u)] = (uint32_t)c;
+	}
+}
+
+// pass 1 (persistent): triangles per task (= 256 consecutive shell points of an active chunk) and per chunk; the
+// non-empty tasks go on the emit list
+__global__ void __launch_bounds__(CTA, 4) k_seam_count(SeamArgs A, const uint32_t* __restrict__ active, uint32_t* __restrict__ counters,
+                                                     uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ emit_list)
+{
+	__shared__ uint32_t s_sum;
+	__shared__ SeamNbr s_tab[27];
+	const uint32_t n_tasks = counters[0] * (uint32_t)A.G.bpc;
+	for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x)
+	{
+		const int c = (int)active[task / (uint32_t)A.G.bpc], b = (int)(task % (uint32_t)A.G.bpc);
+		if (threadIdx.x == 32) s_sum = 0;
+		seam_fill_nbrs(A, c, s_tab);
+		__syncthreads();
+		const int t = b * CTA + threadIdx.x;
+		uint32_t cnt = 0;
+		if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tab, c, t, nullptr);
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+		if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_sum, cnt);
+		__syncthreads();
+		if (threadIdx.x == 0 && s_sum)
+		{
+			const uint32_t gb = (uint32_t)c * (uint32_t)A.G.bpc + (uint32_t)b;
+			blk_cnt[gb] = s_sum;
+			atomicAdd(chunk_cnt + c, s_sum);
+			emit_list[atomicAdd(counters + 1, 1u)] = gb;
+		}
+		__syncthreads();
 	}
 }
 
@@ -247,46 +409,51 @@ __global__ void __launch_bounds__(SEAM_SCAN_CTA) k_seam_scan(const uint32_t* __r
 	if (threadIdx.x == 0) *total = s_carry;
 }
 
-// pass 2: the same cells again, written at chunk base + CTAs before this one + threads before this one
-__global__ void __launch_bounds__(CTA) k_seam_emit(SeamArgs A, const uint32_t* __restrict__ blk_cnt, const unsigned long long* __restrict__ chunk_base,
-                                                    float* __restrict__ out)
+// pass 2 (persistent over the emit list): the same cells again, written at chunk base + tasks of the chunk before this
+// one + threads before this one -- the output order does not depend on the order of the lists
+__global__ void __launch_bounds__(CTA) k_seam_emit(SeamArgs A, const uint32_t* __restrict__ counters, const uint32_t* __restrict__ emit_list,
+                                                    const uint32_t* __restrict__ blk_cnt, const unsigned long long* __restrict__ chunk_base, float* __restrict__ out)
 {
-	__shared__ uint64_t s_tri[256];
 	__shared__ uint32_t s_w[CTA / 32];
 	__shared__ unsigned long long s_base;
-	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
-	const int c = blockIdx.x / A.G.bpc, b = blockIdx.x - c * A.G.bpc;
-	if (blk_cnt[blockIdx.x] == 0) return; // whole CTA
-	if (threadIdx.x == 0) s_base = 0;
-	__syncthreads();
-	// triangles of the CTAs of this chunk before this one
-	{
-		unsigned long long part = 0;
-		for (int q = threadIdx.x; q < b; q += CTA) part += blk_cnt[(size_t)c * A.G.bpc + q];
-#pragma unroll
-		for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-		if ((threadIdx.x & 31) == 0 && part) atomicAdd(&s_base, part);
-	}
-	const int t = b * CTA + threadIdx.x;
-	float tri[45];
-	uint32_t cnt = 0;
-	if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tri, c, t, tri);
+	__shared__ SeamNbr s_tab[27];
+	const uint32_t n_tasks = counters[1];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint32_t inc = cnt;
+	for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x)
+	{
+		const uint32_t gb = emit_list[task];
+		const int c = (int)(gb / (uint32_t)A.G.bpc), b = (int)(gb % (uint32_t)A.G.bpc);
+		if (threadIdx.x == 32) s_base = 0;
+		seam_fill_nbrs(A, c, s_tab);
+		__syncthreads();
+		{
+			unsigned long long part = 0;
+			for (int q = threadIdx.x; q < b; q += CTA) part += blk_cnt[(size_t)c * A.G.bpc + q];
 #pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-		if (lane >= o) inc += u;
-	}
-	if (lane == 31) s_w[warp] = inc;
-	__syncthreads();
-	uint32_t before = inc - cnt;
-	for (int w = 0; w < warp; w++) before += s_w[w];
-	if (cnt)
-	{
-		float* dst = out + 9 * (size_t)(chunk_base[c] + s_base + before);
-		for (uint32_t q = 0; q < 9 * cnt; q++) dst[q] = tri[q];
+			for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+			if (lane == 0 && part) atomicAdd(&s_base, part);
+		}
+		const int t = b * CTA + threadIdx.x;
+		float tri[45];
+		uint32_t cnt = 0;
+		if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tab, c, t, tri);
+		uint32_t inc = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += u;
+		}
+		if (lane == 31) s_w[warp] = inc;
+		__syncthreads();
+		uint32_t before = inc - cnt;
+		for (int w = 0; w < warp; w++) before += s_w[w];
+		if (cnt)
+		{
+			float* dst = out + 9 * (size_t)(chunk_base[c] + s_base + before);
+			for (uint32_t q = 0; q < 9 * cnt; q++) dst[q] = tri[q];
+		}
+		__syncthreads();
 	}
 }
 
