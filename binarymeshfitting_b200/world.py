@@ -113,3 +113,28 @@ def partition(mortons, costs, n_parts):
         parts.append(order[lo:b])
         lo = b
     return parts
+
+
+def border_chunks(pos_size, group):
+    """Multi-GPU seam scheme ("a final host gather ... and a WorldStitcher seam pass"): every rank stitches
+    the dual cells that lie entirely inside its own chunks; the cells that span ranks only involve chunks that touch
+    (face, edge or corner) a chunk of another group.  Returns the indices of those border chunks, in batch order --
+    the batch of the final bmf_batch_stitch(group, cross_group_only=1) pass on the gathering rank."""
+    ps = np.asarray(pos_size, np.float64).reshape(-1, 4)
+    group = np.asarray(group)
+    smin = ps[:, 3].min()
+    org = ps[:, :3].min(axis=0)
+    lo = np.rint((ps[:, :3] - org) / smin).astype(np.int64)
+    ext = np.rint(ps[:, 3] / smin).astype(np.int64)
+    G = (lo + ext[:, None]).max(axis=0)
+    grid = np.full(tuple(G), -1, np.int64)
+    for i in range(len(ps)):
+        grid[lo[i, 0]:lo[i, 0] + ext[i], lo[i, 1]:lo[i, 1] + ext[i], lo[i, 2]:lo[i, 2] + ext[i]] = group[i]
+    out = []
+    for i in range(len(ps)):
+        a = np.maximum(lo[i] - 1, 0)
+        b = np.minimum(lo[i] + ext[i] + 1, G)
+        nb = grid[a[0]:b[0], a[1]:b[1], a[2]:b[2]]
+        if np.any((nb != group[i]) & (nb >= 0)):
+            out.append(i)
+    return np.array(out, np.int64)

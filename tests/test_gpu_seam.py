@@ -93,6 +93,29 @@ def test_seam_group_filters(gpu, oracle):
     assert key(np.concatenate(parts)) == key(full)
 
 
+def test_seam_multi_gpu_scheme_with_border_batch(gpu, oracle):
+    """what N ranks do: own seams per group + one cross-group pass over the border chunks only == the full seam"""
+    from binarymeshfitting_b200 import world as W
+    ps, lv, mc = su.lod_world(3, 1, (90.0, 20.0, -30.0))
+    parts = W.partition(mc, np.ones(len(mc)), 4)
+    group = np.zeros(len(ps), np.int32)
+    for g, part in enumerate(parts):
+        group[part] = g
+    full, _, _ = run(gpu, oracle, ob.TORUS_Z, ps, world_size=600.0)
+    pieces = []
+    for g in range(4):
+        idx = np.sort(parts[g])
+        got, want, _ = run(gpu, oracle, ob.TORUS_Z, ps[idx], world_size=600.0)
+        pieces.append(got)
+    border = W.border_chunks(ps, group)
+    assert 0 < len(border) < len(ps)
+    got, want, _ = run(gpu, oracle, ob.TORUS_Z, ps[border], group=group[border], cross=True, world_size=600.0)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    pieces.append(got)
+    key = lambda t: sorted(np.ascontiguousarray(t).reshape(-1, 9).view(np.uint32).tolist())
+    assert key(np.concatenate(pieces)) == key(full)
+
+
 def test_seam_errors(gpu):
     from binarymeshfitting_b200 import Context
     ctx = Context(0)

@@ -4,6 +4,8 @@ The reference's WorldStitcher is non-functional as committed, so ther
 checked are properties: chunk meshes + seam form a closed, consistently oriented surface on worlds with and without LOD
 changes, and the per-group + cross-group passes (the multi-GPU scheme) partition the full seam exactly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -58,6 +60,66 @@ def test_group_passes_partition_the_seam(oracle):
         parts.append(oracle.seam([chunks[i] for i in idx], ps[idx], DIM, ov))
     assert all(len(p) > 0 for p in parts)
     assert tri_keys(np.concatenate(parts)) == tri_keys(full)
+
+
+SEAM_WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np
+import torch.distributed as dist
+import seam_util as su
+from binarymeshfitting_b200 import world as W
+from oracle import oracle_binding as ob   # CPU stand-in for each rank's GPU: this test is about the multi-rank seam scheme
+dist.init_process_group("gloo")
+rank, ws = dist.get_rank(), dist.get_world_size()
+dim = 32
+ps, lv, mc = su.lod_world(3, 1, (90.0, 20.0, -30.0), dim)
+ov = su.seam_overlap(dim)
+parts = W.partition(mc, np.ones(len(mc)), ws)
+group = np.zeros(len(ps), np.int32)
+for g, part in enumerate(parts):
+    group[part] = g
+O = ob.Oracle()
+s = O.sampler(ob.SPHERE, world_size=700.0)
+mine = np.sort(parts[rank])
+chunks = {int(i): O.chunk(s, ps[i][:3], ps[i][3], dim, ov) for i in mine}
+own = O.seam([chunks[int(i)] for i in mine], ps[mine], dim, ov)            # cells inside this rank's chunks
+border = W.border_chunks(ps, group)
+# the gathering rank needs the border chunks of every rank (sign words + border samples); chunks are a pure function
+# of their descriptor, so it simply re-samples them -- no data-path collective
+gathered = [None] * ws
+dist.all_gather_object(gathered, own.tobytes())
+if rank == 0:
+    bch = [chunks[int(i)] if int(i) in chunks else O.chunk(s, ps[i][:3], ps[i][3], dim, ov) for i in border]
+    cross = O.seam(bch, ps[border], dim, ov, group=group[border], cross_group_only=True)
+    parts_t = [np.frombuffer(b, np.float32).reshape(-1, 3, 3) for b in gathered] + [cross]
+    allc = [O.chunk(s, p[:3], p[3], dim, ov) for p in ps]
+    full = O.seam(allc, ps, dim, ov)
+    key = lambda t: sorted(np.ascontiguousarray(t, np.float32).reshape(-1, 9).view(np.uint32).tolist())
+    print("SEAM", len(full), sum(len(t) for t in parts_t), len(cross), len(border), int(key(np.concatenate(parts_t)) == key(full)))
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_seam_scheme_over_gloo(tmp_path):
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "seam_worker.py"
+    script.write_text(SEAM_WORKER % {"root": root})
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("SEAM")][0].split()
+    full, parts, cross, border, same = (int(v) for v in line[1:])
+    assert full == parts and cross > 0 and border > 0 and same == 1
 
 
 def test_misaligned_chunks_are_rejected(oracle):
