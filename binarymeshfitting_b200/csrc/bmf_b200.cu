@@ -96,6 +96,8 @@ struct bmf_ctx
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	int sm_count = 148;
+	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
+	size_t smooth_smem = 0;    // dynamic shared memory of k_smooth_chunks
 	int smooth_ctas_per_sm = 8; // resident CTAs per SM of the grid-stride smoothing kernels (tuning knob: BMF_SMOOTH_CTAS_PER_SM)
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
@@ -307,6 +309,15 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, n_verts * sizeof(uint32_t), ctx->stream));
 		BMF_LAUNCH(k_csr_fill<N>, grid_for(n_prims, CTA), CTA, 0, inds, n_prims, chunks_dev, n_chunks, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
 		BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
+	}
+
+	if (grid_path && tot && N == 3 && !smooth && !qef && final_primal && ctx->smooth_fused)
+	{
+		// the whole optimize_dual_grid(iters) + optimize_primal_grid sequence, one CTA per chunk out of shared memory:
+		// iters dual steps interleaved with iters primal steps (the last primal is the driver's extra call)
+		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->sm_count), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
+		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)));
+		return BMF_OK;
 	}
 
 	// optimize_dual_grid (MeshProcessor.cpp:130-236)
@@ -528,6 +539,17 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 	cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
 	if (ctx->sm_count <= 0) ctx->sm_count = 148;
 	if (const char* e = getenv("BMF_SMOOTH_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v <= 4096) ctx->smooth_ctas_per_sm = v; }
+	if (const char* e = getenv("BMF_SMOOTH_FUSED")) ctx->smooth_fused = atoi(e) != 0;
+	{
+		int optin = 0;
+		cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+		ctx->smooth_smem = optin > 4096 ? (size_t)optin - 1024 : 0; // leave room for the kernel's static shared memory
+		if (!ctx->smooth_smem || cudaFuncSetAttribute(k_smooth_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smooth_smem) != cudaSuccess)
+		{
+			cudaGetLastError();
+			ctx->smooth_fused = 0;
+		}
+	}
 	cudaMallocHost((void**)&ctx->totals_pinned, sizeof(HostTotals));
 	*out = ctx;
 	return BMF_OK;

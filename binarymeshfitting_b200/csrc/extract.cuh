@@ -705,6 +705,7 @@ __global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long
                              unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
 {
 	tot[7] = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
+	tot[6] = 0; // chunk work counter of k_smooth_chunks
 	for (int k = 0; k < 8; k++) tot_host[k] = tot[k];
 	__threadfence_system();
 }

@@ -311,6 +311,135 @@ __global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj
 		primal_one(v, adj_off, adj, valence, boundary, dp, dc, dn, pos, color, normal, smooth, set_colors, process_boundary);
 }
 
+// ---- all smoothing half-steps of one chunk in ONE CTA (batch path, positions only: colours are provably 1 and
+// SMOOTH_NORMALS is off).  A chunk's mesh is a few thousand vertices: its positions (12 B/vertex) and dual points
+// (12 B/triangle) fit the 227 KB of shared memory of one SM, so the iterations run out of shared memory with a CTA
+// barrier between half-steps -- positions are read from and written to HBM once per batch instead of once per
+// half-step, the dual points never leave the SM, and the gathers cost a shared-memory access instead of an L2 round
+// trip.  Chunks are handed out through an atomic work counter (tot[6]); a chunk too large for shared memory runs the
+// same loop on its global arrays (only this CTA touches them, so the CTA barrier is enough).  The arithmetic per
+// element -- and therefore every result bit -- is that of k_dual<3> / k_primal.
+static constexpr int SMOOTH_CTA = 1024;
+
+__device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off,
+                                                   const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary,
+                                                   uint32_t V, uint32_t T, uint32_t prim0, int half_steps, int process_boundary)
+{
+	// half-step h: even = dual (centroids of the primitives), odd = primal (vertex = mean of its adjacent centroids).
+	// The index / adjacency streams come from global memory: SMOOTH_U elements per thread are in flight at once, all
+	// their loads issued before the first use, so a half-step costs a few memory round trips, not one per element.
+	constexpr int U = 4, KMAX = 8;
+	for (int h = 0; h < half_steps; h++)
+	{
+		if ((h & 1) == 0)
+		{
+			for (uint32_t t0 = threadIdx.x; t0 < T; t0 += U * SMOOTH_CTA)
+			{
+				uint32_t id[U][3];
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					const uint32_t t = t0 + u * SMOOTH_CTA;
+					const bool ok = t < T;
+					id[u][0] = ok ? inds[3 * t] : 0u;
+					id[u][1] = ok ? inds[3 * t + 1] : 0u;
+					id[u][2] = ok ? inds[3 * t + 2] : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					const uint32_t t = t0 + u * SMOOTH_CTA;
+					if (t >= T) continue;
+					f3 sp = { 0, 0, 0 };
+					sp = add3(sp, ld3(P, id[u][0]));
+					sp = add3(sp, ld3(P, id[u][1]));
+					sp = add3(sp, ld3(P, id[u][2]));
+					st3(D, t, div3(sp, 3.0f));
+				}
+			}
+		}
+		else
+		{
+			for (uint32_t v0 = threadIdx.x; v0 < V; v0 += U * SMOOTH_CTA)
+			{
+				int cnt[U];
+				uint32_t off[U], a[U][KMAX];
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					const uint32_t v = v0 + u * SMOOTH_CTA;
+					const bool ok = v < V;
+					const int c = ok ? (int)valence[v] : 0;
+					const bool skip = ok && !process_boundary && boundary[v];
+					cnt[u] = skip ? 0 : c;
+					off[u] = ok ? adj_off[v] : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < U; u++)
+#pragma unroll
+					for (int k = 0; k < KMAX; k++) a[u][k] = k < cnt[u] ? adj[off[u] + k] : prim0;
+#pragma unroll
+				for (int u = 0; u < U; u++)
+				{
+					if (cnt[u] == 0) continue;
+					f3 p = { 0, 0, 0 };
+#pragma unroll
+					for (int k = 0; k < KMAX; k++)
+						if (k < cnt[u]) p = add3(p, ld3(D, a[u][k] - prim0));
+					for (int k = KMAX; k < cnt[u]; k++) p = add3(p, ld3(D, adj[off[u] + k] - prim0));
+					st3(P, v0 + u * SMOOTH_CTA, div3(p, (float)cnt[u]));
+				}
+			}
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCounts* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ inds,
+                                                                   const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj,
+                                                                   const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos,
+                                                                   float* dp_global, int half_steps, int process_boundary, unsigned long long* tot,
+                                                                   unsigned int smem_floats)
+{
+	extern __shared__ float sm_f[];
+	__shared__ int s_chunk;
+	if (tot[7]) return;
+	constexpr uint32_t BIG = 4096; // chunks with at least this many vertices are handed out first (longest first keeps the tail short)
+	for (;;)
+	{
+		if (threadIdx.x == 0) s_chunk = (int)atomicAdd(tot + 6, 1ull);
+		__syncthreads();
+		const int w = s_chunk;
+		__syncthreads();
+		if (w >= 2 * n_chunks) return;
+		const int c = w < n_chunks ? w : w - n_chunks;
+		const ChunkCounts cc = chunks[c];
+		if (!cc.contains_mesh || cc.n_verts == 0 || cc.n_inds < 3) continue;
+		if ((cc.n_verts >= BIG) != (w < n_chunks)) continue;
+		const uint32_t V = cc.n_verts, T = cc.n_inds / 3;
+		const size_t vb = (size_t)cc.vert_base, ib = (size_t)cc.ind_base;
+		const uint32_t prim0 = (uint32_t)(ib / 3);
+		float* gp = pos + 3 * vb;
+		float* gd = dp_global + 3 * (size_t)prim0;
+		if (3ull * ((unsigned long long)V + T) <= smem_floats)
+		{
+			// positions and dual points both in shared memory
+			float* P = sm_f;
+			float* D = sm_f + 3 * (size_t)V;
+			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) P[i] = gp[i];
+			__syncthreads();
+			smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) gp[i] = P[i];
+			__syncthreads();
+		}
+		else if (3ull * T <= smem_floats)
+			// the dual points (the array the primal step gathers from) in shared memory, positions in place
+			smooth_chunk_steps(gp, sm_f, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+		else
+			smooth_chunk_steps(gp, gd, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+	}
+}
+
 // zero the first n (batch path: tot[idx] * mul) 32-bit words of p
 __global__ void __launch_bounds__(CTA) k_zero_u32(uint32_t* __restrict__ p, size_t n, const unsigned long long* __restrict__ tot, int idx, int mul)
 {
