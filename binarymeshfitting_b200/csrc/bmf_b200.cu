@@ -81,6 +81,7 @@ struct bmf_ctx
 	const float* density_cur = nullptr; // density block the emitters read crossing-edge samples from (or null)
 	int relaunches = 0;                 // batches whose emitters had to be re-launched after growing an arena
 	bool density_valid = false, masks_valid = false;
+	bool counts_published = false; // the chunk table of the resident batch has been queued for the host (once per batch, after the emitters)
 	size_t color_ones = 0; // the first color_ones floats of the colour arena are known to be exactly 1.0f
 
 	DevBuf<ChunkGeom> geom, sheet_geom;
@@ -405,6 +406,17 @@ int reserve_mesh(bmf_ctx* ctx, size_t cells, size_t verts, size_t inds)
 	return BMF_OK;
 }
 
+// chunk table -> mapped pinned host memory, after the last kernel of the batch so that it is off the critical path
+int publish_chunks(bmf_ctx* ctx)
+{
+	if (ctx->counts_published) return BMF_OK;
+	const size_t words = (size_t)ctx->n * (sizeof(ChunkCounts) / sizeof(uint32_t));
+	BMF_LAUNCH(k_publish_chunks, std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)), CTA, 0, reinterpret_cast<const uint32_t*>(ctx->counts.p),
+	           reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
+	ctx->counts_published = true;
+	return BMF_OK;
+}
+
 // K4 + K5 of the resident batch, sized by arena capacity and guarded on the device (k_check_caps): no host round trip
 int launch_mesh(bmf_ctx* ctx)
 {
@@ -426,7 +438,7 @@ int launch_mesh(bmf_ctx* ctx)
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return BMF_OK;
+		return publish_chunks(ctx);
 	}
 	const size_t V = caps.verts, I = caps.inds;
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
@@ -466,7 +478,7 @@ int launch_mesh(bmf_ctx* ctx)
 		if (rc) return rc;
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-	return BMF_OK;
+	return publish_chunks(ctx);
 }
 
 // completes the resident batch: waits for the stream, publishes totals / per-chunk counts to the host and, if an output
@@ -792,7 +804,8 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->counts_pinned, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
 	int rc = launch_mesh(ctx);

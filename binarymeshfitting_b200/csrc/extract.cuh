@@ -636,7 +636,7 @@ struct ChunkCounts
 static constexpr int SCAN_CTA = 1024;
 
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __restrict__ chunk_tot, const uint32_t* __restrict__ flags, int n_chunks,
-                                                           ChunkCounts* __restrict__ chunks, ChunkCounts* __restrict__ chunks_host /* mapped pinned host copy */,
+                                                           ChunkCounts* __restrict__ chunks,
                                                            unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
 {
 	__shared__ uint32_t s_w[3][SCAN_CTA / 32];
@@ -684,7 +684,6 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 			cc.vert_base = carry1 + (ib - b + s_w[1][warp]);
 			cc.ind_base = carry2 + (ic - c + s_w[2][warp]);
 			chunks[i] = cc;
-			chunks_host[i] = cc; // straight to the host over PCIe: no copy-engine transfer that could queue behind another context's download
 		}
 		carry0 += s_tot[0]; carry1 += s_tot[1]; carry2 += s_tot[2];
 		__syncthreads();
@@ -695,6 +694,14 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 		totals[0] = carry0; totals[1] = carry1; totals[2] = carry2; totals[3] = overflow ? 1ull : 0ull;
 		totals[4] = 0; totals[5] = 0; // surface-cell list counters (k_bases)
 	}
+}
+
+// The chunk table goes to the host through mapped pinned memory written by the device itself (no copy-engine transfer
+// that could queue behind another context's mesh download); many CTAs, 4-byte words, coalesced -- a single CTA pushing
+// 40-byte records over PCIe used to cost as much as the scan itself.
+__global__ void __launch_bounds__(CTA) k_publish_chunks(const uint32_t* __restrict__ chunks_words, uint32_t* __restrict__ host_words, size_t n_words)
+{
+	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n_words; i += (size_t)gridDim.x * CTA) host_words[i] = chunks_words[i];
 }
 
 // Output arenas are sized from the previous batches so that a submission never has to wait for the host.  This
