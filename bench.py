@@ -116,7 +116,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- ours
 # algorithmic work of each kernel per voxel / vertex / index (DESIGN.md "Kernels"), used for the roofline line
-def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
+def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks, iters=2):
     hbm = peaks["hbm_gbs"]
     words = nvox / 32.0
     algo = {
@@ -140,11 +140,20 @@ def kernel_roofline(name, ms, nvox, V, I, n_chunks, dim, peaks):
         "k_primal": 18.0 * V + 16.0 * I,
         # CSR fill: index + class counters + offset in, adjacency entry out per incidence; cell record + vertex base per cell / triangle
         "k_adj_fill": 16.0 * I + 4.0 * I / 3.0 + 8.0 * I / 9.0,
+        # all half-steps of the batch in one launch (one CTA per chunk, iterations out of shared memory): SURVEY 8(d)'s K5
+        # figure is per iteration, so the algorithmic bytes are iters x (dual + primal) of the two lines above
+        "k_smooth_chunks": iters * ((12 + 4 + 36 + 12) * (I / 3.0) + 18.0 * V + 16.0 * I),
     }
     if name in algo:
         ach = algo[name] / (ms * 1e-3) / 1e9
-        return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
-                "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": int(algo[name])}
+        out = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s", "frac": round(ach / hbm, 4),
+               "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": int(algo[name])}
+        if name == "k_smooth_chunks":
+            # what has to cross HBM when the iterations stay on chip: positions in and out once, the index / adjacency streams once per half-step
+            out["bytes_that_must_cross_hbm"] = int(24.0 * V + iters * (4.0 * I + 6.0 * V + 4.0 * I))
+            out["note"] = ("algorithmic bytes = SURVEY 8(d) K5 figure (per-iteration gathers counted at their algorithmic size); the kernel keeps "
+                           "positions and dual points in shared memory, so most of those bytes never reach HBM -- see bytes_that_must_cross_hbm and traffic")
+        return out
     return None
 
 
@@ -299,7 +308,7 @@ def run_ours(args):
     peaks = load_peaks()
     n_launch_dom = len(agg[dominant]) / reps
     launch_ms = per_kernel[dominant] / n_launch_dom
-    roof = kernel_roofline(dominant, launch_ms, nvox, V, I, n_chunks, dim, peaks)
+    roof = kernel_roofline(dominant, launch_ms, nvox, V, I, n_chunks, dim, peaks, args.iters)
     if roof is None:
         roof = {"kernel": dominant, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
                 "peak_source": peaks["source"], "note": "no HBM model for this kernel (FP32/INT issue bound): see the `issue` view"}
@@ -325,7 +334,7 @@ def run_ours(args):
     # the HBM view of every kernel of the step that has a byte model, each against the measured copy peak
     hbm_lines = {}
     for name, ms in per_kernel.items():
-        r = kernel_roofline(name, ms / (len(agg[name]) / reps), nvox, V, I, n_chunks, dim, peaks)
+        r = kernel_roofline(name, ms / (len(agg[name]) / reps), nvox, V, I, n_chunks, dim, peaks, args.iters)
         if r:
             hbm_lines[name] = {"ms": round(ms, 4), "GB/s": r["achieved"], "frac": r["frac"]}
     # whole step against SURVEY 8(d)'s fused sample->mesh figure: N/8 (sign words) + N (cell masks) + 14 V + 4 I bytes

@@ -118,7 +118,7 @@ struct bmf_ctx
 	DevBuf<int32_t> seam_map, seam_group;
 	DevBuf<uint8_t> seam_clean;
 	DevBuf<uint16_t> seam_layers;
-	DevBuf<uint32_t> seam_active, seam_emit, seam_counters;
+	DevBuf<uint32_t> seam_active, seam_counters, seam_act;
 	DevBuf<uint32_t> seam_blk, seam_cnt;
 	DevBuf<unsigned long long> seam_base; // [n] chunk bases + [1] total
 	DevBuf<float> seam_tris;
@@ -582,7 +582,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
-	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_emit.release(); ctx->seam_counters.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
+	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
 		if (e) cudaEventDestroy(e);
@@ -1177,13 +1177,14 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 	const unsigned nblk = (unsigned)((size_t)n * A.G.bpc);
 	BMF_CUDA(ctx->seam_chunks.reserve(n));
 	BMF_CUDA(ctx->seam_map.reserve(slots));
-	BMF_CUDA(ctx->seam_blk.reserve(nblk));
+	BMF_CUDA(ctx->seam_blk.reserve((size_t)n * SEAM_PARTS)); // triangles per (chunk, part)
 	BMF_CUDA(ctx->seam_cnt.reserve(n));
 	BMF_CUDA(ctx->seam_clean.reserve(n));
 	BMF_CUDA(ctx->seam_layers.reserve(n));
 	BMF_CUDA(ctx->seam_active.reserve(n));
-	BMF_CUDA(ctx->seam_emit.reserve(nblk));
 	BMF_CUDA(ctx->seam_counters.reserve(2));
+	const int act_words = (A.G.npts + 31) / 32 + 1;
+	BMF_CUDA(ctx->seam_act.reserve((size_t)n * act_words));
 	BMF_CUDA(ctx->seam_base.reserve((size_t)n + 1));
 	if (group) BMF_CUDA(ctx->seam_group.reserve(n));
 	if (!ctx->seam_total_pinned) BMF_CUDA(cudaMallocHost((void**)&ctx->seam_total_pinned, sizeof(unsigned long long)));
@@ -1194,14 +1195,17 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 	BMF_CUDA(cudaMemcpyAsync(ctx->seam_map.p, map.data(), sizeof(int32_t) * slots, cudaMemcpyHostToDevice, st));
 	if (group) BMF_CUDA(cudaMemcpyAsync(ctx->seam_group.p, group, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->seam_cnt.p, 0, sizeof(uint32_t) * n, st));
-	BMF_CUDA(cudaMemsetAsync(ctx->seam_blk.p, 0, sizeof(uint32_t) * nblk, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->seam_blk.p, 0, sizeof(uint32_t) * (size_t)n * SEAM_PARTS, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->seam_counters.p, 0, sizeof(uint32_t) * 2, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->seam_act.p, 0, sizeof(uint32_t) * (size_t)n * act_words, st));
 	A.L = L;
 	A.chunks = ctx->seam_chunks.p;
 	A.slot_map = ctx->seam_map.p;
 	A.bits = ctx->bits.p;
 	A.uni = ctx->uni_valid ? ctx->uni.p : nullptr;
 	A.clean = ctx->seam_clean.p;
+	A.act = ctx->seam_act.p;
+	A.act_words = act_words;
 	A.group = group ? ctx->seam_group.p : nullptr;
 	A.cross_group_only = cross_group_only ? 1 : 0;
 	A.geom = ctx->geom.p;
@@ -1215,7 +1219,8 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 	BMF_LAUNCH(k_seam_layers, (unsigned)n, CTA, 0, L, ctx->bits.p, ctx->flags.p, n, ctx->seam_layers.p);
 	BMF_LAUNCH(k_seam_cull, grid_for((size_t)n * 32, CTA), CTA, 0, A.G, ctx->seam_chunks.p, ctx->seam_map.p, ctx->flags.p, ctx->seam_layers.p, ctx->seam_clean.p,
 	           ctx->seam_active.p, ctx->seam_counters.p);
-	BMF_LAUNCH(k_seam_count, pgrid, CTA, 0, A, ctx->seam_active.p, ctx->seam_counters.p, ctx->seam_blk.p, ctx->seam_cnt.p, ctx->seam_emit.p);
+	BMF_LAUNCH(k_seam_classify, std::min((unsigned)n * 6u, (unsigned)(ctx->sm_count * 8)), CTA, 0, A, ctx->seam_active.p, ctx->seam_counters.p, ctx->seam_act.p);
+	BMF_LAUNCH(k_seam_pass<false>, pgrid, CTA, 0, A, ctx->seam_active.p, ctx->seam_counters.p, ctx->seam_blk.p, ctx->seam_cnt.p, ctx->seam_base.p, nullptr);
 	BMF_LAUNCH(k_seam_scan, 1, SEAM_SCAN_CTA, 0, ctx->seam_cnt.p, n, ctx->seam_base.p, ctx->seam_base.p + n);
 	BMF_CUDA(cudaEventRecord(ctx->seam_ev[1], st));
 	BMF_CUDA(cudaMemcpyAsync(ctx->seam_total_pinned, ctx->seam_base.p + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -1225,7 +1230,7 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 	if (T)
 	{
 		BMF_CUDA(ctx->seam_tris.reserve(9 * (size_t)T));
-		BMF_LAUNCH(k_seam_emit, pgrid, CTA, 0, A, ctx->seam_counters.p, ctx->seam_emit.p, ctx->seam_blk.p, ctx->seam_base.p, ctx->seam_tris.p);
+		BMF_LAUNCH(k_seam_pass<true>, pgrid, CTA, 0, A, ctx->seam_active.p, ctx->seam_counters.p, ctx->seam_blk.p, ctx->seam_cnt.p, ctx->seam_base.p, ctx->seam_tris.p);
 	}
 	BMF_CUDA(cudaEventRecord(ctx->seam_ev[2], st));
 	BMF_CUDA(cudaStreamSynchronize(st));

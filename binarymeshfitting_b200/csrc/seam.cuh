@@ -86,6 +86,8 @@ struct SeamArgs
 	const uint32_t* bits;
 	const uint8_t* uni;      // per-chunk uniform flag (2-D terrains without a density block) or null
 	const uint8_t* clean;    // per-chunk, bit f: no dual cell in the interior of face f (x0,x1,y0,y1,z0,z1) changes sign
+	const uint32_t* act;     // per-chunk bitmap over the shell points (k_seam_classify): 0 = certainly nothing to emit
+	int act_words;           // words per chunk in act
 	const int32_t* group;    // per-chunk group id or null
 	int cross_group_only;    // 1: only cells whose nodes span more than one group
 	const ChunkGeom* geom;
@@ -105,35 +107,41 @@ struct SeamNbr
 	int32_t grp;
 };
 
+// the chunk on side (dx,dy,dz) of chunk c (see SeamNbr)
+__device__ __forceinline__ SeamNbr seam_nbr(const SeamArgs& A, int c, int dx, int dy, int dz)
+{
+	const SeamChunk me = A.chunks[c];
+	const int e = 1 << me.lg;
+	const int sx = me.ox + (dx < 0 ? -1 : dx > 0 ? e : 0), sy = me.oy + (dy < 0 ? -1 : dy > 0 ? e : 0), sz = me.oz + (dz < 0 ? -1 : dz > 0 ? e : 0);
+	SeamNbr n;
+	n.m = -1;
+	n.bx = n.by = n.bz = n.lg = n.u = n.grp = 0;
+	if (sx >= 0 && sy >= 0 && sz >= 0 && sx < A.G.gx && sy < A.G.gy && sz < A.G.gz)
+	{
+		const int m = A.slot_map[((size_t)sx * A.G.gy + sy) * A.G.gz + sz];
+		if (m >= 0)
+		{
+			const SeamChunk o = A.chunks[m];
+			if (o.lg >= me.lg)
+			{
+				n.m = m;
+				n.bx = o.ox << A.L.ld; n.by = o.oy << A.L.ld; n.bz = o.oz << A.L.ld;
+				n.lg = o.lg;
+				n.u = A.uni ? (int32_t)A.uni[m] : 0;
+				n.grp = A.group ? A.group[m] : 0;
+			}
+		}
+	}
+	return n;
+}
+
 // filled by the first 27 threads of the CTA for chunk c (direction index = 9 (dx+1) + 3 (dy+1) + (dz+1))
 __device__ __forceinline__ void seam_fill_nbrs(const SeamArgs& A, int c, SeamNbr* tab)
 {
 	if (threadIdx.x < 27)
 	{
-		const int q = threadIdx.x, dx = q / 9 - 1, dy = (q / 3) % 3 - 1, dz = q % 3 - 1;
-		const SeamChunk me = A.chunks[c];
-		const int e = 1 << me.lg;
-		const int sx = me.ox + (dx < 0 ? -1 : dx > 0 ? e : 0), sy = me.oy + (dy < 0 ? -1 : dy > 0 ? e : 0), sz = me.oz + (dz < 0 ? -1 : dz > 0 ? e : 0);
-		SeamNbr n;
-		n.m = -1;
-		n.bx = n.by = n.bz = n.lg = n.u = n.grp = 0;
-		if (sx >= 0 && sy >= 0 && sz >= 0 && sx < A.G.gx && sy < A.G.gy && sz < A.G.gz)
-		{
-			const int m = A.slot_map[((size_t)sx * A.G.gy + sy) * A.G.gz + sz];
-			if (m >= 0)
-			{
-				const SeamChunk o = A.chunks[m];
-				if (o.lg >= me.lg)
-				{
-					n.m = m;
-					n.bx = o.ox << A.L.ld; n.by = o.oy << A.L.ld; n.bz = o.oz << A.L.ld;
-					n.lg = o.lg;
-					n.u = A.uni ? (int32_t)A.uni[m] : 0;
-					n.grp = A.group ? A.group[m] : 0;
-				}
-			}
-		}
-		tab[q] = n;
+		const int q = threadIdx.x;
+		tab[q] = seam_nbr(A, c, q / 9 - 1, (q / 3) % 3 - 1, q % 3 - 1);
 	}
 }
 
@@ -143,12 +151,6 @@ __device__ __forceinline__ int seam_cell(const SeamArgs& A, const SeamNbr* __res
 	const int d = A.L.d, ld = A.L.ld;
 	int i, j, k;
 	seam_shell_point(t, d, i, j, k);
-	{
-		// interior of a face whose two voxel layers (this chunk's and the neighbour's) are uniformly of one sign
-		const int fx = i == 0 ? 0 : i == d ? 1 : -1, fy = j == 0 ? 2 : j == d ? 3 : -1, fz = k == 0 ? 4 : k == d ? 5 : -1;
-		const int nf = (fx >= 0) + (fy >= 0) + (fz >= 0);
-		if (nf == 1 && ((A.clean[c] >> (fx >= 0 ? fx : fy >= 0 ? fy : fz)) & 1)) return 0;
-	}
 	const SeamNbr me = tab[13];
 	const int Px = me.bx + (i << me.lg), Py = me.by + (j << me.lg), Pz = me.bz + (k << me.lg);
 	const int hx = me.bx + (d << me.lg), hy = me.by + (d << me.lg), hz = me.bz + (d << me.lg);
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(CTA) k_seam_layers(Layout L, const uint32_t* _
 //    layers are uniformly of the same sign the face is "clean".
 __global__ void __launch_bounds__(CTA) k_seam_cull(SeamGrid G, const SeamChunk* __restrict__ chunks, const int32_t* __restrict__ slot_map,
                                                     const uint32_t* __restrict__ flags, const uint16_t* __restrict__ layers, uint8_t* __restrict__ clean,
-                                                    uint32_t* __restrict__ active, uint32_t* __restrict__ counters /* [0] active chunks, [1] emit tasks */)
+                                                    uint32_t* __restrict__ active, uint32_t* __restrict__ counters /* [0] active chunks */)
 {
 	const int c = (int)(((size_t)blockIdx.x * CTA + threadIdx.x) >> 5), lane = threadIdx.x & 31;
 	if (c >= G.n) return;
@@ -333,35 +335,261 @@ __global__ void __launch_bounds__(CTA) k_seam_cull(SeamGrid G, const SeamChunk* 
 	}
 }
 
-// pass 1 (persistent): triangles per task (= 256 consecutive shell points of an active chunk) and per chunk; the
-// non-empty tasks go on the emit list
-__global__ void __launch_bounds__(CTA, 4) k_seam_count(SeamArgs A, const uint32_t* __restrict__ active, uint32_t* __restrict__ counters,
-                                                     uint32_t* __restrict__ blk_cnt, uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ emit_list)
+// sign word w of row (x, y) of chunk m (constant for the uniform chunks of the 2-D terrains, whose words are never written)
+__device__ __forceinline__ uint32_t seam_row_word(const SeamArgs& A, int m, int u, int x, int y, int w)
 {
-	__shared__ uint32_t s_sum;
-	__shared__ SeamNbr s_tab[27];
-	const uint32_t n_tasks = counters[0] * (uint32_t)A.G.bpc;
+	if (u) return u == 1 ? 0xFFFFFFFFu : 0u;
+	return A.bits[(size_t)m * A.L.wc + ((((size_t)x << A.L.ld) + y) << A.L.lzc) + w];
+}
+
+__device__ __forceinline__ void seam_or_bits(uint32_t* act, uint32_t t0, uint32_t mask)
+{
+	if (!mask) return;
+	const uint32_t sh = t0 & 31u;
+	atomicOr(act + (t0 >> 5), mask << sh);
+	if (sh && (mask >> (32u - sh))) atomicOr(act + (t0 >> 5) + 1, mask >> (32u - sh));
+}
+
+// pass 0c (persistent over (active chunk, face)): which shell points can emit anything at all.  For a face whose
+// neighbour is a chunk of the SAME level the test is exact and word-parallel for the x and y faces -- 32 dual cells per
+// thread from the four sign rows that meet at the face (two of this chunk, two of the neighbour): a cell is active iff
+// its 2x2x2 voxels are not all of one sign.  A coarser neighbour's rows are stretched to this chunk's resolution first.
+// Edge / corner points are marked "maybe" and resolved by the generic per-point path; faces that are clean, not owned
+// (lower-index neighbour of the same level, finer or missing neighbour) or filtered out by the group rule stay 0.
+__global__ void __launch_bounds__(CTA) k_seam_classify(SeamArgs A, const uint32_t* __restrict__ active, const uint32_t* __restrict__ counters, uint32_t* __restrict__ actmap)
+{
+	const uint32_t n_tasks = counters[0] * 6u;
+	const int d = A.L.d, zc = A.L.zc;
+	const uint32_t fa = (uint32_t)(d + 1) * (d + 1), fb = (uint32_t)(d - 1) * (d + 1), fc = (uint32_t)(d - 1) * (d - 1);
 	for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x)
 	{
-		const int c = (int)active[task / (uint32_t)A.G.bpc], b = (int)(task % (uint32_t)A.G.bpc);
-		if (threadIdx.x == 32) s_sum = 0;
-		seam_fill_nbrs(A, c, s_tab);
-		__syncthreads();
-		const int t = b * CTA + threadIdx.x;
-		uint32_t cnt = 0;
-		if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tab, c, t, nullptr);
-#pragma unroll
-		for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-		if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_sum, cnt);
-		__syncthreads();
-		if (threadIdx.x == 0 && s_sum)
+		const int c = (int)active[task / 6u], F = (int)(task % 6u), axis = F >> 1, hi = F & 1;
+		uint32_t* act = actmap + (size_t)c * A.act_words;
+		// edge and corner points of the shell (on two or three faces at once): generic path
+		if (axis == 0)
 		{
-			const uint32_t gb = (uint32_t)c * (uint32_t)A.G.bpc + (uint32_t)b;
-			blk_cnt[gb] = s_sum;
-			atomicAdd(chunk_cnt + c, s_sum);
-			emit_list[atomicAdd(counters + 1, 1u)] = gb;
+			const uint32_t base = (uint32_t)hi * fa;
+			for (int q = threadIdx.x; q < 4 * (d + 1); q += CTA)
+			{
+				const int side = q / (d + 1), r = q - side * (d + 1);
+				const int j = side == 0 ? 0 : side == 1 ? d : r, k = side < 2 ? r : (side == 2 ? 0 : d);
+				seam_or_bits(act, base + (uint32_t)j * (d + 1) + k, 1u);
+			}
 		}
-		__syncthreads();
+		else if (axis == 1)
+		{
+			const uint32_t base = 2 * fa + (uint32_t)hi * fb;
+			for (int q = threadIdx.x; q < 2 * (d - 1); q += CTA)
+			{
+				const int i = 1 + (q >> 1), k = (q & 1) ? d : 0;
+				seam_or_bits(act, base + (uint32_t)(i - 1) * (d + 1) + k, 1u);
+			}
+		}
+		const SeamNbr nb = seam_nbr(A, c, axis == 0 ? (hi ? 1 : -1) : 0, axis == 1 ? (hi ? 1 : -1) : 0, axis == 2 ? (hi ? 1 : -1) : 0);
+		const SeamChunk me = A.chunks[c];
+		if (nb.m < 0) continue;                                       // finer or missing neighbour: nothing owned on this face
+		if ((A.clean[c] >> F) & 1) continue;                          // both layers uniformly of one sign
+		if (nb.lg == me.lg && nb.m < c) continue;                     // the neighbour owns the face
+		if (A.cross_group_only && nb.grp == (A.group ? A.group[c] : 0)) continue;
+		const int mu = A.uni ? (int)A.uni[c] : 0;
+		// The neighbour's voxels across the face: same in-face coordinates for a chunk of the same level; for a chunk s
+		// levels coarser, voxel (p, q) of this chunk faces voxel (P0 + (p >> s), Q0 + (q >> s)) of the neighbour (this chunk
+		// is aligned to the neighbour's voxel lattice), i.e. every neighbour bit is seen 2^s times in a row.
+		const int s = nb.lg - me.lg;
+		const int obx = (int)me.ox << A.L.ld, oby = (int)me.oy << A.L.ld, obz = (int)me.oz << A.L.ld;
+		const int X0 = (obx - nb.bx) >> nb.lg, Y0 = (oby - nb.by) >> nb.lg, Z0 = (obz - nb.bz) >> nb.lg;
+		const int own = hi ? d - 1 : 0, opp = hi ? 0 : d - 1;
+		if (s > 5)
+		{
+			// more than 5 levels apart (a stretched run would be shorter than one bit per word): generic path for the whole face
+			for (int q = threadIdx.x; q < (d - 1) * (d - 1); q += CTA)
+			{
+				const int u = 1 + q / (d - 1), v = 1 + q % (d - 1);
+				const uint32_t t = axis == 0 ? (uint32_t)hi * fa + (uint32_t)u * (d + 1) + v
+				                 : axis == 1 ? 2 * fa + (uint32_t)hi * fb + (uint32_t)(u - 1) * (d + 1) + v : 2 * fa + 2 * fb + (uint32_t)hi * fc + q;
+				seam_or_bits(act, t, 1u);
+			}
+		}
+		else if (axis < 2)
+		{
+			for (int q = threadIdx.x; q < (d - 1) * zc; q += CTA)
+			{
+				const int r = 1 + q / zc, w = q - (r - 1) * zc; // lattice row r (j for x faces, i for y faces), word w of the z run
+				uint32_t any = 0, all = 0xFFFFFFFFu, anyp = 0, allp = 1u;
+#pragma unroll
+				for (int rr = 0; rr < 2; rr++)
+				{
+					const int line = r - 1 + rr;
+					// this chunk's row
+					{
+						const int x = axis == 0 ? own : line, y = axis == 0 ? line : own;
+						const uint32_t v = seam_row_word(A, c, mu, x, y, w);
+						any |= v; all &= v;
+						if (w > 0)
+						{
+							const uint32_t vp = seam_row_word(A, c, mu, x, y, w - 1) >> 31;
+							anyp |= vp; allp &= vp;
+						}
+					}
+					// the neighbour's row, stretched by 2^s
+					{
+						const int x = axis == 0 ? opp : X0 + (line >> s), y = axis == 0 ? Y0 + (line >> s) : opp;
+						uint32_t v, vp = 0;
+						if (s == 0 || nb.u)
+						{
+							v = seam_row_word(A, nb.m, nb.u, x, y, w);
+							if (w > 0) vp = seam_row_word(A, nb.m, nb.u, x, y, w - 1) >> 31;
+						}
+						else
+						{
+							const int z0 = Z0 + ((32 * w) >> s); // first neighbour voxel of this run; the run never straddles a word
+							const uint32_t cw = seam_row_word(A, nb.m, 0, x, y, z0 >> 5) >> (z0 & 31);
+							v = 0;
+#pragma unroll
+							for (int bit = 0; bit < 32; bit++) v |= ((cw >> (bit >> s)) & 1u) << bit;
+							if (w > 0)
+							{
+								const int zp = Z0 + ((32 * w - 1) >> s);
+								vp = (seam_row_word(A, nb.m, 0, x, y, zp >> 5) >> (zp & 31)) & 1u;
+							}
+						}
+						any |= v; all &= v;
+						if (w > 0) { anyp |= vp; allp &= vp; }
+					}
+				}
+				const uint32_t a2 = any | ((any << 1) | (w > 0 ? anyp : 0u));
+				const uint32_t l2 = all & ((all << 1) | (w > 0 ? allp : 0u));
+				uint32_t m32 = a2 & ~l2;
+				if (w == 0) m32 &= ~1u; // k = 0 is an edge point
+				const uint32_t t0 = (axis == 0 ? (uint32_t)hi * fa + (uint32_t)r * (d + 1) : 2 * fa + (uint32_t)hi * fb + (uint32_t)(r - 1) * (d + 1)) + 32u * w;
+				seam_or_bits(act, t0, m32);
+			}
+		}
+		else
+		{
+			const int wo = hi ? zc - 1 : 0, bo = hi ? 31 : 0, zn = hi ? 0 : d - 1;
+			for (int q = threadIdx.x; q < (d - 1) * (d - 1); q += CTA)
+			{
+				const int i = 1 + q / (d - 1), j = 1 + q % (d - 1);
+				uint32_t any = 0, all = 1;
+#pragma unroll
+				for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+					for (int dy = 0; dy < 2; dy++)
+					{
+						const int x = i - 1 + dx, y = j - 1 + dy;
+						const uint32_t a = (seam_row_word(A, c, mu, x, y, wo) >> bo) & 1u;
+						const uint32_t b = (seam_row_word(A, nb.m, nb.u, X0 + (x >> s), Y0 + (y >> s), zn >> 5) >> (zn & 31)) & 1u;
+						any |= a | b; all &= a & b;
+					}
+				if (any && !all) seam_or_bits(act, 2 * fa + 2 * fb + (uint32_t)hi * fc + q, 1u);
+			}
+		}
+	}
+}
+
+// ---- passes 1 and 2 (persistent over (active chunk, part)) ------------------------------------------------------------
+// A task owns a contiguous range of a chunk's activity words.  256 words at a time, the set bits are compacted IN ORDER
+// into a shared-memory list (popc + block scan), so the expensive per-cell work runs on dense warps whatever the
+// pattern of the marked points; list order = lattice order, so positions stay the defined ones.
+static constexpr int SEAM_PARTS = 4;
+
+// exclusive scan of v over the CTA in thread order; returns the CTA total through `total` (s_w: CTA/32 + 1 words)
+__device__ __forceinline__ uint32_t seam_block_scan(uint32_t v, uint32_t* s_w, uint32_t& total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += u;
+	}
+	__syncthreads(); // s_w may still be read from the previous scan
+	if (lane == 31) s_w[warp] = inc;
+	__syncthreads();
+	uint32_t before = inc - v, tot = 0;
+#pragma unroll
+	for (int w = 0; w < CTA / 32; w++)
+	{
+		const uint32_t x = s_w[w];
+		if (w < warp) before += x;
+		tot += x;
+	}
+	total = tot;
+	return before;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(CTA, EMIT ? 2 : 4) k_seam_pass(SeamArgs A, const uint32_t* __restrict__ active, const uint32_t* __restrict__ counters,
+                                                                  uint32_t* __restrict__ part_cnt, uint32_t* __restrict__ chunk_cnt,
+                                                                  const unsigned long long* __restrict__ chunk_base, float* __restrict__ out)
+{
+	__shared__ SeamNbr s_tab[27];
+	__shared__ uint16_t s_list[CTA * 32];
+	__shared__ uint32_t s_w[CTA / 32];
+	const uint32_t n_tasks = counters[0] * (uint32_t)SEAM_PARTS;
+	const int wpp = (A.act_words + SEAM_PARTS - 1) / SEAM_PARTS; // activity words per part
+	for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x)
+	{
+		const int c = (int)active[task / (uint32_t)SEAM_PARTS], part = (int)(task % (uint32_t)SEAM_PARTS);
+		if (EMIT && chunk_cnt[c] == 0) continue; // whole CTA
+		__syncthreads(); // the previous task is done with s_tab / s_list
+		seam_fill_nbrs(A, c, s_tab);
+		const uint32_t* act = A.act + (size_t)c * A.act_words;
+		unsigned long long base = 0;
+		if (EMIT)
+		{
+			base = chunk_base[c];
+			for (int q = 0; q < part; q++) base += part_cnt[(size_t)c * SEAM_PARTS + q];
+		}
+		uint32_t mine = 0; // triangles counted by this thread (pass 1)
+		const int w_end = min(A.act_words, (part + 1) * wpp);
+		for (int w0 = part * wpp; w0 < w_end; w0 += CTA)
+		{
+			const int w = w0 + threadIdx.x;
+			uint32_t word = w < w_end ? act[w] : 0u;
+			uint32_t n_act;
+			uint32_t off = seam_block_scan((uint32_t)__popc(word), s_w, n_act); // first barrier inside also orders s_tab and the previous round's s_list reads
+			if (n_act == 0) continue;
+			while (word)
+			{
+				const int bit = __ffs(word) - 1;
+				word &= word - 1;
+				s_list[off++] = (uint16_t)((threadIdx.x << 5) | bit);
+			}
+			__syncthreads();
+			for (uint32_t e0 = 0; e0 < n_act; e0 += CTA)
+			{
+				const uint32_t e = e0 + threadIdx.x;
+				float tri[EMIT ? 45 : 1];
+				uint32_t cnt = 0;
+				if (e < n_act) cnt = (uint32_t)seam_cell(A, s_tab, c, (w0 << 5) + (int)s_list[e], EMIT ? tri : nullptr);
+				if (EMIT)
+				{
+					uint32_t round_total;
+					const uint32_t before = seam_block_scan(cnt, s_w, round_total);
+					if (cnt)
+					{
+						float* dst = out + 9 * (size_t)(base + before);
+						for (uint32_t q = 0; q < 9 * cnt; q++) dst[q] = tri[q];
+					}
+					base += round_total;
+				}
+				else
+					mine += cnt;
+			}
+		}
+		if (!EMIT)
+		{
+			uint32_t total;
+			seam_block_scan(mine, s_w, total);
+			if (threadIdx.x == 0)
+			{
+				part_cnt[(size_t)c * SEAM_PARTS + part] = total;
+				if (total) atomicAdd(chunk_cnt + c, total);
+			}
+		}
 	}
 }
 
@@ -407,54 +635,6 @@ __global__ void __launch_bounds__(SEAM_SCAN_CTA) k_seam_scan(const uint32_t* __r
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) *total = s_carry;
-}
-
-// pass 2 (persistent over the emit list): the same cells again, written at chunk base + tasks of the chunk before this
-// one + threads before this one -- the output order does not depend on the order of the lists
-__global__ void __launch_bounds__(CTA) k_seam_emit(SeamArgs A, const uint32_t* __restrict__ counters, const uint32_t* __restrict__ emit_list,
-                                                    const uint32_t* __restrict__ blk_cnt, const unsigned long long* __restrict__ chunk_base, float* __restrict__ out)
-{
-	__shared__ uint32_t s_w[CTA / 32];
-	__shared__ unsigned long long s_base;
-	__shared__ SeamNbr s_tab[27];
-	const uint32_t n_tasks = counters[1];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x)
-	{
-		const uint32_t gb = emit_list[task];
-		const int c = (int)(gb / (uint32_t)A.G.bpc), b = (int)(gb % (uint32_t)A.G.bpc);
-		if (threadIdx.x == 32) s_base = 0;
-		seam_fill_nbrs(A, c, s_tab);
-		__syncthreads();
-		{
-			unsigned long long part = 0;
-			for (int q = threadIdx.x; q < b; q += CTA) part += blk_cnt[(size_t)c * A.G.bpc + q];
-#pragma unroll
-			for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-			if (lane == 0 && part) atomicAdd(&s_base, part);
-		}
-		const int t = b * CTA + threadIdx.x;
-		float tri[45];
-		uint32_t cnt = 0;
-		if (t < A.G.npts) cnt = (uint32_t)seam_cell(A, s_tab, c, t, tri);
-		uint32_t inc = cnt;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-			if (lane >= o) inc += u;
-		}
-		if (lane == 31) s_w[warp] = inc;
-		__syncthreads();
-		uint32_t before = inc - cnt;
-		for (int w = 0; w < warp; w++) before += s_w[w];
-		if (cnt)
-		{
-			float* dst = out + 9 * (size_t)(chunk_base[c] + s_base + before);
-			for (uint32_t q = 0; q < 9 * cnt; q++) dst[q] = tri[q];
-		}
-		__syncthreads();
-	}
 }
 
 } // namespace bmf
