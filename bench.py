@@ -447,6 +447,34 @@ def extras(ctx, args, capi, world):
                                                      "lattice_points_per_s": pts / ((sm["count"] + sm["emit"]) * 1e-3)}
     except Exception as e:  # noqa: BLE001
         ex["lod_rebuild_with_seams"] = {"error": str(e)}
+    # config 1: single 64^3 chunk of the implicit sphere, no processing -- triangles (the reference's emitter) and quads (bmf_params.quads)
+    try:
+        ctx.set_sampler(capi.SPHERE)
+        c1 = capi.make_chunk_descs([[-128, -128, -128, 256.0]])
+        for name, qd in (("tris", False), ("quads", True)):
+            for _ in range(3):
+                ctx.submit(c1, 64, iters=0, quads=qd)
+            ctx.wait()
+            t0 = _t.perf_counter()
+            for _ in range(20):
+                ctx.submit(c1, 64, iters=0, quads=qd)
+            ctx.wait()
+            s = (_t.perf_counter() - t0) / 20
+            ex["single_64_sphere_%s" % name] = {"ms": s * 1e3, "mesh": dict(zip(("cells", "verts", "indices"), ctx.totals()))}
+        # quads on the benchmark batch (emission only)
+        ctx.set_sampler(SAMPLERS[args.sampler])
+        for _ in range(2):
+            ctx.submit(d, args.dim, iters=0, quads=True)
+        ctx.wait()
+        t0 = _t.perf_counter()
+        for _ in range(3):
+            ctx.submit(d, args.dim, iters=0, quads=True)
+        ctx.wait()
+        s = (_t.perf_counter() - t0) / 3
+        ex["quads_4096x64_%s" % args.sampler] = {"ms": s * 1e3, "voxels_per_s": len(d) * args.dim ** 3 / s, "stage_ms": ctx.stage_ms(),
+                                                 "mesh": dict(zip(("cells", "verts", "indices"), ctx.totals()))}
+    except Exception as e:  # noqa: BLE001
+        ex["single_64_sphere_quads"] = {"error": str(e)}
     # config 2: single 128^3 chunk, 2 smoothing iterations
     one = capi.make_chunk_descs([[-64, -64, -64, 128.0]], overlaps=0.045)
     for name, kind in (("terrain2d_pert", capi.TERRAIN2D_PERT), ("terrain3d_pert", capi.TERRAIN3D_PERT)):

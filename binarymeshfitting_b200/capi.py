@@ -23,7 +23,7 @@ EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
-           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms")
+           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris")
 
 
 class SamplerDesc(C.Structure):
@@ -40,7 +40,7 @@ class ChunkDesc(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [("dim", C.c_int32), ("iters", C.c_int32), ("process_boundary", C.c_int32), ("smooth_normals", C.c_int32),
-                ("qef", C.c_int32), ("keep_density", C.c_int32), ("keep_masks", C.c_int32), ("density_on_device", C.c_int32)]
+                ("qef", C.c_int32), ("keep_density", C.c_int32), ("keep_masks", C.c_int32), ("density_on_device", C.c_int32), ("quads", C.c_int32)]
 
 
 class ChunkInfo(C.Structure):
@@ -99,6 +99,7 @@ def load_library(path=SO):
     lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_mesh_process_steps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    lib.bmf_quads_to_tris.argtypes = [vp, vp, C.c_int64, vp]
     lib.bmf_seam_overlap.argtypes = [C.c_int]
     lib.bmf_seam_overlap.restype = C.c_float
     lib.bmf_batch_stitch.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
@@ -166,9 +167,9 @@ class Context:
         return s
 
     def submit(self, descs, dim, iters=0, process_boundary=False, smooth_normals=False, qef=False, keep_density=False, keep_masks=False,
-               density=None, density_device_ptr=None):
+               density=None, density_device_ptr=None, quads=False):
         descs = np.ascontiguousarray(descs, CHUNK_DESC_DTYPE)
-        p = Params(dim, iters, int(process_boundary), int(smooth_normals), int(qef), int(keep_density), int(keep_masks), 1 if density_device_ptr else 0)
+        p = Params(dim, iters, int(process_boundary), int(smooth_normals), int(qef), int(keep_density), int(keep_masks), 1 if density_device_ptr else 0, int(quads))
         dptr = None
         if density_device_ptr:
             dptr = C.c_void_p(density_device_ptr)
@@ -262,6 +263,13 @@ class Context:
         self._check(self.lib.bmf_mesh_process(self.h, _p(pos), _p(color), _p(normal), _p(boundary), None, len(pos), _p(inds), len(inds), prim_n, iters,
                                               int(process_boundary), int(smooth_normals)))
         return pos, color, normal
+
+    def quads_to_tris(self, quads):
+        """MeshProcessor<4>::flush_to_tris: [n,4] quad indices -> [2n,3] triangle indices"""
+        q = np.ascontiguousarray(quads, np.uint32).reshape(-1, 4)
+        t = np.zeros((len(q) * 2, 3), np.uint32)
+        self._check(self.lib.bmf_quads_to_tris(self.h, _p(q), len(q), _p(t)))
+        return t
 
     def seam_overlap(self, dim):
         """the overlap that puts a chunk's samples at its voxel-node centres (what the seam pass expects)"""

@@ -6,6 +6,7 @@
 #include "extract.cuh"
 #include "smooth.cuh"
 #include "seam.cuh"
+#include "quads.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -113,6 +114,10 @@ struct bmf_ctx
 	// qef scratch
 	DevBuf<float> qp, qn, qo, qe;
 	DevBuf<int32_t> qc;
+	// quad emission (quads.cuh)
+	DevBuf<uint32_t> wq, wqq;
+	DevBuf<uint4> wqv;
+	bool quads_processed = false; // MeshProcessor<4> has run on the resident quad batch
 	// seam pass (seam.cuh)
 	DevBuf<SeamChunk> seam_chunks;
 	DevBuf<int32_t> seam_map, seam_group;
@@ -448,6 +453,25 @@ int launch_mesh(bmf_ctx* ctx)
 	src.density = ctx->density_cur;
 	src.hmap = (!ctx->density_cur && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
 	src.sheet_of = ctx->sheet_of.p;
+	if (params->quads)
+	{
+		// dual-marching-cubes quads (quads.cuh); MeshProcessor<4> runs when the batch is completed (it needs the real counts)
+		const size_t n_words = (size_t)n * L.wc;
+		BMF_LAUNCH(k_q_bases, (unsigned)n, CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->counts.p, ctx->wqv.p, ctx->wqq.p, tot);
+		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+		BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, ctx->valence.cap, st));
+		BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, reinterpret_cast<uint32_t*>(ctx->normal.p), 3 * V, tot, 1, 3);
+		if (ctx->color_ones < 3 * V)
+		{
+			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
+			ctx->color_ones = ctx->color.cap;
+		}
+		BMF_LAUNCH(k_q_emit, (unsigned)(n_words / CTA), CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->wqv.p, ctx->wqq.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p,
+		           ctx->pos.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, tot);
+		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+		return publish_chunks(ctx);
+	}
 	if (L.wpt == 4)
 		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count, tot);
@@ -504,6 +528,19 @@ int finish(bmf_ctx* ctx)
 		BMF_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (ctx->totals_pinned->v[7]) return fail(ctx, BMF_ERR_NOMEM, "bmf_batch_wait: output arenas still too small after growing");
 		ctx->relaunches++;
+	}
+	if (ctx->params.quads && ctx->params.iters > 0 && !ctx->quads_processed && ctx->totals[1] && ctx->totals[2] >= 4)
+	{
+		// MeshProcessor<4>(true, smooth_normals): init + optimize_dual_grid(iters, pb) + optimize_primal_grid(false, false, pb)
+		// (the sequence ChunkGenerator.cpp:271-280 / DebugScene.cpp:256-262 run on quads), generic CSR path, real counts
+		BMF_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+		int rc = run_smooth<4>(ctx, (size_t)ctx->totals[1], (size_t)ctx->totals[2], ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p,
+		                       ctx->inds.p, ctx->counts.p, ctx->n, ctx->params.iters, ctx->params.process_boundary, ctx->params.smooth_normals, 0);
+		if (rc) return rc;
+		ctx->color_ones = 0; // the generic path rewrites colours (with the same value); do not rely on the fill any more
+		BMF_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+		BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+		ctx->quads_processed = true;
 	}
 	for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
 	elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
@@ -582,6 +619,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
+	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
@@ -637,6 +675,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (!ctx->sampler_set) return fail(ctx, BMF_ERR_STATE, "bmf_batch_submit: no sampler set");
 	if (!valid_dim(params->dim)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: dim must be 32, 64, 128 or 256");
 	if (params->iters < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: iters < 0");
+	if (params->quads && (params->qef || params->keep_masks)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: quads cannot be combined with qef or keep_masks");
 	const int kind = ctx->sampler.kind;
 	if (kind == BMF_SAMPLER_HOST_DENSITY && !density_in) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: HOST_DENSITY needs a density block");
 	BMF_CUDA(cudaSetDevice(ctx->device));
@@ -645,6 +684,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	ctx->finished = false;
 	ctx->uni_valid = false;
 	ctx->seam_n_tris = -1;
+	ctx->quads_processed = false;
 	ctx->kused = 0;
 	ctx->n = n;
 	ctx->params = *params;
@@ -796,7 +836,14 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	// ---- K3
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
 	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
-	if (L.wpt == 4)
+	if (params->quads)
+	{
+		BMF_CUDA(ctx->wq.reserve(n_words));
+		BMF_CUDA(ctx->wqq.reserve(n_words));
+		BMF_CUDA(ctx->wqv.reserve(n_words));
+		BMF_LAUNCH(k_q_count, (unsigned)(n_words / CTA), CTA, 0, ctx->bits.p, ctx->flags.p, L, ctx->wq.p, ctx->chunk_tot.p);
+	}
+	else if (L.wpt == 4)
 		BMF_LAUNCH(k_count<4>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->chunk_tot.p, masks_w);
 	else
 		BMF_LAUNCH(k_count<8>, nseg, CTA, smem_count, ctx->bits.p, ctx->flags.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->chunk_tot.p, masks_w);
@@ -1101,6 +1148,22 @@ int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, co
 	BMF_LAUNCH(k_qef_batch, grid_for(M, 128), 128, 0, ctx->qp.p, ctx->qn.p, ctx->qc.p, m, ctx->qo.p, ctx->qe.p);
 	BMF_CUDA(cudaMemcpyAsync(out_pos, ctx->qo.p, sizeof(float) * 3 * M, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(out_err, ctx->qe.p, sizeof(float) * M, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+int bmf_quads_to_tris(bmf_ctx* ctx, const uint32_t* quads, int64_t n_quads, uint32_t* tris)
+{
+	if (!ctx || n_quads < 0 || (n_quads && (!quads || !tris))) return fail(ctx, BMF_ERR_INVALID, "bmf_quads_to_tris: bad arguments");
+	if (n_quads == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	// scratch: the adjacency / dual-point arenas of the smoothing stage are free outside a submit
+	BMF_CUDA(ctx->adj.reserve(4 * (size_t)n_quads));
+	BMF_CUDA(ctx->cursor.reserve(6 * (size_t)n_quads));
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(cudaMemcpyAsync(ctx->adj.p, quads, sizeof(uint32_t) * 4 * (size_t)n_quads, cudaMemcpyHostToDevice, st));
+	BMF_LAUNCH(k_quads_to_tris, std::min(grid_for((size_t)n_quads, CTA), (unsigned)(ctx->sm_count * 8)), CTA, 0, ctx->adj.p, (size_t)n_quads, ctx->cursor.p);
+	BMF_CUDA(cudaMemcpyAsync(tris, ctx->cursor.p, sizeof(uint32_t) * 6 * (size_t)n_quads, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaStreamSynchronize(st));
 	return BMF_OK;
 }

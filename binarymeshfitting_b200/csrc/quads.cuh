@@ -1,0 +1,272 @@
+// quads.cuh -- quad emission (bmf_params.quads): the producer MeshProcessor<4> never had in the reference (README.md:72
+// recommends quads, `Processing::MeshProcessor<4>` and Tables::NumVertices / EdgeTable exist, nothing emits a quad;
+// SURVEY 8(f)#4).  Build-defined, UNPINNED; the oracle twin is orc_quads (oracle/bmf_oracle.c), same definition:
+//
+// Nielson's dual marching cubes on the chunk's (d-1)^3 cells.  One dual vertex per surface patch of a cell (c_patch_pack:
+// the connected components of the cell's tri_table triangles), placed at the mean of the patch's edge crossing points
+// (edges in ascending id, crossing = the triangle emitter's iso-vertex formula); one quad per sign-changing grid edge
+// that has all four cells around it, joining the patch vertices that contain the edge.  Vertex ids follow the serial
+// x->y->z cell scan (patches in table order); quads are emitted in the same scan by the cell at the edge's lower end, X
+// then Y then Z edge, wound like the triangle emitter's triangles.
+//
+// Same count -> scan -> emit structure as the triangle path, one thread per 32-cell word; a cell's vertex id anywhere in
+// the chunk is `record.base + prefix(bit planes of the patch counts)` -- one 16-byte load, like the triangle path's
+// word records.
+#pragma once
+#include "extract.cuh"
+
+namespace bmf
+{
+
+__constant__ uint64_t c_patch_pack[256] = BMF_PATCH_PACK_INIT;
+
+// sign rows of the 32 cells of word (x, y, zb): r[2 dx + dy] = row (x+dx, y+dy), s[..] = the same row one voxel up in z
+struct QWord
+{
+	uint32_t r[4], s[4];
+};
+
+__device__ __forceinline__ QWord q_load(const uint32_t* __restrict__ cb, const Layout& L, int x, int y, int zb)
+{
+	QWord q;
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		const size_t row = ((((size_t)(x + (k >> 1)) << L.ld) + (y + (k & 1))) << L.lzc);
+		const uint32_t w = cb[row + zb];
+		const uint32_t nx = zb + 1 < L.zc ? cb[row + zb + 1] : 0u;
+		q.r[k] = w;
+		q.s[k] = (w >> 1) | (nx << 31);
+	}
+	return q;
+}
+
+// corner mask of the cell at bit z of the word (corner = 4 dx + 2 dy + dz)
+__device__ __forceinline__ uint32_t q_mask8(const QWord& q, int z)
+{
+	return ((q.r[0] >> z) & 1u) | (((q.s[0] >> z) & 1u) << 1) | (((q.r[1] >> z) & 1u) << 2) | (((q.s[1] >> z) & 1u) << 3) | (((q.r[2] >> z) & 1u) << 4) |
+	       (((q.s[2] >> z) & 1u) << 5) | (((q.r[3] >> z) & 1u) << 6) | (((q.s[3] >> z) & 1u) << 7);
+}
+
+// bits of the word that are cells of the (d-1)^3 grid
+__device__ __forceinline__ uint32_t q_valid_bits(const Layout& L, int x, int y, int zb)
+{
+	if (x >= L.d - 1 || y >= L.d - 1) return 0u;
+	return zb == L.zc - 1 ? 0x7FFFFFFFu : 0xFFFFFFFFu;
+}
+
+// ---- count: per word (dual vertices | quads << 16) and per chunk (cells, vertices, indices)
+__global__ void __launch_bounds__(CTA) k_q_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, uint32_t* __restrict__ wq,
+                                                  uint32_t* __restrict__ chunk_tot)
+{
+	const size_t gw = (size_t)blockIdx.x * CTA + threadIdx.x; // the CTA's 256 words belong to one chunk
+	const int chunk = (int)(gw >> L.lwc);
+	if (!flags_contain_mesh(flags[chunk])) return; // whole CTA; its words are never read
+	const int w = (int)(gw & (size_t)(L.wc - 1));
+	const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
+	uint32_t nc = 0, nv = 0, nq = 0;
+	uint32_t valid = q_valid_bits(L, x, y, zb);
+	if (valid)
+	{
+		const QWord q = q_load(bits + (size_t)chunk * L.wc, L, x, y, zb);
+		// cells whose eight corners are not all equal
+		const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
+		const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
+		uint32_t act = any & ~all & valid;
+		nc = __popc(act);
+		// quads owned by the cells of this word: sign-changing X / Y / Z edge at the cell's lower corner with all four cells around it
+		const uint32_t zin = zb == 0 ? 0xFFFFFFFEu : 0xFFFFFFFFu; // z >= 1
+		if (y >= 1) nq += __popc((q.r[0] ^ q.r[2]) & valid & zin);
+		if (x >= 1) nq += __popc((q.r[0] ^ q.r[1]) & valid & zin);
+		if (x >= 1 && y >= 1) nq += __popc((q.r[0] ^ q.s[0]) & valid);
+		while (act)
+		{
+			const int z = __ffs(act) - 1;
+			act &= act - 1;
+			nv += (uint32_t)(c_patch_pack[q_mask8(q, z)] >> 60);
+		}
+	}
+	wq[gw] = nv | (nq << 16);
+	uint32_t ni = 4 * nq, tot[3];
+	block_scan3(nc, nv, ni, tot);
+	if (threadIdx.x < 3 && tot[threadIdx.x]) atomicAdd(chunk_tot + 3 * (size_t)chunk + threadIdx.x, tot[threadIdx.x]);
+}
+
+// ---- bases: ordered scan of the words of a chunk (one CTA per chunk, tiles with a running carry).
+// wqv[word] = {chunk-local id of the word's first dual vertex, bit planes 0..2 of its cells' patch counts};
+// wqq[word] = chunk-local number of the word's first quad.
+static constexpr int Q_ITEMS = 4;
+
+__global__ void __launch_bounds__(CTA) k_q_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wq, const ChunkCounts* __restrict__ chunks,
+                                                  uint4* __restrict__ wqv, uint32_t* __restrict__ wqq, const unsigned long long* __restrict__ tot)
+{
+	if (tot[7]) return;
+	const int chunk = blockIdx.x;
+	const ChunkCounts cc = chunks[chunk];
+	if (!cc.contains_mesh || cc.n_verts == 0) return;
+	const uint32_t* cb = bits + (size_t)chunk * L.wc;
+	uint32_t carry_v = 0, carry_q = 0;
+	for (int base = 0; base < L.wc; base += CTA * Q_ITEMS)
+	{
+		const int w0 = base + threadIdx.x * Q_ITEMS;
+		uint32_t cnt[Q_ITEMS], sum[2] = { 0, 0 }, tt[2];
+#pragma unroll
+		for (int k = 0; k < Q_ITEMS; k++)
+		{
+			cnt[k] = wq[(size_t)chunk * L.wc + w0 + k];
+			sum[0] += cnt[k] & 0xFFFFu;
+			sum[1] += cnt[k] >> 16;
+		}
+		block_scan<2>(sum, tt);
+		uint32_t rv = carry_v + sum[0], rq = carry_q + sum[1];
+#pragma unroll
+		for (int k = 0; k < Q_ITEMS; k++)
+		{
+			const int w = w0 + k;
+			if (cnt[k])
+			{
+				uint32_t p0 = 0, p1 = 0, p2 = 0;
+				if (cnt[k] & 0xFFFFu)
+				{
+					const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
+					const QWord q = q_load(cb, L, x, y, zb);
+					const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
+					const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
+					uint32_t act = any & ~all & q_valid_bits(L, x, y, zb);
+					while (act)
+					{
+						const int z = __ffs(act) - 1;
+						act &= act - 1;
+						const uint32_t np = (uint32_t)(c_patch_pack[q_mask8(q, z)] >> 60);
+						p0 |= (np & 1u) << z; p1 |= ((np >> 1) & 1u) << z; p2 |= ((np >> 2) & 1u) << z;
+					}
+				}
+				wqv[(size_t)chunk * L.wc + w] = make_uint4(rv, p0, p1, p2);
+				wqq[(size_t)chunk * L.wc + w] = rq;
+			}
+			rv += cnt[k] & 0xFFFFu;
+			rq += cnt[k] >> 16;
+		}
+		carry_v += tt[0];
+		carry_q += tt[1];
+	}
+}
+
+// chunk-local id of the dual vertex of cell (x, y, z) whose patch contains local edge e
+__device__ __forceinline__ uint32_t q_vertex_id(const uint32_t* __restrict__ cb, const uint4* __restrict__ rec, const Layout& L, int x, int y, int z, int e)
+{
+	const int zb = z >> 5, bit = z & 31;
+	const uint4 r = rec[((((size_t)x << L.ld) + y) << L.lzc) + zb];
+	const uint32_t lt = (1u << bit) - 1u;
+	uint32_t id = r.x + __popc(r.y & lt) + 2u * __popc(r.z & lt) + 4u * __popc(r.w & lt);
+	const QWord q = q_load(cb, L, x, y, zb);
+	const uint64_t pp = c_patch_pack[q_mask8(q, bit)];
+	uint32_t p = 0;
+#pragma unroll
+	for (int k = 1; k < 4; k++)
+		if ((pp >> (12 * k + e)) & 1ull) p = k;
+	return id + p;
+}
+
+// ---- emit: one thread per word with anything to emit
+__global__ void __launch_bounds__(CTA) k_q_emit(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wq, const uint4* __restrict__ wqv,
+                                                 const uint32_t* __restrict__ wqq, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
+                                                 const ChunkGeom* __restrict__ geom, float* __restrict__ pos, uint8_t* __restrict__ boundary,
+                                                 uint8_t* __restrict__ valence, uint32_t* __restrict__ inds, const unsigned long long* __restrict__ tot)
+{
+	if (tot[7]) return;
+	const size_t gw = (size_t)blockIdx.x * CTA + threadIdx.x;
+	const int chunk = (int)(gw >> L.lwc);
+	const ChunkCounts cc = chunks[chunk];
+	if (!cc.contains_mesh || cc.n_verts == 0) return;
+	const uint32_t cnt = wq[gw];
+	if (!cnt) return;
+	const int w = (int)(gw & (size_t)(L.wc - 1));
+	const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
+	const int d = L.d;
+	const uint32_t* cb = bits + (size_t)chunk * L.wc;
+	const uint4* rec = wqv + (size_t)chunk * L.wc;
+	const ChunkGeom g = geom[chunk];
+	const QWord q = q_load(cb, L, x, y, zb);
+	const uint32_t valid = q_valid_bits(L, x, y, zb);
+	const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
+	const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
+	uint32_t act = any & ~all & valid;
+	size_t v = (size_t)cc.vert_base + ((cnt & 0xFFFFu) ? rec[w].x : 0u);
+	size_t qo = (size_t)cc.ind_base + 4 * (size_t)wqq[(size_t)chunk * L.wc + w];
+	while (act)
+	{
+		const int bit = __ffs(act) - 1;
+		act &= act - 1;
+		const int z = zb * 32 + bit;
+		const uint32_t m = q_mask8(q, bit);
+		const uint64_t pp = c_patch_pack[m];
+		const int np = (int)(pp >> 60);
+		const uint8_t bd = (x == 0 || y == 0 || z == 0 || x == d - 2 || y == d - 2 || z == d - 2) ? 1 : 0;
+		for (int p = 0; p < np; p++)
+		{
+			const uint32_t em = (uint32_t)(pp >> (12 * p)) & 0xFFFu;
+			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+			int n = 0;
+			for (int e = 0; e < 12; e++)
+			{
+				if (!((em >> e) & 1u)) continue;
+				const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
+				const int a = axis == 0 ? ((hi << 1) | lo) : axis == 1 ? ((hi << 2) | lo) : ((hi << 2) | (lo << 1));
+				const int x0 = x + (a >> 2), y0 = y + ((a >> 1) & 1), z0 = z + (a & 1);
+				const int x1 = x0 + (axis == 0), y1 = y0 + (axis == 1), z1 = z0 + (axis == 2);
+				const float s0 = density_at(s, src, g, d, chunk, x0, y0, z0), s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
+				// _get_intersection (DMCChunk.cpp:657-662), grid units
+				const float mu = (0.0f - s0) / (s1 - s0);
+				sx += ((float)x1 - (float)x0) * mu + (float)x0;
+				sy += ((float)y1 - (float)y0) * mu + (float)y0;
+				sz += ((float)z1 - (float)z0) * mu + (float)z0;
+				n++;
+			}
+			pos[3 * v] = sx / (float)n;
+			pos[3 * v + 1] = sy / (float)n;
+			pos[3 * v + 2] = sz / (float)n;
+			boundary[v] = bd;
+			v++;
+		}
+		const uint32_t b0 = m & 1u;
+		for (int axis = 0; axis < 3; axis++)
+		{
+			const bool crossed = axis == 0 ? ((m ^ (m >> 4)) & 1u) : axis == 1 ? ((m ^ (m >> 2)) & 1u) : ((m ^ (m >> 1)) & 1u);
+			const bool interior = axis == 0 ? (y >= 1 && z >= 1) : axis == 1 ? (x >= 1 && z >= 1) : (x >= 1 && y >= 1);
+			if (!crossed || !interior) continue;
+			uint32_t id[4];
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+			{
+				// ring of the four cells around the edge, counter-clockwise about the +axis
+				const int du = axis == 1 ? (r >> 1) : ((r == 1 || r == 2) ? 1 : 0);
+				const int dv = axis == 1 ? ((r == 1 || r == 2) ? 1 : 0) : (r >> 1);
+				const int cx = axis == 0 ? x : x - du, cy = axis == 0 ? y - du : (axis == 1 ? y : y - dv), cz = axis == 2 ? z : z - dv;
+				id[r] = q_vertex_id(cb, rec, L, cx, cy, cz, 4 * axis + ((du << 1) | dv));
+			}
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+			{
+				const uint32_t vi = b0 ? id[r] : id[3 - r];
+				inds[qo + r] = vi;
+				const size_t gv = (size_t)cc.vert_base + vi;
+				atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3))); // init_valence++ per corner
+			}
+			qo += 4;
+		}
+	}
+}
+
+// MeshProcessor<4>::flush_to_tris (MeshProcessor.cpp:73-91): (v0,v1,v2,v3) -> (v0,v1,v2),(v2,v3,v0)
+__global__ void __launch_bounds__(CTA) k_quads_to_tris(const uint32_t* __restrict__ quads, size_t n_quads, uint32_t* __restrict__ tris)
+{
+	for (size_t q = (size_t)blockIdx.x * CTA + threadIdx.x; q < n_quads; q += (size_t)gridDim.x * CTA)
+	{
+		const uint4 v = reinterpret_cast<const uint4*>(quads)[q];
+		uint32_t* o = tris + 6 * q;
+		o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.z; o[4] = v.w; o[5] = v.x;
+	}
+}
+
+} // namespace bmf

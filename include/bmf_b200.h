@@ -89,6 +89,9 @@ typedef struct bmf_params
 	int32_t keep_density;     /* 1: materialise the f32 density block (DMCChunk::density_block) so it can be copied out */
 	int32_t keep_masks;       /* 1: materialise the 8-bit cell masks (MasksBlock image) so they can be copied out */
 	int32_t density_on_device; /* HOST_DENSITY only: the density pointer passed to submit is a device pointer */
+	int32_t quads;            /* 1: emit QUADS instead of triangles (Nielson dual marching cubes: one vertex per surface patch of a cell,
+	                             one quad = 4 indices per sign-changing edge; build-defined, the reference has no quad producer) and run
+	                             MeshProcessor<4> for iters > 0; n_inds counts 4 per quad.  bmf_quads_to_tris = flush_to_tris */
 } bmf_params;
 
 typedef struct bmf_chunk_info
@@ -174,6 +177,10 @@ int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal
 /* qef_solve_from_points_3d (qef_simd.h:550-579), m independent systems: system j reads counts[j]
  * (2..12) planes from positions/normals[j*12*3 ...]; writes out_pos[3*j..], out_err[j]. */
 int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err);
+
+/* MeshProcessor<4>::flush_to_tris (MeshProcessor.cpp:73-91): every quad (v0,v1,v2,v3) becomes (v0,v1,v2),(v2,v3,v0).
+ * quads: [n_quads*4] indices in, tris: [n_quads*6] out (host arrays). */
+int bmf_quads_to_tris(bmf_ctx* ctx, const uint32_t* quads, int64_t n_quads, uint32_t* tris);
 
 /* WorldStitcher::stitch_all(root) (WorldStitcher.cpp:26-49 -> stitch_cell :184-239 -> stitch_indexes :491-572): the seam
  * pass over the RESIDENT batch, whose chunks must be aligned leaves of one octree (any mix of levels; a missing

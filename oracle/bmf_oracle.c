@@ -941,3 +941,113 @@ int64_t orc_seam(const orc_seam_chunk* ch, int n, int dim, const int32_t* group,
 }
 
 void orc_free(void* p) { free(p); }
+
+/* ---- quad emission (build-defined, UNPINNED: the reference has the MeshProcessor<4> consumer but no producer) --------
+ * Nielson's dual marching cubes on the chunk's (d-1)^3 cells: one dual vertex per surface patch of a cell (patch_pack:
+ * the connected components of the cell's tri_table triangles), placed at the mean of the patch's edge crossing points
+ * (edges in ascending id, crossing = the triangle emitter's iso-vertex formula); one quad per sign-changing grid edge that
+ * has all four cells around it, joining the patch vertices that contain the edge.  Vertex ids follow the serial x->y->z
+ * cell scan (patches in table order); quads are emitted in the same scan by the cell at the edge's lower end, X then Y
+  * then Z edge; the ring runs counter-clockwise about the +axis and is reversed when the edge's lower endpoint is solid, so
+ * the winding agrees with the triangle emitter's (MCTable.h's triangles are clockwise seen from the air side).  boundary = the cell touches the chunk border. */
+static const uint64_t PATCH_PACK[256] = ORACLE_PATCH_PACK_INIT;
+
+static inline unsigned q_mask(const uint32_t* bits, int d, int zc, int x, int y, int z)
+{
+	unsigned m = 0;
+	for (int o = 0; o < 8; o++) m |= (unsigned)bit_at(bits, d, zc, x + (o >> 2), y + ((o >> 1) & 1), z + (o & 1)) << o;
+	return m;
+}
+
+static inline int q_patch_of(unsigned m, int e)
+{
+	const uint64_t pp = PATCH_PACK[m];
+	const int np = (int)(pp >> 60);
+	for (int p = 0; p < np; p++)
+		if ((pp >> (12 * p)) & (1ull << e)) return p;
+	return -1;
+}
+
+void orc_quads(const float* D, const uint32_t* bits, int dim, orc_mesh* out)
+{
+	const int d = dim, zc = (d + 31) / 32, dc = d - 1;
+	memset(out, 0, sizeof(*out));
+	uint32_t* vbase = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)dc * dc * dc);
+	size_t nc = 0, nv = 0, nq = 0;
+	for (int x = 0; x < dc; x++)
+		for (int y = 0; y < dc; y++)
+			for (int z = 0; z < dc; z++)
+			{
+				const unsigned m = q_mask(bits, d, zc, x, y, z);
+				vbase[((size_t)x * dc + y) * dc + z] = (uint32_t)nv;
+				if (m == 0 || m == 255) continue;
+				nc++;
+				nv += (size_t)(PATCH_PACK[m] >> 60);
+				nq += (((m ^ (m >> 4)) & 1) && y >= 1 && z >= 1) + (((m ^ (m >> 2)) & 1) && x >= 1 && z >= 1) + (((m ^ (m >> 1)) & 1) && x >= 1 && y >= 1);
+			}
+	out->n_cells = (int32_t)nc; out->n_verts = (int32_t)nv; out->n_inds = (int32_t)(4 * nq);
+	out->pos = (float*)malloc(sizeof(float) * 3 * (nv ? nv : 1));
+	out->boundary = (uint8_t*)malloc(nv ? nv : 1);
+	out->valence = (uint8_t*)calloc(nv ? nv : 1, 1);
+	out->inds = (uint32_t*)malloc(sizeof(uint32_t) * (nq ? 4 * nq : 1));
+	size_t v = 0, q = 0;
+	for (int x = 0; x < dc; x++)
+		for (int y = 0; y < dc; y++)
+			for (int z = 0; z < dc; z++)
+			{
+				const unsigned m = q_mask(bits, d, zc, x, y, z);
+				if (m == 0 || m == 255) continue;
+				const uint64_t pp = PATCH_PACK[m];
+				const int np = (int)(pp >> 60);
+				for (int p = 0; p < np; p++)
+				{
+					const unsigned em = (unsigned)((pp >> (12 * p)) & 0xFFF);
+					float sx = 0, sy = 0, sz = 0;
+					int cnt = 0;
+					for (int e = 0; e < 12; e++)
+					{
+						if (!((em >> e) & 1)) continue;
+						int a, b;
+						if (e < 4) { a = (((e >> 1) & 1) << 1) | (e & 1); b = a | 4; }
+						else if (e < 8) { a = ((((e - 4) >> 1) & 1) << 2) | ((e - 4) & 1); b = a | 2; }
+						else { a = ((((e - 8) >> 1) & 1) << 2) | (((e - 8) & 1) << 1); b = a | 1; }
+						float pt[3];
+						uint8_t bd;
+						iso_vertex(D, d, x + (a >> 2), y + ((a >> 1) & 1), z + (a & 1), x + (b >> 2), y + ((b >> 1) & 1), z + (b & 1), pt, &bd);
+						sx += pt[0]; sy += pt[1]; sz += pt[2];
+						cnt++;
+					}
+					out->pos[3 * v] = sx / (float)cnt; out->pos[3 * v + 1] = sy / (float)cnt; out->pos[3 * v + 2] = sz / (float)cnt;
+					out->boundary[v] = (uint8_t)(x == 0 || y == 0 || z == 0 || x == dc - 1 || y == dc - 1 || z == dc - 1);
+					v++;
+				}
+				const int b0 = m & 1;
+				/* ring of (du, dv) offsets of the four cells around an edge, counter-clockwise about the +axis */
+				static const int RX[4][2] = { { 0, 0 }, { 1, 0 }, { 1, 1 }, { 0, 1 } }; /* (dy, dz) */
+				static const int RY[4][2] = { { 0, 0 }, { 0, 1 }, { 1, 1 }, { 1, 0 } }; /* (dx, dz) */
+				static const int RZ[4][2] = { { 0, 0 }, { 1, 0 }, { 1, 1 }, { 0, 1 } }; /* (dx, dy) */
+				for (int axis = 0; axis < 3; axis++)
+				{
+					const int crossed = axis == 0 ? ((m ^ (m >> 4)) & 1) : axis == 1 ? ((m ^ (m >> 2)) & 1) : ((m ^ (m >> 1)) & 1);
+					const int interior = axis == 0 ? (y >= 1 && z >= 1) : axis == 1 ? (x >= 1 && z >= 1) : (x >= 1 && y >= 1);
+					if (!crossed || !interior) continue;
+					uint32_t id[4];
+					for (int r = 0; r < 4; r++)
+					{
+						const int du = axis == 0 ? RX[r][0] : axis == 1 ? RY[r][0] : RZ[r][0], dv = axis == 0 ? RX[r][1] : axis == 1 ? RY[r][1] : RZ[r][1];
+						const int cx = axis == 0 ? x : x - du, cy = axis == 0 ? y - du : (axis == 1 ? y : y - dv), cz = axis == 2 ? z : z - dv;
+						const int e = 4 * axis + ((du << 1) | dv);
+						const unsigned cm = q_mask(bits, d, zc, cx, cy, cz);
+						id[r] = vbase[((size_t)cx * dc + cy) * dc + cz] + (uint32_t)q_patch_of(cm, e);
+					}
+					for (int r = 0; r < 4; r++)
+					{
+						const uint32_t vi = b0 ? id[r] : id[3 - r];
+						out->inds[4 * q + r] = vi;
+						out->valence[vi]++;
+					}
+					q++;
+				}
+			}
+	free(vbase);
+}

@@ -98,6 +98,10 @@ int orc_chunk(const orc_sampler* s, const float pos[3], float size, int dim, flo
 int64_t orc_batch(const orc_sampler* s, const float* pos_size /* n x 4 */, int n, int dim, const float* overlaps, int iters,
                   int process_boundary, int threads, int32_t* counts);
 
+/* quad emission (UNPINNED, build-defined: Nielson dual marching cubes on the sign field; see bmf_oracle.c).  Fills
+ * n_cells / n_verts / n_inds (4 per quad), pos (grid units), boundary, valence, inds; the other members stay null. */
+void orc_quads(const float* density, const uint32_t* bits, int dim, orc_mesh* out);
+
 /* seam pass between chunks (UNPINNED, build-defined: the reference's WorldStitcher is non-functional as committed).
  * bits / density: the chunk's sign words and density block as orc_label_grid / orc_sample_block produce them.
  * Returns the number of triangles (or -1 if the chunks are not aligned octree leaves); *tris_out = malloc'd

@@ -73,6 +73,7 @@ class Oracle:
         lib.orc_qef_solve.restype = C.c_float
         lib.orc_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_qef_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_quads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Mesh)]
         lib.orc_seam.restype = C.c_int64
         lib.orc_seam.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float))]
         lib.orc_free.argtypes = [C.c_void_p]
@@ -182,6 +183,18 @@ class Oracle:
                 p = np.ascontiguousarray(out["pos"], np.float32)
                 self.lib.orc_qef_place(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary))
                 out["pos"] = p
+        return out
+
+    def quads(self, density, bits, dim):
+        """dual-marching-cubes quad mesh of one chunk (build-defined): pos (grid units), boundary, valence, inds (4 per quad)"""
+        m = Mesh()
+        density = np.ascontiguousarray(density, np.float32)
+        bits = np.ascontiguousarray(bits, np.uint32)
+        self.lib.orc_quads(_p(density), _p(bits), dim, C.byref(m))
+        out = {"n_cells": m.n_cells, "n_verts": m.n_verts, "n_inds": m.n_inds,
+               "pos": _np(m.pos, 3 * m.n_verts, np.float32).reshape(-1, 3), "boundary": _np(m.boundary, m.n_verts, np.uint8),
+               "valence": _np(m.valence, m.n_verts, np.uint8), "inds": _np(m.inds, m.n_inds, np.uint32)}
+        self.lib.orc_mesh_free(C.byref(m))
         return out
 
     def seam(self, chunks, pos_size, dim, overlaps, group=None, cross_group_only=False):
