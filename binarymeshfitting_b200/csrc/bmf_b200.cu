@@ -456,18 +456,16 @@ int launch_mesh(bmf_ctx* ctx)
 	if (params->quads)
 	{
 		// dual-marching-cubes quads (quads.cuh); MeshProcessor<4> runs when the batch is completed (it needs the real counts)
-		const size_t n_words = (size_t)n * L.wc;
-		BMF_LAUNCH(k_q_bases, (unsigned)n, CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->counts.p, ctx->wqv.p, ctx->wqq.p, tot);
+		BMF_LAUNCH(k_q_bases, (unsigned)n, CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->counts.p, ctx->wqv.p, ctx->wqq.p, ctx->vcells.p, list_count, tot);
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
-		BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, ctx->valence.cap, st));
 		BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, reinterpret_cast<uint32_t*>(ctx->normal.p), 3 * V, tot, 1, 3);
 		if (ctx->color_ones < 3 * V)
 		{
 			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
 			ctx->color_ones = ctx->color.cap;
 		}
-		BMF_LAUNCH(k_q_emit, (unsigned)(n_words / CTA), CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->wqv.p, ctx->wqq.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p,
-		           ctx->pos.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, tot);
+		BMF_LAUNCH(k_q_emit, (unsigned)(ctx->sm_count * 8), CTA, 0, ctx->bits.p, L, ctx->wq.p, ctx->wqv.p, ctx->wqq.p, ctx->vcells.p, list_count, ctx->counts.p,
+		           ctx->sampler, src, ctx->geom.p, ctx->pos.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, tot);
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
 		return publish_chunks(ctx);

@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(CTA) k_q_count(const uint32_t* __restrict__ bi
 static constexpr int Q_ITEMS = 4;
 
 __global__ void __launch_bounds__(CTA) k_q_bases(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wq, const ChunkCounts* __restrict__ chunks,
-                                                  uint4* __restrict__ wqv, uint32_t* __restrict__ wqq, const unsigned long long* __restrict__ tot)
+                                                  uint4* __restrict__ wqv, uint32_t* __restrict__ wqq, uint2* __restrict__ wlist, unsigned long long* __restrict__ list_count,
+                                                  const unsigned long long* __restrict__ tot)
 {
+	__shared__ uint32_t s_lbase;
 	if (tot[7]) return;
 	const int chunk = blockIdx.x;
 	const ChunkCounts cc = chunks[chunk];
@@ -109,15 +111,38 @@ __global__ void __launch_bounds__(CTA) k_q_bases(const uint32_t* __restrict__ bi
 	for (int base = 0; base < L.wc; base += CTA * Q_ITEMS)
 	{
 		const int w0 = base + threadIdx.x * Q_ITEMS;
-		uint32_t cnt[Q_ITEMS], sum[2] = { 0, 0 }, tt[2];
+		uint32_t cnt[Q_ITEMS], act[Q_ITEMS], p0[Q_ITEMS], p1[Q_ITEMS], p2[Q_ITEMS], sum[3] = { 0, 0, 0 }, tt[3];
 #pragma unroll
 		for (int k = 0; k < Q_ITEMS; k++)
 		{
-			cnt[k] = wq[(size_t)chunk * L.wc + w0 + k];
+			const int w = w0 + k;
+			cnt[k] = wq[(size_t)chunk * L.wc + w];
+			act[k] = p0[k] = p1[k] = p2[k] = 0;
+			if (cnt[k] & 0xFFFFu)
+			{
+				const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
+				const QWord q = q_load(cb, L, x, y, zb);
+				const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
+				const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
+				act[k] = any & ~all & q_valid_bits(L, x, y, zb);
+				uint32_t a = act[k];
+				while (a)
+				{
+					const int z = __ffs(a) - 1;
+					a &= a - 1;
+					const uint32_t np = (uint32_t)(c_patch_pack[q_mask8(q, z)] >> 60);
+					p0[k] |= (np & 1u) << z; p1[k] |= ((np >> 1) & 1u) << z; p2[k] |= ((np >> 2) & 1u) << z;
+				}
+			}
 			sum[0] += cnt[k] & 0xFFFFu;
 			sum[1] += cnt[k] >> 16;
+			sum[2] += __popc(act[k]);
 		}
-		block_scan<2>(sum, tt);
+		block_scan<3>(sum, tt);
+		// the active cells go on a compact list (order irrelevant: every cell finds its own output positions)
+		if (threadIdx.x == 0) s_lbase = tt[2] ? (uint32_t)atomicAdd(list_count, (unsigned long long)tt[2]) : 0u;
+		__syncthreads();
+		uint32_t li = s_lbase + sum[2];
 		uint32_t rv = carry_v + sum[0], rq = carry_q + sum[1];
 #pragma unroll
 		for (int k = 0; k < Q_ITEMS; k++)
@@ -125,30 +150,23 @@ __global__ void __launch_bounds__(CTA) k_q_bases(const uint32_t* __restrict__ bi
 			const int w = w0 + k;
 			if (cnt[k])
 			{
-				uint32_t p0 = 0, p1 = 0, p2 = 0;
-				if (cnt[k] & 0xFFFFu)
+				const uint32_t gw = (uint32_t)((size_t)chunk * L.wc + w);
+				wqv[gw] = make_uint4(rv, p0[k], p1[k], p2[k]);
+				wqq[gw] = rq;
+				uint32_t a = act[k];
+				while (a)
 				{
-					const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
-					const QWord q = q_load(cb, L, x, y, zb);
-					const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
-					const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
-					uint32_t act = any & ~all & q_valid_bits(L, x, y, zb);
-					while (act)
-					{
-						const int z = __ffs(act) - 1;
-						act &= act - 1;
-						const uint32_t np = (uint32_t)(c_patch_pack[q_mask8(q, z)] >> 60);
-						p0 |= (np & 1u) << z; p1 |= ((np >> 1) & 1u) << z; p2 |= ((np >> 2) & 1u) << z;
-					}
+					const int z = __ffs(a) - 1;
+					a &= a - 1;
+					wlist[li++] = make_uint2(gw, (uint32_t)z);
 				}
-				wqv[(size_t)chunk * L.wc + w] = make_uint4(rv, p0, p1, p2);
-				wqq[(size_t)chunk * L.wc + w] = rq;
 			}
 			rv += cnt[k] & 0xFFFFu;
 			rq += cnt[k] >> 16;
 		}
 		carry_v += tt[0];
 		carry_q += tt[1];
+		__syncthreads(); // s_lbase is rewritten in the next tile
 	}
 }
 
@@ -159,6 +177,7 @@ __device__ __forceinline__ uint32_t q_vertex_id(const uint32_t* __restrict__ cb,
 	const uint4 r = rec[((((size_t)x << L.ld) + y) << L.lzc) + zb];
 	const uint32_t lt = (1u << bit) - 1u;
 	uint32_t id = r.x + __popc(r.y & lt) + 2u * __popc(r.z & lt) + 4u * __popc(r.w & lt);
+	if ((((r.z | r.w) >> bit) & 1u) == 0u) return id; // one patch (the common case): no need to look at the cell's corners
 	const QWord q = q_load(cb, L, x, y, zb);
 	const uint64_t pp = c_patch_pack[q_mask8(q, bit)];
 	uint32_t p = 0;
@@ -168,93 +187,116 @@ __device__ __forceinline__ uint32_t q_vertex_id(const uint32_t* __restrict__ cb,
 	return id + p;
 }
 
-// ---- emit: one thread per word with anything to emit
-__global__ void __launch_bounds__(CTA) k_q_emit(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wq, const uint4* __restrict__ wqv,
-                                                 const uint32_t* __restrict__ wqq, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
-                                                 const ChunkGeom* __restrict__ geom, float* __restrict__ pos, uint8_t* __restrict__ boundary,
-                                                 uint8_t* __restrict__ valence, uint32_t* __restrict__ inds, const unsigned long long* __restrict__ tot)
+// ---- emit: one THREAD per listed cell (persistent grid).  A cell's first vertex and first quad follow from its word's
+// record by popc prefixes (patch-count bit planes; X / Y / Z quad-owner masks), so every cell is independent.
+__device__ __forceinline__ void q_emit_word(size_t gw, int bit, const uint32_t* __restrict__ bits, const Layout& L, const uint32_t* __restrict__ wq,
+                                            const uint4* __restrict__ wqv, const uint32_t* __restrict__ wqq, const ChunkCounts* __restrict__ chunks,
+                                            const SamplerDev& s, const DensitySource& src, const ChunkGeom* __restrict__ geom, float* __restrict__ pos,
+                                            uint8_t* __restrict__ boundary, uint8_t* __restrict__ valence, uint32_t* __restrict__ inds)
 {
-	if (tot[7]) return;
-	const size_t gw = (size_t)blockIdx.x * CTA + threadIdx.x;
 	const int chunk = (int)(gw >> L.lwc);
 	const ChunkCounts cc = chunks[chunk];
-	if (!cc.contains_mesh || cc.n_verts == 0) return;
 	const uint32_t cnt = wq[gw];
-	if (!cnt) return;
 	const int w = (int)(gw & (size_t)(L.wc - 1));
 	const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (L.d - 1), x = w >> L.lwp;
 	const int d = L.d;
 	const uint32_t* cb = bits + (size_t)chunk * L.wc;
 	const uint4* rec = wqv + (size_t)chunk * L.wc;
-	const ChunkGeom g = geom[chunk];
 	const QWord q = q_load(cb, L, x, y, zb);
 	const uint32_t valid = q_valid_bits(L, x, y, zb);
 	const uint32_t any = q.r[0] | q.r[1] | q.r[2] | q.r[3] | q.s[0] | q.s[1] | q.s[2] | q.s[3];
 	const uint32_t all = q.r[0] & q.r[1] & q.r[2] & q.r[3] & q.s[0] & q.s[1] & q.s[2] & q.s[3];
-	uint32_t act = any & ~all & valid;
-	size_t v = (size_t)cc.vert_base + ((cnt & 0xFFFFu) ? rec[w].x : 0u);
-	size_t qo = (size_t)cc.ind_base + 4 * (size_t)wqq[(size_t)chunk * L.wc + w];
-	while (act)
+	const uint32_t act = any & ~all & valid;
+	if (!((act >> bit) & 1u)) return;
+	// quad owners of this word (the same masks k_q_count counted)
+	const uint32_t zin = zb == 0 ? 0xFFFFFFFEu : 0xFFFFFFFFu;
+	const uint32_t ox = y >= 1 ? (q.r[0] ^ q.r[2]) & valid & zin : 0u;
+	const uint32_t oy = x >= 1 ? (q.r[0] ^ q.r[1]) & valid & zin : 0u;
+	const uint32_t oz = (x >= 1 && y >= 1) ? (q.r[0] ^ q.s[0]) & valid : 0u;
+	const uint32_t lt = (1u << bit) - 1u;
+	const uint4 r = (cnt & 0xFFFFu) ? rec[w] : make_uint4(0, 0, 0, 0);
+	size_t v = (size_t)cc.vert_base + r.x + __popc(r.y & lt) + 2u * __popc(r.z & lt) + 4u * __popc(r.w & lt);
+	size_t qo = (size_t)cc.ind_base + 4 * ((size_t)wqq[(size_t)chunk * L.wc + w] + __popc(ox & lt) + __popc(oy & lt) + __popc(oz & lt));
+	const ChunkGeom g = geom[chunk];
+	const int z = zb * 32 + bit;
+	const uint32_t m = q_mask8(q, bit);
+	const uint64_t pp = c_patch_pack[m];
+	const int np = (int)(pp >> 60);
+	const uint8_t bd = (x == 0 || y == 0 || z == 0 || x == d - 2 || y == d - 2 || z == d - 2) ? 1 : 0;
+	for (int p = 0; p < np; p++)
 	{
-		const int bit = __ffs(act) - 1;
-		act &= act - 1;
-		const int z = zb * 32 + bit;
-		const uint32_t m = q_mask8(q, bit);
-		const uint64_t pp = c_patch_pack[m];
-		const int np = (int)(pp >> 60);
-		const uint8_t bd = (x == 0 || y == 0 || z == 0 || x == d - 2 || y == d - 2 || z == d - 2) ? 1 : 0;
-		for (int p = 0; p < np; p++)
+		const uint32_t em = (uint32_t)(pp >> (12 * p)) & 0xFFFu;
+		float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+		int n = 0;
+		for (int e = 0; e < 12; e++)
 		{
-			const uint32_t em = (uint32_t)(pp >> (12 * p)) & 0xFFFu;
-			float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-			int n = 0;
-			for (int e = 0; e < 12; e++)
-			{
-				if (!((em >> e) & 1u)) continue;
-				const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
-				const int a = axis == 0 ? ((hi << 1) | lo) : axis == 1 ? ((hi << 2) | lo) : ((hi << 2) | (lo << 1));
-				const int x0 = x + (a >> 2), y0 = y + ((a >> 1) & 1), z0 = z + (a & 1);
-				const int x1 = x0 + (axis == 0), y1 = y0 + (axis == 1), z1 = z0 + (axis == 2);
-				const float s0 = density_at(s, src, g, d, chunk, x0, y0, z0), s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
-				// _get_intersection (DMCChunk.cpp:657-662), grid units
-				const float mu = (0.0f - s0) / (s1 - s0);
-				sx += ((float)x1 - (float)x0) * mu + (float)x0;
-				sy += ((float)y1 - (float)y0) * mu + (float)y0;
-				sz += ((float)z1 - (float)z0) * mu + (float)z0;
-				n++;
-			}
-			pos[3 * v] = sx / (float)n;
-			pos[3 * v + 1] = sy / (float)n;
-			pos[3 * v + 2] = sz / (float)n;
-			boundary[v] = bd;
-			v++;
+			if (!((em >> e) & 1u)) continue;
+			const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
+			const int a = axis == 0 ? ((hi << 1) | lo) : axis == 1 ? ((hi << 2) | lo) : ((hi << 2) | (lo << 1));
+			const int x0 = x + (a >> 2), y0 = y + ((a >> 1) & 1), z0 = z + (a & 1);
+			const int x1 = x0 + (axis == 0), y1 = y0 + (axis == 1), z1 = z0 + (axis == 2);
+			const float s0 = density_at(s, src, g, d, chunk, x0, y0, z0), s1 = density_at(s, src, g, d, chunk, x1, y1, z1);
+			// _get_intersection (DMCChunk.cpp:657-662), grid units
+			const float mu = (0.0f - s0) / (s1 - s0);
+			sx += ((float)x1 - (float)x0) * mu + (float)x0;
+			sy += ((float)y1 - (float)y0) * mu + (float)y0;
+			sz += ((float)z1 - (float)z0) * mu + (float)z0;
+			n++;
 		}
-		const uint32_t b0 = m & 1u;
-		for (int axis = 0; axis < 3; axis++)
+		pos[3 * v] = sx / (float)n;
+		pos[3 * v + 1] = sy / (float)n;
+		pos[3 * v + 2] = sz / (float)n;
+		boundary[v] = bd;
+		// init_valence = quads on this vertex = edges of the patch that have all four cells around them
+		int val = 0;
+		for (int e = 0; e < 12; e++)
 		{
-			const bool crossed = axis == 0 ? ((m ^ (m >> 4)) & 1u) : axis == 1 ? ((m ^ (m >> 2)) & 1u) : ((m ^ (m >> 1)) & 1u);
-			const bool interior = axis == 0 ? (y >= 1 && z >= 1) : axis == 1 ? (x >= 1 && z >= 1) : (x >= 1 && y >= 1);
-			if (!crossed || !interior) continue;
-			uint32_t id[4];
-#pragma unroll
-			for (int r = 0; r < 4; r++)
-			{
-				// ring of the four cells around the edge, counter-clockwise about the +axis
-				const int du = axis == 1 ? (r >> 1) : ((r == 1 || r == 2) ? 1 : 0);
-				const int dv = axis == 1 ? ((r == 1 || r == 2) ? 1 : 0) : (r >> 1);
-				const int cx = axis == 0 ? x : x - du, cy = axis == 0 ? y - du : (axis == 1 ? y : y - dv), cz = axis == 2 ? z : z - dv;
-				id[r] = q_vertex_id(cb, rec, L, cx, cy, cz, 4 * axis + ((du << 1) | dv));
-			}
-#pragma unroll
-			for (int r = 0; r < 4; r++)
-			{
-				const uint32_t vi = b0 ? id[r] : id[3 - r];
-				inds[qo + r] = vi;
-				const size_t gv = (size_t)cc.vert_base + vi;
-				atomicAdd(reinterpret_cast<unsigned int*>(valence + (gv & ~(size_t)3)), 1u << (8 * (gv & 3))); // init_valence++ per corner
-			}
-			qo += 4;
+			if (!((em >> e) & 1u)) continue;
+			const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
+			// lattice coordinates of the edge across its axis
+			const int u = axis == 0 ? y + hi : x + hi, w2 = axis == 2 ? y + lo : z + lo;
+			val += (u >= 1 && u <= d - 2 && w2 >= 1 && w2 <= d - 2) ? 1 : 0;
 		}
+		valence[v] = (uint8_t)val;
+		v++;
+	}
+	const uint32_t b0 = m & 1u;
+	for (int axis = 0; axis < 3; axis++)
+	{
+		const uint32_t own = axis == 0 ? ox : axis == 1 ? oy : oz;
+		if (!((own >> bit) & 1u)) continue;
+		uint32_t id[4];
+#pragma unroll
+		for (int rr = 0; rr < 4; rr++)
+		{
+			// ring of the four cells around the edge, counter-clockwise about the +axis
+			const int du = axis == 1 ? (rr >> 1) : ((rr == 1 || rr == 2) ? 1 : 0);
+			const int dv = axis == 1 ? ((rr == 1 || rr == 2) ? 1 : 0) : (rr >> 1);
+			const int cx = axis == 0 ? x : x - du, cy = axis == 0 ? y - du : (axis == 1 ? y : y - dv), cz = axis == 2 ? z : z - dv;
+			id[rr] = q_vertex_id(cb, rec, L, cx, cy, cz, 4 * axis + ((du << 1) | dv));
+		}
+#pragma unroll
+		for (int rr = 0; rr < 4; rr++)
+		{
+			const uint32_t vi = b0 ? id[rr] : id[3 - rr];
+			inds[qo + rr] = vi;
+		}
+		qo += 4;
+	}
+}
+
+__global__ void __launch_bounds__(CTA) k_q_emit(const uint32_t* __restrict__ bits, Layout L, const uint32_t* __restrict__ wq, const uint4* __restrict__ wqv,
+                                                 const uint32_t* __restrict__ wqq, const uint2* __restrict__ wlist, const unsigned long long* __restrict__ list_count,
+                                                 const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src, const ChunkGeom* __restrict__ geom,
+                                                 float* __restrict__ pos, uint8_t* __restrict__ boundary, uint8_t* __restrict__ valence, uint32_t* __restrict__ inds,
+                                                 const unsigned long long* __restrict__ tot)
+{
+	if (tot[7]) return;
+	const uint32_t n_cells = (uint32_t)list_count[0];
+	for (uint32_t e = blockIdx.x * CTA + threadIdx.x; e < n_cells; e += gridDim.x * CTA)
+	{
+		const uint2 c = wlist[e];
+		q_emit_word((size_t)c.x, (int)c.y, bits, L, wq, wqv, wqq, chunks, s, src, geom, pos, boundary, valence, inds);
 	}
 }
 

@@ -85,10 +85,23 @@ def test_mc_table_properties():
     """packed triangle table: counts are multiples of 3 (<= 15) and every edge id is < 12."""
     import re
     txt = open(os.path.join(os.path.dirname(HERE), "oracle", "mc_tables_oracle.h")).read()
-    vals = [int(v, 16) for v in re.findall(r"0x([0-9a-f]{16})ull", txt)]
-    assert len(vals) == 256
+    allv = [int(v, 16) for v in re.findall(r"0x([0-9a-f]{16})ull", txt)]
+    assert len(allv) == 512  # tri_pack, then patch_pack
+    vals, patches = allv[:256], allv[256:]
     for m, v in enumerate(vals):
         n = v >> 60
         assert n % 3 == 0 and n <= 15
         assert all(((v >> (4 * i)) & 15) < 12 for i in range(n))
     assert vals[0] == 0 and vals[255] == 0
+    # patch table (quad emission): disjoint patches that cover exactly the edges the triangles use
+    for m, (v, pv) in enumerate(zip(vals, patches)):
+        used = 0
+        for i in range(v >> 60):
+            used |= 1 << ((v >> (4 * i)) & 15)
+        npatch, union = pv >> 60, 0
+        assert npatch <= 4
+        for k in range(npatch):
+            pm = (pv >> (12 * k)) & 0xFFF
+            assert pm and not (pm & union)
+            union |= pm
+        assert union == used and (pv >> (12 * npatch)) & ((1 << (60 - 12 * npatch)) - 1) == 0
