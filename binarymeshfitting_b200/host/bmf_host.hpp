@@ -547,6 +547,11 @@ public:
 	int generation_stage = GENERATION_STAGES_UNHANDLED;
 	DMCChunk* chunk = nullptr;
 	GLChunk* gl_chunk = nullptr;
+	// octree links (OctreeNode::parent / children, WorldOctreeNode::world_leaf_flag) and the watcher's split / group mark
+	WorldOctreeNode* parent = nullptr;
+	WorldOctreeNode* children[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool world_leaf_flag = true;
+	int flags = 0; // NODE_FLAGS_SPLIT = 1, NODE_FLAGS_GROUP = 2 (the subset the synchronous watcher needs)
 	WorldOctreeNode() {}
 	WorldOctreeNode(float s, glm::vec3 p, uint8_t l, uint64_t code) : size(s), level(l), pos(p), morton_code(code) {}
 };
@@ -595,7 +600,6 @@ public:
 	// MC-corner order (Tables.hpp:7-9), Morton digit x | y<<1 | z<<2, chunk created for every leaf
 	void split_leaves()
 	{
-		static const int MCDX[8] = { 0, 1, 1, 0, 0, 1, 1, 0 }, MCDY[8] = { 0, 0, 0, 0, 1, 1, 1, 1 }, MCDZ[8] = { 0, 0, 1, 1, 0, 0, 1, 1 };
 		leaves.clear();
 		std::vector<WorldOctreeNode*> stack;
 		stack.push_back(&octree);
@@ -608,18 +612,48 @@ public:
 				leaves.push_back(n);
 				continue;
 			}
-			const float c_size = n->size * 0.5f;
-			for (int i = 0; i < 8; i++)
-			{
-				glm::vec3 c_pos(n->pos.x + (float)MCDX[i] * c_size, n->pos.y + (float)MCDY[i] * c_size, n->pos.z + (float)MCDZ[i] * c_size);
-				const uint64_t code = (n->morton_code << 3) | (uint64_t)(MCDX[i] | (MCDY[i] << 1) | (MCDZ[i] << 2));
-				WorldOctreeNode* c = new WorldOctreeNode(c_size, c_pos, (uint8_t)(n->level + 1), code);
-				owned.push_back(c);
-				stack.push_back(c);
-			}
+			split_node(n);
+			for (int i = 0; i < 8; i++) stack.push_back(n->children[i]);
 		}
 		next_chunk_id = 0;
 		for (WorldOctreeNode* n : leaves) create_chunk(n);
+	}
+
+	// WorldOctree::split_node (WorldOctree.cpp:175-210): eight children in MC-corner order, Morton digit x | y<<1 | z<<2
+	void split_node(WorldOctreeNode* n)
+	{
+		static const int MCDX[8] = { 0, 1, 1, 0, 0, 1, 1, 0 }, MCDY[8] = { 0, 0, 0, 0, 1, 1, 1, 1 }, MCDZ[8] = { 0, 0, 1, 1, 0, 0, 1, 1 };
+		const float c_size = n->size * 0.5f;
+		for (int i = 0; i < 8; i++)
+		{
+			glm::vec3 c_pos(n->pos.x + (float)MCDX[i] * c_size, n->pos.y + (float)MCDY[i] * c_size, n->pos.z + (float)MCDZ[i] * c_size);
+			const uint64_t code = (n->morton_code << 3) | (uint64_t)(MCDX[i] | (MCDY[i] << 1) | (MCDZ[i] << 2));
+			WorldOctreeNode* c = new WorldOctreeNode(c_size, c_pos, (uint8_t)(n->level + 1), code);
+			c->parent = n;
+			owned.push_back(c);
+			n->children[i] = c;
+		}
+		n->world_leaf_flag = false;
+	}
+
+	// WorldOctree::group_node: the children go away, the node is a leaf again (the nodes stay owned until the world dies)
+	void group_node(WorldOctreeNode* n)
+	{
+		for (int i = 0; i < 8; i++) n->children[i] = nullptr;
+		n->world_leaf_flag = true;
+	}
+
+	// WorldOctree::node_needs_group (WorldOctree.cpp:251-261)
+	bool node_needs_group(const glm::vec3& center, const WorldOctreeNode* n) const
+	{
+		if (n->level < properties.min_level) return false;
+		if (n->level > properties.max_level) return true;
+		const float half = n->size * 0.5f;
+		const float mx = n->pos.x + half, my = n->pos.y + half, mz = n->pos.z + half;
+		const float dx = center.x - mx, dy = center.y - my, dz = center.z - mz;
+		const float t0 = dx * dx, t1 = dy * dy, t2 = dz * dz;
+		const float d = std::sqrt(t0 + t1 + t2);
+		return d > n->size * properties.group_multiplier + properties.size_modifier + n->size * 0.5f;
 	}
 
 	void create_chunk(WorldOctreeNode* n)
@@ -847,6 +881,93 @@ private:
 
 	WorldOctree* world = nullptr;
 	std::vector<int> devices;
+};
+
+// ---- WorldWatcher -----------------------------------------------------------------------------------------------
+// WorldWatcher::update (WorldWatcher.cpp:34-134) as one SYNCHRONOUS tick: check_leaves (:155-173) with handle_split_check /
+// handle_group_check (:175-212), process_batch (:214-238) with split_node / group_node_1 (:354-392), the generator call
+// (:69-73), optional restitch (:74-103) and post_process_batch (:240-352).  The watcher thread, the render-thread upload
+// handshake and the draw / stitch flags are the renderer's business and are not mirrored.
+class WorldWatcher
+{
+public:
+	WorldOctree* world = nullptr;
+	ChunkGenerator generator;
+	glm::vec3 focus_pos;
+	std::vector<WorldOctreeNode*> renderables; // the reference's linked list, in link order
+	size_t last_generated = 0;
+
+	void init(WorldOctree* w, const glm::vec3& focus)
+	{
+		world = w;
+		focus_pos = focus;
+		generator.init(w);
+		renderables = w->leaves;
+	}
+
+	// returns false if the generator failed; last_generated = chunks handed to process_queue in this tick
+	bool update(int max_gen = 400)
+	{
+		std::vector<WorldOctreeNode*> dirty;
+		int counter = 0;
+		for (WorldOctreeNode* n : renderables) // check_leaves
+		{
+			if (counter >= max_gen) break;
+			if (world->node_needs_split(focus_pos, n))
+			{
+				if (n->world_leaf_flag && !n->flags) { n->flags = 1; dirty.push_back(n); }
+				counter += 8;
+			}
+			else if (n->world_leaf_flag && n->parent && world->node_needs_group(focus_pos, n->parent))
+			{
+				WorldOctreeNode* par = n->parent;
+				bool can = !par->flags;
+				for (int i = 0; i < 8 && can; i++) can = par->children[i] && par->children[i]->world_leaf_flag && !par->children[i]->flags;
+				if (can) { par->flags = 2; dirty.push_back(par); }
+			}
+		}
+		SmartContainer<WorldOctreeNode*> generate_batch;
+		std::vector<WorldOctreeNode*> gone;
+		for (WorldOctreeNode* n : dirty) // process_batch
+		{
+			if (n->flags == 1)
+			{
+				world->split_node(n);
+				for (int i = 0; i < 8; i++)
+				{
+					n->children[i]->generation_stage = GENERATION_STAGES_GENERATING;
+					generate_batch.push_back(n->children[i]);
+					renderables.push_back(n->children[i]);
+				}
+				gone.push_back(n);
+			}
+			else
+			{
+				for (int i = 0; i < 8; i++) gone.push_back(n->children[i]);
+				world->group_node(n);
+				n->generation_stage = GENERATION_STAGES_GENERATING;
+				generate_batch.push_back(n);
+				renderables.push_back(n);
+			}
+			n->flags = 0;
+		}
+		last_generated = generate_batch.count;
+		bool ok = true;
+		if (generate_batch.count) ok = generator.process_queue(generate_batch);
+		if (ok && generate_batch.count && world->properties.enable_stitching) ok = generator.stitcher.stitch_batch_nodes(world, renderables_alive(gone).data(), renderables_alive(gone).size());
+		if (!gone.empty()) renderables = renderables_alive(gone); // post_process_batch: unlink_renderable
+		return ok;
+	}
+
+private:
+	std::vector<WorldOctreeNode*> renderables_alive(const std::vector<WorldOctreeNode*>& gone) const
+	{
+		std::vector<WorldOctreeNode*> out;
+		out.reserve(renderables.size());
+		for (WorldOctreeNode* r : renderables)
+			if (std::find(gone.begin(), gone.end(), r) == gone.end()) out.push_back(r);
+		return out;
+	}
 };
 
 // ---- MeshProcessor -------------------------------------------------------------------------------------------------

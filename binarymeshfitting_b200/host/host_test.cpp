@@ -215,6 +215,54 @@ int main(int argc, char** argv)
 		       gen.stitcher.vertices.count ? (double)gen.stitcher.vertices[0].color.y : 0.0);
 		return 0;
 	}
+	if (!strcmp(argv[1], "fly") && argc >= 9)
+	{
+		// WorldWatcher ticks while the focus moves from the origin to (fx, fy, fz) in `steps` equal steps, then until quiescent
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), steps = atoi(argv[8]);
+		const glm::vec3 target((float)atof(argv[5]), (float)atof(argv[6]), (float)atof(argv[7]));
+		WorldOctree world;
+		world.sampler = make_sampler(kind);
+		world.properties.chunk_resolution = dim;
+		world.properties.max_level = max_level;
+		world.init(256);
+		world.split_leaves();
+		WorldWatcher watcher;
+		watcher.init(&world, glm::vec3(0, 0, 0));
+		{
+			// the static world first (WorldOctree::generate_outline / the first watcher batch)
+			SmartContainer<WorldOctreeNode*> all;
+			for (WorldOctreeNode* n : world.leaves)
+			{
+				n->generation_stage = GENERATION_STAGES_GENERATING;
+				all.push_back(n);
+			}
+			if (!watcher.generator.process_queue(all)) return 5;
+		}
+		size_t generated = 0, ticks = 0;
+		for (int k = 1; k <= steps + 64; k++)
+		{
+			const float t = k >= steps ? 1.0f : (float)k / (float)steps;
+			watcher.focus_pos = glm::vec3(target.x * t, target.y * t, target.z * t);
+			if (!watcher.update())
+			{
+				fprintf(stderr, "update failed: %s\n", BmfDevice::get().error());
+				return 5;
+			}
+			generated += watcher.last_generated;
+			ticks++;
+			if (k >= steps && watcher.last_generated == 0) break;
+		}
+		uint32_t hc = 0;
+		size_t nv = 0, ni = 0;
+		for (WorldOctreeNode* n : watcher.renderables)
+		{
+			unsigned long long code = n->morton_code;
+			hc = crc32_of(&code, sizeof(code), hc);
+			if (n->chunk && n->chunk->contains_mesh && n->chunk->vi) { nv += n->chunk->vi->vertices.count; ni += n->chunk->vi->mesh_indexes.count; }
+		}
+		printf("fly leaves=%zu generated=%zu ticks=%zu codes_crc=%u verts=%zu inds=%zu\n", watcher.renderables.size(), generated, ticks, hc, nv, ni);
+		return 0;
+	}
 	if (!strcmp(argv[1], "world") && argc >= 7)
 	{
 		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]), iters = atoi(argv[5]);

@@ -138,3 +138,99 @@ def border_chunks(pos_size, group):
         if np.any((nb != group[i]) & (nb >= 0)):
             out.append(i)
     return np.array(out, np.int64)
+
+
+# ---- incremental LOD updates: the WorldWatcher policy (WorldWatcher.cpp:34-134 update, :155-212 check_leaves /
+# handle_split_check / handle_group_check, :214-238 process_batch, :240-352 post_process_batch, :354-392 split_node /
+# group_node_1) as one synchronous tick -- without the watcher thread, the render-thread handshake and the draw flags.
+def node_needs_group(props, focus, pos, size, level, group_multiplier=2.0):
+    """WorldOctree::node_needs_group (WorldOctree.cpp:251-261)"""
+    if level < props.min_level:
+        return False
+    if level > props.max_level:
+        return True
+    half = F(size) * F(0.5)
+    mid = (F(pos[0]) + half, F(pos[1]) + half, F(pos[2]) + half)
+    dx, dy, dz = F(focus[0]) - mid[0], F(focus[1]) - mid[1], F(focus[2]) - mid[2]
+    d = np.sqrt(F(F(dx * dx) + F(dy * dy)) + F(dz * dz), dtype=F)
+    rhs = F(F(F(size) * F(group_multiplier)) + F(props.size_modifier)) + half
+    return bool(d > rhs)
+
+
+class _Node:
+    __slots__ = ("pos", "size", "level", "code", "parent", "children", "leaf", "mark")
+
+    def __init__(self, pos, size, level, code, parent):
+        self.pos, self.size, self.level, self.code, self.parent = pos, size, level, code, parent
+        self.children, self.leaf, self.mark = None, True, 0
+
+
+class LodWatcher:
+    """Leaf set of the world that follows a moving focus point.  `tick(focus)` = check_leaves + process_batch +
+    post_process_batch: walks the renderables (leaves, in list order), marks at most max_gen/8 splits and any number of
+    groups, applies them, and returns the nodes that have to be generated (8 children per split, the parent per group) --
+    the batch WorldWatcher::update hands to ChunkGenerator::process_queue."""
+
+    def __init__(self, props, world_size=256, focus=(0.0, 0.0, 0.0), group_multiplier=2.0):
+        self.props, self.group_multiplier = props, group_multiplier
+        size = F(world_size * 2)
+        p = F(1) * size * F(-0.5)
+        self.root = _Node((p, p, p), size, 0, 1, None)
+        self.renderables = []
+        stack = [self.root]  # WorldOctree::split_leaves order (LIFO)
+        while stack:
+            n = stack.pop()
+            if not node_needs_split(props, focus, n.pos, n.size, n.level):
+                self.renderables.append(n)
+                continue
+            stack.extend(self._split(n))
+
+    def _split(self, n):
+        c_size = F(n.size * F(0.5))
+        n.children = []
+        for i in range(8):
+            cpos = (F(n.pos[0] + F(MCDX[i]) * c_size), F(n.pos[1] + F(MCDY[i]) * c_size), F(n.pos[2] + F(MCDZ[i]) * c_size))
+            n.children.append(_Node(cpos, c_size, n.level + 1, (n.code << 3) | (MCDX[i] | (MCDY[i] << 1) | (MCDZ[i] << 2)), n))
+        n.leaf = False
+        return n.children
+
+    def tick(self, focus, max_gen=400):
+        batch, counter = [], 0
+        for n in self.renderables:  # check_leaves
+            if counter >= max_gen:
+                break
+            if node_needs_split(self.props, focus, n.pos, n.size, n.level):
+                if n.leaf and not n.mark:
+                    n.mark = 1
+                    batch.append(n)
+                counter += 8
+            elif n.leaf and n.parent is not None and node_needs_group(self.props, focus, n.parent.pos, n.parent.size, n.parent.level, self.group_multiplier):
+                par = n.parent
+                if not par.mark and all(c.leaf and not c.mark for c in par.children):
+                    par.mark = 2
+                    batch.append(par)
+        generate, gone = [], set()
+        for n in batch:  # process_batch + post_process_batch
+            if n.mark == 1:
+                kids = self._split(n)
+                generate.extend(kids)
+                self.renderables.extend(kids)
+                gone.add(id(n))
+            else:
+                for c in n.children:
+                    gone.add(id(c))
+                n.children, n.leaf = None, True
+                generate.append(n)
+                self.renderables.append(n)
+            n.mark = 0
+        if gone:
+            self.renderables = [r for r in self.renderables if id(r) not in gone]
+        return generate
+
+    @staticmethod
+    def arrays(nodes):
+        ps = np.array([[n.pos[0], n.pos[1], n.pos[2], n.size] for n in nodes], np.float32).reshape(-1, 4)
+        return ps, np.array([n.level for n in nodes], np.int32), np.array([n.code for n in nodes], np.uint64)
+
+    def leaves(self):
+        return self.arrays(self.renderables)

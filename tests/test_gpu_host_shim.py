@@ -113,3 +113,26 @@ def test_worldstitcher_mirror_closes_a_lod_world(oracle):
     assert (int(out["verts"]), int(out["inds"])) == (sum(c["n_verts"] for c in chunks), sum(c["n_inds"] for c in chunks))
     assert int(out["seam_verts"]) == 3 * len(seam) and int(out["seam_crc"]) == crc(seam)
     assert abs(float(out["color_g"]) - 1.0) < 1e-6
+
+
+def test_worldwatcher_mirror_follows_a_moving_focus(oracle):
+    """C++ WorldWatcher mirror (synchronous tick) against the same policy in Python (world.LodWatcher): same final leaf
+    list in the same link order, and the meshes of exactly those leaves (generated incrementally) match the oracle"""
+    target, dim, max_level, steps = (150.0, 40.0, -60.0), 32, 5, 12
+    out = run("fly", ob.SPHERE, dim, max_level, *target, steps)["fly"]
+    props = W.WorldProperties(max_level=max_level, chunk_resolution=dim)
+    w = W.LodWatcher(props, 256, (0.0, 0.0, 0.0))
+    generated, ticks = 0, 0
+    for k in range(1, steps + 65):
+        t = np.float32(1.0) if k >= steps else np.float32(k) / np.float32(steps)
+        focus = tuple(np.float32(c) * t for c in target)
+        gen = w.tick(focus)
+        generated += len(gen)
+        ticks += 1
+        if k >= steps and not gen:
+            break
+    ps, lv, mc = w.leaves()
+    assert (int(out["leaves"]), int(out["generated"]), int(out["ticks"])) == (len(ps), generated, ticks)
+    assert int(out["codes_crc"]) == crc(mc.astype("<u8"))
+    total, counts = oracle.batch(oracle.sampler(ob.SPHERE), ps, dim, overlaps=[W.chunk_overlap(props, int(l)) for l in lv])
+    assert (int(out["verts"]), int(out["inds"])) == (int(counts[:, 0].sum()), int(counts[:, 1].sum()))

@@ -104,3 +104,43 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("TOTALS")][0].split()
     assert (int(line[1]), int(line[2]), int(line[3])) == (79992, 452400, 232)  # the single-process reference totals (Appendix A)
+
+
+def test_incremental_watcher_policy():
+    """LodWatcher (the WorldWatcher tick): from a coarse start it converges to the static split_leaves set; after the focus
+    moves, no leaf needs a split and no complete sibling group needs grouping; every tick hands out whole splits/groups"""
+    props = W.WorldProperties(max_level=5, chunk_resolution=32)
+    w = W.LodWatcher(props, 256, (0.0, 0.0, 0.0))
+    ps, lv, mc = W.split_leaves(props)
+    lps, llv, lmc = w.leaves()
+    assert np.array_equal(lmc, mc) and np.array_equal(lps, ps)  # same order as the reference's static build
+    # move the focus: ticks until quiescent
+    focus = (150.0, 40.0, -60.0)
+    total, ticks = 0, 0
+    while True:
+        gen = w.tick(focus, max_gen=400)
+        if not gen:
+            break
+        assert len(gen) <= 400 // 8 * 8 + 64 and all(g.leaf for g in gen)
+        total += len(gen)
+        ticks += 1
+        assert ticks < 100
+    assert total > 0
+    lps, llv, lmc = w.leaves()
+    assert len(set(lmc.tolist())) == len(lmc)
+    # a partition of the root cube
+    assert abs(float((lps[:, 3].astype(np.float64) ** 3).sum()) - 512.0 ** 3) < 1e-3
+    for n in w.renderables:
+        assert not W.node_needs_split(props, focus, n.pos, n.size, n.level)
+        if n.parent is not None and all(c.leaf for c in n.parent.children):
+            assert not W.node_needs_group(props, focus, n.parent.pos, n.parent.size, n.parent.level)
+    # hysteresis: the quiescent set contains every leaf of the static build for that focus, or descendants / ancestors of it
+    sps, slv, smc = W.split_leaves(props, 256, focus)
+    static_codes = set(int(c) for c in smc)
+    fine = sum(1 for c in lmc.tolist() if int(c) in static_codes)
+    assert fine > 0.5 * len(smc)
+    # moving back and settling again is deterministic
+    w2 = W.LodWatcher(props, 256, (0.0, 0.0, 0.0))
+    while w2.tick(focus):
+        pass
+    assert np.array_equal(w2.leaves()[2], lmc)
