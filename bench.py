@@ -447,6 +447,30 @@ def extras(ctx, args, capi, world):
                                                      "lattice_points_per_s": pts / ((sm["count"] + sm["emit"]) * 1e-3)}
     except Exception as e:  # noqa: BLE001
         ex["lod_rebuild_with_seams"] = {"error": str(e)}
+    # "ms per LOD rebuild", incremental reading: the WorldWatcher tick (world.LodWatcher) while the focus flies 4 units per
+    # tick along x; every tick's batch (8 children per split, the parent per group) is meshed with 2 smoothing iterations
+    try:
+        ctx.set_sampler(SAMPLERS[args.sampler])
+        wprops = world.WorldProperties(max_level=5, chunk_resolution=64, process_iters=2)
+        lw = world.LodWatcher(wprops, 256, (0.0, 0.0, 0.0))
+        tick_ms, sizes = [], []
+        for k in range(1, 61):
+            gen = lw.tick((4.0 * k, 0.0, 0.0))
+            if not gen:
+                continue
+            gps, glv, gmc = lw.arrays(gen)
+            gd = world.make_descs(wprops, gps, glv, gmc)
+            t0 = _t.perf_counter()
+            ctx.submit(gd, 64, iters=2)
+            ctx.wait()
+            tick_ms.append((_t.perf_counter() - t0) * 1e3)
+            sizes.append(len(gd))
+        if tick_ms:
+            ex["lod_incremental_fly_%s" % args.sampler] = {"ticks_with_work": len(tick_ms), "chunks_per_tick_mean": sum(sizes) / len(sizes), "chunks_per_tick_max": max(sizes),
+                                                           "ms_per_tick_median": sorted(tick_ms)[len(tick_ms) // 2], "ms_per_tick_max": max(tick_ms),
+                                                           "note": "submit + wait per tick (host wall clock); the tick policy itself is host code and not timed"}
+    except Exception as e:  # noqa: BLE001
+        ex["lod_incremental_fly"] = {"error": str(e)}
     # config 1: single 64^3 chunk of the implicit sphere, no processing -- triangles (the reference's emitter) and quads (bmf_params.quads)
     try:
         ctx.set_sampler(capi.SPHERE)
