@@ -447,6 +447,7 @@ int launch_mesh(bmf_ctx* ctx)
 	}
 	const size_t V = caps.verts, I = caps.inds;
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
+	const size_t smem_bases = smem_count + (size_t)L.ws * (sizeof(uint4) + sizeof(uint32_t)); // + the CTA's work list of active words
 
 	// ---- K4
 	DensitySource src;
@@ -471,10 +472,10 @@ int launch_mesh(bmf_ctx* ctx)
 		return publish_chunks(ctx);
 	}
 	if (L.wpt == 4)
-		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_bases, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count, tot);
 	else
-		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_count, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
+		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_bases, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count, tot);
 	BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p, tot);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
@@ -597,6 +598,10 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 			ctx->smooth_fused = 0;
 		}
 	}
+	// k_bases keeps its segment's sign planes plus a work list of active words in dynamic shared memory (57 KB at dim 256)
+	cudaFuncSetAttribute(k_bases<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	cudaFuncSetAttribute(k_bases<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+	cudaGetLastError();
 	cudaMallocHost((void**)&ctx->totals_pinned, sizeof(HostTotals));
 	*out = ctx;
 	return BMF_OK;

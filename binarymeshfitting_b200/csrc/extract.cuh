@@ -761,53 +761,82 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 		}
 	}
 	__syncthreads();
-	uint32_t sc[4] = { 0, 0, 0, 0 }; // verts, indices, vertex cells, index cells
+	uint32_t sc[5] = { 0, 0, 0, 0, 0 }; // verts, indices, vertex cells, index cells, words with active cells
+	uint32_t nvc[WPT], nic[WPT];
 #pragma unroll
 	for (int k = 0; k < WPT; k++)
 	{
+		nvc[k] = nic[k] = 0;
 		if (cnt[k] == 0) continue;
 		const int lw = threadIdx.x * WPT + k;
 		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x0 + lx, y, zb);
+		nvc[k] = __popc(c.ex | c.ey | c.ez);
+		nic[k] = __popc(c.active & c.interior);
 		sc[0] += (cnt[k] >> 8) & 0xFF;
 		sc[1] += cnt[k] >> 16;
-		sc[2] += __popc(c.ex | c.ey | c.ez);
-		sc[3] += __popc(c.active & c.interior);
+		sc[2] += nvc[k];
+		sc[3] += nic[k];
+		sc[4] += 1;
 	}
-	uint32_t cta_tot[4];
-	block_scan<4>(sc, cta_tot);
+	uint32_t cta_tot[5];
+	block_scan<5>(sc, cta_tot);
 	if (threadIdx.x == 0)
 	{
 		s_base[0] = (uint32_t)atomicAdd(&list_count[0], (unsigned long long)cta_tot[2]);
 		s_base[1] = (uint32_t)atomicAdd(&list_count[1], (unsigned long long)cta_tot[3]);
 	}
 	__syncthreads();
-	uint32_t rv = s_pre[0] + sc[0];                          // chunk-local vertex id
-	uint32_t ri = (uint32_t)cc.ind_base + s_pre[1] + sc[1];  // batch-wide index position
-	uint32_t ov = s_base[0] + sc[2], oi = s_base[1] + sc[3];
-	const uint32_t gw0 = (uint32_t)((size_t)seg * L.ws + threadIdx.x * WPT);
-	uint32_t oix[WPT];
-#pragma unroll
-	for (int k = 0; k < WPT; k++)
+	// Phase 2a: every thread walks its own words once more, only to hand each word WITH active cells -- with the four
+	// running positions it starts at -- to a shared work list; the per-cell work below then runs on dense warps instead of
+	// on the few threads whose words happen to be crossed by the surface.
+	uint4* s_job = reinterpret_cast<uint4*>(sb + (size_t)(L.P + 1) * L.wp); // [ws] {local word | vertex id << 12 .., ...}: see below
+	uint32_t* s_job_w = reinterpret_cast<uint32_t*>(s_job + L.ws);
 	{
-		oix[k] = ri;
-		if (cnt[k] == 0) continue; // nothing references a word without active cells
-		const int lw = threadIdx.x * WPT + k;
+		uint32_t rv = s_pre[0] + sc[0];                          // chunk-local vertex id
+		uint32_t ri = (uint32_t)cc.ind_base + s_pre[1] + sc[1];  // batch-wide index position
+		uint32_t ov = s_base[0] + sc[2], oi = s_base[1] + sc[3];
+		uint32_t slot = sc[4];
+		uint32_t oix[WPT];
+#pragma unroll
+		for (int k = 0; k < WPT; k++)
+		{
+			oix[k] = ri;
+			if (cnt[k] == 0) continue; // nothing references a word without active cells
+			s_job[slot] = make_uint4(rv, ri, ov, oi);
+			s_job_w[slot] = threadIdx.x * WPT + k;
+			slot++;
+			rv += (cnt[k] >> 8) & 0xFF;
+			ri += cnt[k] >> 16;
+			ov += nvc[k];
+			oi += nic[k];
+		}
+		uint32_t* o2 = wib + (size_t)seg * L.ws + threadIdx.x * WPT;
+#pragma unroll
+		for (int k = 0; k < WPT; k += 4)
+			*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oix[k], oix[k + 1], oix[k + 2], oix[k + 3]);
+	}
+	__syncthreads();
+	// Phase 2b: one thread per listed word
+	for (uint32_t j = threadIdx.x; j < cta_tot[4]; j += CTA)
+	{
+		const uint4 job = s_job[j];
+		const int lw = (int)s_job_w[j];
+		const uint32_t gw = (uint32_t)((size_t)seg * L.ws + lw);
 		const int zb = lw & (L.zc - 1), y = (lw >> L.lzc) & (L.d - 1), lx = lw >> L.lwp;
 		const WordBits b = load_word_bits(sb, L, lx, y, zb);
 		const WordClass c = classify(b, L, x0 + lx, y, zb);
 		// vertex record of the word: first vertex id + the three edge-owner masks (everything a vertex id needs)
-		wv4[gw0 + k] = make_uint4(rv, c.ex, c.ey, c.ez);
-		rv += (cnt[k] >> 8) & 0xFF;
-		ri += cnt[k] >> 16;
+		wv4[gw] = make_uint4(job.x, c.ex, c.ey, c.ez);
+		uint32_t ov = job.z, oi = job.w;
 		uint32_t m = c.ex | c.ey | c.ez, rank = 0;
 		while (m)
 		{
 			const int bit = __ffs(m) - 1;
 			m &= m - 1;
 			const uint32_t fl = ((c.ex >> bit) & 1u) | (((c.ey >> bit) & 1u) << 1) | (((c.ez >> bit) & 1u) << 2);
-			vcells[ov++] = make_uint2(gw0 + k, (uint32_t)bit | (fl << 5) | (rank << 8));
+			vcells[ov++] = make_uint2(gw, (uint32_t)bit | (fl << 5) | (rank << 8));
 			rank += __popc(fl);
 		}
 		m = c.active & c.interior;
@@ -817,14 +846,10 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 			const int bit = __ffs(m) - 1;
 			m &= m - 1;
 			const uint32_t m8 = mask8_of(b, bit);
-			icells[oi++] = make_uint2(gw0 + k, (uint32_t)bit | (ofs << 5) | (m8 << 16));
+			icells[oi++] = make_uint2(gw, (uint32_t)bit | (ofs << 5) | (m8 << 16));
 			ofs += (uint32_t)(c_tri_pack[m8] >> 60);
 		}
 	}
-	uint32_t* o2 = wib + gw0;
-#pragma unroll
-	for (int k = 0; k < WPT; k += 4)
-		*reinterpret_cast<uint4*>(o2 + k) = make_uint4(oix[k], oix[k + 1], oix[k + 2], oix[k + 3]);
 }
 
 // ---- K4b: vertex emission, one THREAD per cell that owns iso-vertices.
