@@ -905,61 +905,109 @@ __device__ __forceinline__ uint32_t vertex_id_rec(const uint4* __restrict__ rec4
 	return id;
 }
 
-// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + per-class use counts, one THREAD per
-// polygonizing cell.  The cell's corner mask travels in its record; the ids of the edge vertices the triangle table
-// names (EDGE_V, DMCChunk.cpp:32, 543-565) come from the 16-byte vertex records of the neighbouring words.
+// ---- K4c: index emission (polygonize / polygonize_cell, DMCChunk.cpp:514-576) + per-class use counts.  The cell's
+// corner mask travels in its record; the ids of the edge vertices the triangle table names (EDGE_V, DMCChunk.cpp:32,
+// 543-565) come from the 16-byte vertex records of the neighbouring words.
+// A warp takes 32 polygonizing cells.  A cell uses 3..12 edges and emits 3..15 indices, so one thread per cell would
+// leave most lanes idle most of the time; instead both steps are flattened over the warp: lane j takes the j-th
+// (cell, used edge) pair of the 32 cells, then the j-th (cell, index) pair -- prefix sums over the warp,
+// the owning cell of every pair written into a small shared table by the cells themselves, ids handed over through
+// shared memory.
 __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict__ wv4, const uint32_t* __restrict__ wib,
                                                 const ChunkCounts* __restrict__ chunks, const uint2* __restrict__ icells,
                                                 const unsigned long long* __restrict__ list_count, uint32_t* __restrict__ inds, uint32_t* __restrict__ cls,
                                                 const unsigned long long* __restrict__ tot)
 {
 	__shared__ uint64_t s_tri[256];
+	__shared__ uint32_t s_id[CTA][12];
+	__shared__ uint64_t s_tp[CTA];
+	__shared__ uint32_t s_xyz[CTA], s_chunk[CTA], s_used[CTA], s_out[CTA], s_vb[CTA];
+	__shared__ uint32_t s_pre[CTA / 32][33];
+	__shared__ uint8_t s_own[CTA / 32][480]; // owning cell (0..31) of every (cell, edge) / (cell, index) pair of the warp
 	if (tot[7]) return;
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
 	const uint32_t stride = gridDim.x * CTA;
-	const int d = L.d;
-	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
+	const int d = L.d, lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+	uint32_t* pre = s_pre[threadIdx.x >> 5];
+	for (uint32_t i0 = blockIdx.x * CTA + wbase; i0 < n_cells; i0 += stride) // warp-uniform
 	{
-		const uint2 rec = icells[i];
-		const uint32_t gw = rec.x;
-		const int bit = rec.y & 31;
-		const uint32_t ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
-		const int chunk = (int)(gw >> L.lwc);
-		const int w = (int)(gw & (uint32_t)(L.wc - 1));
-		const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
-		const int z = zb * 32 + bit;
-		const uint4* rec4 = wv4 + (size_t)chunk * L.wc;
-		const uint64_t tp = s_tri[m8];
-		const int n = (int)(tp >> 60);
-		// which of the 12 edges the table uses: compute each id once
-		uint32_t used = 0;
-		for (int t = 0; t < n; t++) used |= 1u << ((tp >> (4 * t)) & 15);
-		uint32_t id[12];
-#pragma unroll
-		for (int e = 0; e < 12; e++)
+		const uint32_t i = i0 + lane;
+		uint32_t used = 0, n = 0;
+		if (i < n_cells)
 		{
+			const uint2 rec = icells[i];
+			const uint32_t gw = rec.x, ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
+			const uint64_t tp = s_tri[m8];
+			n = (uint32_t)(tp >> 60);
+			// the edges the table uses = the cell's sign-changing edges: X-edges e0-3 <-> corner pairs (a, a+4), Y-edges e4-7 <-> pairs
+			// (0,2),(1,3),(4,6),(5,7), Z-edges e8-11 <-> pairs (0,1),(2,3),(4,5),(6,7)
+			const uint32_t tx = (m8 ^ (m8 >> 4)) & 0xFu, ty = m8 ^ (m8 >> 2), tz = m8 ^ (m8 >> 1);
+			used = tx | ((ty & 3u) << 4) | (((ty >> 4) & 3u) << 6) | ((tz & 1u) << 8) | (((tz >> 2) & 1u) << 9) | (((tz >> 4) & 1u) << 10) | (((tz >> 6) & 1u) << 11);
+			const int w = (int)(gw & (uint32_t)(L.wc - 1));
+			s_tp[threadIdx.x] = tp;
+			s_xyz[threadIdx.x] = (uint32_t)(w >> L.lwp) | ((uint32_t)((w >> L.lzc) & (d - 1)) << 10) | ((uint32_t)((w & (L.zc - 1)) * 32 + (rec.y & 31)) << 20);
+			s_chunk[threadIdx.x] = gw >> L.lwc;
+			s_used[threadIdx.x] = used;
+			s_out[threadIdx.x] = wib[gw] + ofs;
+			s_vb[threadIdx.x] = (uint32_t)chunks[gw >> L.lwc].vert_base;
+		}
+		// ---- step 1: vertex ids of the used edges, one (cell, edge) pair per lane and round
+		uint32_t inc = __popc(used);
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += u;
+		}
+		uint8_t* own = s_own[threadIdx.x >> 5];
+		pre[lane + 1] = inc;
+		if (lane == 0) pre[0] = 0;
+		{
+			const uint32_t u = __popc(used);
+			for (uint32_t q = inc - u; q < inc; q++) own[q] = (uint8_t)lane;
+		}
+		__syncwarp();
+		const uint32_t n_pairs = pre[32];
+		for (uint32_t j = lane; j < n_pairs; j += 32)
+		{
+			const int c = own[j];
+			const int e = (int)__fns(s_used[wbase + c], 0, (int)(j - pre[c]) + 1);
+			const uint32_t xyz = s_xyz[wbase + c];
+			const int x = (int)(xyz & 1023u), y = (int)((xyz >> 10) & 1023u), z = (int)(xyz >> 20);
 			const int axis = e >> 2, hi = (e >> 1) & 1, lo = e & 1;
 			const int dx = axis == 0 ? 0 : hi;
 			const int dy = axis == 0 ? hi : (axis == 1 ? 0 : lo);
 			const int dz = axis == 2 ? 0 : lo;
-			id[e] = ((used >> e) & 1u) ? vertex_id_rec(rec4, L, x + dx, y + dy, z + dz, axis) : 0u;
+			s_id[wbase + c][e] = vertex_id_rec(wv4 + ((size_t)s_chunk[wbase + c] << L.lwc), L, x + dx, y + dy, z + dz, axis);
 		}
-		const size_t out0 = (size_t)wib[gw] + ofs;
-		const size_t vbase = (size_t)chunks[chunk].vert_base;
-		for (int t = 0; t < n; t++)
-		{
-			const int e = (int)(tp >> (4 * t)) & 15;
-			uint32_t vid = 0;
+		__syncwarp();
+		// ---- step 2: the indices, one (cell, index) pair per lane and round
+		inc = n;
 #pragma unroll
-			for (int q = 0; q < 12; q++) vid = (e == q) ? id[q] : vid;
-			inds[out0 + t] = vid;
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += u;
+		}
+		pre[lane + 1] = inc;
+		for (uint32_t q = inc - n; q < inc; q++) own[q] = (uint8_t)lane;
+		__syncwarp();
+		const uint32_t n_inds = pre[32];
+		for (uint32_t j = lane; j < n_inds; j += 32)
+		{
+			const int c = own[j];
+			const uint32_t t = j - pre[c];
+			const uint32_t e = (uint32_t)(s_tp[wbase + c] >> (4 * t)) & 15u;
+			const uint32_t vid = s_id[wbase + c][e];
+			inds[(size_t)s_out[wbase + c] + t] = vid;
 			// init_valence++ (DMCChunk.cpp:573), kept per "cell class": a vertex is shared by at most the four cells
 			// around its grid edge and class = 3 - (e & 3) is this cell's place among them in scan order; byte c of
 			// cls[v] counts the uses by the class-c cell (the sort-free CSR build in smooth.cuh needs the split)
-			atomicAdd(cls + vbase + vid, 1u << (8 * (3 - (e & 3))));
+			atomicAdd(cls + s_vb[wbase + c] + vid, 1u << (8 * (3 - (e & 3))));
 		}
+		__syncwarp(); // the next round overwrites the warp's shared slots
 	}
 }
 
