@@ -152,41 +152,73 @@ __global__ void __launch_bounds__(CTA) k_csr_sort(const uint32_t* __restrict__ a
 // k_inds3 counted the uses of every vertex per class (4 bytes of cls[v]); the slot of use (cell, t) in the
 // vertex's list is therefore (uses by lower classes) + (earlier uses of the same edge inside this cell's table
 // row): every list comes out ascending in primitive id, exactly init_primitives' order (:114-127).
+// Like k_inds3 the work is flattened over the warp: lane j takes the j-th (cell, index) pair of the warp's 32 cells, so
+// the index reads are coalesced and no lane waits for a neighbour with a longer table row.
 __global__ void __launch_bounds__(CTA) k_adj_fill(Layout L, const uint32_t* __restrict__ wib, const ChunkCounts* __restrict__ chunks,
                                                    const uint2* __restrict__ icells, const unsigned long long* __restrict__ list_count,
                                                    const uint32_t* __restrict__ inds, const uint32_t* __restrict__ cls, const uint32_t* __restrict__ adj_off,
                                                    uint32_t* __restrict__ adj, uint32_t* __restrict__ prim_vbase, const unsigned long long* __restrict__ tot)
 {
 	__shared__ uint64_t s_tri[256];
+	__shared__ uint64_t s_tp[CTA];
+	__shared__ uint32_t s_out[CTA], s_vb[CTA];
+	__shared__ uint32_t s_pre[CTA / 32][33];
+	__shared__ uint8_t s_own[CTA / 32][480];
 	if (tot[7]) return;
 	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
 	const uint32_t stride = gridDim.x * CTA;
-	for (uint32_t i = blockIdx.x * CTA + threadIdx.x; i < n_cells; i += stride)
+	const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+	uint32_t* pre = s_pre[threadIdx.x >> 5];
+	uint8_t* own = s_own[threadIdx.x >> 5];
+	for (uint32_t i0 = blockIdx.x * CTA + wbase; i0 < n_cells; i0 += stride) // warp-uniform
 	{
-		const uint2 rec = icells[i];
-		const uint32_t gw = rec.x;
-		const uint32_t ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
-		const int chunk = (int)(gw >> L.lwc);
-		const uint64_t tp = s_tri[m8];
-		const int n = (int)(tp >> 60);
-		const size_t out0 = (size_t)wib[gw] + ofs;
-		const uint32_t vbase = (uint32_t)chunks[chunk].vert_base;
-		uint64_t seen = 0; // 4-bit use counter per local edge id
-		for (int t = 0; t < n; t++)
+		const uint32_t i = i0 + lane;
+		uint32_t n = 0;
+		if (i < n_cells)
 		{
-			const uint32_t e = (uint32_t)(tp >> (4 * t)) & 15u;
-			const uint32_t prim = (uint32_t)((out0 + t) / 3);
-			if ((t % 3) == 0) prim_vbase[prim] = vbase;
-			const uint32_t local = (uint32_t)(seen >> (4 * e)) & 15u;
-			seen += 1ull << (4 * e);
-			const uint32_t v = vbase + inds[out0 + t];
-			const uint32_t c = 3u - (e & 3u);
-			const uint32_t below = cls[v] & ((1u << (8 * c)) - 1u); // c <= 3: the shift stays below 32
-			const uint32_t pre = (below & 0xFF) + ((below >> 8) & 0xFF) + ((below >> 16) & 0xFF);
-			adj[adj_off[v] + pre + local] = prim;
+			const uint2 rec = icells[i];
+			const uint32_t gw = rec.x, ofs = (rec.y >> 5) & 0x7FF, m8 = (rec.y >> 16) & 0xFF;
+			const uint64_t tp = s_tri[m8];
+			n = (uint32_t)(tp >> 60);
+			s_tp[threadIdx.x] = tp;
+			s_out[threadIdx.x] = wib[gw] + ofs;
+			s_vb[threadIdx.x] = (uint32_t)chunks[gw >> L.lwc].vert_base;
 		}
+		uint32_t inc = n;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+			if (lane >= o) inc += u;
+		}
+		pre[lane + 1] = inc;
+		if (lane == 0) pre[0] = 0;
+		for (uint32_t q = inc - n; q < inc; q++) own[q] = (uint8_t)lane;
+		__syncwarp();
+		const uint32_t n_pairs = pre[32];
+		for (uint32_t j = lane; j < n_pairs; j += 32)
+		{
+			const int c = own[j];
+			const uint32_t t = j - pre[c];
+			const uint64_t tp = s_tp[wbase + c];
+			const uint32_t e = (uint32_t)(tp >> (4 * t)) & 15u;
+			const uint32_t out = s_out[wbase + c] + t, vbase = s_vb[wbase + c];
+			const uint32_t prim = out / 3;
+			if ((t % 3) == 0) prim_vbase[prim] = vbase;
+			// earlier uses of the same edge inside this cell's table row: nibbles below t that equal e
+			uint64_t x = tp ^ (0x1111111111111111ull * e);             // equal nibbles become 0
+			x = (x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x1111111111111111ull; // 1 per nibble that differs
+			const uint64_t below = t ? (~0ull >> (64 - 4 * t)) : 0ull;
+			const uint32_t local = t - (uint32_t)__popcll(x & below);
+			const uint32_t v = vbase + inds[out];
+			const uint32_t cl = 3u - (e & 3u);
+			const uint32_t lower = cls[v] & ((1u << (8 * cl)) - 1u); // cl <= 3: the shift stays below 32
+			const uint32_t before = (lower & 0xFF) + ((lower >> 8) & 0xFF) + ((lower >> 16) & 0xFF);
+			adj[adj_off[v] + before + local] = prim;
+		}
+		__syncwarp();
 	}
 }
 
