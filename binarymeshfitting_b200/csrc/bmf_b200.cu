@@ -411,17 +411,6 @@ int reserve_mesh(bmf_ctx* ctx, size_t cells, size_t verts, size_t inds)
 	return BMF_OK;
 }
 
-// chunk table -> mapped pinned host memory, after the last kernel of the batch so that it is off the critical path
-int publish_chunks(bmf_ctx* ctx)
-{
-	if (ctx->counts_published) return BMF_OK;
-	const size_t words = (size_t)ctx->n * (sizeof(ChunkCounts) / sizeof(uint32_t));
-	BMF_LAUNCH(k_publish_chunks, std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)), CTA, 0, reinterpret_cast<const uint32_t*>(ctx->counts.p),
-	           reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
-	ctx->counts_published = true;
-	return BMF_OK;
-}
-
 // K4 + K5 of the resident batch, sized by arena capacity and guarded on the device (k_check_caps): no host round trip
 int launch_mesh(bmf_ctx* ctx)
 {
@@ -434,7 +423,13 @@ int launch_mesh(bmf_ctx* ctx)
 	unsigned long long* list_count = tot + 4;
 	// totals and the chunk table reach the host through mapped pinned memory written by the kernels themselves (UVA):
 	// no D2H transfer sits in this stream, so nothing here can queue behind another context's mesh download
-	BMF_LAUNCH(k_check_caps, 1, 1, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
+	{
+		// + the chunk table for the host (once per batch), in the same launch
+		const size_t words = ctx->counts_published ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
+		BMF_LAUNCH(k_check_caps, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells,
+		           (unsigned long long)caps.verts, (unsigned long long)caps.inds, reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
+		ctx->counts_published = true;
+	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 	{
@@ -443,7 +438,7 @@ int launch_mesh(bmf_ctx* ctx)
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return publish_chunks(ctx);
+		return BMF_OK;
 	}
 	const size_t V = caps.verts, I = caps.inds;
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
@@ -469,7 +464,7 @@ int launch_mesh(bmf_ctx* ctx)
 		           ctx->sampler, src, ctx->geom.p, ctx->pos.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, tot);
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return publish_chunks(ctx);
+		return BMF_OK;
 	}
 	if (L.wpt == 4)
 		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_bases, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
@@ -477,11 +472,8 @@ int launch_mesh(bmf_ctx* ctx)
 	else
 		BMF_LAUNCH(k_bases<8>, nseg, CTA, smem_bases, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
 		           ctx->icells.p, list_count, tot);
-	BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p, tot);
+	BMF_LAUNCH(k_verts3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->counts.p, ctx->sampler, src, ctx->geom.p, ctx->vcells.p, list_count, ctx->pos.p, ctx->boundary.p, ctx->cls.p, ctx->normal.p, tot);
 	BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
-	// only the part of the arenas this batch uses is cleared (the count is on the device)
-	BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, ctx->cls.p, V, tot, 1, 1);
-	BMF_LAUNCH(k_zero_u32, ctx->sm_count * 4, CTA, 0, reinterpret_cast<uint32_t*>(ctx->normal.p), 3 * V, tot, 1, 3);
 	if (ctx->color_ones < 3 * V)
 	{
 		// calculate_dual_vertex: color = (1,1,1) (DMCChunk.cpp:681).  The batch path never writes another colour
@@ -501,7 +493,7 @@ int launch_mesh(bmf_ctx* ctx)
 		if (rc) return rc;
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-	return publish_chunks(ctx);
+	return BMF_OK;
 }
 
 // completes the resident batch: waits for the stream, publishes totals / per-chunk counts to the host and, if an output

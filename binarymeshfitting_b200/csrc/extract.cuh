@@ -696,25 +696,29 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 	}
 }
 
-// The chunk table goes to the host through mapped pinned memory written by the device itself (no copy-engine transfer
-// that could queue behind another context's mesh download); many CTAs, 4-byte words, coalesced -- a single CTA pushing
-// 40-byte records over PCIe used to cost as much as the scan itself.
-__global__ void __launch_bounds__(CTA) k_publish_chunks(const uint32_t* __restrict__ chunks_words, uint32_t* __restrict__ host_words, size_t n_words)
-{
-	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n_words; i += (size_t)gridDim.x * CTA) host_words[i] = chunks_words[i];
-}
-
 // Output arenas are sized from the previous batches so that a submission never has to wait for the host.  This
 // one-thread kernel compares the totals of THIS batch with the capacities the emitters were launched with; if
 // anything does not fit it raises tot[7] and every emitter below returns at once -- the host then grows the
 // arenas and re-launches them (bmf_batch_wait).  tot = {cells, verts, indices, >2^32, list counters x2, -, too small}
-__global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long long* __restrict__ tot_host /* mapped pinned host copy */,
-                             unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
+// The same launch publishes the chunk table to the host through mapped pinned memory written by the device itself (no
+// copy-engine transfer that could queue behind another context's mesh download): chunks_words -> host_words, coalesced
+// 4-byte words over all its CTAs (a single CTA pushing 40-byte records over PCIe used to cost as much as the scan itself),
+// unless that has been done for this batch already (n_words = 0).
+__global__ void __launch_bounds__(CTA) k_check_caps(unsigned long long* __restrict__ tot, unsigned long long* __restrict__ tot_host /* mapped pinned host copy */,
+                                                     unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds,
+                                                     const uint32_t* __restrict__ chunks_words, uint32_t* __restrict__ host_words, size_t n_words)
 {
-	tot[7] = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
-	tot[6] = 0; // chunk work counter of k_smooth_chunks
-	for (int k = 0; k < 8; k++) tot_host[k] = tot[k];
-	__threadfence_system();
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		const unsigned long long small = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
+		tot[7] = small;
+		tot[6] = 0; // chunk work counter of k_smooth_chunks
+		for (int k = 0; k < 6; k++) tot_host[k] = tot[k];
+		tot_host[6] = 0;
+		tot_host[7] = small;
+		__threadfence_system();
+	}
+	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n_words; i += (size_t)gridDim.x * CTA) host_words[i] = chunks_words[i];
 }
 
 // ---- K4a: per-word output bases + compaction of the CELLS that emit anything.  One CTA per segment with
@@ -857,7 +861,7 @@ __global__ void __launch_bounds__(CTA) k_bases(const uint32_t* __restrict__ bits
 __global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint4* __restrict__ wv4, const ChunkCounts* __restrict__ chunks, SamplerDev s, DensitySource src,
                                                  const ChunkGeom* __restrict__ geom, const uint2* __restrict__ vcells,
                                                  const unsigned long long* __restrict__ list_count, float* __restrict__ pos, uint8_t* __restrict__ boundary,
-                                                 const unsigned long long* __restrict__ tot)
+                                                 uint32_t* __restrict__ cls, float* __restrict__ normal, const unsigned long long* __restrict__ tot)
 {
 	if (tot[7]) return;
 	const uint32_t n_cells = (uint32_t)list_count[0];
@@ -888,6 +892,9 @@ __global__ void __launch_bounds__(CTA) k_verts3(Layout L, const uint4* __restric
 			pos[3 * v + 1] = ((float)y1 - (float)y) * mu + (float)y;
 			pos[3 * v + 2] = ((float)z1 - (float)z) * mu + (float)z;
 			boundary[v] = (b0 || x1 == d - 1 || y1 == d - 1 || z1 == d - 1) ? 1 : 0;
+			// every vertex is written exactly once, here: its use counters (k_inds3 adds to them) and its normal start at zero
+			cls[v] = 0u;
+			normal[3 * v + 0] = 0.0f; normal[3 * v + 1] = 0.0f; normal[3 * v + 2] = 0.0f;
 			v++;
 		}
 	}
