@@ -317,7 +317,9 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		BMF_LAUNCH(k_csr_sort, grid_for(n_verts, CTA), CTA, 0, ctx->adj_off.p, valence, n_verts, ctx->adj.p);
 	}
 
-	if (grid_path && tot && N == 3 && !smooth && !qef && final_primal && ctx->smooth_fused)
+	// one CTA per chunk only pays when there are chunks for every SM; a few (or one large) chunks keep the per-step kernels,
+	// which spread every half-step over the whole GPU
+	if (grid_path && tot && N == 3 && !smooth && !qef && final_primal && ctx->smooth_fused && n_chunks >= 2 * ctx->sm_count)
 	{
 		// the whole optimize_dual_grid(iters) + optimize_primal_grid sequence, one CTA per chunk out of shared memory:
 		// iters dual steps interleaved with iters primal steps (the last primal is the driver's extra call)

@@ -12,8 +12,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # per-kernel counters of the steady state (the first batches grow the arenas and re-launch the emitters)
 ncu --metrics $M --clock-control none -s 60 -c 80 --csv --log-file $OUT/${TAG}_kernels.csv $B > $OUT/${TAG}_kernels.out 2>&1
 # full-set captures of the top kernels
-for k in k_smooth_chunks k_inds3 k_bases k_adj_fill k_terrain2d_sheet; do
+for k in k_smooth_chunks k_inds3 k_bases k_adj_fill k_terrain2d_sheet k_terrain2d_bits k_count; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${TAG}_$k $B > $OUT/${TAG}_$k.out 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:k_seam_count -s 2 -c 1 -f -o $OUT/${TAG}_k_seam_count python scratch/seam_probe.py > $OUT/${TAG}_k_seam_count.out 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_seam_pass -s 2 -c 1 -f -o $OUT/${TAG}_k_seam_pass python scratch/seam_probe.py > $OUT/${TAG}_k_seam_pass.out 2>&1
 ls -la $OUT | grep $TAG
