@@ -44,6 +44,10 @@ def test_quads_config1_single_chunk(gpu, oracle, kind, dim):
     check_batch(gpu, oracle, kind, np.array([[-128, -128, -128, 256.0]], np.float32), dim)
 
 
+def test_quads_dim_256(gpu, oracle):
+    check_batch(gpu, oracle, ob.TORUS_Z, np.array([[-128, -128, -128, 256.0]], np.float32), 256)
+
+
 def test_quads_batch_terrain_and_smoothing(gpu, oracle):
     ps = np.array([[x, y, z, 32.0] for x in (-32.0, 0.0) for y in (-32.0, 0.0) for z in (-32.0, 0.0)], np.float32)
     check_batch(gpu, oracle, ob.TERRAIN2D_PERT, ps, 32, overlap=0.045)

@@ -64,6 +64,31 @@ def test_seam_terrain3d_and_dim64(gpu, oracle):
     np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+def test_seam_dim128_two_levels_apart(gpu, oracle):
+    # a 128^3-voxel fine chunk next to chunks two levels coarser (the stretched-row classification with s = 2), dim 128
+    ps = np.array([[0, 0, 0, 16.0], [16, 0, 0, 16.0], [0, 16, 0, 16.0], [16, 16, 0, 16.0], [0, 0, 16, 16.0], [16, 0, 16, 16.0], [0, 16, 16, 16.0],
+                   [16, 16, 16, 16.0], [32, 0, 0, 32.0], [-64, 0, 0, 64.0], [0, -64, 0, 64.0], [-64, -64, 0, 64.0]], np.float32)
+    got, want, _ = run(gpu, oracle, ob.SPHERE, ps, dim=128, world_size=150.0)
+    assert len(want) > 0
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    got, want, _ = run(gpu, oracle, ob.TERRAIN2D_PERT, ps, dim=32)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_seam_after_quads_and_after_smoothing(gpu, oracle):
+    # the seam pass only reads sign words and samples: it does not depend on what the batch emitted
+    ps, lv, mc = su.lod_world(2, 1, (0.0, 0.0, 0.0))
+    s = oracle.sampler(ob.SPHERE)
+    ov = su.seam_overlap(DIM)
+    chunks = [oracle.chunk(s, p[:3], p[3], DIM, ov) for p in ps]
+    want = oracle.seam(chunks, ps, DIM, ov)
+    gpu.set_sampler(ob.SPHERE)
+    for kw in ({"quads": True}, {"iters": 3}, {"iters": 2, "smooth_normals": True}):
+        gpu.submit(capi.make_chunk_descs(ps, overlaps=ov), DIM, **kw)
+        got = gpu.stitch()
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_seam_host_density(gpu, oracle):
     rng = np.random.default_rng(7)
     ps = np.array([[0, 0, 0, 8.0], [8, 0, 0, 8.0], [0, 8, 0, 8.0], [8, 8, 0, 8.0], [0, 0, 8, 8.0], [8, 0, 8, 8.0], [0, 8, 8, 8.0], [8, 8, 8, 8.0],
