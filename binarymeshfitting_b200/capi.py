@@ -23,7 +23,7 @@ EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
-           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris")
+           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads")
 
 
 class SamplerDesc(C.Structure):
@@ -100,6 +100,7 @@ def load_library(path=SO):
     lib.bmf_mesh_process_steps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     lib.bmf_quads_to_tris.argtypes = [vp, vp, C.c_int64, vp]
+    lib.bmf_batch_download_flat_quads.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.bmf_seam_overlap.argtypes = [C.c_int]
     lib.bmf_seam_overlap.restype = C.c_float
     lib.bmf_batch_stitch.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
@@ -270,6 +271,14 @@ class Context:
         t = np.zeros((len(q) * 2, 3), np.uint32)
         self._check(self.lib.bmf_quads_to_tris(self.h, _p(q), len(q), _p(t)))
         return t
+
+    def download_flat_quads(self, smooth_normals=False):
+        """GLChunk::format_data(..., unwind_verts=True, smooth_normals) of the resident quad batch: [n_inds, 3] p / n / c"""
+        self.wait()
+        ni = self.totals()[2]
+        p, n, c = (np.zeros((ni, 3), np.float32) for _ in range(3))
+        self._check(self.lib.bmf_batch_download_flat_quads(self.h, int(smooth_normals), _p(p), _p(n), _p(c)))
+        return p, n, c
 
     def seam_overlap(self, dim):
         """the overlap that puts a chunk's samples at its voxel-node centres (what the seam pass expects)"""

@@ -1165,6 +1165,29 @@ int bmf_quads_to_tris(bmf_ctx* ctx, const uint32_t* quads, int64_t n_quads, uint
 	return BMF_OK;
 }
 
+int bmf_batch_download_flat_quads(bmf_ctx* ctx, int smooth_normals, float* p_data, float* n_data, float* c_data)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download_flat_quads: no batch submitted");
+	if (!ctx->params.quads) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download_flat_quads: the resident batch is not a quad batch");
+	int rc = finish(ctx);
+	if (rc) return rc;
+	const size_t I = (size_t)ctx->totals[2], Q = I / 4;
+	if (Q == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	BMF_CUDA(ctx->dp.reserve(3 * I));
+	BMF_CUDA(ctx->dn.reserve(3 * I));
+	BMF_CUDA(ctx->dc.reserve(3 * I));
+	cudaStream_t st = ctx->stream;
+	BMF_LAUNCH(k_format_unwind, std::min(grid_for(Q, CTA), (unsigned)(ctx->sm_count * 8)), CTA, 0, ctx->pos.p, ctx->normal.p, ctx->color.p, ctx->inds.p, Q, ctx->counts.p,
+	           ctx->n, smooth_normals ? 1 : 0, ctx->dp.p, ctx->dn.p, ctx->dc.p);
+	if (p_data) BMF_CUDA(cudaMemcpyAsync(p_data, ctx->dp.p, sizeof(float) * 3 * I, cudaMemcpyDeviceToHost, st));
+	if (n_data) BMF_CUDA(cudaMemcpyAsync(n_data, ctx->dn.p, sizeof(float) * 3 * I, cudaMemcpyDeviceToHost, st));
+	if (c_data) BMF_CUDA(cudaMemcpyAsync(c_data, ctx->dc.p, sizeof(float) * 3 * I, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
 float bmf_seam_overlap(int dim) { return dim > 0 ? -0.5f / (float)dim : 0.0f; }
 
 int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, int64_t* n_tris)

@@ -14,6 +14,7 @@
 // word records.
 #pragma once
 #include "extract.cuh"
+#include "smooth.cuh"
 
 namespace bmf
 {
@@ -308,6 +309,46 @@ __global__ void __launch_bounds__(CTA) k_quads_to_tris(const uint32_t* __restric
 		const uint4 v = reinterpret_cast<const uint4*>(quads)[q];
 		uint32_t* o = tris + 6 * q;
 		o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.z; o[4] = v.w; o[5] = v.x;
+	}
+}
+
+// GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335) over the whole quad
+// batch: per quad the four corner positions / colours and one normal for all four -- the mean of the corner normals
+// (smooth) or -normalize((n0 + n1) / 2) of the two triangle normals with the reference's NaN guards.  One thread per quad.
+__global__ void __launch_bounds__(CTA) k_format_unwind(const float* __restrict__ pos, const float* __restrict__ normal, const float* __restrict__ color,
+                                                        const uint32_t* __restrict__ inds, size_t n_quads, const ChunkCounts* __restrict__ chunks, int n_chunks,
+                                                        int smooth_normals, float* __restrict__ p_out, float* __restrict__ n_out, float* __restrict__ c_out)
+{
+	for (size_t q = (size_t)blockIdx.x * CTA + threadIdx.x; q < n_quads; q += (size_t)gridDim.x * CTA)
+	{
+		const size_t vb = (size_t)chunks[chunk_of_index(chunks, n_chunks, 4 * (uint64_t)q)].vert_base;
+		const uint4 iv = reinterpret_cast<const uint4*>(inds)[q];
+		const size_t v[4] = { vb + iv.x, vb + iv.y, vb + iv.z, vb + iv.w };
+		f3 p[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			p[k] = ld3(pos, v[k]);
+			st3(p_out, 4 * q + k, p[k]);
+			st3(c_out, 4 * q + k, ld3(color, v[k]));
+		}
+		f3 n;
+		if (smooth_normals)
+		{
+			const f3 a = ld3(normal, v[0]), b = ld3(normal, v[1]), c = ld3(normal, v[2]), d = ld3(normal, v[3]);
+			n = mul3(add3(add3(add3(a, b), c), d), 0.25f);
+		}
+		else
+		{
+			f3 n0 = cross3(normalize3(sub3(p[0], p[1])), normalize3(sub3(p[0], p[2])));
+			f3 n1 = cross3(normalize3(sub3(p[2], p[3])), normalize3(sub3(p[2], p[0])));
+			if (isnan(n0.x)) n0 = n1;
+			if (isnan(n1.x)) n1 = n0;
+			const f3 h = normalize3(mul3(add3(n0, n1), 0.5f));
+			n = { -h.x, -h.y, -h.z };
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) st3(n_out, 4 * q + k, n);
 	}
 }
 

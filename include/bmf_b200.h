@@ -182,6 +182,12 @@ int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, co
  * quads: [n_quads*4] indices in, tris: [n_quads*6] out (host arrays). */
 int bmf_quads_to_tris(bmf_ctx* ctx, const uint32_t* quads, int64_t n_quads, uint32_t* tris);
 
+/* GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335; DebugScene.cpp:286
+ * with FLAT_QUADS) for the resident QUAD batch: per quad corner position / normal / colour, [n_inds][3] floats each; the
+ * normal of a quad is the mean of its corner normals (smooth_normals) or the reference's two-triangle face normal.
+ * Any pointer may be NULL. */
+int bmf_batch_download_flat_quads(bmf_ctx* ctx, int smooth_normals, float* p_data, float* n_data, float* c_data);
+
 /* WorldStitcher::stitch_all(root) (WorldStitcher.cpp:26-49 -> stitch_cell :184-239 -> stitch_indexes :491-572): the seam
  * pass over the RESIDENT batch, whose chunks must be aligned leaves of one octree (any mix of levels; a missing
  * neighbour simply gets no seam).  Every dual cell formed by 8 voxel nodes that do not all belong to one chunk is

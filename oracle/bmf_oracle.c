@@ -1051,3 +1051,46 @@ void orc_quads(const float* D, const uint32_t* bits, int dim, orc_mesh* out)
 			}
 	free(vbase);
 }
+
+/* ---- GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335): flat quads.
+ * Per quad the four corner positions and colours are copied out; the normal of all four is the mean of the corner
+ * normals (smooth) or -normalize((n0 + n1) / 2) of the two triangle normals with the reference's NaN guards.
+ * Pinned against the compiled reference (tests/test_oracle_vs_ref.py). */
+static void v3_sub(const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+
+void orc_format_unwind(const float* pos, const float* normal, const float* color, const uint32_t* inds, int n_inds, int smooth_normals,
+                       float* p_out, float* n_out, float* c_out)
+{
+	for (int i = 0; i + 3 < n_inds; i += 4)
+	{
+		const float* p[4];
+		for (int k = 0; k < 4; k++)
+		{
+			p[k] = pos + 3 * (size_t)inds[i + k];
+			memcpy(p_out + 3 * (size_t)(i + k), p[k], 12);
+			memcpy(c_out + 3 * (size_t)(i + k), color + 3 * (size_t)inds[i + k], 12);
+		}
+		float n[3];
+		if (smooth_normals)
+		{
+			const float* a = normal + 3 * (size_t)inds[i], *b = normal + 3 * (size_t)inds[i + 1], *c = normal + 3 * (size_t)inds[i + 2], *d = normal + 3 * (size_t)inds[i + 3];
+			for (int x = 0; x < 3; x++) n[x] = (((a[x] + b[x]) + c[x]) + d[x]) * 0.25f;
+		}
+		else
+		{
+			float e0[3], e1[3], n0[3], n1[3];
+			v3_sub(p[0], p[1], e0); v3_normalize(e0);
+			v3_sub(p[0], p[2], e1); v3_normalize(e1);
+			v3_cross(e0, e1, n0);
+			v3_sub(p[2], p[3], e0); v3_normalize(e0);
+			v3_sub(p[2], p[0], e1); v3_normalize(e1);
+			v3_cross(e0, e1, n1);
+			if (isnan(n0[0])) memcpy(n0, n1, 12);
+			if (isnan(n1[0])) memcpy(n1, n0, 12);
+			for (int x = 0; x < 3; x++) n[x] = (n0[x] + n1[x]) * 0.5f;
+			v3_normalize(n);
+			n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2];
+		}
+		for (int k = 0; k < 4; k++) memcpy(n_out + 3 * (size_t)(i + k), n, 12);
+	}
+}

@@ -102,6 +102,11 @@ int64_t orc_batch(const orc_sampler* s, const float* pos_size /* n x 4 */, int n
  * n_cells / n_verts / n_inds (4 per quad), pos (grid units), boundary, valence, inds; the other members stay null. */
 void orc_quads(const float* density, const uint32_t* bits, int dim, orc_mesh* out);
 
+/* GLChunk::format_data(vertices, indexes, true, smooth_normals) (GLChunk.cpp:278-335): per quad corner p / n / c
+ * ([n_inds][3] each); pinned against the compiled reference */
+void orc_format_unwind(const float* pos, const float* normal, const float* color, const uint32_t* inds, int n_inds, int smooth_normals,
+                       float* p_out, float* n_out, float* c_out);
+
 /* seam pass between chunks (UNPINNED, build-defined: the reference's WorldStitcher is non-functional as committed).
  * bits / density: the chunk's sign words and density block as orc_label_grid / orc_sample_block produce them.
  * Returns the number of triangles (or -1 if the chunks are not aligned octree leaves); *tris_out = malloc'd

@@ -73,6 +73,7 @@ class Oracle:
         lib.orc_qef_solve.restype = C.c_float
         lib.orc_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_qef_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_format_unwind.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_quads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Mesh)]
         lib.orc_seam.restype = C.c_int64
         lib.orc_seam.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.POINTER(C.c_float))]
@@ -196,6 +197,14 @@ class Oracle:
                "valence": _np(m.valence, m.n_verts, np.uint8), "inds": _np(m.inds, m.n_inds, np.uint32)}
         self.lib.orc_mesh_free(C.byref(m))
         return out
+
+    def format_unwind(self, pos, normal, color, inds, smooth_normals=False):
+        """GLChunk::format_data(vertices, indexes, true, smooth_normals): flat quads, [n_inds, 3] p / n / c"""
+        pos, normal, color = (np.ascontiguousarray(a, np.float32).reshape(-1, 3) for a in (pos, normal, color))
+        inds = np.ascontiguousarray(inds, np.uint32)
+        p, n, c = (np.zeros((len(inds), 3), np.float32) for _ in range(3))
+        self.lib.orc_format_unwind(_p(pos), _p(normal), _p(color), _p(inds), len(inds), int(smooth_normals), _p(p), _p(n), _p(c))
+        return p, n, c
 
     def seam(self, chunks, pos_size, dim, overlaps, group=None, cross_group_only=False):
         """seam pass over chunks = [self.chunk(...) dicts] (needs their "bits" and "density") -> [n_tris, 3, 3]"""

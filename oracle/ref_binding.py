@@ -44,6 +44,7 @@ class RefLib:
         lib.ref_chunk_copy.argtypes = [C.c_void_p] * 9
         lib.ref_chunk_destroy.argtypes = [C.c_void_p]
         lib.ref_mesh_process.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.ref_format_unwind.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ref_qef_solve.restype = C.c_float
         lib.ref_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.ref_implicit_value.restype = C.c_float
@@ -103,6 +104,14 @@ class RefLib:
         i = np.array(inds, np.uint32, copy=True)
         self.lib.ref_mesh_process(_fp(v), len(v), _fp(i), len(i), prim_n, iters, int(process_boundary), int(smooth_normals))
         return v, i
+
+    def format_unwind(self, verts, inds, smooth_normals=False):
+        """GLChunk::format_data(vertices, indexes, true, smooth_normals): per quad corner p / n / c"""
+        v = np.array(verts, DUALVERTEX_DTYPE, copy=True)
+        i = np.array(inds, np.uint32, copy=True)
+        p, n, c = (np.zeros((len(i), 3), np.float32) for _ in range(3))
+        self.lib.ref_format_unwind(_fp(v), len(v), _fp(i), len(i), int(smooth_normals), _fp(p), _fp(n), _fp(c))
+        return p, n, c
 
     def qef_solve(self, positions, normals):
         p = np.ascontiguousarray(positions, np.float32)

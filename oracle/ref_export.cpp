@@ -255,6 +255,20 @@ void ref_mesh_process(void* vertices, int n_verts, uint32_t* indices, int n_inds
 	memcpy(indices, idx.elements, (size_t)n_inds * sizeof(uint32_t));
 }
 
+// GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335): the flat-quad SoA
+void ref_format_unwind(void* vertices, int n_verts, uint32_t* indices, int n_inds, int smooth_normals, float* p_out, float* n_out, float* c_out)
+{
+	SmartContainer<DualVertex> v;
+	SmartContainer<uint32_t> idx;
+	v.push_back((DualVertex*)vertices, (size_t)n_verts);
+	idx.push_back(indices, (size_t)n_inds);
+	GLChunk g;
+	g.format_data(v, idx, true, smooth_normals != 0);
+	memcpy(p_out, g.p_data.elements, g.p_data.count * sizeof(glm::vec3));
+	memcpy(n_out, g.n_data.elements, g.n_data.count * sizeof(glm::vec3));
+	memcpy(c_out, g.c_data.elements, g.c_data.count * sizeof(glm::vec3));
+}
+
 float ref_qef_solve(const float* positions, const float* normals, int count, float* solved)
 {
 	return qef_solve_from_points_3d(positions, normals, count, solved);

@@ -65,6 +65,27 @@ def test_quads_random_density_all_patch_cases(gpu, oracle):
     assert out["valence"].max() >= 4
 
 
+@pytest.mark.parametrize("smooth", [False, True])
+def test_flat_quads_format(gpu, oracle, smooth):
+    """GLChunk::format_data(vertices, indexes, true, smooth_normals) on the resident quad batch (oracle pinned to the
+    compiled reference in tests/test_oracle_vs_ref.py)"""
+    ps = np.array([[x, -16.0, z, 32.0] for x in (-32.0, 0.0) for z in (-32.0, 0.0)], np.float32)
+    gpu.set_sampler(ob.TERRAIN2D_PERT)
+    gpu.submit(capi.make_chunk_descs(ps, overlaps=0.045), 32, iters=4 if smooth else 2, smooth_normals=smooth, quads=True)
+    gpu.wait()
+    infos, out = gpu.chunk_infos(), gpu.download()
+    p, n, c = gpu.download_flat_quads(smooth)
+    assert len(p) == gpu.totals()[2] > 0
+    for i in range(len(ps)):
+        v0, i0, nv, ni = int(infos[i]["vert_offset"]), int(infos[i]["ind_offset"]), int(infos[i]["n_verts"]), int(infos[i]["n_inds"])
+        if not ni:
+            continue
+        wp, wn, wc = oracle.format_unwind(out["pos"][v0:v0 + nv], out["normal"][v0:v0 + nv], out["color"][v0:v0 + nv], out["inds"][i0:i0 + ni], smooth)
+        np.testing.assert_array_equal(p[i0:i0 + ni].view(np.uint32), wp.view(np.uint32))
+        np.testing.assert_array_equal(c[i0:i0 + ni].view(np.uint32), wc.view(np.uint32))
+        np.testing.assert_array_equal(n[i0:i0 + ni].view(np.uint32), wn.view(np.uint32))
+
+
 def test_flush_to_tris(gpu):
     q = np.arange(40, dtype=np.uint32).reshape(-1, 4)
     t = gpu.quads_to_tris(q)

@@ -111,3 +111,22 @@ def test_world_batch_totals(ref, oracle):
     total, counts = oracle.batch(oracle.sampler(ob.SPHERE), ps, 32, overlaps=[W.chunk_overlap(props, int(l)) for l in lv], threads=4)
     assert (n, nv, ni) == (232, 79992, 452400)
     assert int(counts[:, 0].sum()) == nv and int(counts[:, 1].sum()) == ni
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_flat_quad_format_matches_reference(oracle, ref, smooth):
+    """GLChunk::format_data(vertices, indexes, unwind_verts=true, smooth_normals) (GLChunk.cpp:278-335) on a quad mesh"""
+    from oracle import ref_binding as rb
+    ch = oracle.chunk(oracle.sampler(ob.TORUS_Z), (-128, -128, -128), 256.0, 32)
+    q = oracle.quads(ch["density"], ch["bits"], 32)
+    nv = q["n_verts"]
+    rng = np.random.default_rng(5)
+    nrm, col = rng.standard_normal((nv, 3)).astype(np.float32), rng.random((nv, 3)).astype(np.float32)
+    inds = q["inds"].copy()
+    inds[4:8] = inds[4]  # a degenerate quad: the NaN guards of the face normal
+    v = np.zeros(nv, rb.DUALVERTEX_DTYPE)
+    v["p"], v["n"], v["color"] = q["pos"], nrm, col
+    want = ref.format_unwind(v, inds, smooth)
+    got = oracle.format_unwind(q["pos"], nrm, col, inds, smooth)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
