@@ -413,6 +413,23 @@ def extras(ctx, args, capi, world):
     ctx.set_sampler(capi.TERRAIN3D_PERT)
     s = timed(d, args.dim, args.iters, reps=3)
     ex["terrain3d_pert_4096x64"] = {"ms_per_step": s * 1e3, "voxels_per_s": len(d) * args.dim ** 3 / s, "stage_ms": ctx.stage_ms()}
+    # the noise stage is FP32 / INT32 issue bound and its denominators are to be MEASURED: dependent-free chains
+    # of FFMA / IMAD / (2 LOP3 + LEA) per thread, 2048 threads per SM (csrc/smooth.cuh k_ubench_issue); 1e9 thread-level steps/s
+    try:
+        pk = ctx.ubench_issue()
+        sass_per_step = {"fp32_fma": 1, "int32_imad": 1, "int32_logic_step": 3, "fma_plus_logic_step": 2}  # SASS instructions per chain step (cuobjdump)
+        peaks_inst = {k: v * sass_per_step[k] for k, v in pk.items()}  # 1e9 thread-level instructions/s
+        inst_per_voxel = 2168.0  # ncu smsp__thread_inst_executed of k_terrain3d<NT_SIMPLEX> per voxel (profiles/r1_ncu_full_summary_v1.txt)
+        ach = ex["terrain3d_pert_4096x64"]["voxels_per_s"] * inst_per_voxel / 1e9
+        ex["issue_peaks_measured"] = {"chain_steps_G_per_s": pk, "thread_inst_G_per_s": peaks_inst, "unit": "1e9 thread-level operations per second, whole GPU",
+                                      "nominal_fp32_fma_G_per_s": 148 * 128 * 1.965}
+        ex["terrain3d_pert_4096x64"]["issue"] = {"thread_inst_G_per_s": ach, "inst_per_voxel": inst_per_voxel,
+                                                 "frac_of_measured_fma_peak": ach / peaks_inst["fp32_fma"],
+                                                 "note": "all instructions of the kernel against the measured full-rate (FFMA) issue peak; INT32 logic / IMAD issue at half "
+                                                         "that rate on B200 (measured above), and ncu puts this kernel's ALU (INT) pipe at 80 % and its FMA pipe at 41 % busy: "
+                                                         "it is bound by INT32 issue"}
+    except Exception as e:  # noqa: BLE001
+        ex["issue_peaks_measured"] = {"error": str(e)}
     # config 4: LOD world, 2048^3 effective voxels at the finest level (dim 64, max_level 5) = 232 leaves
     props = world.WorldProperties(max_level=5, chunk_resolution=64, process_iters=2)
     lps, lv, mc = world.split_leaves(props)

@@ -23,7 +23,7 @@ EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
-           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads")
+           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue")
 
 
 class SamplerDesc(C.Structure):
@@ -101,6 +101,7 @@ def load_library(path=SO):
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
     lib.bmf_quads_to_tris.argtypes = [vp, vp, C.c_int64, vp]
     lib.bmf_batch_download_flat_quads.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.bmf_ubench_issue.argtypes = [vp, vp]
     lib.bmf_seam_overlap.argtypes = [C.c_int]
     lib.bmf_seam_overlap.restype = C.c_float
     lib.bmf_batch_stitch.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
@@ -279,6 +280,12 @@ class Context:
         p, n, c = (np.zeros((ni, 3), np.float32) for _ in range(3))
         self._check(self.lib.bmf_batch_download_flat_quads(self.h, int(smooth_normals), _p(p), _p(n), _p(c)))
         return p, n, c
+
+    def ubench_issue(self):
+        """measured issue peaks (1e9 chain steps/s): fp32 fma, int32 imad, int32 logic step, fma + logic step interleaved"""
+        g = np.zeros(4, np.float32)
+        self._check(self.lib.bmf_ubench_issue(self.h, _p(g)))
+        return {"fp32_fma": float(g[0]), "int32_imad": float(g[1]), "int32_logic_step": float(g[2]), "fma_plus_logic_step": float(g[3])}
 
     def seam_overlap(self, dim):
         """the overlap that puts a chunk's samples at its voxel-node centres (what the seam pass expects)"""

@@ -1188,6 +1188,43 @@ int bmf_batch_download_flat_quads(bmf_ctx* ctx, int smooth_normals, float* p_dat
 	return BMF_OK;
 }
 
+int bmf_ubench_issue(bmf_ctx* ctx, float* gops /* [4] */)
+{
+	if (!ctx || !gops) return BMF_ERR_INVALID;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	BMF_CUDA(ctx->qe.reserve(4));
+	cudaEvent_t a, b;
+	BMF_CUDA(cudaEventCreate(&a));
+	BMF_CUDA(cudaEventCreate(&b));
+	const int iters = 4096;
+	const unsigned grid = (unsigned)(ctx->sm_count * 8 * 4);
+	for (int op = 0; op < 4; op++)
+	{
+		float best = 0.0f;
+		for (int rep = 0; rep < 4; rep++)
+		{
+			cudaEventRecord(a, ctx->stream);
+			if (op == 0) BMF_LAUNCH(k_ubench_issue<0>, grid, CTA, 0, iters, 1.0001f, 12345, ctx->qe.p);
+			if (op == 1) BMF_LAUNCH(k_ubench_issue<1>, grid, CTA, 0, iters, 1.0001f, 12345, ctx->qe.p);
+			if (op == 2) BMF_LAUNCH(k_ubench_issue<2>, grid, CTA, 0, iters, 1.0001f, 12345, ctx->qe.p);
+			if (op == 3) BMF_LAUNCH(k_ubench_issue<3>, grid, CTA, 0, iters, 1.0001f, 12345, ctx->qe.p);
+			cudaEventRecord(b, ctx->stream);
+			BMF_CUDA(cudaEventSynchronize(b));
+			float ms = 0.0f;
+			cudaEventElapsedTime(&ms, a, b);
+			// thread-level operations per second: OP 2 is two instructions (LOP3 + IADD3/SHF...) per chain step as written; reported per
+			// chain step, the harness converts with the SASS instruction count per step
+			const double ops = (double)grid * CTA * (double)iters * 8.0 * (op == 3 ? 2.0 : 1.0);
+			const float g = (float)(ops / (ms * 1e-3) / 1e9);
+			if (rep > 0 && g > best) best = g;
+		}
+		gops[op] = best;
+	}
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	return BMF_OK;
+}
+
 float bmf_seam_overlap(int dim) { return dim > 0 ? -0.5f / (float)dim : 0.0f; }
 
 int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, int64_t* n_tris)

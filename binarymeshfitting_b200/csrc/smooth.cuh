@@ -661,4 +661,37 @@ __global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ 
 		qef_place_one(v, adj_off, adj, valence, boundary, dp, dn, pos, process_boundary);
 }
 
+// ---- issue-rate microbenchmarks (the noise and QEF stages are bound by FP32 / INT32 issue, so their
+// roofline denominators are MEASURED here, not nominal).  Eight independent dependency chains per thread, 2048
+// resident threads per SM, enough CTAs for four waves.  OP 0: FP32 FMA (FFMA), 1: INT32 multiply-add (IMAD),
+// 2: INT32 logic + add (LOP3 / IADD3 -- the hashing mix of the noise kernels), 3: FP32 FMA and INT32 logic interleaved.
+template <int OP>
+__global__ void __launch_bounds__(CTA) k_ubench_issue(int iters, float fseed, int iseed, float* __restrict__ sink)
+{
+	float f[8];
+	int g[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+	{
+		f[k] = fseed + (float)(threadIdx.x + k);
+		g[k] = iseed + (int)threadIdx.x * (k + 1);
+	}
+	const float fb = fseed * 0.5f + 0.25f, fc = fseed - 1.0f;
+	const int ib = iseed | 3, ic = iseed ^ 0x5bd1e995;
+	for (int i = 0; i < iters; i++)
+	{
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+		{
+			if (OP == 0 || OP == 3) f[k] = __fmaf_rn(f[k], fb, fc);
+			if (OP == 1) g[k] = g[k] * ib + ic;
+			if (OP == 2 || OP == 3) g[k] = ((g[k] ^ ic) & ib) + (g[k] >> 3);
+		}
+	}
+	float acc = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 8; k++) acc += f[k] + (float)g[k];
+	if (acc == 12345.678f) sink[0] = acc; // never true in practice: keeps the chains alive
+}
+
 } // namespace bmf

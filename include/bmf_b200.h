@@ -182,6 +182,10 @@ int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, co
  * quads: [n_quads*4] indices in, tris: [n_quads*6] out (host arrays). */
 int bmf_quads_to_tris(bmf_ctx* ctx, const uint32_t* quads, int64_t n_quads, uint32_t* tris);
 
+/* Measured issue-rate denominators for the FP32 / INT32 bound stages: chain steps per second, in 1e9, of
+ * [0] FP32 FMA, [1] INT32 multiply-add, [2] INT32 logic+shift+add step, [3] FMA and the INT32 step interleaved (both counted). */
+int bmf_ubench_issue(bmf_ctx* ctx, float* gops /* [4] */);
+
 /* GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335; DebugScene.cpp:286
  * with FLAT_QUADS) for the resident QUAD batch: per quad corner position / normal / colour, [n_inds][3] floats each; the
  * normal of a quad is the mean of its corner normals (smooth_normals) or the reference's two-triangle face normal.
