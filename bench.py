@@ -585,11 +585,13 @@ class RefPool:
     """All host cores: floor(cores/8) worker processes x 8 OpenMP threads (8 is the reference's hard limit:
     Sampler::noise_samplers[8] indexed by omp_get_thread_num(), Sampler.hpp:30 / DMCChunk.cpp:109)."""
 
-    def __init__(self, kind, dim, iters, ps):
+    def __init__(self, kind, dim, iters, ps, max_procs=None):
         import multiprocessing as mp
         cores = os.cpu_count() or 8
         self.threads = min(8, cores)
         self.nproc = max(1, cores // 8)
+        if max_procs:
+            self.nproc = min(self.nproc, max_procs)
         self.nproc = min(self.nproc, max(1, len(ps) // 8))
         ctxm = mp.get_context("spawn")
         self.conns, self.procs = [], []
@@ -646,7 +648,20 @@ def cpu_baseline(args, ps, overlap):
     cores = pool.cores
     tot = pool.close()
     nv = len(sample) * args.dim ** 3
-    return {"value": nv / best, "unit": "voxels/s", "cores": cores, "kind": "reference",
+    # the reference as shipped is limited to 8 OpenMP threads (noise_samplers[8]); report that number too
+    eight = None
+    if cores > 8:
+        p8 = RefPool(kind, args.dim, args.iters, sample, max_procs=1)
+        p8.step()
+        eight = nv / min(p8.step() for _ in range(2))
+        p8.close()
+    cpu_model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), "")
+    except OSError:
+        pass
+    return {"value": nv / best, "unit": "voxels/s", "cores": cores, "kind": "reference", "cpu_model": cpu_model, "value_8_threads": eight,
             "sample": "every %d-th chunk of the workload (%d chunks), 1 warm-up + best of 3, %d process(es) x %d OMP threads; noise = scalar restatement of FastNoiseSIMD" %
                       (stride, len(sample), pool.nproc, pool.threads),
             "ms": best * 1e3, "chunks_per_s": len(sample) / best, "mesh": {"chunks_with_mesh": tot[0], "verts": tot[1], "indices": tot[2]}}
