@@ -51,6 +51,12 @@ def test_sass_is_sm_100a_and_has_the_kernels():
     if r.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in r.stdout
+    r = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True)
+    names = r.stdout
+    for k in ("k_terrain2d_sheet", "k_terrain2d_bits", "k_terrain3d", "k_sample_implicit", "k_pack_density", "k_count", "k_scan_chunks", "k_bases", "k_verts3",
+              "k_inds3", "k_valence_offsets", "k_adj_fill", "k_smooth_chunks", "k_dual", "k_primal", "k_qef_batch", "k_qef_place",
+              "k_seam_layers", "k_seam_cull", "k_seam_classify", "k_seam_pass", "k_q_count", "k_q_bases", "k_q_emit", "k_format_unwind", "k_ubench_issue"):
+        assert k in names, k
 
 
 def test_no_cpu_fallback_without_a_device():
