@@ -91,3 +91,30 @@ def test_growing_batches_all_samplers(gpu):
             if n == 2 and first is None:
                 first = sig
         assert sig == first
+
+
+def test_cluster_smoothing_variant_is_bit_identical(gpu):
+    """BMF_SMOOTH_CLUSTER=1: the two-CTA-cluster (DSMEM) form of the fused smoothing kernel gives the same bits"""
+    import os
+    from binarymeshfitting_b200 import Context, capi, world
+    ps = world.grid_chunks(8, 16.0, origin=(-64.0, -48.0, -64.0))  # 512 chunks: enough for the fused path
+    descs = capi.make_chunk_descs(ps, overlaps=0.045)
+    gpu.set_sampler(capi.TERRAIN2D_PERT)
+    gpu.submit(descs, 64, iters=3)
+    gpu.wait()
+    want = gpu.download(want=("pos", "inds"))
+    os.environ["BMF_SMOOTH_CLUSTER"] = "1"
+    try:
+        ctx = Context(0)
+    finally:
+        del os.environ["BMF_SMOOTH_CLUSTER"]
+    ctx.set_sampler(capi.TERRAIN2D_PERT)
+    ctx.set_kernel_timing(True)
+    ctx.submit(descs, 64, iters=3)
+    ctx.wait()
+    assert any(name == "k_smooth_chunks2" for name, _ in ctx.kernel_times())
+    got = ctx.download(want=("pos", "inds"))
+    ctx.close()
+    assert len(want["pos"]) > 100000
+    np.testing.assert_array_equal(got["inds"], want["inds"])
+    np.testing.assert_array_equal(got["pos"].view(np.uint32), want["pos"].view(np.uint32))
