@@ -326,6 +326,11 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	{
 		// the whole optimize_dual_grid(iters) + optimize_primal_grid sequence, one CTA per chunk out of shared memory:
 		// iters dual steps interleaved with iters primal steps (the last primal is the driver's extra call)
+		// the in-loop primal step with set_colors (m == 3, or m == 0 when iters <= 3) turns the zero normals of the processed vertices into
+		// NaN in the reference (and in k_primal); nan_step = its half-step index, -1 if there is none
+		int nan_step = -1;
+		for (int m = 0; m < iters - 1 && nan_step < 0; m++)
+			if (m == 3 || (m == 0 && iters <= 3)) nan_step = 2 * m + 1;
 		if (ctx->smooth_cluster)
 		{
 			// two-CTA clusters: chunks too large for one SM's shared memory are split over a pair of SMs (DSMEM)
@@ -333,11 +338,11 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 			BMF_CUDA(cudaMemsetAsync(ctx->smooth_cnt.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
 			const unsigned grid = (unsigned)std::max(2, std::min(2 * ((n_chunks + 1) / 2), ctx->sm_count & ~1));
 			BMF_LAUNCH(k_smooth_chunks2, grid, SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p, valence, boundary, pos, ctx->dp.p,
-			           2 * iters, pb, tot, ctx->smooth_cnt.p, (unsigned)(ctx->smooth_smem / sizeof(float)));
+			           2 * iters, pb, tot, ctx->smooth_cnt.p, (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step);
 			return BMF_OK;
 		}
 		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->sm_count), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
-		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)));
+		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step);
 		return BMF_OK;
 	}
 

@@ -357,8 +357,11 @@ static constexpr int SMOOTH_CTA = 1024;
 
 __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off,
                                                    const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary,
-                                                   uint32_t V, uint32_t T, uint32_t prim0, int half_steps, int process_boundary)
+                                                   uint32_t V, uint32_t T, uint32_t prim0, int half_steps, int process_boundary, float* __restrict__ normal, int nan_step)
 {
+	// normal / nan_step: with smooth normals off the reference still "normalises" the zero normal of every processed vertex in
+	// the primal step that has set_colors (MeshProcessor.cpp:229-232, 296-303): normalize(0) = NaN and `n.y != 0` is true for a
+	// NaN, so v.n becomes NaN there and stays NaN.  nan_step is that half-step (or -1); the same expression as k_primal's.
 	// half-step h: even = dual (centroids of the primitives), odd = primal (vertex = mean of its adjacent centroids).
 	// The index / adjacency streams come from global memory: SMOOTH_U elements per thread are in flight at once, all
 	// their loads issued before the first use, so a half-step costs a few memory round trips, not one per element.
@@ -422,6 +425,7 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 						if (k < cnt[u]) p = add3(p, ld3(D, a[u][k] - prim0));
 					for (int k = KMAX; k < cnt[u]; k++) p = add3(p, ld3(D, adj[off[u] + k] - prim0));
 					st3(P, v0 + u * SMOOTH_CTA, div3(p, (float)cnt[u]));
+					if (h == nan_step) st3(normal, v0 + u * SMOOTH_CTA, normalize3({ 0.0f, 0.0f, 0.0f }));
 				}
 			}
 		}
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
                                                                    const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj,
                                                                    const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos,
                                                                    float* dp_global, int half_steps, int process_boundary, unsigned long long* tot,
-                                                                   unsigned int smem_floats)
+                                                                   unsigned int smem_floats, float* __restrict__ normal, int nan_step)
 {
 	extern __shared__ float sm_f[];
 	__shared__ int s_chunk;
@@ -462,15 +466,15 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
 			float* D = sm_f + 3 * (size_t)V;
 			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) P[i] = gp[i];
 			__syncthreads();
-			smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+			smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
 			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) gp[i] = P[i];
 			__syncthreads();
 		}
 		else if (3ull * T <= smem_floats)
 			// the dual points (the array the primal step gathers from) in shared memory, positions in place
-			smooth_chunk_steps(gp, sm_f, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+			smooth_chunk_steps(gp, sm_f, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
 		else
-			smooth_chunk_steps(gp, gd, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary);
+			smooth_chunk_steps(gp, gd, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
 	}
 }
 
@@ -501,7 +505,8 @@ struct SplitArray
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMOOTH_CTA, 1)
     k_smooth_chunks2(const ChunkCounts* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off,
                      const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos, float* dp_global,
-                     int half_steps, int process_boundary, const unsigned long long* __restrict__ tot, unsigned long long* __restrict__ cnt, unsigned int smem_floats)
+                     int half_steps, int process_boundary, const unsigned long long* __restrict__ tot, unsigned long long* __restrict__ cnt, unsigned int smem_floats,
+                     float* __restrict__ normal, int nan_step)
 {
 	namespace cg = cooperative_groups;
 	extern __shared__ float sm_f[];
@@ -558,6 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMOOTH_CTA, 1)
 						f3 p = { 0, 0, 0 };
 						for (int k = 0; k < n; k++) p = add3(p, ld3cg(gd, a[k] - prim0));
 						st3(gp, v, div3(p, (float)n));
+						if (h == nan_step) st3(normal + 3 * vb, v, normalize3({ 0.0f, 0.0f, 0.0f }));
 					}
 				__threadfence();
 				cluster.sync();
@@ -628,6 +634,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMOOTH_CTA, 1)
 							if (k < n[u]) p = add3(p, D.get(a[u][k] - prim0));
 						for (int k = KMAX; k < n[u]; k++) p = add3(p, D.get(adj[off[u] + k] - prim0));
 						P.put_local(v0 + u * SMOOTH_CTA, div3(p, (float)n[u]));
+						if (h == nan_step) st3(normal + 3 * vb, v0 + u * SMOOTH_CTA, normalize3({ 0.0f, 0.0f, 0.0f }));
 					}
 				}
 			}
@@ -655,7 +662,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMOOTH_CTA, 1)
 		float* D = sm_f + 3 * (size_t)V;
 		for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) P[i] = gp[i];
 		__syncthreads();
-		smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, (uint32_t)(ib / 3), half_steps, process_boundary);
+		smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, (uint32_t)(ib / 3), half_steps, process_boundary, normal + 3 * vb, nan_step);
 		for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) gp[i] = P[i];
 	}
 	cluster.sync(); // a CTA must not exit while its peer could still address its shared memory

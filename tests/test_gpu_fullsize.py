@@ -102,7 +102,28 @@ def test_cluster_smoothing_variant_is_bit_identical(gpu):
     gpu.set_sampler(capi.TERRAIN2D_PERT)
     gpu.submit(descs, 64, iters=3)
     gpu.wait()
-    want = gpu.download(want=("pos", "inds"))
+    want = gpu.download(want=("pos", "inds", "normal"))
+    # the per-step kernels (the reference's own structure) on the same batch: same positions AND the same normals, including
+    # the NaN the reference leaves in every processed vertex when iters is 2, 3 or >= 5 and smooth normals are off
+    os.environ["BMF_SMOOTH_FUSED"] = "0"
+    try:
+        ctx0 = Context(0)
+    finally:
+        del os.environ["BMF_SMOOTH_FUSED"]
+    ctx0.set_sampler(capi.TERRAIN2D_PERT)
+    for iters in (1, 2, 3, 4, 5):
+        ctx0.submit(descs, 64, iters=iters)
+        ctx0.wait()
+        a = ctx0.download(want=("pos", "normal"))
+        gpu.submit(descs, 64, iters=iters)
+        gpu.wait()
+        b = gpu.download(want=("pos", "normal"))
+        np.testing.assert_array_equal(a["pos"].view(np.uint32), b["pos"].view(np.uint32))
+        np.testing.assert_array_equal(a["normal"], b["normal"])
+        assert bool(np.isnan(b["normal"]).any()) == (iters in (2, 3, 5))
+    ctx0.close()
+    gpu.submit(descs, 64, iters=3)
+    gpu.wait()
     os.environ["BMF_SMOOTH_CLUSTER"] = "1"
     try:
         ctx = Context(0)
@@ -113,8 +134,65 @@ def test_cluster_smoothing_variant_is_bit_identical(gpu):
     ctx.submit(descs, 64, iters=3)
     ctx.wait()
     assert any(name == "k_smooth_chunks2" for name, _ in ctx.kernel_times())
-    got = ctx.download(want=("pos", "inds"))
+    got = ctx.download(want=("pos", "inds", "normal"))
     ctx.close()
     assert len(want["pos"]) > 100000
     np.testing.assert_array_equal(got["inds"], want["inds"])
     np.testing.assert_array_equal(got["pos"].view(np.uint32), want["pos"].view(np.uint32))
+    np.testing.assert_array_equal(got["normal"], want["normal"])
+
+
+def test_mode_switching_on_one_context_keeps_every_result_right(gpu):
+    """one context, many kinds of batches back to back (triangles / quads / seams / smoothing variants / host density): no state
+    of an earlier batch (colour fill, published chunk table, quad flags, arena contents) may leak into a later one"""
+    from oracle import oracle_binding as ob
+    orc = ob.Oracle()
+    ps = np.array([[x, y, z, 32.0] for x in (-32.0, 0.0) for y in (-32.0, 0.0) for z in (-32.0, 0.0)], np.float32)
+    rng = np.random.default_rng(3)
+    dens = rng.standard_normal((len(ps), 32 ** 3)).astype(np.float32)
+
+    def tri_check(kind, iters, sn=False, density=None, **kw):
+        gpu.set_sampler(kind, **kw)
+        gpu.submit(capi.make_chunk_descs(ps, overlaps=0.045), 32, iters=iters, smooth_normals=sn, density=density)
+        gpu.wait()
+        infos, out = gpu.chunk_infos(), gpu.download()
+        s = orc.sampler(kind, **kw)
+        for i, p in enumerate(ps):
+            o = orc.chunk(s, p[:3], p[3], 32, 0.045, iters=iters, smooth_normals=sn, host_density=None if density is None else density[i])
+            assert (int(infos[i]["n_verts"]), int(infos[i]["n_inds"])) == (o["n_verts"], o["n_inds"])
+            if o["n_verts"]:
+                v0, i0 = int(infos[i]["vert_offset"]), int(infos[i]["ind_offset"])
+                np.testing.assert_array_equal(out["inds"][i0:i0 + o["n_inds"]], o["inds"])
+                np.testing.assert_array_equal(out["pos"][v0:v0 + o["n_verts"]].view(np.uint32), o["pos"].view(np.uint32))
+                np.testing.assert_array_equal(out["color"][v0:v0 + o["n_verts"]].view(np.uint32), o["color"].view(np.uint32))
+                # NaN-aware: with smooth normals off the reference leaves normalize(0) = NaN in every processed vertex for some iteration counts
+                np.testing.assert_array_equal(out["normal"][v0:v0 + o["n_verts"]], o["normal"])
+
+    def quad_check(kind, iters):
+        gpu.set_sampler(kind)
+        gpu.submit(capi.make_chunk_descs(ps, overlaps=0.045), 32, iters=iters, quads=True)
+        gpu.wait()
+        infos, out = gpu.chunk_infos(), gpu.download()
+        s = orc.sampler(kind)
+        for i, p in enumerate(ps):
+            ch = orc.chunk(s, p[:3], p[3], 32, 0.045)
+            if not ch["contains_mesh"]:
+                continue
+            q = orc.quads(ch["density"], ch["bits"], 32)
+            nv, ni = q["n_verts"], q["n_inds"]
+            want = q["pos"]
+            if iters and nv and ni:
+                want, _, _ = orc.smooth(q["pos"], np.ones((nv, 3), np.float32), np.zeros((nv, 3), np.float32), q["boundary"], q["valence"], q["inds"], 4, iters, False, False)
+            v0, i0 = int(infos[i]["vert_offset"]), int(infos[i]["ind_offset"])
+            np.testing.assert_array_equal(out["inds"][i0:i0 + ni], q["inds"])
+            np.testing.assert_array_equal(out["pos"][v0:v0 + nv].view(np.uint32), np.ascontiguousarray(want, np.float32).view(np.uint32))
+
+    tri_check(capi.TERRAIN2D_PERT, 2)
+    quad_check(capi.TERRAIN2D_PERT, 2)
+    tri_check(capi.TERRAIN2D_PERT, 4, sn=True)
+    tri_check(capi.HOST_DENSITY, 1, density=dens)
+    quad_check(capi.SPHERE, 0)
+    tri_check(capi.TERRAIN3D_PERT, 2)
+    assert gpu.stitch(download=False) >= 0
+    tri_check(capi.TERRAIN2D_PERT, 2)
+    tri_check(capi.TORUS_Z, 0)
