@@ -86,6 +86,17 @@ def test_flat_quads_format(gpu, oracle, smooth):
         np.testing.assert_array_equal(n[i0:i0 + ni].view(np.uint32), wn.view(np.uint32))
 
 
+def test_quads_arena_growth_relaunch(oracle):
+    """a fresh context meets a small quad batch, then a much larger one: the emitters are re-launched after the arenas grow"""
+    from binarymeshfitting_b200 import Context
+    ctx = Context(0)
+    small = np.array([[x, y, z, 32.0] for x in (-32.0, 0.0) for y in (-32.0, 0.0) for z in (-32.0, 0.0)], np.float32)
+    big = np.array([[x, y, z, 32.0] for x in (-64.0, -32.0, 0.0, 32.0) for y in (-64.0, -32.0, 0.0, 32.0) for z in (-64.0, -32.0, 0.0, 32.0)], np.float32)
+    for ps in (small, big, small):
+        check_batch(ctx, oracle, ob.TERRAIN2D_PERT, ps, 32, iters=2, overlap=0.045)
+    ctx.close()
+
+
 def test_flush_to_tris(gpu):
     q = np.arange(40, dtype=np.uint32).reshape(-1, 4)
     t = gpu.quads_to_tris(q)
