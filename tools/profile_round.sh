@@ -15,5 +15,5 @@ ncu --metrics $M --clock-control none -s 60 -c 80 --csv --log-file $OUT/${TAG}_k
 for k in k_smooth_chunks k_inds3 k_bases k_adj_fill k_terrain2d_sheet k_terrain2d_bits k_count; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${TAG}_$k $B > $OUT/${TAG}_$k.out 2>&1
 done
-ncu --set full --clock-control none --import-source on -k regex:k_seam_pass -s 2 -c 1 -f -o $OUT/${TAG}_k_seam_pass python scratch/seam_probe.py > $OUT/${TAG}_k_seam_pass.out 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_seam_pass -s 2 -c 1 -f -o $OUT/${TAG}_k_seam_pass python tools/seam_probe.py > $OUT/${TAG}_k_seam_pass.out 2>&1
 ls -la $OUT | grep $TAG
