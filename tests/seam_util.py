@@ -26,7 +26,7 @@ def world_triangles(chunks, dim):
     return np.concatenate(out) if out else np.zeros((0, 3, 3))
 
 
-def edge_report(tris, eps):
+def edge_report(tris, eps, return_open=False):
     """weld corners closer than eps, drop collapsed triangles, count how often every directed edge is matched by its
     opposite.  Returns (n_triangles_kept, n_unmatched_directed_edges, n_nonmanifold_edges)."""
     pts = np.asarray(tris, np.float64).reshape(-1, 3)
@@ -55,4 +55,11 @@ def edge_report(tris, eps):
         fwd[(a, b)] = fwd.get((a, b), 0) + 1
     unmatched = sum(abs(c - fwd.get((b, a), 0)) for (a, b), c in fwd.items() if a < b or (b, a) not in fwd)
     nonmanifold = sum(1 for (a, b), c in fwd.items() if c > 1)
+    if return_open:
+        # positions of the end points of every directed edge without an opposite
+        rep = {}
+        for i, r in enumerate(np.array([find(i) for i in range(len(pts))])):
+            rep.setdefault(int(r), pts[i])
+        open_pts = [rep[int(a)] for (a, b), c in fwd.items() if fwd.get((b, a), 0) != c] + [rep[int(b)] for (a, b), c in fwd.items() if fwd.get((b, a), 0) != c]
+        return int(keep.sum()), int(unmatched), int(nonmanifold), np.array(open_pts, np.float64).reshape(-1, 3)
     return int(keep.sum()), int(unmatched), int(nonmanifold)

@@ -46,6 +46,28 @@ def test_seam_closes_the_world(oracle, name, max_level, focus, kind, ws):
         assert len(np.unique(lv)) > 1               # the world really has LOD changes
 
 
+def test_terrain_seams_leave_open_edges_only_at_the_world_border(oracle):
+    """a heightfield never closes: after the seam pass the only open edges of a noise-terrain LOD world are where the surface
+    leaves the world (or runs along its outermost voxel layer), nowhere between chunks"""
+    ps, lv, mc = su.lod_world(3, 1, (40.0, -10.0, 25.0), DIM)
+    ov = su.seam_overlap(DIM)
+    s = oracle.sampler(ob.TERRAIN2D_PERT)
+    chunks = [oracle.chunk(s, p[:3], p[3], DIM, ov) for p in ps]
+    seam = oracle.seam(chunks, ps, DIM, ov)
+    ct = su.world_triangles(chunks, DIM)
+    assert len(seam) > 0 and len(np.unique(lv)) > 1
+    coarse_voxel = float(ps[:, 3].max()) / DIM
+    eps = 1e-3 * float(ps[:, 3].min()) / DIM
+    _, open_before, _, pts_before = su.edge_report(ct, eps, return_open=True)
+    _, open_after, nonmanifold, pts = su.edge_report(np.concatenate([ct, seam.astype(np.float64)]), eps, return_open=True)
+    assert open_after < open_before and nonmanifold == 0
+    lo, hi = ps[:, :3].min(axis=0).astype(np.float64), (ps[:, :3] + ps[:, 3:4]).max(axis=0).astype(np.float64)
+    dist_to_border = np.minimum(pts - lo, hi - pts).min(axis=1)
+    assert dist_to_border.max() <= 1.01 * coarse_voxel  # every open edge hugs the outside of the world
+    inner_before = (np.minimum(pts_before - lo, hi - pts_before).min(axis=1) > 1.01 * coarse_voxel).sum()
+    assert inner_before > 0  # while the chunk meshes alone are open all over the interior
+
+
 def test_group_passes_partition_the_seam(oracle):
     name, max_level, focus, kind, ws = WORLDS[1]
     ps, lv, mc, ov, chunks = build(oracle, max_level, focus, kind, ws)
