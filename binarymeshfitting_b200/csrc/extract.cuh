@@ -1032,31 +1032,33 @@ __global__ void __launch_bounds__(CTA) k_valence_offsets(const uint32_t* __restr
 	if (cc.n_verts == 0) return;
 	const size_t v0 = (size_t)cc.vert_base;
 	uint32_t carry = (uint32_t)cc.ind_base;
+	// a tile is VAL_ITEMS rows of CTA consecutive vertices; thread t holds vertex t of every row, so that every load and store of
+	// a warp is one contiguous run (a thread-contiguous layout made every byte store of a warp touch 8 different sectors)
 	for (uint32_t base = 0; base < cc.n_verts; base += CTA * VAL_ITEMS)
 	{
-		const uint32_t i0 = base + threadIdx.x * VAL_ITEMS;
-		uint32_t val[VAL_ITEMS], sum = 0;
+		uint32_t val[VAL_ITEMS], sc[VAL_ITEMS], rt[VAL_ITEMS];
 #pragma unroll
 		for (int k = 0; k < VAL_ITEMS; k++)
 		{
-			uint32_t w = (i0 + k < cc.n_verts) ? cls[v0 + i0 + k] : 0u;
+			const uint32_t i = base + k * CTA + threadIdx.x;
+			const uint32_t w = i < cc.n_verts ? cls[v0 + i] : 0u;
 			val[k] = (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
-			sum += val[k];
+			sc[k] = val[k];
 		}
-		uint32_t sc[1] = { sum }, tot[1];
-		block_scan<1>(sc, tot);
-		uint32_t run = carry + sc[0];
+		block_scan<VAL_ITEMS>(sc, rt); // per row: exclusive prefix over the threads, row total
+		uint32_t run = carry;
 #pragma unroll
 		for (int k = 0; k < VAL_ITEMS; k++)
 		{
-			if (i0 + k < cc.n_verts)
+			const uint32_t i = base + k * CTA + threadIdx.x;
+			if (i < cc.n_verts)
 			{
-				valence[v0 + i0 + k] = (uint8_t)val[k];
-				adj_off[v0 + i0 + k] = run;
+				valence[v0 + i] = (uint8_t)val[k];
+				adj_off[v0 + i] = run + sc[k];
 			}
-			run += val[k];
+			run += rt[k];
 		}
-		carry += tot[0];
+		carry = run;
 	}
 }
 
