@@ -832,7 +832,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		{
 			// no density block wanted: chunks entirely above / below the surface are classified from the sheet range and
 			// skipped; the rest get compare-only sign words (binary search + warp bit transpose, no per-voxel arithmetic)
-			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p, ctx->uni_pinned);
+			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p);
 			BMF_LAUNCH(k_terrain2d_bits, (unsigned)((size_t)n * L.d * L.zc * L.zc / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
 			           ctx->uni.p, ctx->bits.p, ctx->flags.p);
 			ctx->uni_valid = true;
@@ -986,7 +986,13 @@ int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* ind
 	const Layout& L = ctx->L;
 	const size_t nvox = (size_t)L.d * L.d * L.d;
 	cudaStream_t st = ctx->stream;
-	const uint8_t uniform = ctx->uni_valid ? ctx->uni_pinned[i] : 0; // chunk skipped by the 2-D terrain classifier: all ones (1) / all zeros (2)
+	uint8_t uniform = 0; // chunk skipped by the 2-D terrain classifier: all ones (1) / all zeros (2); fetched on demand (this is the only host use)
+	if (ctx->uni_valid)
+	{
+		BMF_CUDA(cudaMemcpyAsync(ctx->uni_pinned, ctx->uni.p + i, 1, cudaMemcpyDeviceToHost, ctx->stream));
+		BMF_CUDA(cudaStreamSynchronize(ctx->stream));
+		uniform = ctx->uni_pinned[0];
+	}
 	if (bits && uniform) memset(bits, uniform == 1 ? 0xFF : 0x00, sizeof(uint32_t) * L.wc);
 	else if (bits) BMF_CUDA(cudaMemcpyAsync(bits, ctx->bits.p + (size_t)i * L.wc, sizeof(uint32_t) * L.wc, cudaMemcpyDeviceToHost, st));
 	if (masks)

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 // (bmf_batch_copy_chunk synthesises them on request).  uni: 0 = mixed, 1 = all air (ones), 2 = all solid (zeros).
 __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, const int* __restrict__ sheet_of,
                                                              const uint32_t* __restrict__ sheet_mm, int n_sheets, int n_chunks, uint32_t* __restrict__ flags,
-                                                             uint8_t* __restrict__ uni, uint8_t* __restrict__ uni_host /* mapped pinned host copy */)
+                                                             uint8_t* __restrict__ uni)
 {
 	const int c = blockIdx.x * CTA + threadIdx.x;
 	if (c >= n_chunks) return;
@@ -241,7 +241,6 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const 
 		else if (!(bot < tmax)) u = 2;
 	}
 	uni[c] = u;
-	uni_host[c] = u;
 	if (u) flags[c] = (u == 1) ? CF_ONES : CF_ZERO;
 }
 
