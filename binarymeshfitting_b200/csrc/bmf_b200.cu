@@ -444,11 +444,13 @@ int launch_mesh(bmf_ctx* ctx)
 	// totals and the chunk table reach the host through mapped pinned memory written by the kernels themselves (UVA):
 	// no D2H transfer sits in this stream, so nothing here can queue behind another context's mesh download
 	{
-		// + the chunk table for the host (once per batch), in the same launch
-		const size_t words = ctx->counts_published ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
+		// + the chunk table for the host (once per batch), in the same launch -- unless k_valence_offsets (one CTA per chunk, triangle
+		// path with allocated arenas) will hand it over for free further down
+		const bool later = !ctx->counts_published && !params->quads && caps.cells && caps.verts && caps.inds;
+		const size_t words = (ctx->counts_published || later) ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
 		BMF_LAUNCH(k_check_caps, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells,
 		           (unsigned long long)caps.verts, (unsigned long long)caps.inds, reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
-		ctx->counts_published = true;
+		if (!later) ctx->counts_published = true;
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
@@ -502,7 +504,9 @@ int launch_mesh(bmf_ctx* ctx)
 		ctx->color_ones = ctx->color.cap;
 	}
 	BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p, tot);
-	BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p, tot);
+	BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p, tot,
+	           ctx->counts_published ? nullptr : reinterpret_cast<uint32_t*>(ctx->counts_pinned));
+	ctx->counts_published = true;
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 
 	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it

@@ -1024,8 +1024,13 @@ __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict
 static constexpr int VAL_ITEMS = 8; // (32 items per thread was measured slower: 64 us against 38 us)
 
 __global__ void __launch_bounds__(CTA) k_valence_offsets(const uint32_t* __restrict__ cls, const ChunkCounts* __restrict__ chunks, uint8_t* __restrict__ valence,
-                                                          uint32_t* __restrict__ adj_off, const unsigned long long* __restrict__ tot)
+                                                          uint32_t* __restrict__ adj_off, const unsigned long long* __restrict__ tot,
+                                                          uint32_t* __restrict__ host_table /* mapped pinned copy of the chunk table, or null */)
 {
+	// one CTA per chunk: the natural place to hand the chunk's table record to the host (posted PCIe writes, nobody waits for them)
+	constexpr int REC = (int)(sizeof(ChunkCounts) / sizeof(uint32_t));
+	if (host_table && threadIdx.x < REC)
+		host_table[(size_t)blockIdx.x * REC + threadIdx.x] = reinterpret_cast<const uint32_t*>(chunks)[(size_t)blockIdx.x * REC + threadIdx.x];
 	if (tot[7]) return;
 	const ChunkCounts cc = chunks[blockIdx.x];
 	if (cc.n_verts == 0) return;
