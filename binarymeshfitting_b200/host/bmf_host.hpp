@@ -35,6 +35,7 @@
 #include <cstring>
 #include <functional>
 #include <algorithm>
+#include <array>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -696,6 +697,96 @@ public:
 	bool stitch_batch_nodes(WorldOctree* world, WorldOctreeNode* const* nodes, size_t count, int device_slot = 0, int device_id = 0)
 	{
 		vertices.count = 0;
+		std::vector<float> tris;
+		if (!seam_pass(world, nodes, count, nullptr, false, device_slot, device_id, tris, last_ms)) return false;
+		return append_soup(tris);
+	}
+
+	// Several GPUs ("a final host gather ... and a WorldStitcher seam pass"): the leaves are dealt to the
+	// devices in contiguous Morton-ordered ranges like ChunkGenerator::process_queue does; every device stitches the dual
+	// cells that lie inside its own chunks (one host thread per device), then the first device stitches the cells that span
+	// devices from the border chunks only (group ids + cross_group_only).  Chunks are pure functions of their descriptors, so
+	// that device re-samples the border chunks instead of receiving them: no collective.  The union of the passes is exactly
+	// the single-device seam (as a set of triangles; the order is per device, then the cross pass).
+	bool stitch_all(WorldOctree* world, const std::vector<int>& devices)
+	{
+		vertices.count = 0;
+		if (!world || world->leaves.empty()) return true;
+		const int n_dev = (int)devices.size();
+		if (n_dev <= 1) return stitch_all(world, 0, devices.empty() ? 0 : devices[0]);
+		const std::vector<WorldOctreeNode*>& leaves = world->leaves;
+		const size_t n = leaves.size();
+		std::vector<int> order(n);
+		for (size_t i = 0; i < n; i++) order[i] = (int)i;
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return leaves[a]->morton_code < leaves[b]->morton_code; });
+		std::vector<int32_t> group(n, 0);
+		for (int k = 0; k < n_dev; k++)
+			for (size_t q = n * k / n_dev; q < n * (k + 1) / n_dev; q++) group[order[q]] = k;
+		std::vector<std::vector<WorldOctreeNode*>> part(n_dev);
+		for (size_t i = 0; i < n; i++) part[group[i]].push_back(leaves[i]); // batch order inside a part
+		std::vector<std::vector<float>> soup(n_dev + 1);
+		std::vector<char> ok(n_dev, 1);
+		std::vector<std::thread> th;
+		for (int k = 0; k < n_dev; k++)
+			th.emplace_back([&, k] {
+				float ms[2];
+				ok[k] = part[k].empty() ? 1 : (seam_pass(world, part[k].data(), part[k].size(), nullptr, false, k, devices[k], soup[k], ms) ? 1 : 0);
+			});
+		for (std::thread& t : th) t.join();
+		for (char r : ok)
+			if (!r) return false;
+		// border chunks: those that touch (face, edge or corner) a chunk of another group
+		std::vector<WorldOctreeNode*> border;
+		std::vector<int32_t> border_group;
+		{
+			float smin = leaves[0]->size, org[3] = { leaves[0]->pos.x, leaves[0]->pos.y, leaves[0]->pos.z };
+			for (const WorldOctreeNode* l : leaves)
+			{
+				smin = std::min(smin, l->size);
+				org[0] = std::min(org[0], l->pos.x); org[1] = std::min(org[1], l->pos.y); org[2] = std::min(org[2], l->pos.z);
+			}
+			std::vector<std::array<long long, 4>> lat(n); // origin (slots), extent
+			long long G[3] = { 0, 0, 0 };
+			for (size_t i = 0; i < n; i++)
+			{
+				const WorldOctreeNode* l = leaves[i];
+				const long long e = std::llround((double)l->size / smin);
+				lat[i] = { std::llround(((double)l->pos.x - org[0]) / smin), std::llround(((double)l->pos.y - org[1]) / smin), std::llround(((double)l->pos.z - org[2]) / smin), e };
+				for (int a = 0; a < 3; a++) G[a] = std::max(G[a], lat[i][a] + e);
+			}
+			std::vector<int32_t> grid((size_t)(G[0] * G[1] * G[2]), -1);
+			for (size_t i = 0; i < n; i++)
+				for (long long x = lat[i][0]; x < lat[i][0] + lat[i][3]; x++)
+					for (long long y = lat[i][1]; y < lat[i][1] + lat[i][3]; y++)
+						for (long long z = lat[i][2]; z < lat[i][2] + lat[i][3]; z++) grid[(size_t)((x * G[1] + y) * G[2] + z)] = group[i];
+			for (size_t i = 0; i < n; i++)
+			{
+				bool touches = false;
+				for (long long x = std::max(0LL, lat[i][0] - 1); x < std::min(G[0], lat[i][0] + lat[i][3] + 1) && !touches; x++)
+					for (long long y = std::max(0LL, lat[i][1] - 1); y < std::min(G[1], lat[i][1] + lat[i][3] + 1) && !touches; y++)
+						for (long long z = std::max(0LL, lat[i][2] - 1); z < std::min(G[2], lat[i][2] + lat[i][3] + 1) && !touches; z++)
+						{
+							const int32_t g = grid[(size_t)((x * G[1] + y) * G[2] + z)];
+							touches = g >= 0 && g != group[i];
+						}
+				if (touches)
+				{
+					border.push_back(leaves[i]);
+					border_group.push_back(group[i]);
+				}
+			}
+		}
+		if (!border.empty() && !seam_pass(world, border.data(), border.size(), border_group.data(), true, 0, devices[0], soup[n_dev], last_ms)) return false;
+		for (const std::vector<float>& t : soup)
+			if (!append_soup(t)) return false;
+		return true;
+	}
+
+private:
+	// one device: submit the nodes at voxel-node centres (signs and border samples only) and run the seam pass
+	static bool seam_pass(WorldOctree* world, WorldOctreeNode* const* nodes, size_t count, const int32_t* group, bool cross_only, int device_slot, int device_id,
+	                      std::vector<float>& tris, float ms[2])
+	{
 		BmfDevice& dev = BmfDevice::slot(device_slot, device_id);
 		if (!dev.ok()) return false;
 		std::vector<bmf_chunk_desc> descs(count);
@@ -721,15 +812,22 @@ public:
 		p.dim = dim; // signs and border samples only: no smoothing
 		if (bmf_batch_submit(dev.ctx, descs.data(), (int)count, &p, nullptr) != BMF_OK) return false;
 		int64_t nt = 0;
-		if (bmf_batch_stitch(dev.ctx, nullptr, 0, &nt) != BMF_OK) return false;
-		bmf_seam_stage_ms(dev.ctx, last_ms);
-		std::vector<float> tris(9 * (size_t)nt + 9);
-		if (bmf_seam_download(dev.ctx, tris.data()) != BMF_OK) return false;
-		if (!vertices.prepare(3 * (size_t)nt)) return false;
-		vertices.count = 3 * (size_t)nt;
-		for (size_t v = 0; v < 3 * (size_t)nt; v++)
+		if (bmf_batch_stitch(dev.ctx, group, cross_only ? 1 : 0, &nt) != BMF_OK) return false;
+		bmf_seam_stage_ms(dev.ctx, ms);
+		tris.assign(9 * (size_t)nt, 0.0f);
+		if (nt && bmf_seam_download(dev.ctx, tris.data()) != BMF_OK) return false;
+		return true;
+	}
+
+	bool append_soup(const std::vector<float>& tris)
+	{
+		const size_t nv = tris.size() / 3, v0 = vertices.count;
+		if (!nv) return true;
+		if (!vertices.prepare(nv)) return false;
+		vertices.count = v0 + nv;
+		for (size_t v = 0; v < nv; v++)
 		{
-			DualVertex& dv = vertices[v];
+			DualVertex& dv = vertices[(int)(v0 + v)];
 			std::memset((void*)&dv, 0, sizeof(dv));
 			dv.p = glm::vec3(tris[3 * v], tris[3 * v + 1], tris[3 * v + 2]);
 			dv.color = glm::vec3(0.85f, 1.0f, 0.85f); // DUAL_VERTEX (WorldStitcher.cpp:484-487)
@@ -737,6 +835,7 @@ public:
 		return true;
 	}
 
+public:
 	// GLChunk::format_data_tris(vertices): positions and colours of the soup, flat
 	void format()
 	{

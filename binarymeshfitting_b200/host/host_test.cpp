@@ -201,7 +201,11 @@ int main(int argc, char** argv)
 			n->generation_stage = GENERATION_STAGES_GENERATING;
 			batch.push_back(n);
 		}
-		if (!gen.process_queue(batch) || !gen.stitcher.stitch_all(&world))
+		// optional 9th argument: device list for the multi-GPU seam scheme, e.g. 0,0 (two contexts on GPU 0)
+		std::vector<int> sdevs;
+		if (argc >= 9)
+			for (char* tok = strtok(argv[8], ","); tok; tok = strtok(nullptr, ",")) sdevs.push_back(atoi(tok));
+		if (!gen.process_queue(batch) || !(sdevs.empty() ? gen.stitcher.stitch_all(&world) : gen.stitcher.stitch_all(&world, sdevs)))
 		{
 			fprintf(stderr, "stitch failed: %s\n", BmfDevice::get().error());
 			return 5;
@@ -211,7 +215,10 @@ int main(int argc, char** argv)
 		for (WorldOctreeNode* n : world.leaves)
 			if (n->chunk->contains_mesh && n->chunk->vi) { nv += n->chunk->vi->vertices.count; ni += n->chunk->vi->mesh_indexes.count; }
 		const uint32_t hp = crc32_of(gen.stitcher.gl_chunk.p_data.elements, gen.stitcher.gl_chunk.p_data.count * 12, 0);
-		printf("stitch chunks=%zu verts=%zu inds=%zu seam_verts=%zu seam_crc=%u color_g=%g\n", world.leaves.size(), nv, ni, gen.stitcher.vertices.count, hp,
+		// order-independent checksum over the triangles (the multi-device scheme emits them in another order)
+		unsigned long long tsum = 0;
+		for (size_t t = 0; t + 2 < gen.stitcher.gl_chunk.p_data.count; t += 3) tsum += crc32_of(gen.stitcher.gl_chunk.p_data.elements + t, 36, 0);
+		printf("stitch chunks=%zu verts=%zu inds=%zu seam_verts=%zu seam_crc=%u tri_sum=%llu color_g=%g\n", world.leaves.size(), nv, ni, gen.stitcher.vertices.count, hp, tsum,
 		       gen.stitcher.vertices.count ? (double)gen.stitcher.vertices[0].color.y : 0.0);
 		return 0;
 	}

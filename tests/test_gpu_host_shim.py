@@ -113,6 +113,12 @@ def test_worldstitcher_mirror_closes_a_lod_world(oracle):
     assert (int(out["verts"]), int(out["inds"])) == (sum(c["n_verts"] for c in chunks), sum(c["n_inds"] for c in chunks))
     assert int(out["seam_verts"]) == 3 * len(seam) and int(out["seam_crc"]) == crc(seam)
     assert abs(float(out["color_g"]) - 1.0) < 1e-6
+    tri_sum = sum(zlib.crc32(t.tobytes()) & 0xFFFFFFFF for t in np.ascontiguousarray(seam, np.float32))
+    assert int(out["tri_sum"]) == tri_sum
+    # the multi-GPU scheme (here: several contexts on GPU 0): per-device seams + one cross-device pass over the border chunks
+    for devices in ("0,0", "0,0,0"):
+        multi = run("stitch", ob.TORUS_Z, dim, max_level, *focus, devices)["stitch"]
+        assert int(multi["seam_verts"]) == 3 * len(seam) and int(multi["tri_sum"]) == tri_sum
 
 
 def test_worldwatcher_mirror_follows_a_moving_focus(oracle):
