@@ -996,12 +996,21 @@ public:
 	std::vector<WorldOctreeNode*> renderables; // the reference's linked list, in link order
 	size_t last_generated = 0;
 
-	void init(WorldOctree* w, const glm::vec3& focus)
+	// from_root = true: like WorldWatcher::init (WorldWatcher.cpp:21-31) only the root is drawable and the ticks build the
+	// world (the sequence of batches and the final list then equal the reference's, tests/golden/watcher_golden.json);
+	// false: start from the leaves of a previous WorldOctree::split_leaves
+	void init(WorldOctree* w, const glm::vec3& focus, bool from_root = false)
 	{
 		world = w;
 		focus_pos = focus;
 		generator.init(w);
-		renderables = w->leaves;
+		if (from_root)
+		{
+			renderables.clear();
+			renderables.push_back(&w->octree);
+		}
+		else
+			renderables = w->leaves;
 	}
 
 	// returns false if the generator failed; last_generated = chunks handed to process_queue in this tick

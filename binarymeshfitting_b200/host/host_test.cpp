@@ -222,6 +222,37 @@ int main(int argc, char** argv)
 		       gen.stitcher.vertices.count ? (double)gen.stitcher.vertices[0].color.y : 0.0);
 		return 0;
 	}
+	if (!strcmp(argv[1], "watch") && argc >= 6)
+	{
+		// the reference's own start: only the root is drawable; one tick per focus point read from a file ("x y z" per line)
+		int kind = atoi(argv[2]), dim = atoi(argv[3]), max_level = atoi(argv[4]);
+		WorldOctree world;
+		world.sampler = make_sampler(kind);
+		world.properties.chunk_resolution = dim;
+		world.properties.max_level = max_level;
+		world.init(256);
+		WorldWatcher watcher;
+		watcher.init(&world, glm::vec3(0, 0, 0), true);
+		FILE* f = fopen(argv[5], "r");
+		if (!f) return 4;
+		float x, y, z;
+		printf("watch gens=");
+		while (fscanf(f, "%f %f %f", &x, &y, &z) == 3)
+		{
+			watcher.focus_pos = glm::vec3(x, y, z);
+			if (!watcher.update()) return 5;
+			printf("%zu,", watcher.last_generated);
+		}
+		fclose(f);
+		uint32_t hc = 0;
+		for (WorldOctreeNode* n : watcher.renderables)
+		{
+			unsigned long long code = n->morton_code;
+			hc = crc32_of(&code, sizeof(code), hc);
+		}
+		printf(" leaves=%zu codes_crc=%u\n", watcher.renderables.size(), hc);
+		return 0;
+	}
 	if (!strcmp(argv[1], "fly") && argc >= 9)
 	{
 		// WorldWatcher ticks while the focus moves from the origin to (fx, fy, fz) in `steps` equal steps, then until quiescent

@@ -171,12 +171,17 @@ class LodWatcher:
     groups, applies them, and returns the nodes that have to be generated (8 children per split, the parent per group) --
     the batch WorldWatcher::update hands to ChunkGenerator::process_queue."""
 
-    def __init__(self, props, world_size=256, focus=(0.0, 0.0, 0.0), group_multiplier=2.0):
+    def __init__(self, props, world_size=256, focus=(0.0, 0.0, 0.0), group_multiplier=2.0, start="static"):
+        """start = "static": the renderables are the leaves of WorldOctree::split_leaves for `focus`; start = "root": only the
+        root is drawable, like right after WorldWatcher::init (WorldWatcher.cpp:21-31) -- the ticks then build the world."""
         self.props, self.group_multiplier = props, group_multiplier
         size = F(world_size * 2)
         p = F(1) * size * F(-0.5)
         self.root = _Node((p, p, p), size, 0, 1, None)
         self.renderables = []
+        if start == "root":
+            self.renderables.append(self.root)
+            return
         stack = [self.root]  # WorldOctree::split_leaves order (LIFO)
         while stack:
             n = stack.pop()

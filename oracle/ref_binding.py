@@ -53,6 +53,7 @@ class RefLib:
         lib.ref_world_create.restype = C.c_void_p
         lib.ref_world_create.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ref_world_split_leaves.argtypes = [C.c_void_p]
+        lib.ref_watcher_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         lib.ref_world_add_chunks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.ref_world_count.argtypes = [C.c_void_p]
         lib.ref_world_leaf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -143,6 +144,16 @@ class RefLib:
 class RefWorld:
     def __init__(self, ref, handle, dim):
         self.ref, self.h, self.dim = ref, handle, dim
+
+    def watcher_run(self, focus_per_tick, cap=1 << 16):
+        """WorldWatcher ticks (check_leaves -> process_batch -> process_queue -> post_process_batch) from the root, one focus
+        point per tick -> (Morton codes of the renderables in link order, chunks generated per tick)"""
+        f = np.ascontiguousarray(focus_per_tick, np.float32).reshape(-1, 3)
+        codes = np.zeros(cap, np.uint64)
+        gen = np.zeros(len(f), np.int32)
+        n = self.ref.lib.ref_watcher_run(self.h, _fp(f), len(f), _fp(codes), cap, _fp(gen))
+        assert n <= cap
+        return codes[:n].copy(), gen
 
     def split_leaves(self):
         return self.ref.lib.ref_world_split_leaves(self.h)

@@ -5,6 +5,25 @@
 // classes exactly like ChunkGenerator::extract_chunk (ChunkGenerator.cpp:80-147) does and copies
 // their public fields out.
 #include "PCH.h"
+// the watcher's tick functions (check_leaves / process_batch / post_process_batch) are private members; this driver only
+// CALLS them, in the order WorldWatcher::update does (g++ does not reorder members across access specifiers)
+#include <atomic>
+#include <condition_variable>
+#include <list>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include "ThreadDebug.hpp"
+#include "SmartContainer.hpp"
+#include "ChunkGenerator.hpp"
+#include "WorldOctreeNode.hpp"
+#include "HashMap.hpp"
+#include "sparsepp/spp.h"
+#define private public
+#include "WorldWatcher.hpp"
+#undef private
 #include "WorldOctree.hpp"
 #include "ImplicitSampler.hpp"
 #include "NoiseSampler.hpp"
@@ -329,6 +348,39 @@ int ref_world_split_leaves(void* h)
 		rb->batch.push_back(n);
 	}
 	return (int)rb->batch.count;
+}
+
+// The watcher's tick without its thread: WorldWatcher::init minus std::thread (:21-31), then per tick the body of
+// WorldWatcher::update (:56-112): check_leaves(dirty, 400) -> process_batch -> generator.process_queue -> post_process_batch.
+// focus: [ticks][3]; codes_out: up to cap Morton codes of the renderables list (link order) after the last tick;
+// gen_counts: chunks handed to the generator per tick.  Returns the number of renderables.
+int ref_watcher_run(void* h, const float* focus, int ticks, uint64_t* codes_out, int cap, int* gen_counts)
+{
+	CoutSilencer quiet;
+	RefBatch* rb = (RefBatch*)h;
+	WorldWatcher& w = rb->world->watcher;
+	w.world = rb->world;
+	w.renderables_head = &rb->world->octree;
+	w.renderables_tail = &rb->world->octree;
+	w.renderables_count = 1;
+	SmartContainer<WorldOctreeNode*> dirty, generate, stitch;
+	for (int t = 0; t < ticks; t++)
+	{
+		w.focus_pos = glm::vec3(focus[3 * t], focus[3 * t + 1], focus[3 * t + 2]);
+		dirty.count = 0; generate.count = 0; stitch.count = 0;
+		w.check_leaves(dirty, 400);
+		w.process_batch(dirty, generate, stitch);
+		if (generate.count) w.generator.process_queue(generate);
+		w.post_process_batch(dirty);
+		if (gen_counts) gen_counts[t] = (int)generate.count;
+	}
+	int n = 0;
+	for (WorldOctreeNode* r = w.renderables_head; r; r = r->renderable_next)
+	{
+		if (n < cap) codes_out[n] = r->morton_code.code;
+		n++;
+	}
+	return n;
 }
 
 // Explicit chunk list (config 3): nodes made by hand, chunks by WorldOctree::create_chunk via process_queue.

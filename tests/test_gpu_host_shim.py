@@ -142,3 +142,17 @@ def test_worldwatcher_mirror_follows_a_moving_focus(oracle):
     assert int(out["codes_crc"]) == crc(mc.astype("<u8"))
     total, counts = oracle.batch(oracle.sampler(ob.SPHERE), ps, dim, overlaps=[W.chunk_overlap(props, int(l)) for l in lv])
     assert (int(out["verts"]), int(out["inds"])) == (int(counts[:, 0].sum()), int(counts[:, 1].sum()))
+
+
+WATCHER_GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "watcher_golden.json")))
+
+
+@pytest.mark.parametrize("g", WATCHER_GOLD[:3], ids=lambda g: g["name"])
+def test_worldwatcher_mirror_matches_the_reference_watcher(tmp_path, g):
+    """C++ WorldWatcher mirror started from the root, one tick per focus point: the batches and the final renderables list of
+    the compiled reference's watcher (golden vectors, tests/golden/make_watcher_golden.py)"""
+    f = tmp_path / "path.txt"
+    f.write_text("".join("%r %r %r\n" % tuple(p) for p in g["path"]))
+    out = run("watch", ob.SPHERE, 32, g["max_level"], f)["watch"]
+    assert [int(v) for v in out["gens"].strip(",").split(",")] == g["generated_per_tick"]
+    assert int(out["leaves"]) == g["renderables"] and int(out["codes_crc"]) == g["codes_crc"]

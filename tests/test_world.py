@@ -144,3 +144,21 @@ def test_incremental_watcher_policy():
     while w2.tick(focus):
         pass
     assert np.array_equal(w2.leaves()[2], lmc)
+
+
+WATCHER_GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "watcher_golden.json")))
+
+
+@pytest.mark.parametrize("g", WATCHER_GOLD, ids=lambda g: g["name"])
+def test_incremental_policy_matches_the_reference_watcher(g):
+    """LodWatcher, started from the root like WorldWatcher::init, against golden vectors generated from the compiled
+    reference's own check_leaves / process_batch / post_process_batch (tests/golden/make_watcher_golden.py): the same
+    number of chunks generated in every tick and the same renderables list, in link order, at the end"""
+    import zlib
+    props = W.WorldProperties(max_level=g["max_level"], chunk_resolution=32)
+    lw = W.LodWatcher(props, 256, (0.0, 0.0, 0.0), start="root")
+    gens = [len(lw.tick(tuple(np.float32(c) for c in f))) for f in g["path"]]
+    assert gens == g["generated_per_tick"]
+    codes = lw.leaves()[2]
+    assert len(codes) == g["renderables"]
+    assert (zlib.crc32(codes.astype("<u8").tobytes()) & 0xFFFFFFFF) == g["codes_crc"]
