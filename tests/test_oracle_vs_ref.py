@@ -130,3 +130,17 @@ def test_flat_quad_format_matches_reference(oracle, ref, smooth):
     got = oracle.format_unwind(q["pos"], nrm, col, inds, smooth)
     for a, b in zip(got, want):
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_incremental_policy_matches_reference_watcher_live(ref):
+    """world.LodWatcher against the compiled reference's WorldWatcher tick functions on a random focus walk"""
+    from binarymeshfitting_b200 import world as W
+    rng = np.random.default_rng(17)
+    steps = np.cumsum(rng.normal(scale=14.0, size=(40, 3)), axis=0).astype(np.float32)
+    path = [(0.0, 0.0, 0.0)] * 6 + [tuple(float(c) for c in p) for p in steps]
+    w = ref.world(ob.SPHERE, 32, max_level=5)
+    codes, gen = w.watcher_run(np.array(path, np.float32))
+    lw = W.LodWatcher(W.WorldProperties(max_level=5, chunk_resolution=32), 256, (0.0, 0.0, 0.0), start="root")
+    mine = [len(lw.tick(tuple(np.float32(c) for c in f))) for f in path]
+    assert mine == gen.tolist()
+    assert np.array_equal(lw.leaves()[2], codes)
