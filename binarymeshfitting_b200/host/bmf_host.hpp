@@ -836,14 +836,16 @@ private:
 	}
 
 public:
-	// GLChunk::format_data_tris(vertices): positions and colours of the soup, flat
+	// GLChunk::format_data_tris(vertices) (GLChunk.cpp:257-276): positions, normals (the stitcher never sets them: zero) and
+	// colours of the soup, flat
 	void format()
 	{
 		gl_chunk.p_data.count = gl_chunk.c_data.count = gl_chunk.n_data.count = 0;
 		for (size_t v = 0; v < vertices.count; v++)
 		{
-			gl_chunk.p_data.push_back(vertices[v].p);
-			gl_chunk.c_data.push_back(vertices[v].color);
+			gl_chunk.p_data.push_back(vertices[(int)v].p);
+			gl_chunk.n_data.push_back(vertices[(int)v].n);
+			gl_chunk.c_data.push_back(vertices[(int)v].color);
 		}
 	}
 };
