@@ -1274,13 +1274,26 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 
 	// the chunk lattice: one slot = the extent of the finest chunk; every chunk must be a power-of-two number of slots
 	// wide and sit at a multiple of its own extent (leaves of one octree do: WorldOctree.cpp:175-210)
-	float smin = ctx->descs[0].size, o[3] = { ctx->descs[0].pos[0], ctx->descs[0].pos[1], ctx->descs[0].pos[2] };
+	// The lattice is anchored to the OCTREE, not to the batch: a sub-range of an octree's leaves (one GPU's share, the border
+	// chunks of the cross-rank pass) may have its minimum corner set by a fine chunk that does not sit on a multiple of the
+	// coarser chunks' extent.  Every leaf sits at root + k * size, so the largest chunk of the batch is congruent to the root
+	// modulo its own size, and stepping down from it in whole multiples of that size to (or below) the minimum corner gives an
+	// origin every chunk of a valid leaf set is aligned to.
+	float smin = ctx->descs[0].size, smax = ctx->descs[0].size;
+	double lo[3] = { ctx->descs[0].pos[0], ctx->descs[0].pos[1], ctx->descs[0].pos[2] }, o[3];
+	int largest = 0;
 	for (int i = 0; i < n; i++)
 	{
 		const bmf_chunk_desc& c = ctx->descs[i];
 		if (!(c.size > 0.0f)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunk size must be positive");
 		smin = std::min(smin, c.size);
-		for (int a = 0; a < 3; a++) o[a] = std::min(o[a], c.pos[a]);
+		if (c.size > smax) { smax = c.size; largest = i; }
+		for (int a = 0; a < 3; a++) lo[a] = std::min(lo[a], (double)c.pos[a]);
+	}
+	for (int a = 0; a < 3; a++)
+	{
+		const double pl = (double)ctx->descs[largest].pos[a];
+		o[a] = pl - std::ceil((pl - lo[a]) / (double)smax - 1e-6) * (double)smax;
 	}
 	std::vector<SeamChunk> sc(n);
 	int g[3] = { 0, 0, 0 };
@@ -1294,7 +1307,7 @@ int bmf_batch_stitch(bmf_ctx* ctx, const int32_t* group, int cross_group_only, i
 		int org[3];
 		for (int a = 0; a < 3; a++)
 		{
-			const double q = ((double)c.pos[a] - (double)o[a]) / (double)smin;
+			const double q = ((double)c.pos[a] - o[a]) / (double)smin;
 			const long long qi = llround(q);
 			if (std::fabs(q - (double)qi) > 1e-3 || qi < 0 || qi > (1 << 20) || (qi % ei))
 				return fail(ctx, BMF_ERR_INVALID, "bmf_batch_stitch: chunks must be aligned leaves of one octree");

@@ -342,6 +342,10 @@ public:
 	}
 	bmf_ctx* ctx = nullptr;
 	int device = 0;
+	// a bmf_ctx is single-threaded (bmf_b200.h); callers that share this context from several threads -- the reference runs
+	// label_grid / label_edges / polygonize per chunk inside `#pragma omp parallel for` (ChunkGenerator.cpp:93-108) -- hold this lock
+	// for one whole device transaction (sampler + submit + fetch)
+	std::mutex lock;
 	bool ok() const { return ctx != nullptr; }
 	const char* error() const { return ctx ? bmf_last_error(ctx) : "no CUDA device / libbmf_b200 context (no CPU fallback)"; }
 
@@ -444,6 +448,11 @@ public:
 			sampler.block(sampler.world_size, overlap_pos, glm::ivec3((int)dim, (int)dim, (int)dim), delta, &out, nullptr, nullptr, 0, sizeof(float), &properties);
 			host_density = density_block->data;
 		}
+		// One device transaction under the context lock: the whole pipeline of THIS chunk runs here and everything the later
+		// stages publish (cell count, vertex records, indices) is fetched into the chunk itself, so label_edges / polygonize are
+		// host-only and chunks may be interleaved (grid A, grid B, edges A) or driven from several threads like the reference's
+		// OpenMP loop without ever reading another chunk's resident batch.
+		std::lock_guard<std::mutex> guard(dev.lock);
 		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
 		bmf_chunk_desc c;
 		c.pos[0] = pos.x; c.pos[1] = pos.y; c.pos[2] = pos.z; c.size = size; c.level = level; c.overlap = overlap; c.morton = parent_code;
@@ -455,7 +464,12 @@ public:
 		bmf_chunk_info info;
 		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
 		contains_mesh = info.contains_mesh != 0;
-		return bmf_batch_copy_chunk(dev.ctx, 0, nullptr, nullptr, binary_block->data, nullptr, d.kind == BMF_SAMPLER_HOST_DENSITY ? nullptr : density_block->data) == BMF_OK;
+		staged_cells = (size_t)info.n_cells;
+		staged_verts.assign((size_t)info.n_verts * 84, 0);
+		staged_inds.assign((size_t)info.n_inds, 0u);
+		staged = true;
+		return bmf_batch_copy_chunk(dev.ctx, 0, staged_verts.empty() ? nullptr : staged_verts.data(), staged_inds.empty() ? nullptr : staged_inds.data(), binary_block->data, nullptr,
+		                            d.kind == BMF_SAMPLER_HOST_DENSITY ? nullptr : density_block->data) == BMF_OK;
 	}
 
 	// publishes the iso-vertices (positions, boundary flags; valences still 0) -- DMCChunk.cpp:168-508
@@ -463,31 +477,25 @@ public:
 	                 ResourceAllocator<DensityBlock>* /*density_allocator*/, ResourceAllocator<MasksBlock>* /*masks_allocator*/)
 	{
 		if (!contains_mesh) return true;
-		BmfDevice& dev = BmfDevice::get();
-		if (!dev.ok()) return false;
+		if (!staged) return false; // label_grid of THIS chunk has not run
 		if (!vi) { vi = vi_allocator->new_element(); vi->init(); }
 		if (!cell_block) { cell_block = cell_allocator->new_element(); cell_block->init(); }
-		bmf_chunk_info info;
-		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
 		cell_block->cells.count = 0;
-		cell_block->cells.prepare((size_t)info.n_cells);
-		cell_block->cells.count = (size_t)info.n_cells;
-		return fetch(dev, info, false);
+		cell_block->cells.prepare(staged_cells);
+		cell_block->cells.count = staged_cells;
+		return publish_vertices(false);
 	}
 
 	// publishes the index buffer and init_valence -- DMCChunk.cpp:514-576
 	bool polygonize()
 	{
 		if (!contains_mesh) return true;
-		BmfDevice& dev = BmfDevice::get();
-		if (!dev.ok() || !vi) return false;
-		bmf_chunk_info info;
-		if (bmf_batch_chunk_info(dev.ctx, 0, &info) != BMF_OK) return false;
+		if (!staged || !vi) return false;
 		vi->mesh_indexes.count = 0;
-		vi->mesh_indexes.prepare((size_t)info.n_inds);
-		vi->mesh_indexes.count = (size_t)info.n_inds;
-		if (bmf_batch_copy_chunk(dev.ctx, 0, nullptr, vi->mesh_indexes.elements, nullptr, nullptr, nullptr) != BMF_OK) return false;
-		return fetch(dev, info, true);
+		vi->mesh_indexes.prepare(staged_inds.size());
+		if (!staged_inds.empty()) std::memcpy((void*)vi->mesh_indexes.elements, staged_inds.data(), staged_inds.size() * sizeof(uint32_t));
+		vi->mesh_indexes.count = staged_inds.size();
+		return publish_vertices(true);
 	}
 
 	void copy_verts_and_inds(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& i_out)
@@ -501,14 +509,19 @@ public:
 	}
 
 private:
-	bool fetch(BmfDevice& dev, const bmf_chunk_info& info, bool with_valence)
+	// what label_grid fetched from the device for this chunk (84-byte DualVertex records, index buffer, active-cell count)
+	bool staged = false;
+	size_t staged_cells = 0;
+	std::vector<uint8_t> staged_verts;
+	std::vector<uint32_t> staged_inds;
+
+	bool publish_vertices(bool with_valence)
 	{
-		std::vector<uint8_t> rec((size_t)info.n_verts * 84);
-		if (bmf_batch_copy_chunk(dev.ctx, 0, rec.data(), nullptr, nullptr, nullptr, nullptr) != BMF_OK) return false;
+		const size_t nv = staged_verts.size() / 84;
 		vi->vertices.count = 0;
-		vi->vertices.prepare((size_t)info.n_verts);
-		std::memcpy((void*)vi->vertices.elements, rec.data(), rec.size());
-		vi->vertices.count = (size_t)info.n_verts;
+		vi->vertices.prepare(nv);
+		if (nv) std::memcpy((void*)vi->vertices.elements, staged_verts.data(), staged_verts.size());
+		vi->vertices.count = nv;
 		if (!with_valence)
 			for (size_t i = 0; i < vi->vertices.count; i++) vi->vertices.elements[i].init_valence = 0;
 		return true;
@@ -556,6 +569,17 @@ public:
 	WorldOctreeNode() {}
 	WorldOctreeNode(float s, glm::vec3 p, uint8_t l, uint64_t code) : size(s), level(l), pos(p), morton_code(code) {}
 };
+
+// Depth-normalised Z-curve order of WorldOctreeNode::morton_code values (sentinel 1, then 3 bits per level).  The raw codes
+// order level-major (deeper nodes are numerically larger), which scatters a device's share over the LODs; stripping the
+// sentinel and left-aligning the digits orders leaves of mixed levels along one curve.  Ties break by level.
+inline bool morton_less(uint64_t a, uint64_t b)
+{
+	auto level_of = [](uint64_t c) { int bits = 0; while (c >> bits) bits++; return (bits - 1) / 3; };
+	const int la = a ? level_of(a) : 0, lb = b ? level_of(b) : 0;
+	const uint64_t ka = (a ^ (a ? (uint64_t)1 << (3 * la) : 0)) << (3 * (20 - la)), kb = (b ^ (b ? (uint64_t)1 << (3 * lb) : 0)) << (3 * (20 - lb));
+	return ka != kb ? ka < kb : la < lb;
+}
 
 class WorldOctree
 {
@@ -718,7 +742,7 @@ public:
 		const size_t n = leaves.size();
 		std::vector<int> order(n);
 		for (size_t i = 0; i < n; i++) order[i] = (int)i;
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return leaves[a]->morton_code < leaves[b]->morton_code; });
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return morton_less(leaves[a]->morton_code, leaves[b]->morton_code); });
 		std::vector<int32_t> group(n, 0);
 		for (int k = 0; k < n_dev; k++)
 			for (size_t q = n * k / n_dev; q < n * (k + 1) / n_dev; q++) group[order[q]] = k;
@@ -806,6 +830,7 @@ private:
 			const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
 			d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
 		}
+		std::lock_guard<std::mutex> guard(dev.lock);
 		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
 		bmf_params p;
 		std::memset(&p, 0, sizeof(p));
@@ -894,7 +919,7 @@ public:
 			else
 			{
 				std::vector<int> order(who);
-				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return batch[a]->morton_code < batch[b]->morton_code; });
+				std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return morton_less(batch[a]->morton_code, batch[b]->morton_code); });
 				std::vector<std::vector<int>> parts(n_dev);
 				for (int k = 0; k < n_dev; k++)
 					parts[k].assign(order.begin() + (size_t)order.size() * k / n_dev, order.begin() + (size_t)order.size() * (k + 1) / n_dev);
@@ -936,6 +961,7 @@ private:
 			const NoiseSamplers::NoiseSamplerProperties& np = world->noise_properties;
 			d.g_scale = np.g_scale; d.height = np.height; d.octaves = np.octaves; d.amp = np.amp; d.frequency = np.frequency; d.gain = np.gain;
 		}
+		std::lock_guard<std::mutex> guard(dev.lock);
 		if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
 		bmf_params p;
 		std::memset(&p, 0, sizeof(p));
@@ -1156,15 +1182,20 @@ private:
 			nrm[3 * i] = v.n.x; nrm[3 * i + 1] = v.n.y; nrm[3 * i + 2] = v.n.z;
 			bnd[i] = v.boundary ? 1 : 0;
 		}
-		if (bmf_mesh_process_steps(dev.ctx, pos.data(), col.data(), nrm.data(), bnd.data(), nullptr, (int)n, indices.data(), (int)indices.size(), N, iters, pb ? 1 : 0,
-		                           smooth_normals ? 1 : 0, final_primal) != BMF_OK)
-			return false;
+		{
+			std::lock_guard<std::mutex> guard(dev.lock);
+			if (bmf_mesh_process_steps(dev.ctx, pos.data(), col.data(), nrm.data(), bnd.data(), nullptr, (int)n, indices.data(), (int)indices.size(), N, iters, pb ? 1 : 0,
+			                           smooth_normals ? 1 : 0, final_primal) != BMF_OK)
+				return false;
+		}
 		for (size_t i = 0; i < n; i++)
 		{
 			DualVertex& v = vertices.elements[i];
 			v.p = glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
 			v.color = glm::vec3(col[3 * i], col[3 * i + 1], col[3 * i + 2]);
-			if (smooth_normals) v.n = glm::vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+			// always: with smooth normals off the reference's set_colors step still turns the zero normal of every processed vertex
+			// into NaN (MeshProcessor.cpp:229-232, 296-303) -- the batch path reproduces that, so the mirror must as well
+			v.n = glm::vec3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
 			v.s = 0.0f;
 		}
 		return true;

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 static uint32_t crc32_of(const void* data, size_t n, uint32_t crc = 0)
 {
@@ -113,6 +114,37 @@ int main(int argc, char** argv)
 			mp.flush(v_out, i_out);
 			print_chunk("processed", c);
 		}
+		return 0;
+	}
+	if (!strcmp(argv[1], "interleave") && argc >= 4)
+	{
+		// the reference drives label_grid / label_edges / polygonize per chunk inside `#pragma omp parallel for`
+		// (ChunkGenerator.cpp:93-108): chunks interleave on the shared device context.  mode 0: grid A, grid B, edges A, poly A,
+		// edges B, poly B on one thread; mode 1: one thread per chunk.  Every chunk must come out as if it had run alone.
+		const int dim = atoi(argv[2]), mode = atoi(argv[3]);
+		Sampler sa = make_sampler(BMF_SAMPLER_SPHERE), sb = make_sampler(BMF_SAMPLER_TORUS_Z);
+		DMCChunk a(glm::vec3(-128, -128, -128), 256.0f, 0, sa, 1), b(glm::vec3(-128, -128, -128), 256.0f, 0, sb, 1);
+		a.dim = b.dim = dim;
+		auto stage12 = [&](DMCChunk& c) {
+			c.label_edges(&vi_allocator, &cell_allocator, &inds_allocator, &density_allocator, &masks_allocator);
+			c.polygonize();
+		};
+		if (mode == 0)
+		{
+			a.label_grid(&binary_allocator, &density_allocator, &noise_allocator, 0.0f, props);
+			b.label_grid(&binary_allocator, &density_allocator, &noise_allocator, 0.0f, props);
+			stage12(a);
+			stage12(b);
+		}
+		else
+		{
+			std::thread ta([&] { a.label_grid(&binary_allocator, &density_allocator, &noise_allocator, 0.0f, props); stage12(a); });
+			std::thread tb([&] { b.label_grid(&binary_allocator, &density_allocator, &noise_allocator, 0.0f, props); stage12(b); });
+			ta.join();
+			tb.join();
+		}
+		print_chunk("A", a);
+		print_chunk("B", b);
 		return 0;
 	}
 	if (!strcmp(argv[1], "hostfn") && argc >= 3)

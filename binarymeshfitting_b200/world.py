@@ -99,10 +99,41 @@ def grid_chunks(n_per_axis=16, chunk_size=16.0, origin=(-128.0, -128.0, -128.0))
     return np.ascontiguousarray(ps, np.float32)
 
 
+MORTON_MAX_LEVEL = 20  # 3 bits per level + the sentinel fit 64 bits
+
+
+def morton_key(code):
+    """Depth-normalised sort key of a WorldOctreeNode::morton_code (sentinel 1, then 3 bits per level: x | y<<1 | z<<2,
+    WorldOctree.cpp:196-200).  The raw code orders level-major (deeper nodes are numerically larger); stripping the sentinel
+    and left-aligning the digits orders leaves of MIXED levels along one Z-curve, so contiguous ranges are spatially compact.
+    Ties (a node and its first descendants) break by level."""
+    code = int(code)
+    level = (code.bit_length() - 1) // 3
+    return ((code ^ (1 << (3 * level))) << (3 * (MORTON_MAX_LEVEL - level)), level)
+
+
+def morton_order(mortons):
+    keys = [morton_key(c) for c in np.asarray(mortons, np.uint64).tolist()]
+    return np.array(sorted(range(len(keys)), key=keys.__getitem__), np.int64)
+
+
+def grid_mortons(n_per_axis):
+    """Morton codes (reference convention: sentinel, digit = x | y<<1 | z<<2 per level) of grid_chunks' n^3 chunks, n a power of two."""
+    levels = int(n_per_axis).bit_length() - 1
+    assert 1 << levels == n_per_axis
+    i = np.arange(n_per_axis, dtype=np.uint64)
+    X, Y, Z = (a.ravel() for a in np.meshgrid(i, i, i, indexing="ij"))
+    code = np.full(X.size, 1, np.uint64)
+    for l in range(levels - 1, -1, -1):
+        digit = ((X >> np.uint64(l)) & np.uint64(1)) | (((Y >> np.uint64(l)) & np.uint64(1)) << np.uint64(1)) | (((Z >> np.uint64(l)) & np.uint64(1)) << np.uint64(2))
+        code = (code << np.uint64(3)) | digit
+    return code
+
+
 def partition(mortons, costs, n_parts):
-    """Multi-GPU sharding by octree node: sort leaves by Morton code and deal contiguous,
-    cost-balanced ranges.  Returns a list of index arrays (into the original order), one per part."""
-    order = np.argsort(np.asarray(mortons, np.uint64), kind="stable")
+    """Multi-GPU sharding by octree node: sort leaves along the Z-curve (depth-normalised Morton key) and deal
+    contiguous, cost-balanced ranges.  Returns a list of index arrays (into the original order), one per part."""
+    order = morton_order(mortons)
     c = np.asarray(costs, np.float64)[order]
     cum = np.cumsum(c)
     total = cum[-1] if len(cum) else 0.0
@@ -123,7 +154,9 @@ def border_chunks(pos_size, group):
     ps = np.asarray(pos_size, np.float64).reshape(-1, 4)
     group = np.asarray(group)
     smin = ps[:, 3].min()
-    org = ps[:, :3].min(axis=0)
+    # lattice origin anchored to the octree like bmf_batch_stitch: step down from the largest chunk in multiples of its size
+    big = int(np.argmax(ps[:, 3]))
+    org = ps[big, :3] - np.ceil((ps[big, :3] - ps[:, :3].min(axis=0)) / ps[big, 3] - 1e-6) * ps[big, 3]
     lo = np.rint((ps[:, :3] - org) / smin).astype(np.int64)
     ext = np.rint(ps[:, 3] / smin).astype(np.int64)
     G = (lo + ext[:, None]).max(axis=0)

@@ -836,11 +836,21 @@ int64_t orc_seam(const orc_seam_chunk* ch, int n, int dim, const int32_t* group,
 	const int d = dim, zc = d / 32;
 	*tris_out = 0;
 	if (n <= 0) return 0;
-	float smin = ch[0].size, org[3] = { ch[0].pos[0], ch[0].pos[1], ch[0].pos[2] };
+	/* lattice origin anchored to the octree (the largest chunk is congruent to the root modulo its own size), not to the
+	   batch's minimum corner: valid sub-ranges of a leaf set may have a fine chunk at their minimum corner */
+	float smin = ch[0].size, smax = ch[0].size;
+	double lo[3] = { ch[0].pos[0], ch[0].pos[1], ch[0].pos[2] }, org[3];
+	int largest = 0;
 	for (int i = 0; i < n; i++)
 	{
 		if (ch[i].size < smin) smin = ch[i].size;
-		for (int a = 0; a < 3; a++) if (ch[i].pos[a] < org[a]) org[a] = ch[i].pos[a];
+		if (ch[i].size > smax) { smax = ch[i].size; largest = i; }
+		for (int a = 0; a < 3; a++) if (ch[i].pos[a] < lo[a]) lo[a] = ch[i].pos[a];
+	}
+	for (int a = 0; a < 3; a++)
+	{
+		const double pl = (double)ch[largest].pos[a];
+		org[a] = pl - ceil((pl - lo[a]) / (double)smax - 1e-6) * (double)smax;
 	}
 	seam_lat* lat = (seam_lat*)malloc(sizeof(seam_lat) * (size_t)n);
 	float (*geo)[4] = (float (*)[4])malloc(sizeof(float) * 4 * (size_t)n);
@@ -852,8 +862,9 @@ int64_t orc_seam(const orc_seam_chunk* ch, int n, int dim, const int32_t* group,
 		lat[i].lg = seam_ilog2(e);
 		for (int a = 0; a < 3; a++)
 		{
-			long long q = llround(((double)ch[i].pos[a] - (double)org[a]) / (double)smin);
-			if (q % e) { free(lat); free(geo); return -1; }
+			const double qf = ((double)ch[i].pos[a] - org[a]) / (double)smin;
+			long long q = llround(qf);
+			if (fabs(qf - (double)q) > 1e-3 || q < 0 || (q % e)) { free(lat); free(geo); return -1; }
 			lat[i].o[a] = (int)q;
 			if (q + e > G[a]) G[a] = (int)(q + e);
 		}

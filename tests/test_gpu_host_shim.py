@@ -62,6 +62,15 @@ def test_dmcchunk_staged_calls_and_meshprocessor(oracle, kind, dim, overlap, ite
         check(out["processed"], o1, processed=True)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_dmcchunk_interleaved_and_threaded_chunks_keep_their_own_results(oracle, mode):
+    """ChunkGenerator.cpp:93-108 runs the three DMCChunk stages per chunk inside an OpenMP loop: two chunks interleaved on one
+    thread (grid A, grid B, edges A, ...) or driven from two threads must each publish their OWN vertices and indices."""
+    out = run("interleave", 64, mode)
+    for tag, kind in (("A", ob.SPHERE), ("B", ob.TORUS_Z)):
+        check(out[tag], oracle.chunk(oracle.sampler(kind), (-128, -128, -128), 256.0, 64, np.float32(0.0)))
+
+
 def test_arbitrary_host_callback_sampler(oracle, tmp_path):
     f = tmp_path / "density.bin"
     out = run("hostfn", 32, f)

@@ -141,6 +141,25 @@ def test_seam_multi_gpu_scheme_with_border_batch(gpu, oracle):
     assert key(np.concatenate(pieces)) == key(full)
 
 
+def test_seam_subset_whose_minimum_corner_is_a_fine_chunk(gpu, oracle):
+    """a Morton sub-range of an octree's leaves whose minimum corner is a fine chunk (z offset 1 slot, extent 2) used to
+    be rejected as misaligned; the lattice is now anchored to the octree.  Also a fuzz of contiguous Z-curve ranges."""
+    from binarymeshfitting_b200 import world as W
+    ps = np.array([[0, -256, 0, 256.0], [0, 0, 0, 256.0], [-256, -256, -128, 128.0]], np.float32)
+    got, want, _ = run(gpu, oracle, ob.SPHERE, ps, world_size=700.0)
+    assert len(want) > 0
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    rng = np.random.default_rng(11)
+    lps, lv, mc = su.lod_world(4, 1, (150.0, 40.0, -60.0))
+    order = W.morton_order(mc)
+    gpu.set_sampler(capi.SPHERE, world_size=700.0)
+    for _ in range(60):
+        a = int(rng.integers(0, len(lps) - 1))
+        b = int(rng.integers(a + 1, min(len(lps), a + 40) + 1))
+        gpu.submit(capi.make_chunk_descs(lps[order[a:b]], overlaps=su.seam_overlap(DIM)), DIM, iters=0)
+        gpu.stitch(download=False)  # raises BmfError if the range is rejected
+
+
 def test_seam_errors(gpu):
     from binarymeshfitting_b200 import Context
     ctx = Context(0)

@@ -144,6 +144,41 @@ def test_two_rank_seam_scheme_over_gloo(tmp_path):
     assert full == parts and cross > 0 and border > 0 and same == 1
 
 
+def test_subset_whose_minimum_corner_is_a_fine_chunk(oracle):
+    """A valid sub-range of an octree's leaves (one GPU's share, the border batch of the cross-rank pass) may have its minimum
+    corner set by a fine chunk: the slot lattice is anchored to the octree (through the largest chunk), not to that corner."""
+    ps = np.array([[0, -256, 0, 256.0], [0, 0, 0, 256.0], [-256, -256, -128, 128.0]], np.float32)
+    s = oracle.sampler(ob.SPHERE, world_size=700.0)
+    ov = su.seam_overlap(DIM)
+    chunks = [oracle.chunk(s, p[:3], p[3], DIM, ov) for p in ps]
+    tris = oracle.seam(chunks, ps, DIM, ov)
+    assert len(tris) > 0
+    from binarymeshfitting_b200 import world as W
+    assert W.border_chunks(ps, np.array([0, 1, 2])).tolist() == [0, 1]  # the two coarse chunks share a face; the fine one touches neither
+
+
+def test_random_morton_subranges_are_accepted(oracle):
+    """every contiguous Z-curve range of a LOD world's leaves is a valid seam batch (fuzz of the alignment test only: dim 32,
+    plane sampler far away so the pass itself is trivial)"""
+    from binarymeshfitting_b200 import world as W
+    rng = np.random.default_rng(5)
+    s = oracle.sampler(ob.PLANE_Y)
+    for focus in ((0.0, 0.0, 0.0), (150.0, 40.0, -60.0), (-200.0, 10.0, 90.0)):
+        ps, lv, mc = su.lod_world(4, 1, focus, DIM)
+        ps = ps.copy()
+        ps[:, 1] += 4096.0  # lift the world far above the plane: every chunk is uniformly air
+        order = W.morton_order(mc)
+        cache = {}
+        for _ in range(40):
+            a = int(rng.integers(0, len(ps) - 1))
+            b = int(rng.integers(a + 1, min(len(ps), a + 24) + 1))
+            idx = order[a:b]
+            for i in idx:
+                if int(i) not in cache:
+                    cache[int(i)] = oracle.chunk(s, ps[i][:3], ps[i][3], DIM, su.seam_overlap(DIM))
+            oracle.seam([cache[int(i)] for i in idx], ps[idx], DIM, su.seam_overlap(DIM))  # raises ValueError if rejected
+
+
 def test_misaligned_chunks_are_rejected(oracle):
     s = oracle.sampler(ob.SPHERE)
     ps = np.array([[0, 0, 0, 32.0], [40.0, 0, 0, 64.0]], np.float32)

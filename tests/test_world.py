@@ -51,11 +51,32 @@ def test_partition_is_a_balanced_cover():
         assert sorted(allidx.tolist()) == list(range(len(mc)))
         sizes = [len(p) for p in parts]
         assert max(sizes) - min(sizes) <= 1
-        # contiguous in Morton order
-        for p in parts:
-            if len(p):
-                assert (np.diff(mc[p].astype(np.int64)) > 0).all()
+        # contiguous along the depth-normalised Z-curve (NOT in raw code order, which is level-major)
+        keys = [W.morton_key(c) for c in mc.tolist()]
+        flat = [keys[i] for p in parts for i in p]
+        assert flat == sorted(keys)
     assert W.partition(mc[:3], np.ones(3), 8)[0].size <= 1  # more parts than chunks: empty parts allowed
+
+
+def test_morton_key_orders_mixed_levels_along_one_curve():
+    """a leaf's key lies between the keys of the leaves before / after its subtree: the raw sentinel-prefixed codes do not"""
+    ps, lv, mc = W.split_leaves(W.WorldProperties(max_level=5))
+    order = W.morton_order(mc)
+    # spatial check: walking the leaves in key order, consecutive leaves of a Z-curve always touch or share an ancestor
+    # region; concretely the curve never returns to a (level-2) ancestor cell it has left
+    anc = [int(c) >> (3 * (int(l) - 2)) if l >= 2 else -1 for c, l in zip(mc[order], lv[order])]
+    seen, last = set(), None
+    for a in anc:
+        if a != last:
+            assert a not in seen
+            seen.add(a)
+            last = a
+    raw = np.argsort(mc, kind="stable")
+    anc_raw = [int(c) >> (3 * (int(l) - 2)) if l >= 2 else -1 for c, l in zip(mc[raw], lv[raw])]
+    assert sum(1 for a, b in zip(anc_raw, anc_raw[1:]) if a != b) > len(seen)  # the raw order revisits cells (level-major)
+    # grid codes: the reference's digit convention x | y<<1 | z<<2
+    g = W.grid_mortons(2)
+    assert g.tolist() == [8 | 0, 8 | 4, 8 | 2, 8 | 6, 8 | 1, 8 | 5, 8 | 3, 8 | 7]  # grid_chunks is x-major, z fastest
 
 
 def test_grid_chunks():
