@@ -23,7 +23,8 @@ EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
-           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue")
+           "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue",
+           "bmf_batch_download_enqueue", "bmf_host_alloc", "bmf_host_free", "bmf_host_register", "bmf_host_unregister")
 
 
 class SamplerDesc(C.Structure):
@@ -45,12 +46,20 @@ class Params(C.Structure):
 
 class ChunkInfo(C.Structure):
     _fields_ = [("contains_mesh", C.c_int32), ("n_cells", C.c_int32), ("n_verts", C.c_int32), ("n_inds", C.c_int32),
-                ("vert_offset", C.c_int64), ("ind_offset", C.c_int64), ("overlap_pos", C.c_float * 3), ("scale", C.c_float)]
+                ("vert_offset", C.c_int64), ("ind_offset", C.c_int64), ("overlap_pos", C.c_float * 3), ("scale", C.c_float),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class DownloadDesc(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("normal", C.c_void_p), ("color", C.c_void_p), ("boundary", C.c_void_p), ("valence", C.c_void_p),
+                ("indices32", C.c_void_p), ("indices16", C.c_void_p), ("cap_verts", C.c_int64), ("cap_inds", C.c_int64)]
 
 
 CHUNK_DESC_DTYPE = np.dtype([("pos", "<f4", 3), ("size", "<f4"), ("level", "<i4"), ("overlap", "<f4"), ("morton", "<u8")])
 CHUNK_INFO_DTYPE = np.dtype([("contains_mesh", "<i4"), ("n_cells", "<i4"), ("n_verts", "<i4"), ("n_inds", "<i4"),
-                             ("vert_offset", "<i8"), ("ind_offset", "<i8"), ("overlap_pos", "<f4", 3), ("scale", "<f4")])
+                             ("vert_offset", "<i8"), ("ind_offset", "<i8"), ("overlap_pos", "<f4", 3), ("scale", "<f4"),
+                             ("flags", "<i4"), ("reserved", "<i4")])
+CHUNK_COLOR_ONE, CHUNK_NORMAL_ZERO, CHUNK_INDEX16 = 1, 2, 4
 assert CHUNK_DESC_DTYPE.itemsize == C.sizeof(ChunkDesc) and CHUNK_INFO_DTYPE.itemsize == C.sizeof(ChunkInfo)
 
 DUALVERTEX_DTYPE = np.dtype({
@@ -107,6 +116,12 @@ def load_library(path=SO):
     lib.bmf_batch_stitch.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int64)]
     lib.bmf_seam_download.argtypes = [vp, vp]
     lib.bmf_seam_stage_ms.argtypes = [vp, vp]
+    lib.bmf_batch_download_enqueue.argtypes = [vp, C.POINTER(DownloadDesc)]
+    lib.bmf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.bmf_host_free.argtypes = [vp]
+    lib.bmf_host_free.restype = None
+    lib.bmf_host_register.argtypes = [vp, C.c_size_t]
+    lib.bmf_host_unregister.argtypes = [vp]
     return lib
 
 
@@ -123,6 +138,39 @@ def make_chunk_descs(pos_size, overlaps=0.0, levels=0):
     d["level"] = levels
     d["morton"] = np.arange(1, len(ps) + 1)
     return d
+
+
+class PinnedBuffer:
+    """bmf_host_alloc'ed (page-locked, device-mapped) host memory viewed as a numpy array -- or, with `existing`, a numpy view of
+    memory the caller owns (e.g. a shared-memory segment) registered with bmf_host_register."""
+
+    def __init__(self, lib, nbytes=0, existing=None):
+        self.lib, self.owned = lib, existing is None
+        if existing is None:
+            p = C.c_void_p()
+            if lib.bmf_host_alloc(max(int(nbytes), 1), C.byref(p)) != 0 or not p:
+                raise BmfError("bmf_host_alloc(%d) failed" % nbytes)
+            self.ptr, self.nbytes = p.value, max(int(nbytes), 1)
+            self.u8 = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+        else:
+            self.u8 = existing.view(np.uint8).reshape(-1)
+            self.ptr, self.nbytes = self.u8.ctypes.data, self.u8.nbytes
+            if lib.bmf_host_register(C.c_void_p(self.ptr), self.nbytes) != 0:
+                raise BmfError("bmf_host_register failed")
+
+    def view(self, dtype, offset=0, count=None):
+        dt = np.dtype(dtype)
+        n = (self.nbytes - offset) // dt.itemsize if count is None else count
+        return self.u8[offset:offset + n * dt.itemsize].view(dt)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.u8 = None
+            if self.owned:
+                self.lib.bmf_host_free(C.c_void_p(self.ptr))
+            else:
+                self.lib.bmf_host_unregister(C.c_void_p(self.ptr))
+            self.ptr = None
 
 
 class Context:
@@ -212,6 +260,21 @@ class Context:
         fn = self.lib.bmf_batch_download if wait else self.lib.bmf_batch_download_async
         self._check(fn(self.h, _p(pos), _p(nrm), _p(col), _p(bnd), _p(val), _p(ind)))
         return out
+
+    def download_enqueue(self, pos=None, normal=None, color=None, boundary=None, valence=None, inds32=None, inds16=None):
+        """bmf_batch_download_enqueue: numpy views of PINNED host memory (PinnedBuffer.view); returns at once, wait() completes it."""
+        d = DownloadDesc()
+        cap_v, cap_i = None, None
+        for name, a, per in (("pos", pos, 3), ("normal", normal, 3), ("color", color, 3), ("boundary", boundary, 1), ("valence", valence, 1)):
+            if a is not None:
+                setattr(d, name, a.ctypes.data)
+                cap_v = a.size // per if cap_v is None else min(cap_v, a.size // per)
+        for name, a in (("indices32", inds32), ("indices16", inds16)):
+            if a is not None:
+                setattr(d, name, a.ctypes.data)
+                cap_i = a.size
+        d.cap_verts, d.cap_inds = cap_v or 0, cap_i or 0
+        self._check(self.lib.bmf_batch_download_enqueue(self.h, C.byref(d)))
 
     def copy_chunk(self, i, want=("verts", "inds", "bits")):
         info = ChunkInfo()

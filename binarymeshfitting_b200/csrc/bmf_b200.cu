@@ -7,6 +7,7 @@
 #include "smooth.cuh"
 #include "seam.cuh"
 #include "quads.cuh"
+#include "download.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -52,7 +53,7 @@ struct DevBuf
 
 struct HostTotals
 {
-	unsigned long long v[8]; // cells, verts, indices, >2^32 flag, list counters x2, -, arena-too-small flag
+	unsigned long long v[16]; // the device's totals block (download.cuh TOT_*): cells, verts, indices, >2^32 flag, list counters x2, -, arena-too-small flag, largest chunk, download error
 };
 
 } // namespace
@@ -134,6 +135,11 @@ struct bmf_ctx
 	int64_t seam_n_tris = -1; // -1: no seam pass run on the resident batch
 	cudaEvent_t seam_ev[3] = {};
 	float seam_ms[2] = { 0, 0 };
+
+	// device-driven download (bmf_batch_download_enqueue) of the resident batch, kept so that a re-launch after an arena grew can repeat it
+	bool dl_pending = false;
+	DownloadArgs dl_args;
+	int download_ctas = 32; // grid of k_download (BMF_DOWNLOAD_CTAS): the PCIe link is the limit, not the SMs
 
 	HostTotals* totals_pinned = nullptr;
 	ChunkCounts* counts_pinned = nullptr;
@@ -272,6 +278,7 @@ bool is_terrain3d(int k) { return k == BMF_SAMPLER_TERRAIN3D || k == BMF_SAMPLER
 bool is_implicit(int k) { return k >= BMF_SAMPLER_SPHERE && k <= BMF_SAMPLER_CSG; }
 
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+int nan_half_step(int iters);
 
 // MeshProcessor<N> on device arrays (all batch-wide); chunks_dev maps index positions to vertex bases.
 template <int N>
@@ -328,9 +335,7 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		// iters dual steps interleaved with iters primal steps (the last primal is the driver's extra call)
 		// the in-loop primal step with set_colors (m == 3, or m == 0 when iters <= 3) turns the zero normals of the processed vertices into
 		// NaN in the reference (and in k_primal); nan_step = its half-step index, -1 if there is none
-		int nan_step = -1;
-		for (int m = 0; m < iters - 1 && nan_step < 0; m++)
-			if (m == 3 || (m == 0 && iters <= 3)) nan_step = 2 * m + 1;
+		const int nan_step = nan_half_step(iters);
 		if (ctx->smooth_cluster)
 		{
 			// two-CTA clusters: chunks too large for one SM's shared memory are split over a pair of SMs (DSMEM)
@@ -520,6 +525,24 @@ int launch_mesh(bmf_ctx* ctx)
 	return BMF_OK;
 }
 
+// the in-loop primal step with set_colors (m == 3, or m == 0 when iters <= 3; MeshProcessor.cpp:229-232) turns the zero normals of the
+// processed vertices into NaN when smooth normals are off; returns that half-step index, -1 if there is none
+int nan_half_step(int iters)
+{
+	for (int m = 0; m < iters - 1; m++)
+		if (m == 3 || (m == 0 && iters <= 3)) return 2 * m + 1;
+	return -1;
+}
+
+int launch_download(bmf_ctx* ctx)
+{
+	DownloadArgs A = ctx->dl_args;
+	A.d_pos = ctx->pos.p; A.d_normal = ctx->normal.p; A.d_color = ctx->color.p;
+	A.d_boundary = ctx->boundary.p; A.d_valence = ctx->valence.p; A.d_inds = ctx->inds.p;
+	BMF_LAUNCH(k_download, (unsigned)ctx->download_ctas, CTA, 0, A, ctx->totals_dev.p, ctx->totals_pinned->v);
+	return BMF_OK;
+}
+
 // completes the resident batch: waits for the stream, publishes totals / per-chunk counts to the host and, if an output
 // arena was too small for this batch, grows it and runs the emitters again (the front half of the pipeline is kept)
 int finish(bmf_ctx* ctx)
@@ -540,6 +563,11 @@ int finish(bmf_ctx* ctx)
 		BMF_CUDA(cudaMemsetAsync(ctx->totals_dev.p + 4, 0, 2 * sizeof(unsigned long long), ctx->stream)); // list counters
 		rc = launch_mesh(ctx);
 		if (rc) return rc;
+		if (ctx->dl_pending && !(ctx->params.quads && ctx->params.iters > 0))
+		{
+			rc = launch_download(ctx); // the first attempt returned at once (TOT_SMALL was set)
+			if (rc) return rc;
+		}
 		BMF_CUDA(cudaStreamSynchronize(ctx->stream));
 		if (ctx->totals_pinned->v[7]) return fail(ctx, BMF_ERR_NOMEM, "bmf_batch_wait: output arenas still too small after growing");
 		ctx->relaunches++;
@@ -560,6 +588,13 @@ int finish(bmf_ctx* ctx)
 	for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
 	elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
 	ctx->finished = true;
+	if (ctx->dl_pending)
+	{
+		ctx->dl_pending = false;
+		const unsigned long long e = ctx->totals_pinned->v[TOT_DLERR];
+		if (e == 1) return fail(ctx, BMF_ERR_NOMEM, "bmf_batch_download_enqueue: host buffers too small for this batch (nothing was written)");
+		if (e == 2) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_enqueue: uint16 indices requested but a chunk has >= 65536 vertices (nothing was written)");
+	}
 	return BMF_OK;
 }
 
@@ -604,6 +639,7 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 	if (ctx->sm_count <= 0) ctx->sm_count = 148;
 	if (const char* e = getenv("BMF_SMOOTH_CTAS_PER_SM")) { const int v = atoi(e); if (v > 0 && v <= 4096) ctx->smooth_ctas_per_sm = v; }
 	if (const char* e = getenv("BMF_SMOOTH_FUSED")) ctx->smooth_fused = atoi(e) != 0;
+	if (const char* e = getenv("BMF_DOWNLOAD_CTAS")) { const int v = atoi(e); if (v > 0 && v <= 4096) ctx->download_ctas = v; }
 	{
 		int optin = 0;
 		cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -710,6 +746,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	ctx->uni_valid = false;
 	ctx->seam_n_tris = -1;
 	ctx->quads_processed = false;
+	ctx->dl_pending = false;
 	ctx->kused = 0;
 	ctx->n = n;
 	ctx->params = *params;
@@ -742,7 +779,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
 	BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
 	BMF_CUDA(ctx->counts.reserve(n));
-	BMF_CUDA(ctx->totals_dev.reserve(8));
+	BMF_CUDA(ctx->totals_dev.reserve(TOT_SLOTS));
 	if ((size_t)n > ctx->counts_pinned_cap)
 	{
 		BMF_CUDA(cudaStreamSynchronize(ctx->stream)); // an earlier batch may still be copying into the old buffer
@@ -932,6 +969,12 @@ int bmf_batch_chunk_info(bmf_ctx* ctx, int i, bmf_chunk_info* out)
 	out->ind_offset = (int64_t)c.ind_base;
 	out->overlap_pos[0] = g.ox; out->overlap_pos[1] = g.oy; out->overlap_pos[2] = g.oz;
 	out->scale = g.delta;
+	out->flags = 0;
+	out->reserved = 0;
+	const bmf_params& pr = ctx->params;
+	if (ctx->color_ones >= 3 * (size_t)(c.vert_base + c.n_verts)) out->flags |= BMF_CHUNK_COLOR_ONE;
+	if (!pr.smooth_normals && !pr.qef && nan_half_step(pr.iters) < 0) out->flags |= BMF_CHUNK_NORMAL_ZERO;
+	if (c.n_verts < 65536u) out->flags |= BMF_CHUNK_INDEX16;
 	return BMF_OK;
 }
 
@@ -974,6 +1017,67 @@ int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* col
 	}
 	if (I && indices) BMF_CUDA(cudaMemcpyAsync(indices, ctx->inds.p, sizeof(uint32_t) * I, cudaMemcpyDeviceToHost, st));
 	return BMF_OK;
+}
+
+int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc)
+{
+	if (!ctx || !desc) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download_enqueue: no batch submitted");
+	if (desc->indices32 && desc->indices16) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_enqueue: pass indices32 or indices16, not both");
+	if (desc->cap_verts < 0 || desc->cap_inds < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_enqueue: negative capacity");
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	if (ctx->params.quads && ctx->params.iters > 0)
+	{
+		// MeshProcessor<4> on a quad batch runs when the batch is completed (it needs the real counts on the host)
+		int frc = finish(ctx);
+		if (frc) return frc;
+		ctx->finished = false;
+	}
+	DownloadArgs A;
+	memset(&A, 0, sizeof(A));
+	void* host[7] = { desc->pos, desc->normal, desc->color, desc->boundary, desc->valence, desc->indices32, desc->indices16 };
+	void* dev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	for (int k = 0; k < 7; k++)
+	{
+		if (!host[k]) continue;
+		if (cudaHostGetDevicePointer(&dev[k], host[k], 0) != cudaSuccess)
+		{
+			cudaGetLastError();
+			return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_enqueue: host buffers must be page-locked and device-mapped (bmf_host_alloc / bmf_host_register)");
+		}
+	}
+	A.pos = (float*)dev[0]; A.normal = (float*)dev[1]; A.color = (float*)dev[2]; A.boundary = (uint8_t*)dev[3]; A.valence = (uint8_t*)dev[4];
+	A.inds32 = (uint32_t*)dev[5]; A.inds16 = (uint16_t*)dev[6];
+	A.cap_verts = (unsigned long long)desc->cap_verts;
+	A.cap_inds = (unsigned long long)desc->cap_inds;
+	ctx->dl_args = A;
+	ctx->dl_pending = true;
+	ctx->finished = false; // bmf_batch_wait must also complete (and check) this download
+	return launch_download(ctx);
+}
+
+int bmf_host_alloc(size_t bytes, void** out)
+{
+	if (!out) return BMF_ERR_INVALID;
+	*out = nullptr;
+	return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess ? BMF_OK : BMF_ERR_NOMEM;
+}
+
+void bmf_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+int bmf_host_register(void* p, size_t bytes)
+{
+	if (!p || !bytes) return BMF_ERR_INVALID;
+	return cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess ? BMF_OK : BMF_ERR_CUDA;
+}
+
+int bmf_host_unregister(void* p)
+{
+	if (!p) return BMF_ERR_INVALID;
+	return cudaHostUnregister(p) == cudaSuccess ? BMF_OK : BMF_ERR_CUDA;
 }
 
 int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* indices, uint32_t* bits, uint8_t* masks, float* density)
@@ -1123,8 +1227,16 @@ int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal
 	if (prim_n != 3 && prim_n != 4) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: prim_n must be 3 or 4");
 	if (smooth_normals && !normal) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: smooth_normals needs a normal array");
 	if (n_verts == 0 || n_inds < prim_n || iters <= 0) return BMF_OK;
-	for (int i = 0; i < n_inds; i++)
-		if (indices[i] >= (uint32_t)n_verts) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: index out of range");
+	{
+		// init_valence is a uint8 in the reference (Vertices.hpp:12) and the device keeps four byte counters per 32-bit word: a vertex
+		// used more than 255 times would carry into its neighbour's counter, so such a mesh is refused instead of being smoothed wrongly
+		std::vector<uint16_t> uses((size_t)n_verts, 0);
+		for (int i = 0; i < n_inds; i++)
+		{
+			if (indices[i] >= (uint32_t)n_verts) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: index out of range");
+			if (i < (n_inds / prim_n) * prim_n && ++uses[indices[i]] > 255) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_process: a vertex is referenced more than 255 times (init_valence is 8 bits)");
+		}
+	}
 	BMF_CUDA(cudaSetDevice(ctx->device));
 	ctx->have_batch = false; // the arenas are reused
 	ctx->color_ones = 0;

@@ -638,10 +638,16 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
                                                            ChunkCounts* __restrict__ chunks,
                                                            unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
 {
-	__shared__ uint32_t s_w[3][SCAN_CTA / 32];
-	__shared__ uint32_t s_tot[3];
+	// 64-bit throughout: a tile of 1024 chunks of dim 256 can hold more than 2^32 indices (15 * 256^3 per chunk), and a sum that
+	// wrapped inside the tile would slip past the > 2^32 guard below
+	typedef unsigned long long u64;
+	__shared__ u64 s_w[3][SCAN_CTA / 32];
+	__shared__ u64 s_tot[3];
+	__shared__ uint32_t s_maxv;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-	unsigned long long carry0 = 0, carry1 = 0, carry2 = 0;
+	if (t == 0) s_maxv = 0;
+	uint32_t maxv = 0;
+	u64 carry0 = 0, carry1 = 0, carry2 = 0;
 	for (int base = 0; base < n_chunks; base += SCAN_CTA)
 	{
 		const int i = base + t;
@@ -651,23 +657,24 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 			f = flags_contain_mesh(flags[i]) ? 1u : 0u;
 			if (f) { a = chunk_tot[3 * (size_t)i]; b = chunk_tot[3 * (size_t)i + 1]; c = chunk_tot[3 * (size_t)i + 2]; }
 		}
-		uint32_t ia = a, ib = b, ic = c;
+		maxv = max(maxv, b);
+		u64 ia = a, ib = b, ic = c;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
-			uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+			u64 ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
 			if (lane >= o) { ia += ta; ib += tb; ic += tc; }
 		}
 		if (lane == 31) { s_w[0][warp] = ia; s_w[1][warp] = ib; s_w[2][warp] = ic; }
 		__syncthreads();
 		if (warp == 0)
 		{
-			uint32_t va = s_w[0][lane], vb = s_w[1][lane], vc = s_w[2][lane];
-			uint32_t ja = va, jb = vb, jc = vc;
+			u64 va = s_w[0][lane], vb = s_w[1][lane], vc = s_w[2][lane];
+			u64 ja = va, jb = vb, jc = vc;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
 			{
-				uint32_t ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
+				u64 ta = __shfl_up_sync(0xffffffffu, ja, o), tb = __shfl_up_sync(0xffffffffu, jb, o), tc = __shfl_up_sync(0xffffffffu, jc, o);
 				if (lane >= o) { ja += ta; jb += tb; jc += tc; }
 			}
 			s_w[0][lane] = ja - va; s_w[1][lane] = jb - vb; s_w[2][lane] = jc - vc;
@@ -687,11 +694,17 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 		carry0 += s_tot[0]; carry1 += s_tot[1]; carry2 += s_tot[2];
 		__syncthreads();
 	}
+#pragma unroll
+	for (int o = 16; o >= 1; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
+	if (lane == 0 && maxv) atomicMax(&s_maxv, maxv);
+	__syncthreads();
 	if (t == 0)
 	{
 		const bool overflow = carry0 >= 0xFFFFFFFFull || carry1 >= 0xFFFFFFFFull || carry2 >= 0xFFFFFFFFull;
 		totals[0] = carry0; totals[1] = carry1; totals[2] = carry2; totals[3] = overflow ? 1ull : 0ull;
 		totals[4] = 0; totals[5] = 0; // surface-cell list counters (k_bases)
+		totals[8] = s_maxv;           // largest chunk (vertices): decides whether chunk-local indices fit 16 bits (download.cuh)
+		totals[9] = 0;                // download error flag
 	}
 }
 
@@ -715,6 +728,8 @@ __global__ void __launch_bounds__(CTA) k_check_caps(unsigned long long* __restri
 		for (int k = 0; k < 6; k++) tot_host[k] = tot[k];
 		tot_host[6] = 0;
 		tot_host[7] = small;
+		tot_host[8] = tot[8];
+		tot_host[9] = 0;
 		__threadfence_system();
 	}
 	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n_words; i += (size_t)gridDim.x * CTA) host_words[i] = chunks_words[i];

@@ -17,6 +17,7 @@
 #ifndef BMF_B200_H
 #define BMF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -94,6 +95,14 @@ typedef struct bmf_params
 	                             MeshProcessor<4> for iters > 0; n_inds counts 4 per quad.  bmf_quads_to_tris = flush_to_tris */
 } bmf_params;
 
+/* bmf_chunk_info.flags: what a consumer may synthesise instead of receiving (bmf_batch_download_enqueue can skip these streams) */
+enum
+{
+	BMF_CHUNK_COLOR_ONE = 1,   /* every vertex colour of the chunk is exactly (1,1,1) (calculate_dual_vertex, DMCChunk.cpp:681; smoothing keeps it) */
+	BMF_CHUNK_NORMAL_ZERO = 2, /* every vertex normal of the chunk is exactly (0,0,0) (no step of this batch writes v.n) */
+	BMF_CHUNK_INDEX16 = 4      /* n_verts < 65536: the chunk-local indices fit uint16 */
+};
+
 typedef struct bmf_chunk_info
 {
 	int32_t contains_mesh; /* DMCChunk::contains_mesh (DMCChunk.cpp:159-162) */
@@ -101,6 +110,8 @@ typedef struct bmf_chunk_info
 	int64_t vert_offset, ind_offset; /* into the batch-wide SoA arrays */
 	float overlap_pos[3];            /* DMCChunk::overlap_pos (DMCChunk.cpp:97) */
 	float scale;                     /* DMCChunk::scale = delta (DMCChunk.cpp:94,98) */
+	int32_t flags;                   /* BMF_CHUNK_* */
+	int32_t reserved;
 } bmf_chunk_info;
 
 enum
@@ -144,6 +155,34 @@ int bmf_batch_download(bmf_ctx* ctx, float* pos, float* normal, float* color, ui
 /* same, but only enqueues the copies on the ctx stream (use pinned host buffers); bmf_batch_wait completes them.
  * Two contexts on one GPU ping-pong this way: the copies of batch i overlap the kernels of batch i+1. */
 int bmf_batch_download_async(bmf_ctx* ctx, float* pos, float* normal, float* color, uint8_t* boundary, uint8_t* valence, uint32_t* indices);
+
+/* Host-asynchronous, device-driven download (csrc/download.cuh): a kernel on the ctx stream stores the batch's arrays straight
+ * into the caller's PINNED host buffers, sized by the totals it reads on the device -- the call neither waits for the batch nor
+ * for the copy; bmf_batch_wait (or any query) completes both and reports a buffer that was too small (BMF_ERR_NOMEM, nothing
+ * written) or uint16 indices that do not fit (BMF_ERR_INVALID).  Buffers must come from bmf_host_alloc or be registered with
+ * bmf_host_register (page-locked and device-mapped); they should be 16-byte aligned.  This is the OPT-IN compact form of
+ * GLChunk::format_data's output (GLChunk.cpp:278-296): leave a stream NULL to skip it -- bmf_chunk_info.flags says which ones
+ * are constant and can be synthesised by the consumer -- and pass indices16 instead of indices32 to receive the chunk-local
+ * indices as uint16 (valid when every chunk of the batch has < 65536 vertices; bmf_chunk_info.flags & BMF_CHUNK_INDEX16).
+ * bmf_batch_download stays the reference-layout default. */
+typedef struct bmf_download_desc
+{
+	float* pos;          /* [cap_verts][3] or NULL */
+	float* normal;       /* [cap_verts][3] or NULL */
+	float* color;        /* [cap_verts][3] or NULL */
+	uint8_t* boundary;   /* [cap_verts] or NULL */
+	uint8_t* valence;    /* [cap_verts] or NULL */
+	uint32_t* indices32; /* [cap_inds] or NULL */
+	uint16_t* indices16; /* [cap_inds] or NULL (at most one of indices32 / indices16) */
+	int64_t cap_verts, cap_inds; /* capacity of the buffers above, in vertices / indices */
+} bmf_download_desc;
+int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc);
+/* page-locked, device-mapped host memory for the call above (cudaHostAlloc portable + mapped) -- so that a host program needs no
+ * CUDA headers -- and registration of memory the caller already owns (e.g. a shared-memory segment several ranks write into) */
+int bmf_host_alloc(size_t bytes, void** out);
+void bmf_host_free(void* p);
+int bmf_host_register(void* p, size_t bytes);
+int bmf_host_unregister(void* p);
 
 /* One chunk in the reference's own layouts: DualVertex[n_verts] (84-byte records, Vertices.hpp:5-24),
  * mesh_indexes, BinaryBlock words (dim^3/32), MasksBlock byte image (dim^3, needs keep_masks),

@@ -159,7 +159,12 @@ def test_noise_terrain(gpu, oracle, kind, dim):
     diff = np.abs(g["density"] - o["density"])
     flips = int(((g["density"] < 0) != (o["density"] < 0)).sum())
     print("kind %d dim %d: max |d_gpu - d_oracle| = %.3g, sign flips = %d of %d" % (kind, dim, diff.max(), flips, dim ** 3))
-    assert diff.max() <= 1e-5 * max(1.0, float(np.abs(o["density"]).max()) / 75.0) or diff.max() <= 1e-5
+    # contract (north_star): 1e-5 ABSOLUTE against the reference's noise.  The reference's noise library is not on this box, so the
+    # comparison is against the restatement (oracle/fastnoise_ref.h), and against that the device is not merely within 1e-5 but
+    # bit-identical: every FMA of the FMA SIMD level is an explicit __fmaf_rn on the device and an fmaf() in the oracle.
+    assert diff.max() <= 1e-5
+    assert diff.max() == 0.0 and flips == 0
+    np.testing.assert_array_equal(g["density"].view(np.uint32), o["density"].view(np.uint32))
     # topology must be exact given identical density samples: feed the GPU's density to the oracle
     o2 = oracle.chunk(oracle.sampler(ob.HOST_DENSITY), pos, size, dim, overlap, host_density=g["density"])
     assert_same_topology(g, o2)
@@ -183,7 +188,8 @@ def test_smoothing_matches_oracle(gpu, oracle, iters, pb, sn):
         gn, on = g["verts"]["n"], o["normal"]
         np.testing.assert_array_equal(np.isnan(gn), np.isnan(on))
         m = ~np.isnan(on)
-        assert np.abs(gn[m] - on[m]).max() <= 1e-5
+        assert np.abs(gn[m] - on[m]).max() <= 1e-5  # the contract
+        np.testing.assert_array_equal(gn[m].view(np.uint32), on[m].view(np.uint32))  # measured: identical bits
 
 
 def test_batch_of_chunks_matches_per_chunk_oracle(gpu, oracle):

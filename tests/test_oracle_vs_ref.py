@@ -85,7 +85,7 @@ def test_implicit_values_and_gradients(ref, oracle):
 
 def test_qef_vs_reference_with_outlier_count(ref, oracle):
     rng = np.random.default_rng(9)
-    m, bad, worst = 3000, 0, 0.0
+    m, ds = 3000, []
     for j in range(m):
         c = int(rng.integers(2, 13))
         p = rng.random((c, 3), dtype=np.float32)
@@ -93,11 +93,16 @@ def test_qef_vs_reference_with_outlier_count(ref, oracle):
         n /= np.linalg.norm(n, axis=1, keepdims=True)
         xr, _ = ref.qef_solve(p, n)
         xo, _ = oracle.qef_solve(p, n)
-        d = float(np.abs(xr - xo).max())
-        worst = max(worst, d if d < 1e-3 else 0.0)
-        bad += d > 1e-4
-    # p99 1.6e-4, 0.06 % > 1e-3 (pseudo-inverse threshold flips under the rsqrt approximation)
-    assert bad <= 0.03 * m, "%d of %d beyond 1e-4" % (bad, m)
+        ds.append(float(np.abs(xr - xo).max()))
+    ds = np.array(ds)
+    bad, big = int((ds > 1e-4).sum()), int((ds > 1e-3).sum())
+    print("QEF oracle vs compiled reference (_mm_rsqrt_ps): %d of %d systems beyond 1e-4, %d beyond 1e-3, p50 %.3g p99 %.3g max %.3g"
+          % (bad, m, big, np.percentile(ds, 50), np.percentile(ds, 99), ds.max()))
+    # measured in the authoring container (Intel, AVX-512): 23 of 3000 beyond 1e-4 (0.77 %), none beyond 1e-3, p99 7.2e-5, max 4.3e-4
+    # (inputs in the unit cube).  The only difference between the two solvers is the reference's 12-bit _mm_rsqrt_ps (qef_simd.h:196),
+    # which is CPU-specific; the bar leaves room for another vendor's approximation, not for an algorithmic difference.
+    assert bad <= 0.01 * m, "%d of %d beyond 1e-4" % (bad, m)
+    assert big == 0 and ds.max() <= 1e-3
 
 
 def test_world_batch_totals(ref, oracle):
