@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbmf_b200.so")
 SOURCES = ["bmf_b200.cu"]
-DEPS = ["bmf_b200.cu", "extract.cuh", "smooth.cuh", "seam.cuh", "quads.cuh", "noise.cuh", "mc_tables.h", os.path.join("..", "..", "include", "bmf_b200.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [os.path.join("..", "..", "include", "bmf_b200.h")]
 NVCC = os.environ.get("BMF_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]

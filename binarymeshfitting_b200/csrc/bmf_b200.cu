@@ -8,6 +8,7 @@
 #include "seam.cuh"
 #include "quads.cuh"
 #include "download.cuh"
+#include "fused.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -98,6 +99,14 @@ struct bmf_ctx
 	DevBuf<uint32_t> flags, bits, wcnt, wib, seg_tot, chunk_tot;
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
+	// fused per-chunk extraction (fused.cuh): one CTA per mesh chunk does label_edges + polygonize + MeshProcessor::init
+	int fused_extract = 0;    // BMF_FUSED=1: k_chunk_mesh for dim <= 64 triangle batches (bit-identical, 6 launches instead of 12; not yet faster, see DESIGN)
+	bool batch_fused = false; // the resident batch went through k_chunk_mesh
+	size_t fused_smem = 0;
+	DevBuf<int> mesh_list;
+	DevBuf<unsigned int> fz_status;
+	DevBuf<unsigned long long> fz_agg, fz_inc, fz_prof;
+	bool fused_prof = false; // BMF_FUSED_PROF=1: per-phase SM clocks of k_chunk_mesh, mean printed to stderr when the batch completes
 	int sm_count = 148;
 	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
 	size_t smooth_smem = 0;    // dynamic shared memory of k_smooth_chunks
@@ -315,7 +324,11 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
 		BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, valence, n_verts, ctx->block_sums.p, ctx->adj_off.p);
 	}
-	if (grid_path)
+	if (grid_path && ctx->batch_fused)
+	{
+		// k_chunk_mesh built the CSR (adj, prim_vbase) together with the mesh
+	}
+	else if (grid_path)
 	{
 		BMF_LAUNCH(k_adj_fill, ctx->sm_count * 8, CTA, 0, ctx->L, ctx->wib.p, chunks_dev, ctx->icells.p, ctx->totals_dev.p + 4, inds, ctx->cls.p, ctx->adj_off.p, ctx->adj.p,
 		           ctx->prim_vbase.p, tot);
@@ -446,6 +459,57 @@ int launch_mesh(bmf_ctx* ctx)
 	const MeshCaps caps = mesh_caps(ctx);
 	unsigned long long* tot = ctx->totals_dev.p;
 	unsigned long long* list_count = tot + 4;
+	if (ctx->batch_fused)
+	{
+		// ---- dim <= 64, triangles: k_mesh_list + ONE launch of k_chunk_mesh (fused.cuh) for label_edges, polygonize and
+		// MeshProcessor::init of the whole batch; totals, capacity verdict and chunk table are published by the kernel itself
+		uint32_t* host_table = ctx->counts_published ? nullptr : reinterpret_cast<uint32_t*>(ctx->counts_pinned);
+		BMF_LAUNCH(k_mesh_list, 1, SCAN_CTA, 0, ctx->flags.p, n, ctx->mesh_list.p, ctx->fz_status.p, ctx->counts.p, host_table, tot, ctx->totals_pinned->v);
+		BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
+		if (caps.verts && ctx->color_ones < 3 * caps.verts)
+		{
+			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
+			ctx->color_ones = ctx->color.cap;
+		}
+		FusedArgs A;
+		memset(&A, 0, sizeof(A));
+		A.L = L; A.n = n;
+		A.bits = ctx->bits.p; A.flags = ctx->flags.p; A.mesh_list = ctx->mesh_list.p;
+		A.chunks = ctx->counts.p; A.host_table = host_table;
+		A.status = ctx->fz_status.p; A.agg = ctx->fz_agg.p; A.inc = ctx->fz_inc.p;
+		A.tot = tot; A.tot_host = ctx->totals_pinned->v;
+		const bool have = caps.cells && caps.verts && caps.inds; // nothing allocated yet: every chunk reports "does not fit", the host sizes the arenas
+		A.cap_cells = have ? caps.cells : 0; A.cap_verts = have ? caps.verts : 0; A.cap_inds = have ? caps.inds : 0;
+		A.vcells = ctx->vcells.p; A.icells = ctx->icells.p;
+		A.s = ctx->sampler;
+		A.src.density = ctx->density_cur;
+		A.src.hmap = (!ctx->density_cur && is_terrain2d(kind)) ? ctx->hmap.p : nullptr;
+		A.src.sheet_of = ctx->sheet_of.p;
+		A.geom = ctx->geom.p;
+		A.pos = ctx->pos.p; A.boundary = ctx->boundary.p; A.normal = ctx->normal.p; A.cls = ctx->cls.p; A.inds = ctx->inds.p;
+		A.valence = ctx->valence.p; A.adj_off = ctx->adj_off.p;
+		A.adj = params->iters > 0 ? ctx->adj.p : nullptr;
+		A.prim_vbase = ctx->prim_vbase.p;
+		A.masks = params->keep_masks ? ctx->masks.p : nullptr;
+		if (ctx->fused_prof)
+		{
+			BMF_CUDA(ctx->fz_prof.reserve(16 * (size_t)n));
+			BMF_CUDA(cudaMemsetAsync(ctx->fz_prof.p, 0, 16 * (size_t)n * sizeof(unsigned long long), st));
+			A.prof = ctx->fz_prof.p;
+		}
+		BMF_LAUNCH(k_chunk_mesh<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->sm_count), FUSED_NT, ctx->fused_smem, A);
+		ctx->counts_published = true;
+		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+		if (have && params->iters > 0)
+		{
+			int rc = run_smooth<3>(ctx, caps.verts, caps.inds, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
+			                       params->iters, params->process_boundary, params->smooth_normals, params->qef, 1, true, tot);
+			if (rc) return rc;
+		}
+		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+		return BMF_OK;
+	}
 	// totals and the chunk table reach the host through mapped pinned memory written by the kernels themselves (UVA):
 	// no D2H transfer sits in this stream, so nothing here can queue behind another context's mesh download
 	{
@@ -588,6 +652,23 @@ int finish(bmf_ctx* ctx)
 	for (int s = 0; s < 6; s++) elapsed(ctx, s, s + 1, &ctx->stage_ms[s]);
 	elapsed(ctx, 0, 6, &ctx->stage_ms[BMF_STAGE_TOTAL]);
 	ctx->finished = true;
+	if (ctx->fused_prof && ctx->batch_fused && ctx->fz_prof.p)
+	{
+		std::vector<unsigned long long> h(16 * (size_t)ctx->n);
+		cudaMemcpy(h.data(), ctx->fz_prof.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+		double sum[16] = {};
+		int m = 0;
+		for (int j = 0; j < ctx->n; j++)
+		{
+			const unsigned long long* r = &h[16 * (size_t)j];
+			if (!r[0] || !r[10]) continue;
+			m++;
+			for (int k = 1; k <= 10; k++) sum[k] += (double)(r[k] - r[k - 1]);
+		}
+		fprintf(stderr, "k_chunk_mesh phases (mean SM cycles over %d chunks with smoothing CSR): stage %.0f classify %.0f scan %.0f lookback %.0f table %.0f | fix %.0f lists %.0f verts %.0f inds %.0f valence %.0f adj %.0f\n",
+		        m, m ? sum[1] / m : 0, m ? sum[2] / m : 0, m ? sum[3] / m : 0, m ? sum[4] / m : 0, m ? sum[5] / m : 0, 0.0, m ? sum[6] / m : 0, m ? sum[7] / m : 0, m ? sum[8] / m : 0,
+		        m ? sum[9] / m : 0, m ? sum[10] / m : 0);
+	}
 	if (ctx->dl_pending)
 	{
 		ctx->dl_pending = false;
@@ -656,6 +737,14 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 			ctx->smooth_cluster = 0;
 		}
 	}
+	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e) != 0;
+	if (const char* e = getenv("BMF_FUSED_PROF")) ctx->fused_prof = atoi(e) != 0;
+	ctx->fused_smem = fused_smem_bytes(make_layout(64), FUSED_NT);
+	if (cudaFuncSetAttribute(k_chunk_mesh<FUSED_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
+	{
+		cudaGetLastError();
+		ctx->fused_extract = 0;
+	}
 	// k_bases keeps its segment's sign planes plus a work list of active words in dynamic shared memory (57 KB at dim 256)
 	cudaFuncSetAttribute(k_bases<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaFuncSetAttribute(k_bases<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -681,6 +770,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
 	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release(); ctx->smooth_cnt.release();
+	ctx->mesh_list.release(); ctx->fz_status.release(); ctx->fz_agg.release(); ctx->fz_inc.release(); ctx->fz_prof.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
@@ -770,14 +860,25 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		g.oz = c.pos[2] - so;
 		ctx->geom_host[i] = g;
 	}
+	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64;
 	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
-	BMF_CUDA(ctx->wcnt.reserve(n_words));
-	BMF_CUDA(ctx->wv4.reserve(n_words));
-	BMF_CUDA(ctx->wib.reserve(n_words));
-	BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
-	BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
+	if (fused)
+	{
+		BMF_CUDA(ctx->mesh_list.reserve(n));
+		BMF_CUDA(ctx->fz_status.reserve(n));
+		BMF_CUDA(ctx->fz_agg.reserve(3 * (size_t)n));
+		BMF_CUDA(ctx->fz_inc.reserve(3 * (size_t)n));
+	}
+	else
+	{
+		BMF_CUDA(ctx->wcnt.reserve(n_words));
+		BMF_CUDA(ctx->wv4.reserve(n_words));
+		BMF_CUDA(ctx->wib.reserve(n_words));
+		BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
+		BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
+	}
 	BMF_CUDA(ctx->counts.reserve(n));
 	BMF_CUDA(ctx->totals_dev.reserve(TOT_SLOTS));
 	if ((size_t)n > ctx->counts_pinned_cap)
@@ -847,7 +948,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (host_density && !params->density_on_device)
 		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
-	BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st));
+	if (!fused) BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st));
 	if (n_sheets)
 	{
 		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_geom.p, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * n_sheets, cudaMemcpyHostToDevice, st));
@@ -898,7 +999,11 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	// ---- K3
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
 	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
-	if (params->quads)
+	if (fused)
+	{
+		// classification, counts and the chunk scan happen inside k_chunk_mesh (launch_mesh)
+	}
+	else if (params->quads)
 	{
 		BMF_CUDA(ctx->wq.reserve(n_words));
 		BMF_CUDA(ctx->wqq.reserve(n_words));
@@ -913,7 +1018,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	if (!fused) BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
 	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
@@ -1037,9 +1142,11 @@ int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc)
 	memset(&A, 0, sizeof(A));
 	void* host[7] = { desc->pos, desc->normal, desc->color, desc->boundary, desc->valence, desc->indices32, desc->indices16 };
 	void* dev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	const uintptr_t align[7] = { 4, 4, 4, 1, 1, 4, 2 };
 	for (int k = 0; k < 7; k++)
 	{
 		if (!host[k]) continue;
+		if (reinterpret_cast<uintptr_t>(host[k]) & (align[k] - 1)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_enqueue: a host buffer is not aligned to its element type");
 		if (cudaHostGetDevicePointer(&dev[k], host[k], 0) != cudaSuccess)
 		{
 			cudaGetLastError();

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(CTA) k_download(DownloadArgs A, unsigned long 
 	if (tot[TOT_SMALL]) return; // the emitters did not run: the host grows the arenas, re-launches them and this kernel
 	const unsigned long long V = tot[TOT_VERTS], I = tot[TOT_INDS];
 	unsigned long long err = 0;
-	if (V > A.cap_verts || ((A.inds32 || A.inds16) && I > A.cap_inds)) err = 1;
+	const bool want_v = A.pos || A.normal || A.color || A.boundary || A.valence, want_i = A.inds32 || A.inds16;
+	if ((want_v && V > A.cap_verts) || (want_i && I > A.cap_inds)) err = 1;
 	else if (A.inds16 && tot[TOT_MAXV] > 65535ull) err = 2;
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{

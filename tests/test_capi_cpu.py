@@ -32,7 +32,7 @@ def test_header_functions_are_exported():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(capi.SamplerDesc) == 80 and C.sizeof(capi.ChunkDesc) == 32
-    assert C.sizeof(capi.Params) == 36 and C.sizeof(capi.ChunkInfo) == 48
+    assert C.sizeof(capi.Params) == 36 and C.sizeof(capi.ChunkInfo) == 56 and C.sizeof(capi.DownloadDesc) == 72
 
 
 def test_sampler_defaults_are_the_reference_world_defaults():

@@ -62,7 +62,7 @@ def test_enqueue_on_a_fresh_context_without_any_host_sync():
     ctx.close()
 
 
-@pytest.mark.parametrize("misalign", [0, 4, 1])
+@pytest.mark.parametrize("misalign", [0, 4, 2])
 def test_odd_sizes_and_unaligned_buffers(misalign):
     ctx = Context(0)
     ctx.set_sampler(capi.SPHERE)
@@ -71,7 +71,7 @@ def test_odd_sizes_and_unaligned_buffers(misalign):
     ref = ctx.download()
     raw = {k: capi.PinnedBuffer(ctx.lib, nb + 64) for k, nb in (("pos", 12 * v), ("i32", 4 * i), ("i16", 2 * i), ("val", v))}
     ctx.submit(capi.make_chunk_descs([[-128, -128, -128, 256.0]]), 64, iters=0)
-    pos = raw["pos"].view(np.uint8)[misalign:misalign + 12 * v]
+    pos = raw["pos"].view(np.uint8)[(misalign + 3) // 4 * 4:(misalign + 3) // 4 * 4 + 12 * v]  # floats stay 4-byte aligned
     i16 = raw["i16"].view(np.uint8)[misalign:misalign + 2 * i]
     val = raw["val"].view(np.uint8)[misalign:misalign + v]
     d = capi.DownloadDesc()
@@ -102,6 +102,13 @@ def test_error_paths():
     ctx.submit(d1, 64, iters=0)
     with pytest.raises(capi.BmfError, match="page-locked"):
         ctx.download_enqueue(pos=np.zeros(3 * v, np.float32))
+    # element-type alignment is checked up front
+    odd = capi.PinnedBuffer(ctx.lib, 12 * v + 64)
+    d = capi.DownloadDesc()
+    d.pos, d.cap_verts = odd.view(np.uint8)[1:].ctypes.data, v
+    import ctypes as C
+    assert ctx.lib.bmf_batch_download_enqueue(ctx.h, C.byref(d)) == -1
+    odd.close()
     # a chunk with >= 65536 vertices cannot travel as uint16
     rng = np.random.default_rng(3)
     dens = rng.standard_normal(64 ** 3).astype(np.float32)
