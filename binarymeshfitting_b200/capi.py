@@ -22,7 +22,7 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
            "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
-           "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve",
+           "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve", "bmf_sampler_gradient", "bmf_color_map", "bmf_mesh_collapse_bad_quads",
            "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue",
            "bmf_batch_download_enqueue", "bmf_host_alloc", "bmf_host_free", "bmf_host_register", "bmf_host_unregister")
 
@@ -108,6 +108,9 @@ def load_library(path=SO):
     lib.bmf_mesh_process.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_mesh_process_steps.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bmf_qef_solve.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp]
+    lib.bmf_sampler_gradient.argtypes = [vp, vp, C.c_int64, C.c_float, vp]
+    lib.bmf_color_map.argtypes = [vp, vp, C.c_int64, vp]
+    lib.bmf_mesh_collapse_bad_quads.argtypes = [vp, vp, C.c_int, vp, C.c_int64, vp, vp, vp, vp, vp]
     lib.bmf_quads_to_tris.argtypes = [vp, vp, C.c_int64, vp]
     lib.bmf_batch_download_flat_quads.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.bmf_ubench_issue.argtypes = [vp, vp]
@@ -369,6 +372,31 @@ class Context:
         ms = np.zeros(2, np.float32)
         self._check(self.lib.bmf_seam_stage_ms(self.h, _p(ms)))
         return {"count": float(ms[0]), "emit": float(ms[1])}
+
+    def sampler_gradient(self, points, h=0.01):
+        """Sampler::gradient of the current sampler at [m,3] world-space points -> [m,3] raw differences"""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        out = np.zeros_like(pts)
+        self._check(self.lib.bmf_sampler_gradient(self.h, _p(pts), len(pts), h, _p(out)))
+        return out
+
+    def color_map(self, pos):
+        """ColorMapper::generate_colors: [n,3] positions -> [n,3] colours"""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        col = np.zeros_like(pos)
+        self._check(self.lib.bmf_color_map(self.h, _p(pos), len(pos), _p(col)))
+        return col
+
+    def collapse_bad_quads(self, pos, quads):
+        """MeshProcessor<4>::init + collapse_bad_quads (+ flush) -> dict(pos, quads (rewired), destroyed, adj_next, bad_count, flushed)"""
+        pos = np.array(pos, np.float32, copy=True).reshape(-1, 3)
+        q = np.array(quads, np.uint32, copy=True).reshape(-1, 4)
+        destroyed = np.zeros(len(q), np.uint8)
+        adj_next = np.zeros(len(pos), np.uint8)
+        flushed = np.zeros_like(q)
+        nf, bad = C.c_int64(), C.c_int64()
+        self._check(self.lib.bmf_mesh_collapse_bad_quads(self.h, _p(pos), len(pos), _p(q), len(q), _p(destroyed), _p(adj_next), _p(flushed), C.byref(nf), C.byref(bad)))
+        return {"pos": pos, "quads": q, "destroyed": destroyed, "adj_next": adj_next, "bad_count": int(bad.value), "flushed": flushed[:nf.value].copy()}
 
     def qef_solve(self, positions, normals, counts):
         """positions/normals: [m,12,3]; counts: [m]."""

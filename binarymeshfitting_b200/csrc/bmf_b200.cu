@@ -9,6 +9,7 @@
 #include "quads.cuh"
 #include "download.cuh"
 #include "fused.cuh"
+#include "post.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -386,7 +387,14 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 	if (qef)
 	{
 		// build-defined placement: planes = (dual_p, face normal) of the final positions' primitives
-		BMF_LAUNCH(k_dual<N>, g_prims, CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1, tot);
+		if (qef == 2)
+		{
+			// planes = (dual_p, normalised sampler gradient at dual_p): MeshProcessor.cpp:224 (commented out in the reference), h = 0.01 (ImplicitSampler.hpp:38)
+			BMF_LAUNCH(k_dual<N>, g_prims, CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 0, 0, tot);
+			BMF_LAUNCH(k_dual_gradient, g_prims, CTA, 0, ctx->sampler, chunks_dev, ctx->geom.p, n_chunks, n_prims, ctx->dp.p, ctx->dn.p, 0.01f, tot);
+		}
+		else
+			BMF_LAUNCH(k_dual<N>, g_prims, CTA, 0, inds, ctx->prim_vbase.p, n_prims, pos, color, normal, ctx->dp.p, dcp, ctx->dn.p, 1, 1, tot);
 		BMF_LAUNCH(k_qef_place, g_qef, 128, 0, ctx->adj_off.p, ctx->adj.p, valence, boundary, n_verts, ctx->dp.p, ctx->dn.p, pos, pb, tot);
 	}
 	return BMF_OK;
@@ -827,6 +835,8 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (!valid_dim(params->dim)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: dim must be 32, 64, 128 or 256");
 	if (params->iters < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: iters < 0");
 	if (params->quads && (params->qef || params->keep_masks)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: quads cannot be combined with qef or keep_masks");
+	if (params->qef < 0 || params->qef > 2) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: qef must be 0, 1 (face normals) or 2 (sampler gradients)");
+	if (params->qef == 2 && !is_implicit(ctx->sampler.kind)) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: qef = 2 needs an analytic sampler (the value callback of the noise samplers is the constant 0, NoiseSampler.cpp:99-102)");
 	const int kind = ctx->sampler.kind;
 	if (kind == BMF_SAMPLER_HOST_DENSITY && !density_in) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_submit: HOST_DENSITY needs a density block");
 	BMF_CUDA(cudaSetDevice(ctx->device));
@@ -1399,6 +1409,123 @@ int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, co
 	BMF_CUDA(cudaMemcpyAsync(out_pos, ctx->qo.p, sizeof(float) * 3 * M, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaMemcpyAsync(out_err, ctx->qe.p, sizeof(float) * M, cudaMemcpyDeviceToHost, st));
 	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+int bmf_sampler_gradient(bmf_ctx* ctx, const float* points, int64_t m, float h, float* out)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (m < 0 || (m && (!points || !out))) return fail(ctx, BMF_ERR_INVALID, "bmf_sampler_gradient: bad arguments");
+	if (!ctx->sampler_set) return fail(ctx, BMF_ERR_STATE, "bmf_sampler_gradient: no sampler set");
+	if (ctx->sampler.kind == BMF_SAMPLER_HOST_DENSITY) return fail(ctx, BMF_ERR_STATE, "bmf_sampler_gradient: a HOST_DENSITY sampler has no device value function (call the host callback)");
+	if (m == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	// scratch: the QEF arenas are free outside bmf_qef_solve
+	const size_t M = (size_t)m;
+	BMF_CUDA(ctx->qp.reserve(3 * M));
+	BMF_CUDA(ctx->qo.reserve(3 * M));
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(cudaMemcpyAsync(ctx->qp.p, points, sizeof(float) * 3 * M, cudaMemcpyHostToDevice, st));
+	BMF_LAUNCH(k_sampler_gradient, std::min(grid_for(M, CTA), (unsigned)(ctx->sm_count * 8)), CTA, 0, ctx->sampler, ctx->qp.p, M, h, ctx->qo.p);
+	BMF_CUDA(cudaMemcpyAsync(out, ctx->qo.p, sizeof(float) * 3 * M, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+int bmf_color_map(bmf_ctx* ctx, const float* pos, int64_t n, float* color)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (n < 0 || (n && (!pos || !color))) return fail(ctx, BMF_ERR_INVALID, "bmf_color_map: bad arguments");
+	if (n == 0) return BMF_OK;
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	// ColorMapper::ColorMapper + get_noise (ColorMapper.cpp:6-9, 45-47): a fresh FastNoiseSIMD object (library defaults, seed 1337),
+	// SetNoiseType(SimplexFractal), SetFractalOctaves(4), SetFractalType(FBM)
+	bmf_sampler_desc d;
+	bmf_sampler_defaults(&d, BMF_SAMPLER_SPHERE);
+	SamplerDev sd;
+	build_sampler(d, &sd);
+	NoiseState ns = sd.ns;
+	ns.seed = 1337;
+	ns.base = NT_SIMPLEX; ns.fractal = 1; ns.octaves = 4; ns.fractal_type = FT_FBM; ns.perturb = 0;
+	ns.fractal_bounding = bounding(ns.gain, ns.octaves);
+	const size_t N = (size_t)n;
+	BMF_CUDA(ctx->qp.reserve(3 * N));
+	BMF_CUDA(ctx->qo.reserve(3 * N));
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(cudaMemcpyAsync(ctx->qp.p, pos, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, st));
+	BMF_LAUNCH(k_color_map, std::min(grid_for(N, CTA), (unsigned)(ctx->sm_count * 8)), CTA, 0, ns, ctx->qp.p, N, ctx->qo.p);
+	BMF_CUDA(cudaMemcpyAsync(color, ctx->qo.p, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	return BMF_OK;
+}
+
+int bmf_mesh_collapse_bad_quads(bmf_ctx* ctx, float* pos, int n_verts, uint32_t* quads, int64_t n_quads, uint8_t* destroyed, uint8_t* adj_next, uint32_t* flushed,
+                                int64_t* n_flushed, int64_t* bad_count)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (n_flushed) *n_flushed = 0;
+	if (bad_count) *bad_count = 0;
+	if (n_verts < 0 || n_quads < 0 || (n_quads && (!pos || !quads))) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_collapse_bad_quads: bad arguments");
+	if (n_quads > 0x3FFFFFFFll) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_collapse_bad_quads: more than 2^30 quads");
+	if (n_verts == 0 || n_quads == 0) return BMF_OK; // MeshProcessor::init returns at once (MeshProcessor.cpp:28-29)
+	const size_t V = (size_t)n_verts, Q = (size_t)n_quads, I = 4 * Q;
+	{
+		std::vector<uint16_t> uses(V, 0);
+		for (size_t i = 0; i < I; i++)
+		{
+			if (quads[i] >= (uint32_t)n_verts) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_collapse_bad_quads: index out of range");
+			if (++uses[quads[i]] > 255) return fail(ctx, BMF_ERR_INVALID, "bmf_mesh_collapse_bad_quads: a vertex is referenced more than 255 times (adj_next is 8 bits)");
+		}
+	}
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	ctx->have_batch = false; // the arenas are reused
+	ctx->color_ones = 0;
+	cudaStream_t st = ctx->stream;
+	BMF_CUDA(ctx->pos.reserve(3 * V + 4));
+	BMF_CUDA(ctx->valence.reserve(V + 16));
+	BMF_CUDA(ctx->boundary.reserve(Q + 16));   // Primitive::destroyed
+	BMF_CUDA(ctx->inds.reserve(I + 4));
+	BMF_CUDA(ctx->cls.reserve(I + 4));         // the flushed index buffer
+	BMF_CUDA(ctx->adj_off.reserve(V));
+	BMF_CUDA(ctx->cursor.reserve(V));
+	BMF_CUDA(ctx->adj.reserve(2 * I + 4));     // init's lists + one new 4-entry list per collapse (adj_block.push_back, :384-387)
+	BMF_CUDA(ctx->prim_vbase.reserve(Q));
+	BMF_CUDA(ctx->counts.reserve(1));
+	BMF_CUDA(ctx->totals_dev.reserve(TOT_SLOTS));
+	const size_t per_block = (size_t)CTA * SCAN_ITEMS;
+	const unsigned nblk = grid_for(V, (int)per_block);
+	BMF_CUDA(ctx->block_sums.reserve(nblk));
+	BMF_CUDA(cudaMemcpyAsync(ctx->pos.p, pos, sizeof(float) * 3 * V, cudaMemcpyHostToDevice, st));
+	BMF_CUDA(cudaMemcpyAsync(ctx->inds.p, quads, sizeof(uint32_t) * I, cudaMemcpyHostToDevice, st));
+	ChunkCounts one;
+	memset(&one, 0, sizeof(one));
+	one.contains_mesh = 1; one.n_verts = (uint32_t)V; one.n_inds = (uint32_t)I;
+	BMF_CUDA(cudaMemcpyAsync(ctx->counts.p, &one, sizeof(one), cudaMemcpyHostToDevice, st));
+	// MeshProcessor<4>::init (MeshProcessor.cpp:25-55, 98-128): adj_next = uses, adj_offset = their exclusive prefix, lists in (prim, corner) order
+	BMF_CUDA(cudaMemsetAsync(ctx->valence.p, 0, V + 16, st));
+	BMF_LAUNCH(k_valence_from_inds, grid_for(I, CTA), CTA, 0, ctx->inds.p, I, ctx->valence.p);
+	BMF_LAUNCH(k_scan8_partial, nblk, CTA, 0, ctx->valence.p, V, ctx->block_sums.p);
+	BMF_LAUNCH(k_scan_block_sums, 1, SCAN_CTA, 0, ctx->block_sums.p, (int)nblk);
+	BMF_LAUNCH(k_scan8_final, nblk, CTA, 0, ctx->valence.p, V, ctx->block_sums.p, ctx->adj_off.p);
+	BMF_CUDA(cudaMemsetAsync(ctx->cursor.p, 0, V * sizeof(uint32_t), st));
+	BMF_LAUNCH(k_csr_fill<4>, grid_for(Q, CTA), CTA, 0, ctx->inds.p, Q, ctx->counts.p, 1, ctx->adj_off.p, ctx->cursor.p, ctx->adj.p, ctx->prim_vbase.p);
+	BMF_LAUNCH(k_csr_sort, grid_for(V, CTA), CTA, 0, ctx->adj_off.p, ctx->valence.p, V, ctx->adj.p);
+	BMF_LAUNCH(k_collapse_bad_quads, 1, COLLAPSE_CTA, 0, ctx->inds.p, (uint32_t)Q, ctx->pos.p, ctx->valence.p, ctx->adj_off.p, ctx->adj.p, (uint32_t)I, ctx->boundary.p,
+	           ctx->cls.p, ctx->totals_dev.p);
+	unsigned long long res[2] = { 0, 0 };
+	BMF_CUDA(cudaMemcpyAsync(res, ctx->totals_dev.p, sizeof(res), cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(pos, ctx->pos.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaMemcpyAsync(quads, ctx->inds.p, sizeof(uint32_t) * I, cudaMemcpyDeviceToHost, st));
+	if (destroyed) BMF_CUDA(cudaMemcpyAsync(destroyed, ctx->boundary.p, Q, cudaMemcpyDeviceToHost, st));
+	if (adj_next) BMF_CUDA(cudaMemcpyAsync(adj_next, ctx->valence.p, V, cudaMemcpyDeviceToHost, st));
+	BMF_CUDA(cudaStreamSynchronize(st));
+	if (flushed && res[1]) 
+	{
+		BMF_CUDA(cudaMemcpyAsync(flushed, ctx->cls.p, sizeof(uint32_t) * 4 * (size_t)res[1], cudaMemcpyDeviceToHost, st));
+		BMF_CUDA(cudaStreamSynchronize(st));
+	}
+	if (bad_count) *bad_count = (int64_t)res[0];
+	if (n_flushed) *n_flushed = (int64_t)res[1];
 	return BMF_OK;
 }
 

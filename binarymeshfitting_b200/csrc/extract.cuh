@@ -75,11 +75,9 @@ __constant__ uint64_t c_tri_pack[256] = BMF_TRI_PACK_INIT;
 
 // ---- density of one grid point for the analytic / heightmap samplers ----------------------------------
 // implicit_block (ImplicitSampler.hpp:14-36): coordinate = p + (float)i * scale
-__device__ __forceinline__ float implicit_point(const SamplerDev& s, const ChunkGeom& g, int x, int y, int z)
+// Sampler::value at a world-space point for the analytic kinds (primitive or the build-defined CSG of two primitives)
+__device__ __forceinline__ float analytic_value(const SamplerDev& s, float px, float py, float pz)
 {
-	float px = g.ox + (float)x * g.delta;
-	float py = g.oy + (float)y * g.delta;
-	float pz = g.oz + (float)z * g.delta;
 	if (s.kind == 4)
 	{
 		float a = implicit_value(s.csg_kind_a, s.csg_ws_a, px - s.csg_off_a[0], py - s.csg_off_a[1], pz - s.csg_off_a[2]);
@@ -87,6 +85,26 @@ __device__ __forceinline__ float implicit_point(const SamplerDev& s, const Chunk
 		return s.csg_op == 0 ? fmaxf(a, b) : s.csg_op == 1 ? fminf(a, b) : fminf(a, -b);
 	}
 	return implicit_value(s.kind, s.world_size, px, py, pz);
+}
+
+__device__ __forceinline__ float implicit_point(const SamplerDev& s, const ChunkGeom& g, int x, int y, int z)
+{
+	float px = g.ox + (float)x * g.delta;
+	float py = g.oy + (float)y * g.delta;
+	float pz = g.oz + (float)z * g.delta;
+	return analytic_value(s, px, py, pz);
+}
+
+// Sampler::gradient = implicit_gradient bound to the sampler's VALUE callback (ImplicitSampler.hpp:38-49, 57; NoiseSampler.hpp:35-47,
+// 76-136): six evaluations, raw differences -- not normalised, not divided by 2h.  The value callback of every noise sampler is
+// NoiseSamplers::noise3d, the constant 0 (NoiseSampler.cpp:99-102), so their gradient is (0-0, 0-0, 0-0).
+__device__ __forceinline__ void sampler_gradient_at(const SamplerDev& s, float px, float py, float pz, float h, float out[3])
+{
+	const bool analytic = s.kind >= 0 && s.kind <= 4;
+	const float dxp = analytic ? analytic_value(s, px + h, py, pz) : 0.0f, dxm = analytic ? analytic_value(s, px - h, py, pz) : 0.0f;
+	const float dyp = analytic ? analytic_value(s, px, py + h, pz) : 0.0f, dym = analytic ? analytic_value(s, px, py - h, pz) : 0.0f;
+	const float dzp = analytic ? analytic_value(s, px, py, pz + h) : 0.0f, dzm = analytic ? analytic_value(s, px, py, pz - h) : 0.0f;
+	out[0] = dxp - dxm; out[1] = dyp - dym; out[2] = dzp - dzm;
 }
 
 // terrain*_block tail (NoiseSampler.cpp:136-143, 180-187, 216-223, 250-257): density from a noise value

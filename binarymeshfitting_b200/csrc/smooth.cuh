@@ -857,6 +857,47 @@ __global__ void __launch_bounds__(128) k_qef_place(const uint32_t* __restrict__ 
 		qef_place_one(v, adj_off, adj, valence, boundary, dp, dn, pos, process_boundary);
 }
 
+// ---- Sampler::gradient for a list of world-space points (bmf_sampler_gradient)
+__global__ void __launch_bounds__(CTA) k_sampler_gradient(SamplerDev s, const float* __restrict__ pts, size_t m, float h, float* __restrict__ out)
+{
+	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < m; i += (size_t)gridDim.x * CTA)
+	{
+		float g[3];
+		sampler_gradient_at(s, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], h, g);
+		out[3 * i] = g[0]; out[3 * i + 1] = g[1]; out[3 * i + 2] = g[2];
+	}
+}
+
+// ---- bmf_params.qef = 2: dual normals from the sampler's gradient -- `t.dual_n = normalize(sampler.gradient(sampler.world_size,
+// t.dual_p, h))`, the line the reference's author left commented out at the end of optimize_dual_grid (MeshProcessor.cpp:224).
+// dual_p is in grid units of its chunk; world position = overlap_pos + p * scale (DMCChunk.cpp:94-98).  The chunk of a primitive is
+// the last one whose ind_base is <= the primitive's first index (binary search over the chunk table).
+__global__ void __launch_bounds__(CTA) k_dual_gradient(SamplerDev s, const ChunkCounts* __restrict__ chunks, const ChunkGeom* __restrict__ geom, int n_chunks,
+                                                        size_t n_prims, const float* __restrict__ dp, float* __restrict__ dn, float h,
+                                                        const unsigned long long* __restrict__ tot)
+{
+	if (tot)
+	{
+		if (tot[7]) return;
+		n_prims = (size_t)(tot[2] / 3);
+	}
+	for (size_t t = (size_t)blockIdx.x * CTA + threadIdx.x; t < n_prims; t += (size_t)gridDim.x * CTA)
+	{
+		const unsigned long long first = 3ull * t;
+		int lo = 0, hi = n_chunks - 1;
+		while (lo < hi)
+		{
+			const int mid = (lo + hi + 1) >> 1;
+			if (chunks[mid].ind_base <= first) lo = mid; else hi = mid - 1;
+		}
+		const ChunkGeom g = geom[lo];
+		const f3 p = ld3(dp, t);
+		float gr[3];
+		sampler_gradient_at(s, g.ox + p.x * g.delta, g.oy + p.y * g.delta, g.oz + p.z * g.delta, h, gr);
+		st3(dn, t, normalize3({ gr[0], gr[1], gr[2] }));
+	}
+}
+
 // ---- issue-rate microbenchmarks (the noise and QEF stages are bound by FP32 / INT32 issue, so their
 // roofline denominators are MEASURED here, not nominal).  Eight independent dependency chains per thread, 2048
 // resident threads per SM, enough CTAs for four waves.  OP 0: FP32 FMA (FFMA), 1: INT32 multiply-add (IMAD),

@@ -200,6 +200,8 @@ inline const float noise3d(const float, const glm::vec3&) { return 0; }
 inline void make(Sampler* s, int kind)
 {
 	s->value = noise3d;
+	// s->gradient = std::bind(implicit_gradient, noise3d, _1, _2, _3) (NoiseSampler.hpp:86-136): differences of the constant 0
+	s->gradient = [](const float, const glm::vec3&, float) { return glm::vec3(0.0f - 0.0f, 0.0f - 0.0f, 0.0f - 0.0f); };
 	bmf_sampler_defaults(&s->device, kind);
 	s->device.world_size = s->world_size;
 }
@@ -356,6 +358,22 @@ private:
 	}
 	~BmfDevice() { bmf_ctx_destroy(ctx); }
 };
+
+// Sampler::gradient (Sampler.hpp:29) for many points at once on the device: the same six evaluations and raw differences per point
+// as implicit_gradient (ImplicitSampler.hpp:38-49), bit-identical to calling s.gradient(world_size, p[i], h) on the host for the
+// samplers the device knows (s.device.kind); false for host-callback samplers (call s.gradient per point instead).
+inline bool sampler_gradient_block(const Sampler& s, const glm::vec3* p, size_t m, float h, glm::vec3* out, int device = 0)
+{
+	static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "glm::vec3 must be three packed floats");
+	if (s.device.kind == BMF_SAMPLER_HOST_DENSITY) return false;
+	BmfDevice& dev = BmfDevice::get(device);
+	if (!dev.ok()) return false;
+	std::lock_guard<std::mutex> guard(dev.lock);
+	bmf_sampler_desc d = s.device;
+	d.world_size = s.world_size;
+	if (bmf_sampler_set(dev.ctx, &d) != BMF_OK) return false;
+	return bmf_sampler_gradient(dev.ctx, reinterpret_cast<const float*>(p), (int64_t)m, h, reinterpret_cast<float*>(out)) == BMF_OK;
+}
 
 namespace bmf_detail
 {
@@ -1123,6 +1141,7 @@ public:
 		vertices.count = 0;
 		vertices.push_back(v);
 		indices.assign(inds.elements, inds.elements + inds.count / N * N);
+		destroyed.clear();
 		uint32_t a = 0;
 		for (size_t i = 0; i < vertices.count; i++)
 		{
@@ -1146,12 +1165,48 @@ public:
 		if (pending_iters > 0) run(pending_iters, pending_pb, 1);
 		pending_iters = 0;
 	}
+	// MeshProcessor.cpp:308-396: quads only (N != 4 returns at once, :311-312); serial order kept by the device kernel (csrc/post.cuh)
+	void collapse_bad_quads()
+	{
+		if (N != 4 || vertices.count == 0 || indices.size() < 4) return;
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok()) return;
+		const size_t n = vertices.count, nq = indices.size() / 4;
+		std::vector<float> pos(3 * n);
+		std::vector<uint8_t> adj_next(n);
+		for (size_t i = 0; i < n; i++)
+		{
+			const DualVertex& v = vertices.elements[i];
+			pos[3 * i] = v.p.x; pos[3 * i + 1] = v.p.y; pos[3 * i + 2] = v.p.z;
+		}
+		destroyed.assign(nq, 0);
+		int64_t bad = 0;
+		{
+			std::lock_guard<std::mutex> guard(dev.lock);
+			if (bmf_mesh_collapse_bad_quads(dev.ctx, pos.data(), (int)n, indices.data(), (int64_t)nq, destroyed.data(), adj_next.data(), nullptr, nullptr, &bad) != BMF_OK)
+			{
+				destroyed.clear();
+				return;
+			}
+		}
+		for (size_t i = 0; i < n; i++)
+		{
+			DualVertex& v = vertices.elements[i];
+			v.p = glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			v.adj_next = adj_next[i];
+		}
+		bad_quads = (uint32_t)bad; // the reference prints "detected N bad quads..." (:395)
+	}
+	uint32_t bad_quads = 0;
 	void flush(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& inds)
 	{
 		if (pending_iters > 0) run(pending_iters, pending_pb, 0);
 		pending_iters = 0;
 		v_out.push_back(vertices);
-		inds.push_back(indices.data(), indices.size());
+		if (destroyed.empty()) inds.push_back(indices.data(), indices.size());
+		else
+			for (size_t t = 0; t < indices.size() / N; t++) // `if (t.destroyed) continue;` (MeshProcessor.cpp:64-65)
+				if (!destroyed[t]) inds.push_back(&indices[t * N], N);
 	}
 	void flush_to_tris(SmartContainer<DualVertex>& v_out, SmartContainer<uint32_t>& inds) // quad -> (0,1,2),(2,3,0), MeshProcessor.cpp:73-91
 	{
@@ -1160,6 +1215,7 @@ public:
 		v_out.push_back(vertices);
 		for (size_t t = 0; t + 3 < indices.size() + 1 && N == 4; t += 4)
 		{
+			if (!destroyed.empty() && destroyed[t / 4]) continue;
 			const uint32_t* q = &indices[t];
 			const uint32_t tri[6] = { q[0], q[1], q[2], q[2], q[3], q[0] };
 			inds.push_back(tri, 6);
@@ -1203,8 +1259,36 @@ private:
 
 	SmartContainer<DualVertex> vertices;
 	std::vector<uint32_t> indices;
+	std::vector<uint8_t> destroyed; // Primitive::destroyed, only after collapse_bad_quads
 	bool smooth_normals;
 	int pending_iters = 0;
 	bool pending_pb = true;
 };
 } // namespace Processing
+
+// ---- ColorMapper (ColorMapper.hpp:7-24, ColorMapper.cpp:15-60) ----------------------------------------------------
+class ColorMapper
+{
+public:
+	FastNoiseSIMD* noise_context = nullptr; // the noise library is replaced by the device kernel
+	ColorMapper() {}
+	~ColorMapper() {}
+	void generate_colors(SmartContainer<DualVertex>& verts)
+	{
+		if (!verts.count) return;
+		BmfDevice& dev = BmfDevice::get();
+		if (!dev.ok()) return;
+		const size_t n = verts.count;
+		std::vector<float> pos(3 * n), col(3 * n);
+		for (size_t i = 0; i < n; i++)
+		{
+			const DualVertex& v = verts.elements[i];
+			pos[3 * i] = v.p.x; pos[3 * i + 1] = v.p.y; pos[3 * i + 2] = v.p.z;
+		}
+		{
+			std::lock_guard<std::mutex> guard(dev.lock);
+			if (bmf_color_map(dev.ctx, pos.data(), (int64_t)n, col.data()) != BMF_OK) return;
+		}
+		for (size_t i = 0; i < n; i++) verts.elements[i].color = glm::vec3(col[3 * i], col[3 * i + 1], col[3 * i + 2]);
+	}
+};

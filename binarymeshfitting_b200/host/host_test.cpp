@@ -147,6 +147,72 @@ int main(int argc, char** argv)
 		print_chunk("B", b);
 		return 0;
 	}
+	if (!strcmp(argv[1], "gradient") && argc >= 4)
+	{
+		// Sampler::gradient per point on the host (the reference's way, ImplicitSampler.hpp:38-49) against the device block evaluation
+		const int kind = atoi(argv[2]), m = atoi(argv[3]);
+		Sampler s = make_sampler(kind);
+		std::vector<glm::vec3> p(m), dev(m);
+		uint32_t r = 12345u;
+		auto rnd = [&] { r = r * 1664525u + 1013904223u; return ((float)(r >> 8) / 16777216.0f - 0.5f) * 300.0f; };
+		for (int i = 0; i < m; i++) p[i] = glm::vec3(rnd(), rnd(), rnd());
+		if (!sampler_gradient_block(s, p.data(), p.size(), 0.01f, dev.data())) { fprintf(stderr, "sampler_gradient_block failed: %s\n", BmfDevice::get().error()); return 4; }
+		int mismatches = 0;
+		for (int i = 0; i < m; i++)
+		{
+			const glm::vec3 h = s.gradient(s.world_size, p[i], 0.01f);
+			if (memcmp(&h, &dev[i], sizeof(h))) mismatches++;
+		}
+		printf("gradient n=%d mismatches=%d crc=%u\n", m, mismatches, crc32_of(dev.data(), sizeof(glm::vec3) * (size_t)m));
+		return 0;
+	}
+	if (!strcmp(argv[1], "quadpost") && argc >= 4)
+	{
+		// the sequence the reference's author left commented out (DebugScene.cpp:253-262 / ChunkGenerator.cpp:271-281):
+		// MeshProcessor<4> mp; mp.init(v, i); mp.collapse_bad_quads(); mp.flush_to_tris(v_out, i_out); + ColorMapper::generate_colors
+		// input: a quad mesh written by the test (n_verts, n_quads, then floats / uint32s)
+		FILE* f = fopen(argv[2], "rb");
+		if (!f) return 5;
+		uint32_t hdr[2];
+		if (fread(hdr, 4, 2, f) != 2) return 5;
+		std::vector<float> pos(3 * (size_t)hdr[0]);
+		std::vector<uint32_t> q(4 * (size_t)hdr[1]);
+		if (fread(pos.data(), 4, pos.size(), f) != pos.size() || fread(q.data(), 4, q.size(), f) != q.size()) return 5;
+		fclose(f);
+		SmartContainer<DualVertex> v, v_out;
+		SmartContainer<uint32_t> idx, i_out;
+		std::vector<uint8_t> val(hdr[0], 0);
+		for (uint32_t k : q) val[k]++;
+		for (uint32_t i = 0; i < hdr[0]; i++)
+		{
+			DualVertex dv;
+			memset((void*)&dv, 0, sizeof(dv));
+			dv.index = i; dv.init_valence = val[i];
+			dv.p = glm::vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+			v.push_back(dv);
+		}
+		idx.push_back(q.data(), q.size());
+		Sampler s = make_sampler(0);
+		Processing::MeshProcessor<4> mp(true, false);
+		mp.init(v, idx, s);
+		mp.collapse_bad_quads();
+		const bool tris = atoi(argv[3]) != 0;
+		if (tris) mp.flush_to_tris(v_out, i_out); else mp.flush(v_out, i_out);
+		ColorMapper cm;
+		cm.generate_colors(v_out);
+		std::vector<float> p, c;
+		std::vector<uint8_t> an;
+		for (size_t i = 0; i < v_out.count; i++)
+		{
+			const DualVertex& dv = v_out.elements[i];
+			p.push_back(dv.p.x); p.push_back(dv.p.y); p.push_back(dv.p.z);
+			c.push_back(dv.color.x); c.push_back(dv.color.y); c.push_back(dv.color.z);
+			an.push_back(dv.adj_next);
+		}
+		printf("quadpost bad=%u verts=%zu inds=%zu inds_crc=%u pos_crc=%u color_crc=%u adj_next_crc=%u\n", mp.bad_quads, v_out.count, i_out.count,
+		       crc32_of(i_out.elements, i_out.count * 4), crc32_of(p.data(), p.size() * 4), crc32_of(c.data(), c.size() * 4), crc32_of(an.data(), an.size()));
+		return 0;
+	}
 	if (!strcmp(argv[1], "hostfn") && argc >= 3)
 	{
 		int dim = atoi(argv[2]);

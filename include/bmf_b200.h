@@ -86,7 +86,9 @@ typedef struct bmf_params
 	int32_t iters;            /* process_iters: MeshProcessor<3> iterations, 0 = none */
 	int32_t process_boundary; /* boundary_processing */
 	int32_t smooth_normals;   /* SMOOTH_NORMALS */
-	int32_t qef;              /* 1: after smoothing, re-place each vertex by the QEF of its adjacent primitives (build-defined policy) */
+	int32_t qef;              /* after smoothing, re-place each vertex by the QEF (qef_simd.h:411-579) of its adjacent primitives' planes (build-defined policy):
+	                           * 1 = (dual_p, face normal); 2 = (dual_p, normalised Sampler::gradient at dual_p, h = 0.01) -- the line the reference
+	                           * left commented out at MeshProcessor.cpp:224; analytic samplers only */
 	int32_t keep_density;     /* 1: materialise the f32 density block (DMCChunk::density_block) so it can be copied out */
 	int32_t keep_masks;       /* 1: materialise the 8-bit cell masks (MasksBlock image) so they can be copied out */
 	int32_t density_on_device; /* HOST_DENSITY only: the density pointer passed to submit is a device pointer */
@@ -216,6 +218,27 @@ int bmf_mesh_process_steps(bmf_ctx* ctx, float* pos, float* color, float* normal
 /* qef_solve_from_points_3d (qef_simd.h:550-579), m independent systems: system j reads counts[j]
  * (2..12) planes from positions/normals[j*12*3 ...]; writes out_pos[3*j..], out_err[j]. */
 int bmf_qef_solve(bmf_ctx* ctx, const float* positions, const float* normals, const int32_t* counts, int m, float* out_pos, float* out_err);
+
+/* Sampler::gradient (Sampler.hpp:29; implicit_gradient, ImplicitSampler.hpp:38-49 = NoiseSampler.hpp:35-47) of the ctx's sampler at
+ * m world-space points: six evaluations of the sampler's value callback per point, raw differences (not normalised, not divided
+ * by 2h; the reference's default h is 0.01).  points / out: [m*3] host arrays.  CSG: differences of the combinator; noise kinds:
+ * their value callback is NoiseSamplers::noise3d == 0 (NoiseSampler.cpp:99-102), so the result is (0,0,0); HOST_DENSITY: BMF_ERR_STATE. */
+int bmf_sampler_gradient(bmf_ctx* ctx, const float* points, int64_t m, float h, float* out);
+
+/* ColorMapper::generate_colors (ColorMapper.cpp:15-60): per vertex, 4-octave simplex FBM (fresh FastNoiseSIMD object, seed 1337) at the
+ * vertex position, n = noise * 4, colour = hsl_to_rgb((n + 1) * 0.5 * 360, 0.72, 1) (ColorMapper.cpp:62-121).  pos / color: [n*3] host arrays. */
+int bmf_color_map(bmf_ctx* ctx, const float* pos, int64_t n, float* color);
+
+/* Processing::MeshProcessor<4>::init + collapse_bad_quads (MeshProcessor.cpp:25-55, 98-128, 308-396) [+ flush, :57-71] on caller arrays.
+ * A quad whose two opposite corners have exactly three adjacent quads is collapsed: the first of them moves to the quad's centre and
+ * becomes valence 4, the other is rewired to it in the four surrounding quads, the quad is marked destroyed.  The reference's loop is
+ * serial and order-dependent; the result here is that of the serial order.
+ *   pos [n_verts*3] in/out; quads [n_quads*4] in/out (Primitive::v after the rewiring, all quads);
+ *   destroyed [n_quads] out (Primitive::destroyed), adj_next [n_verts] out (DualVertex::adj_next) -- either may be NULL;
+ *   flushed [n_quads*4] out (NULL ok): the corners of the surviving quads in order, what flush() appends; *n_flushed = their number (quads);
+ *   *bad_count = the count the reference prints. */
+int bmf_mesh_collapse_bad_quads(bmf_ctx* ctx, float* pos, int n_verts, uint32_t* quads, int64_t n_quads, uint8_t* destroyed, uint8_t* adj_next,
+                                uint32_t* flushed, int64_t* n_flushed, int64_t* bad_count);
 
 /* MeshProcessor<4>::flush_to_tris (MeshProcessor.cpp:73-91): every quad (v0,v1,v2,v3) becomes (v0,v1,v2),(v2,v3,v0).
  * quads: [n_quads*4] indices in, tris: [n_quads*6] out (host arrays). */

@@ -104,6 +104,22 @@ float orc_sampler_value(const orc_sampler* s, const float p[3])
 	return orc_implicit_value(s->kind, s->world_size, p);
 }
 
+/* Sampler::gradient of any sampler kind: create_sampler binds implicit_gradient to the sampler's VALUE callback
+ * (ImplicitSampler.hpp:57, NoiseSampler.hpp:76-136).  For the noise samplers that callback is NoiseSamplers::noise3d, which
+ * returns 0 (NoiseSampler.cpp:99-102), so their gradient is (0-0, 0-0, 0-0); the CSG value is the build-defined combinator. */
+void orc_sampler_gradient(const orc_sampler* s, const float p[3], float h, float out[3])
+{
+	const int analytic = s->kind == ORC_CSG || (s->kind >= 0 && s->kind <= 3);
+	for (int a = 0; a < 3; a++)
+	{
+		float pp[3] = { p[0], p[1], p[2] }, pm[3] = { p[0], p[1], p[2] };
+		pp[a] = p[a] + h;
+		pm[a] = p[a] - h;
+		const float vp = analytic ? orc_sampler_value(s, pp) : 0.0f, vm = analytic ? orc_sampler_value(s, pm) : 0.0f;
+		out[a] = vp - vm;
+	}
+}
+
 /* DMCChunk.cpp:94-101 */
 void orc_chunk_geometry(const float pos[3], float size, int dim, float overlap, float overlap_pos[3], float* delta)
 {
@@ -702,7 +718,26 @@ float orc_qef_solve(const float* positions, const float* normals, int count, flo
  * MeshProcessor.cpp:239).  Restated here only so the GPU policy has a CPU twin: after smoothing, every processed
  * vertex with >= 2 adjacent triangles is moved to the QEF minimiser of the planes (centroid, face normal) of its
  * first <= 12 adjacent triangles (ascending triangle id), clamped to the bounding box of those centroids. */
+static void qef_place_impl(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int pb,
+                           const orc_sampler* gs, const float* gop, float gdelta, float gh);
+
 void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int pb)
+{
+	qef_place_impl(pos, boundary, valence, n_verts, inds, n_inds, pb, NULL, NULL, 0.0f, 0.0f);
+}
+
+/* bmf_params.qef = 2 (config 5 "with gradients"): the same placement, but the plane normal of a triangle is the sampler's
+ * gradient at the triangle's centroid, normalised -- what the reference's author left commented out in optimize_dual_grid,
+ * `t.dual_n = normalize(sampler.gradient(sampler.world_size, t.dual_p, ...))` (MeshProcessor.cpp:224).  The centroid is in grid
+ * units; its world position is overlap_pos + p * scale (DMCChunk.cpp:94-98).  UNPINNED policy, pinned gradient. */
+void orc_qef_place_gradient(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int pb,
+                            const orc_sampler* s, const float overlap_pos[3], float delta, float h)
+{
+	qef_place_impl(pos, boundary, valence, n_verts, inds, n_inds, pb, s, overlap_pos, delta, h);
+}
+
+static void qef_place_impl(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int pb,
+                           const orc_sampler* gs, const float* gop, float gdelta, float gh)
 {
 	const int np = n_inds / 3;
 	if (n_verts == 0 || np == 0) return;
@@ -719,6 +754,15 @@ void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, 
 	{
 		const float *p0 = pos + 3 * (size_t)inds[3 * (size_t)t], *p1 = pos + 3 * (size_t)inds[3 * (size_t)t + 1], *p2 = pos + 3 * (size_t)inds[3 * (size_t)t + 2];
 		for (int c = 0; c < 3; c++) dp[3 * (size_t)t + c] = (((0.0f + p0[c]) + p1[c]) + p2[c]) / 3.0f;
+		if (gs)
+		{
+			float wp[3], g[3];
+			for (int c = 0; c < 3; c++) wp[c] = gop[c] + dp[3 * (size_t)t + c] * gdelta;
+			orc_sampler_gradient(gs, wp, gh, g);
+			v3_normalize(g);
+			dn[3 * (size_t)t] = g[0]; dn[3 * (size_t)t + 1] = g[1]; dn[3 * (size_t)t + 2] = g[2];
+			continue;
+		}
 		float u[3] = { p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2] }, w[3] = { p0[0] - p2[0], p0[1] - p2[1], p0[2] - p2[2] }, cr[3];
 		v3_normalize(u); v3_normalize(w);
 		v3_cross(u, w, cr);
@@ -749,6 +793,126 @@ void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, 
 	}
 	memcpy(pos, out, sizeof(float) * 3 * (size_t)n_verts);
 	free(off); free(cnt); free(adj); free(dp); free(dn); free(out);
+}
+
+/* ---- ColorMapper::generate_colors (ColorMapper.cpp:15-60) -------------------------------------------- */
+/* hsl_to_rgb (ColorMapper.cpp:62-121) */
+static void hsl_to_rgb(float h, float s, float v, float out[3])
+{
+	float r = 0, g = 0, b = 0;
+	if (s <= 0.0f) { out[0] = v; out[1] = v; out[2] = v; return; }
+	float hh = h;
+	hh = fmodf(fabsf(hh), 360.0f);
+	hh /= 60.0f;
+	int i = (int)hh;
+	float ff = hh - i;
+	float p = v * (1.0f - s);
+	float q = v * (1.0f - (s * ff));
+	float t = v * (1.0f - (s * (1.0f - ff)));
+	switch (i)
+	{
+	case 0: r = v; g = t; b = p; break;
+	case 1: r = q; g = v; b = p; break;
+	case 2: r = p; g = v; b = t; break;
+	case 3: r = p; g = q; b = v; break;
+	case 4: r = t; g = p; b = v; break;
+	default: r = v; g = p; b = q; break;
+	}
+	out[0] = r; out[1] = g; out[2] = b;
+}
+
+/* get_noise (:27-48): a fresh FastNoiseSIMD (seed 1337), SimplexFractal, 4 octaves, FBM, vector set = vertex positions * 1.0;
+ * map_noise (:50-60): n = noise * 4; colour = hsl_to_rgb((n + 1) * 0.5 * 360, 0.72, 1).  pos, color: [n][3] */
+void orc_color_map(const float* pos, int n, float* color)
+{
+	if (n <= 0) return;
+	fnr_state st;
+	fnr_init(&st, 1337);
+	st.noise_type = FNR_SIMPLEX_FRACTAL;
+	fnr_set_fractal_octaves(&st, 4);
+	st.fractal_type = FNR_FBM;
+	const float scale = 1.0f;
+	float* xs = (float*)malloc(sizeof(float) * 4 * (size_t)n);
+	float *ys = xs + n, *zs = ys + n, *noise = zs + n;
+	for (int i = 0; i < n; i++)
+	{
+		xs[i] = pos[3 * (size_t)i] * scale;
+		ys[i] = pos[3 * (size_t)i + 1] * scale;
+		zs[i] = pos[3 * (size_t)i + 2] * scale;
+	}
+	fnr_fill_noise_set(&st, noise, xs, ys, zs, n, 0.0f, 0.0f, 0.0f);
+	for (int i = 0; i < n; i++)
+	{
+		float nn = noise[i] * 4.0f;
+		hsl_to_rgb((nn + 1.0f) * 0.5f * 360.0f, 0.72f, 1.0f, color + 3 * (size_t)i);
+	}
+	free(xs);
+}
+
+/* ---- MeshProcessor<4>::init + collapse_bad_quads (MeshProcessor.cpp:25-55, 98-128, 308-396) ------------
+ * Serial and order-dependent, restated in the reference's order.  pos [n_verts][3] and quads [n_quads][4] are updated in
+ * place (a collapsed quad's kept corner moves to the quad centre, its opposite corner is rewired to it in the neighbouring
+ * quads); destroyed [n_quads] and adj_next [n_verts] (optional) receive Primitive::destroyed / DualVertex::adj_next.
+ * Returns the reference's bad_count. */
+int orc_collapse_bad_quads(float* pos, int n_verts, uint32_t* quads, int n_quads, uint8_t* destroyed, uint8_t* adj_next_out)
+{
+	if (n_verts <= 0 || n_quads <= 0) return 0;
+	uint32_t* cnt = (uint32_t*)calloc((size_t)n_verts, sizeof(uint32_t));
+	for (size_t k = 0; k < 4 * (size_t)n_quads; k++) cnt[quads[k]]++;
+	uint32_t* off = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n_verts);
+	uint32_t a = 0;
+	for (int i = 0; i < n_verts; i++) { off[i] = a; a += cnt[i]; }
+	/* init_primitives: adj_block[adj_offset + adj_next++] = i in (prim, corner) order; room for one 4-entry list per collapse */
+	uint32_t* adj = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)a + 4 * (size_t)n_quads + 4));
+	uint32_t* next = (uint32_t*)calloc((size_t)n_verts, sizeof(uint32_t));
+	for (int i = 0; i < n_quads; i++)
+		for (int k = 0; k < 4; k++) { uint32_t v = quads[4 * (size_t)i + k]; adj[off[v] + next[v]++] = (uint32_t)i; }
+	uint32_t adj_count = a;
+	memset(destroyed, 0, (size_t)n_quads);
+	int bad = 0;
+	for (uint32_t i = 0; i < (uint32_t)n_quads; i++)
+	{
+		uint32_t* pv = quads + 4 * (size_t)i;
+		uint32_t pair[4], p_out[12] = { 0, 0, 0, 0 };
+		int next_p = 0, nx = 0;
+		for (int k = 0; k < 4; k++)
+		{
+			const uint32_t dv = pv[k];
+			if (next[dv] == 3)
+			{
+				pair[nx++] = (uint32_t)k;
+				for (int q = 0; q < 3; q++)
+				{
+					const uint32_t e = adj[off[dv] + q];
+					if (e != 0xFFFFFFFFu && e != i) p_out[next_p++] = e;
+				}
+			}
+		}
+		if (nx == 4 && next_p == 8) continue;
+		if (nx != 2 || next_p != 4 || pair[1] - pair[0] != 2) continue;
+		float np3[3] = { 0.0f, 0.0f, 0.0f };
+		const uint32_t new_index = pv[pair[0]];
+		for (int k = 0; k < 4; k++)
+			for (int c = 0; c < 3; c++) np3[c] = np3[c] + pos[3 * (size_t)pv[k] + c];
+		for (int c = 0; c < 3; c++) pos[3 * (size_t)new_index + c] = np3[c] * 0.25f;
+		next[new_index] = 4;
+		const uint32_t p_other = pv[pair[1]];
+		for (int k = 0; k < 4; k++)
+		{
+			uint32_t* nv = quads + 4 * (size_t)p_out[k];
+			if (nv[0] == new_index || nv[1] == new_index || nv[2] == new_index || nv[3] == new_index) continue;
+			for (int j = 0; j < 4; j++)
+				if (nv[j] == p_other) { nv[j] = new_index; break; }
+		}
+		off[new_index] = adj_count;
+		for (int k = 0; k < 4; k++) adj[adj_count++] = p_out[k];
+		destroyed[i] = 1;
+		bad++;
+	}
+	if (adj_next_out)
+		for (int i = 0; i < n_verts; i++) adj_next_out[i] = (uint8_t)next[i];
+	free(cnt); free(off); free(adj); free(next);
+	return bad;
 }
 
 /* ---- whole chunk / batch --------------------------------------------------------------------------- */

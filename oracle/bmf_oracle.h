@@ -49,6 +49,8 @@ void orc_chunk_geometry(const float pos[3], float size, int dim, float overlap, 
 
 float orc_implicit_value(int kind, float world_size, const float p[3]);
 void orc_implicit_gradient(int kind, float world_size, const float p[3], float h, float out[3]);
+/* Sampler::gradient for any sampler kind (CSG: differences of the combinator; noise kinds: the value callback is the constant 0) */
+void orc_sampler_gradient(const orc_sampler* s, const float p[3], float h, float out[3]);
 float orc_sampler_value(const orc_sampler* s, const float p[3]); /* implicit kinds + CSG only */
 
 /* sampler.block(...) : density[(x*d + y)*d + z] at overlap_pos + (x,y,z)*delta */
@@ -87,6 +89,13 @@ float orc_qef_solve(const float* positions, const float* normals, int count, flo
 
 /* build-defined QEF placement after smoothing (UNPINNED policy; N = 3) */
 void orc_qef_place(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int process_boundary);
+/* ColorMapper::generate_colors (ColorMapper.cpp:15-60): 4-octave simplex FBM at the vertex positions -> HSL -> RGB; pos, color [n][3] */
+void orc_color_map(const float* pos, int n, float* color);
+/* MeshProcessor<4>::init + collapse_bad_quads (MeshProcessor.cpp:308-396); pos / quads updated in place, returns bad_count */
+int orc_collapse_bad_quads(float* pos, int n_verts, uint32_t* quads, int n_quads, uint8_t* destroyed, uint8_t* adj_next_out);
+/* qef = 2: plane normals = normalised sampler gradient at the triangle centroids (MeshProcessor.cpp:224, commented out there) */
+void orc_qef_place_gradient(float* pos, const uint8_t* boundary, const uint8_t* valence, int n_verts, const uint32_t* inds, int n_inds, int process_boundary,
+                            const orc_sampler* s, const float overlap_pos[3], float delta, float h);
 
 /* whole chunk: geometry -> sample -> bits -> masks -> extract -> smooth; returns contains_mesh.
  * density_io: if kind == ORC_HOST_DENSITY it is the input, else (if non-null) receives the samples. */

@@ -73,6 +73,10 @@ class Oracle:
         lib.orc_qef_solve.restype = C.c_float
         lib.orc_qef_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.orc_qef_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_qef_place_gradient.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(Sampler), C.c_void_p, C.c_float, C.c_float]
+        lib.orc_sampler_gradient.argtypes = [C.POINTER(Sampler), C.c_void_p, C.c_float, C.c_void_p]
+        lib.orc_color_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.orc_collapse_bad_quads.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.orc_format_unwind.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.orc_quads.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Mesh)]
         lib.orc_seam.restype = C.c_int64
@@ -107,6 +111,30 @@ class Oracle:
         out = np.zeros(3, np.float32)
         self.lib.orc_implicit_gradient(kind, world_size, _p(p), h, _p(out))
         return out
+
+    def sampler_gradient(self, sampler, points, h=0.01):
+        """Sampler::gradient at [m,3] world-space points -> [m,3] raw differences"""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        out = np.zeros_like(pts)
+        for i in range(len(pts)):
+            self.lib.orc_sampler_gradient(C.byref(sampler), _p(pts[i]), h, _p(out[i]))
+        return out
+
+    def color_map(self, pos):
+        """ColorMapper::generate_colors: [n,3] positions -> [n,3] colours"""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        col = np.zeros_like(pos)
+        self.lib.orc_color_map(_p(pos), len(pos), _p(col))
+        return col
+
+    def collapse_bad_quads(self, pos, quads):
+        """MeshProcessor<4>::init + collapse_bad_quads -> dict(pos, quads (rewired, all of them), destroyed, adj_next, bad_count, flushed)"""
+        pos = np.array(pos, np.float32, copy=True).reshape(-1, 3)
+        q = np.array(quads, np.uint32, copy=True).reshape(-1, 4)
+        destroyed = np.zeros(len(q), np.uint8)
+        adj_next = np.zeros(len(pos), np.uint8)
+        bad = self.lib.orc_collapse_bad_quads(_p(pos), len(pos), _p(q), len(q), _p(destroyed), _p(adj_next))
+        return {"pos": pos, "quads": q, "destroyed": destroyed, "adj_next": adj_next, "bad_count": int(bad), "flushed": q[destroyed == 0].copy()}
 
     def sample_block(self, sampler, overlap_pos, delta, dim):
         op = np.asarray(overlap_pos, np.float32)
@@ -182,7 +210,11 @@ class Oracle:
                                                                   out["inds"], 3, iters, process_boundary, smooth_normals)
             if qef:
                 p = np.ascontiguousarray(out["pos"], np.float32)
-                self.lib.orc_qef_place(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary))
+                if int(qef) == 2:
+                    self.lib.orc_qef_place_gradient(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary),
+                                                    C.byref(sampler), _p(np.asarray(op, np.float32)), delta, 0.01)
+                else:
+                    self.lib.orc_qef_place(_p(p), _p(out["boundary"]), _p(out["valence"]), nv, _p(out["inds"]), out["n_inds"], int(process_boundary))
                 out["pos"] = p
         return out
 

@@ -106,6 +106,20 @@ class RefLib:
         self.lib.ref_mesh_process(_fp(v), len(v), _fp(i), len(i), prim_n, iters, int(process_boundary), int(smooth_normals))
         return v, i
 
+    def collapse_bad_quads(self, verts, inds):
+        """MeshProcessor<4>::init + collapse_bad_quads + flush: (DualVertex records after, surviving quads [m,4])"""
+        v = np.array(verts, DUALVERTEX_DTYPE, copy=True)
+        i = np.array(inds, np.uint32, copy=True).reshape(-1)
+        self.lib.ref_collapse_bad_quads.restype = C.c_int
+        n = self.lib.ref_collapse_bad_quads(_fp(v), len(v), _fp(i), len(i))
+        return v, i[:n].reshape(-1, 4).copy()
+
+    def color_map(self, verts):
+        """ColorMapper::generate_colors: DualVertex records with .color filled"""
+        v = np.array(verts, DUALVERTEX_DTYPE, copy=True)
+        self.lib.ref_color_map(_fp(v), len(v))
+        return v
+
     def format_unwind(self, verts, inds, smooth_normals=False):
         """GLChunk::format_data(vertices, indexes, true, smooth_normals): per quad corner p / n / c"""
         v = np.array(verts, DUALVERTEX_DTYPE, copy=True)

@@ -28,6 +28,7 @@
 #include "ImplicitSampler.hpp"
 #include "NoiseSampler.hpp"
 #include "MeshProcessor.hpp"
+#include "ColorMapper.hpp"
 #include "DefaultOptions.h"
 #include <omp.h>
 #include <chrono>
@@ -272,6 +273,36 @@ void ref_mesh_process(void* vertices, int n_verts, uint32_t* indices, int n_inds
 	}
 	memcpy(vertices, v.elements, (size_t)n_verts * sizeof(DualVertex));
 	memcpy(indices, idx.elements, (size_t)n_inds * sizeof(uint32_t));
+}
+
+// MeshProcessor<4>::init + collapse_bad_quads + flush (MeshProcessor.cpp:25-71, 308-396) on caller arrays; returns the number of
+// surviving quads * 4 written back into indices.  (collapse_bad_quads prints its count to std::cout.)
+int ref_collapse_bad_quads(void* vertices, int n_verts, uint32_t* indices, int n_inds)
+{
+	SmartContainer<DualVertex> v;
+	SmartContainer<uint32_t> idx;
+	v.push_back((DualVertex*)vertices, (size_t)n_verts);
+	idx.push_back(indices, (size_t)n_inds);
+	Sampler s = ImplicitFunctions::create_sampler(ImplicitFunctions::sphere);
+	s.world_size = 256;
+	Processing::MeshProcessor<4> mp(true, false);
+	mp.init(v, idx, s);
+	mp.collapse_bad_quads();
+	v.count = 0; idx.count = 0;
+	mp.flush(v, idx);
+	memcpy(vertices, v.elements, (size_t)n_verts * sizeof(DualVertex));
+	memcpy(indices, idx.elements, idx.count * sizeof(uint32_t));
+	return (int)idx.count;
+}
+
+// ColorMapper::generate_colors (ColorMapper.cpp:15-25) on caller DualVertex records
+void ref_color_map(void* vertices, int n_verts)
+{
+	SmartContainer<DualVertex> v;
+	v.push_back((DualVertex*)vertices, (size_t)n_verts);
+	ColorMapper cm;
+	cm.generate_colors(v);
+	memcpy(vertices, v.elements, (size_t)n_verts * sizeof(DualVertex));
 }
 
 // GLChunk::format_data(vertices, indexes, unwind_verts = true, smooth_normals) (GLChunk.cpp:278-335): the flat-quad SoA

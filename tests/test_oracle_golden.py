@@ -105,3 +105,26 @@ def test_mc_table_properties():
             assert pm and not (pm & union)
             union |= pm
         assert union == used and (pv >> (12 * npatch)) & ((1 << (60 - 12 * npatch)) - 1) == 0
+
+
+# ---- round 2: gradient, collapse_bad_quads, ColorMapper (tests/golden/make_post_golden.py, outputs of the compiled reference)
+POST = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "post_golden.npz"))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_gradient_golden(oracle, kind):
+    g = oracle.sampler_gradient(oracle.sampler(kind), POST["grad_points"])
+    np.testing.assert_array_equal(g.view(np.uint32), POST["grad_%d" % kind].view(np.uint32))
+
+
+def test_color_map_golden(oracle):
+    np.testing.assert_array_equal(oracle.color_map(POST["color_points"]).view(np.uint32), POST["color_rgb"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["sphere32", "torus64"])
+def test_collapse_bad_quads_golden(oracle, name):
+    o = oracle.collapse_bad_quads(POST["cq_%s_pos_in" % name], POST["cq_%s_quads_in" % name])
+    np.testing.assert_array_equal(o["flushed"], POST["cq_%s_flushed" % name])
+    np.testing.assert_array_equal(o["pos"].view(np.uint32), POST["cq_%s_pos_out" % name].view(np.uint32))
+    np.testing.assert_array_equal(o["adj_next"], POST["cq_%s_adj_next" % name])
+    assert o["bad_count"] == len(o["quads"]) - len(o["flushed"]) > 0

@@ -83,6 +83,71 @@ def test_implicit_values_and_gradients(ref, oracle):
             np.testing.assert_array_equal(ref.implicit_gradient(kind, p).view(np.uint32), oracle.implicit_gradient(kind, p).view(np.uint32))
 
 
+def quad_mesh(oracle, kind, dim, pos=(-128.0, -128.0, -128.0), size=256.0):
+    if kind == "random":  # smoothed random field: a busy surface with many valence-3 vertices in every configuration
+        rng = np.random.default_rng(dim)
+        f = rng.standard_normal((dim, dim, dim)).astype(np.float32)
+        for ax in range(3):
+            f = (f + np.roll(f, 1, ax) + np.roll(f, -1, ax)).astype(np.float32)
+        dens = np.ascontiguousarray(f).reshape(-1)
+    else:
+        s = oracle.sampler(kind)
+        op, delta = oracle.geometry(pos, size, dim, 0.0)
+        dens = oracle.sample_block(s, op, delta, dim)
+    bits, _ = oracle.label_grid(dens, dim)
+    return oracle.quads(dens, bits, dim)
+
+
+@pytest.mark.parametrize("kind,dim", [(ob.SPHERE, 32), (ob.TORUS_Z, 64), ("random", 32), (ob.TERRAIN3D_PERT, 32)])
+def test_collapse_bad_quads_matches_the_compiled_reference(ref, oracle, kind, dim, capfd):
+    """MeshProcessor<4>::init + collapse_bad_quads + flush (MeshProcessor.cpp:308-396): vertex positions, adj_next and the surviving
+    (rewired) quads of the oracle's serial restatement equal the compiled reference's, bit for bit"""
+    from oracle import ref_binding as rb
+    q = quad_mesh(oracle, kind, dim)
+    nv = q["n_verts"]
+    assert nv > 100
+    v = np.zeros(nv, rb.DUALVERTEX_DTYPE)
+    v["p"], v["color"], v["boundary"], v["init_valence"] = q["pos"], 1.0, q["boundary"], q["valence"]
+    rv, rq = ref.collapse_bad_quads(v, q["inds"])
+    capfd.readouterr()  # the reference prints "detected N bad quads..."
+    o = oracle.collapse_bad_quads(q["pos"], q["inds"])
+    assert o["bad_count"] > 0, "the DMC quad mesh of this shape has valence-3 pairs to collapse"
+    np.testing.assert_array_equal(rq, o["flushed"])
+    np.testing.assert_array_equal(rv["p"].view(np.uint32), o["pos"].view(np.uint32))
+    np.testing.assert_array_equal(rv["adj_next"], o["adj_next"])
+    assert len(o["flushed"]) == len(o["quads"]) - o["bad_count"]
+
+
+def test_color_map_matches_the_compiled_reference(ref, oracle):
+    """ColorMapper::generate_colors (ColorMapper.cpp:15-60) call sites + HSL->RGB pinned on top of the (unpinned) noise restatement"""
+    from oracle import ref_binding as rb
+    rng = np.random.default_rng(21)
+    pos = (rng.random((3000, 3), dtype=np.float32) * 512 - 256).astype(np.float32)
+    v = np.zeros(len(pos), rb.DUALVERTEX_DTYPE)
+    v["p"] = pos
+    rc = ref.color_map(v)["color"]
+    oc = oracle.color_map(pos)
+    np.testing.assert_array_equal(rc.view(np.uint32), oc.view(np.uint32))
+    assert oc.min() >= 0.28 - 1e-6 and oc.max() <= 1.0 and len(np.unique(oc.round(3), axis=0)) > 1000  # s = 0.72, v = 1: channels in [0.28, 1]
+
+
+def test_sampler_gradient_of_any_kind(ref, oracle):
+    """orc_sampler_gradient: primitives = the compiled reference's implicit_gradient bit for bit; noise kinds = differences of the
+    constant-0 value callback (NoiseSampler.cpp:99-102); CSG = differences of the build-defined combinator"""
+    rng = np.random.default_rng(11)
+    pts = (rng.random((40, 3), dtype=np.float32) * 300 - 150).astype(np.float32)
+    for kind in (ob.SPHERE, ob.TORUS_Z, ob.CUBOID, ob.PLANE_Y):
+        g = oracle.sampler_gradient(oracle.sampler(kind), pts)
+        for p, gi in zip(pts, g):
+            np.testing.assert_array_equal(ref.implicit_gradient(kind, p).view(np.uint32), gi.view(np.uint32))
+    assert not oracle.sampler_gradient(oracle.sampler(ob.TERRAIN3D_PERT), pts).any()
+    s = oracle.sampler(ob.CSG, csg_op=ob.CSG_UNION, csg_kind_a=ob.SPHERE, csg_kind_b=ob.TORUS_Z)
+    far = np.array([[100.0, 0.0, 0.0]], np.float32)  # outside the torus tube, nearer the sphere: union = max = ... whichever is larger
+    g = oracle.sampler_gradient(s, far)
+    a, b = oracle.implicit_gradient(ob.SPHERE, far[0]), oracle.implicit_gradient(ob.TORUS_Z, far[0])
+    assert np.array_equal(g[0], a) or np.array_equal(g[0], b)
+
+
 def test_qef_vs_reference_with_outlier_count(ref, oracle):
     rng = np.random.default_rng(9)
     m, ds = 3000, []
