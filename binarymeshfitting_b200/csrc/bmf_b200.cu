@@ -101,12 +101,11 @@ struct bmf_ctx
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	// fused per-chunk extraction (fused.cuh): one CTA per mesh chunk does label_edges + polygonize + MeshProcessor::init
-	int fused_extract = 0;    // BMF_FUSED=1: k_chunk_mesh for dim <= 64 triangle batches (bit-identical, 6 launches instead of 12; not yet faster, see DESIGN)
+	int fused_extract = 1;    // BMF_FUSED=0: the multi-kernel path for every dim (it always serves dim 128 / 256 and quads)
 	bool batch_fused = false; // the resident batch went through k_chunk_mesh
 	size_t fused_smem = 0;
-	DevBuf<int> mesh_list;
-	DevBuf<unsigned int> fz_status;
-	DevBuf<unsigned long long> fz_agg, fz_inc, fz_prof;
+	DevBuf<unsigned long long> fz_prof;
+	DevBuf<int> emit_list, mixed_list;
 	bool fused_prof = false; // BMF_FUSED_PROF=1: per-phase SM clocks of k_chunk_mesh, mean printed to stderr when the batch completes
 	int sm_count = 148;
 	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
@@ -469,12 +468,21 @@ int launch_mesh(bmf_ctx* ctx)
 	unsigned long long* list_count = tot + 4;
 	if (ctx->batch_fused)
 	{
-		// ---- dim <= 64, triangles: k_mesh_list + ONE launch of k_chunk_mesh (fused.cuh) for label_edges, polygonize and
-		// MeshProcessor::init of the whole batch; totals, capacity verdict and chunk table are published by the kernel itself
-		uint32_t* host_table = ctx->counts_published ? nullptr : reinterpret_cast<uint32_t*>(ctx->counts_pinned);
-		BMF_LAUNCH(k_mesh_list, 1, SCAN_CTA, 0, ctx->flags.p, n, ctx->mesh_list.p, ctx->fz_status.p, ctx->counts.p, host_table, tot, ctx->totals_pinned->v);
+		// ---- dim <= 64, triangles: k_chunk_emit (fused.cuh) does label_edges' emission, polygonize and MeshProcessor::init of a chunk in one CTA
+		const size_t words = ctx->counts_published ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
+		BMF_LAUNCH(k_check_caps, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells,
+		           (unsigned long long)caps.verts, (unsigned long long)caps.inds, reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
+		ctx->counts_published = true;
 		BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
-		if (caps.verts && ctx->color_ones < 3 * caps.verts)
+		if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
+		{
+			// nothing allocated yet: k_check_caps has raised the flag unless the batch is empty; bmf_batch_wait sizes the arenas and calls again
+			BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
+			BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
+			BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
+			return BMF_OK;
+		}
+		if (ctx->color_ones < 3 * caps.verts)
 		{
 			BMF_LAUNCH(k_fill_f32, grid_for(ctx->color.cap, CTA), CTA, 0, ctx->color.p, ctx->color.cap, 1.0f);
 			ctx->color_ones = ctx->color.cap;
@@ -482,12 +490,9 @@ int launch_mesh(bmf_ctx* ctx)
 		FusedArgs A;
 		memset(&A, 0, sizeof(A));
 		A.L = L; A.n = n;
-		A.bits = ctx->bits.p; A.flags = ctx->flags.p; A.mesh_list = ctx->mesh_list.p;
-		A.chunks = ctx->counts.p; A.host_table = host_table;
-		A.status = ctx->fz_status.p; A.agg = ctx->fz_agg.p; A.inc = ctx->fz_inc.p;
-		A.tot = tot; A.tot_host = ctx->totals_pinned->v;
-		const bool have = caps.cells && caps.verts && caps.inds; // nothing allocated yet: every chunk reports "does not fit", the host sizes the arenas
-		A.cap_cells = have ? caps.cells : 0; A.cap_verts = have ? caps.verts : 0; A.cap_inds = have ? caps.inds : 0;
+		A.bits = ctx->bits.p; A.wcnt = ctx->wcnt.p; A.emit_list = ctx->emit_list.p;
+		A.chunks = ctx->counts.p;
+		A.tot = tot;
 		A.vcells = ctx->vcells.p; A.icells = ctx->icells.p;
 		A.s = ctx->sampler;
 		A.src.density = ctx->density_cur;
@@ -498,18 +503,16 @@ int launch_mesh(bmf_ctx* ctx)
 		A.valence = ctx->valence.p; A.adj_off = ctx->adj_off.p;
 		A.adj = params->iters > 0 ? ctx->adj.p : nullptr;
 		A.prim_vbase = ctx->prim_vbase.p;
-		A.masks = params->keep_masks ? ctx->masks.p : nullptr;
 		if (ctx->fused_prof)
 		{
 			BMF_CUDA(ctx->fz_prof.reserve(16 * (size_t)n));
 			BMF_CUDA(cudaMemsetAsync(ctx->fz_prof.p, 0, 16 * (size_t)n * sizeof(unsigned long long), st));
 			A.prof = ctx->fz_prof.p;
 		}
-		BMF_LAUNCH(k_chunk_mesh<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->sm_count), FUSED_NT, ctx->fused_smem, A);
-		ctx->counts_published = true;
+		BMF_LAUNCH(k_chunk_emit<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->sm_count), FUSED_NT, ctx->fused_smem, A);
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
-		if (have && params->iters > 0)
+		if (params->iters > 0)
 		{
 			int rc = run_smooth<3>(ctx, caps.verts, caps.inds, ctx->pos.p, ctx->color.p, ctx->normal.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, ctx->counts.p, n,
 			                       params->iters, params->process_boundary, params->smooth_normals, params->qef, 1, true, tot);
@@ -669,13 +672,12 @@ int finish(bmf_ctx* ctx)
 		for (int j = 0; j < ctx->n; j++)
 		{
 			const unsigned long long* r = &h[16 * (size_t)j];
-			if (!r[0] || !r[10]) continue;
+			if (!r[0] || !r[7]) continue;
 			m++;
-			for (int k = 1; k <= 10; k++) sum[k] += (double)(r[k] - r[k - 1]);
+			for (int k = 1; k <= 7; k++) sum[k] += (double)(r[k] - r[k - 1]);
 		}
-		fprintf(stderr, "k_chunk_mesh phases (mean SM cycles over %d chunks with smoothing CSR): stage %.0f classify %.0f scan %.0f lookback %.0f table %.0f | fix %.0f lists %.0f verts %.0f inds %.0f valence %.0f adj %.0f\n",
-		        m, m ? sum[1] / m : 0, m ? sum[2] / m : 0, m ? sum[3] / m : 0, m ? sum[4] / m : 0, m ? sum[5] / m : 0, 0.0, m ? sum[6] / m : 0, m ? sum[7] / m : 0, m ? sum[8] / m : 0,
-		        m ? sum[9] / m : 0, m ? sum[10] / m : 0);
+		fprintf(stderr, "k_chunk_emit phases (mean SM cycles over %d chunks): stage %.0f scan %.0f lists %.0f verts %.0f inds %.0f valence %.0f adj %.0f\n",
+		        m, m ? sum[1] / m : 0, m ? sum[2] / m : 0, m ? sum[3] / m : 0, m ? sum[4] / m : 0, m ? sum[5] / m : 0, m ? sum[6] / m : 0, m ? sum[7] / m : 0);
 	}
 	if (ctx->dl_pending)
 	{
@@ -748,7 +750,7 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e) != 0;
 	if (const char* e = getenv("BMF_FUSED_PROF")) ctx->fused_prof = atoi(e) != 0;
 	ctx->fused_smem = fused_smem_bytes(make_layout(64), FUSED_NT);
-	if (cudaFuncSetAttribute(k_chunk_mesh<FUSED_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_chunk_emit<FUSED_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
 	{
 		cudaGetLastError();
 		ctx->fused_extract = 0;
@@ -778,7 +780,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
 	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release(); ctx->smooth_cnt.release();
-	ctx->mesh_list.release(); ctx->fz_status.release(); ctx->fz_agg.release(); ctx->fz_inc.release(); ctx->fz_prof.release();
+	ctx->fz_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
@@ -874,20 +876,14 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
-	if (fused)
+	BMF_CUDA(ctx->wcnt.reserve(n_words));
+	BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
+	if (fused) BMF_CUDA(ctx->emit_list.reserve(n));
+	if (!fused)
 	{
-		BMF_CUDA(ctx->mesh_list.reserve(n));
-		BMF_CUDA(ctx->fz_status.reserve(n));
-		BMF_CUDA(ctx->fz_agg.reserve(3 * (size_t)n));
-		BMF_CUDA(ctx->fz_inc.reserve(3 * (size_t)n));
-	}
-	else
-	{
-		BMF_CUDA(ctx->wcnt.reserve(n_words));
 		BMF_CUDA(ctx->wv4.reserve(n_words));
 		BMF_CUDA(ctx->wib.reserve(n_words));
 		BMF_CUDA(ctx->seg_tot.reserve(3 * (size_t)nseg));
-		BMF_CUDA(ctx->chunk_tot.reserve(3 * (size_t)n));
 	}
 	BMF_CUDA(ctx->counts.reserve(n));
 	BMF_CUDA(ctx->totals_dev.reserve(TOT_SLOTS));
@@ -958,7 +954,8 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (host_density && !params->density_on_device)
 		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
-	if (!fused) BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st));
+	BMF_CUDA(cudaMemsetAsync(ctx->totals_dev.p + TOT_MESH, 0, 4 * sizeof(unsigned long long), st)); // list lengths and tickets: TOT_MESH, TOT_TICKET, TOT_CAND, TOT_CTICKET
+	if (!fused) BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st)); // k_count adds to it; k_chunk_count stores
 	if (n_sheets)
 	{
 		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_geom.p, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * n_sheets, cudaMemcpyHostToDevice, st));
@@ -984,9 +981,15 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		{
 			// no density block wanted: chunks entirely above / below the surface are classified from the sheet range and
 			// skipped; the rest get compare-only sign words (binary search + warp bit transpose, no per-voxel arithmetic)
-			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p);
-			BMF_LAUNCH(k_terrain2d_bits, (unsigned)((size_t)n * L.d * L.zc * L.zc / (CTA / 32)), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
-			           ctx->uni.p, ctx->bits.p, ctx->flags.p);
+			// (totals_dev[12] = length of the list of chunks the surface crosses; k_scan_chunks does not touch that slot)
+			BMF_CUDA(ctx->mixed_list.reserve(n));
+			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p,
+			           ctx->mixed_list.p, ctx->totals_dev.p + TOT_CAND);
+			{
+				const size_t groups = (size_t)n * L.d * L.zc * L.zc / (CTA / 32);
+				BMF_LAUNCH(k_terrain2d_bits, (unsigned)std::min(groups, (size_t)ctx->sm_count * 16), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
+				           ctx->mixed_list.p, ctx->totals_dev.p + TOT_CAND, ctx->bits.p, ctx->flags.p);
+			}
 			ctx->uni_valid = true;
 		}
 	}
@@ -1011,7 +1014,10 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	uint8_t* masks_w = params->keep_masks ? ctx->masks.p : nullptr;
 	if (fused)
 	{
-		// classification, counts and the chunk scan happen inside k_chunk_mesh (launch_mesh)
+		// chunks without a mesh keep chunk_tot = 0 (k_scan_chunks only reads the totals of mesh chunks); TOT_MESH / TOT_CTICKET restart
+		const bool have_cand = ctx->uni_valid; // the 2-D terrain classifier has listed the chunks it could not cull
+		BMF_LAUNCH(k_chunk_count<COUNT_NT>, (unsigned)std::min(n, 6 * ctx->sm_count), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+		           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
 	}
 	else if (params->quads)
 	{
@@ -1028,7 +1034,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	if (!fused) BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
 	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;

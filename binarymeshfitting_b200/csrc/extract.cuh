@@ -72,6 +72,9 @@ __host__ inline Layout make_layout(int d)
 }
 
 __constant__ uint64_t c_tri_pack[256] = BMF_TRI_PACK_INIT;
+// the same table in global memory: a constant-bank read with a different index in every lane is serialised (32 replays per warp),
+// so the kernels that stage the table in shared memory fill it from here with one coalesced load
+__device__ const uint64_t g_tri_pack[256] = BMF_TRI_PACK_INIT;
 
 // ---- density of one grid point for the analytic / heightmap samplers ----------------------------------
 // implicit_block (ImplicitSampler.hpp:14-36): coordinate = p + (float)i * scale
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 // (bmf_batch_copy_chunk synthesises them on request).  uni: 0 = mixed, 1 = all air (ones), 2 = all solid (zeros).
 __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const ChunkGeom* __restrict__ geom, int d, const int* __restrict__ sheet_of,
                                                              const uint32_t* __restrict__ sheet_mm, int n_sheets, int n_chunks, uint32_t* __restrict__ flags,
-                                                             uint8_t* __restrict__ uni)
+                                                             uint8_t* __restrict__ uni, int* __restrict__ mixed_list, unsigned long long* __restrict__ mixed_count)
 {
 	const int c = blockIdx.x * CTA + threadIdx.x;
 	if (c >= n_chunks) return;
@@ -260,6 +263,17 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_classify(SamplerDev s, const 
 	}
 	uni[c] = u;
 	if (u) flags[c] = (u == 1) ? CF_ONES : CF_ZERO;
+	else if (mixed_list)
+	{
+		// the chunks k_terrain2d_bits has to visit (order irrelevant); one atomic per warp
+		const uint32_t bal = __activemask();
+		const uint32_t mine = __ballot_sync(bal, true);
+		const int leader = __ffs(mine) - 1, lane = threadIdx.x & 31;
+		unsigned long long o = 0;
+		if (lane == leader) o = atomicAdd(mixed_count, (unsigned long long)__popc(mine));
+		o = __shfl_sync(mine, o, leader);
+		mixed_list[o + __popc(mine & ((1u << lane) - 1u))] = c;
+	}
 }
 
 __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
@@ -298,17 +312,13 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const C
 // first y of ITS column where the bit turns on with a 5-step shuffle binary search, forms the column's 32-bit
 // y-mask with one shift, and a 5-stage warp bit-matrix transpose turns the 32 column masks into the 32 row
 // words -> one coalesced store.  ~70 instructions per 1024 voxels; a non-monotone tile falls back to 32 ballots.
-__global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
-                                                         const int* __restrict__ sheet_of, const uint8_t* __restrict__ uni, uint32_t* __restrict__ bits,
-                                                         uint32_t* __restrict__ flags)
+__device__ __forceinline__ void terrain2d_bits_task(const SamplerDev& s, const ChunkGeom* __restrict__ geom, const Layout& L, const float* __restrict__ hmap,
+                                                    const int* __restrict__ sheet_of, int chunk, int task /* (x, yb, zb) inside the chunk */, int lane,
+                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
 {
-	const int lane = threadIdx.x & 31;
-	const size_t task = ((size_t)blockIdx.x * CTA + threadIdx.x) >> 5; // (chunk, x, yb, zb); tasks per chunk = d * zc^2, a multiple of 8
-	const int chunk = (int)(task >> (2 * L.lzc + L.ld));
-	if (uni[chunk]) return; // entirely above / below the surface (the whole CTA belongs to one chunk)
-	const int zb = (int)task & (L.zc - 1);
-	const int yb = (int)(task >> L.lzc) & (L.zc - 1);
-	const int x = (int)(task >> (2 * L.lzc)) & (L.d - 1);
+	const int zb = task & (L.zc - 1);
+	const int yb = (task >> L.lzc) & (L.zc - 1);
+	const int x = (task >> (2 * L.lzc)) & (L.d - 1);
 	const ChunkGeom g = geom[chunk];
 	const float n = hmap[((size_t)sheet_of[chunk] << (2 * L.ld)) + ((size_t)x << L.ld) + zb * 32 + lane];
 	const float t = n * s.nm;
@@ -360,6 +370,19 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const Chun
 	}
 	bits[(size_t)chunk * L.wc + ((((size_t)x << L.ld) + y) << L.lzc) + zb] = mine;
 	merge_flags(word_flags(mine), flags + chunk);
+}
+
+__global__ void __launch_bounds__(CTA) k_terrain2d_bits(SamplerDev s, const ChunkGeom* __restrict__ geom, Layout L, const float* __restrict__ hmap,
+                                                         const int* __restrict__ sheet_of, const int* __restrict__ mixed_list,
+                                                         const unsigned long long* __restrict__ mixed_count, uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
+{
+	// grid-stride over (listed chunk, CTA-sized group of tasks): the chunks that lie entirely above / below the surface are not on the
+	// list, so no CTA is launched for them (an empty CTA per 8 tasks of every culled chunk used to cost more than the kernel's work)
+	const int lane = threadIdx.x & 31;
+	const int ltc = 2 * L.lzc + L.ld - 3;  // log2(CTA-groups per chunk): tasks per chunk = d * zc^2, CTA / 32 == 8 tasks per group
+	const size_t n_groups = (size_t)*mixed_count << ltc;
+	for (size_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+		terrain2d_bits_task(s, geom, L, hmap, sheet_of, mixed_list[grp >> ltc], (int)(((grp & (((size_t)1 << ltc) - 1)) << 3) + (threadIdx.x >> 5)), lane, bits, flags);
 }
 
 // ---- K1c: 3-D terrains: one noise evaluation per voxel, density always materialised (4 B/voxel is
@@ -723,6 +746,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 		totals[4] = 0; totals[5] = 0; // surface-cell list counters (k_bases)
 		totals[8] = s_maxv;           // largest chunk (vertices): decides whether chunk-local indices fit 16 bits (download.cuh)
 		totals[9] = 0;                // download error flag
+		totals[11] = 0;               // chunk ticket of k_chunk_emit (fused.cuh)
 	}
 }
 
@@ -964,7 +988,7 @@ __global__ void __launch_bounds__(CTA) k_inds3(Layout L, const uint4* __restrict
 	__shared__ uint32_t s_pre[CTA / 32][33];
 	__shared__ uint8_t s_own[CTA / 32][480]; // owning cell (0..31) of every (cell, edge) / (cell, index) pair of the warp
 	if (tot[7]) return;
-	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
+	s_tri[threadIdx.x] = g_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
 	const uint32_t stride = gridDim.x * CTA;

@@ -26,9 +26,7 @@
 namespace bmf
 {
 
-// the triangle table again, in global memory: only the rare sign-changing cells read it (a threadIdx-indexed fill of
-// shared memory from __constant__ serialises 32 ways per warp and would cost more than the cells themselves)
-__device__ const uint64_t g_tri_pack[256] = BMF_TRI_PACK_INIT;
+// the triangle table in global memory (g_tri_pack, extract.cuh): only the rare sign-changing cells read it
 
 struct SeamChunk
 {

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(CTA) k_adj_fill(Layout L, const uint32_t* __re
 	__shared__ uint32_t s_pre[CTA / 32][33];
 	__shared__ uint8_t s_own[CTA / 32][480];
 	if (tot[7]) return;
-	s_tri[threadIdx.x] = c_tri_pack[threadIdx.x];
+	s_tri[threadIdx.x] = g_tri_pack[threadIdx.x];
 	__syncthreads();
 	const uint32_t n_cells = (uint32_t)list_count[1];
 	const uint32_t stride = gridDim.x * CTA;
