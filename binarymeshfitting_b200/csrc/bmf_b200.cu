@@ -360,7 +360,8 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 			return BMF_OK;
 		}
 		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->sm_count), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
-		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step);
+		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step,
+		           ctx->batch_fused ? ctx->emit_list.p : nullptr);
 		return BMF_OK;
 	}
 

@@ -523,10 +523,13 @@ __device__ __forceinline__ WordClass classify(const WordBits& b, const Layout& L
 	return c;
 }
 
+// corner mask of the cell at `bit`: bit (4 dx + 2 dy + dz).  The (z, z + 1) samples of a row are two consecutive bits of the row
+// extended by its successor's first bit (= bit 31 of the shifted copy), so one funnel shift per row fetches both.
 __device__ __forceinline__ uint32_t mask8_of(const WordBits& b, int bit)
 {
-	return ((b.A >> bit) & 1u) | (((b.A1 >> bit) & 1u) << 1) | (((b.B >> bit) & 1u) << 2) | (((b.B1 >> bit) & 1u) << 3) |
-	       (((b.C >> bit) & 1u) << 4) | (((b.C1 >> bit) & 1u) << 5) | (((b.D >> bit) & 1u) << 6) | (((b.D1 >> bit) & 1u) << 7);
+	const uint32_t a = __funnelshift_r(b.A, b.A1 >> 31, bit) & 3u, bb = __funnelshift_r(b.B, b.B1 >> 31, bit) & 3u;
+	const uint32_t c = __funnelshift_r(b.C, b.C1 >> 31, bit) & 3u, dd = __funnelshift_r(b.D, b.D1 >> 31, bit) & 3u;
+	return a | (bb << 2) | (c << 4) | (dd << 6);
 }
 
 // packed per-word counts: cells [0,8) verts [8,16) indices [16,32)

@@ -33,7 +33,8 @@ enum
 };
 
 typedef unsigned long long u64;
-static constexpr int FUSED_NT = 512; // threads per chunk CTA: two CTAs per SM at 64^3 (87 KB of shared memory each)
+static constexpr int FUSED_NT = 512; // threads per chunk CTA: two CTAs per SM at 64^3 (107 KB of shared memory each)
+static constexpr int FUSED_CAPV = 8192; // chunks with at most this many vertices keep their use counters and adjacency offsets in shared memory
 
 struct FusedArgs
 {
@@ -67,7 +68,7 @@ struct FusedArgs
 __host__ __device__ inline size_t fused_smem_bytes(const Layout& L, int nt)
 {
 	const size_t scratch = (size_t)44 * nt + 256, jobs = (size_t)2 * L.wc;
-	return ((size_t)(L.d + 1) * L.wp + L.wc) * 4 + (size_t)(L.wc / 32) * 8 + (scratch > jobs ? scratch : jobs);
+	return ((size_t)(L.d + 1) * L.wp + L.wc) * 4 + (size_t)(L.wc / 32) * 8 + (scratch > jobs ? scratch : jobs) + (size_t)FUSED_CAPV * 2;
 }
 
 template <int NT, int K>
@@ -197,8 +198,12 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 		}
 		__syncthreads();
 		uint32_t cells = 0, tv = 0, ti = 0;
-		for (int w = tid; w < wc; w += NT)
+		for (int j = 0; j < wc / NT; j++)
 		{
+			// a warp takes 32 consecutive words (coalesced count stores) of round j -- a DIFFERENT slot of the round every time: with a fixed
+			// slot a warp would see the same band of y rows at every x, and the one warp whose band holds the surface would do all the
+			// per-cell work while the others wait at the barrier
+			const int w = j * NT + (((wid + j) & (NT / 32 - 1)) << 5) + lane;
 			const int zb = w & (L.zc - 1), y = (w >> L.lzc) & (d - 1), x = w >> L.lwp;
 			const WordBits b = load_word_bits(sb, L, x, y, zb);
 			const WordClass c = classify(b, L, x, y, zb);
@@ -264,6 +269,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 	uint32_t* s_out = s_xyz + NT;                                               // [NT] 5d: first index position inside the chunk; 5f: first primitive
 	uint32_t* s_pre_all = s_out + NT;                                           // [NW][40]
 	uint8_t* s_own_all = reinterpret_cast<uint8_t*>(s_pre_all + NW * 40);       // [NW][480]
+	// per-vertex use counters, 4 bits per "cell class" (a cell uses one vertex at most 5 times), 16 bits per vertex, two vertices per word
+	const size_t r_bytes = ((size_t)44 * NT + 256 > (size_t)2 * wc) ? (size_t)44 * NT + 256 : (size_t)2 * wc;
+	uint32_t* s_cls = reinterpret_cast<uint32_t*>(s_r + r_bytes);                // [FUSED_CAPV / 2]
+	uint32_t* s_aoff = sb;                                                       // [FUSED_CAPV] adjacency offsets, over the sign words once 5d is done
 	__shared__ u64 s_tri[256], s_loc[256];
 	__shared__ uint32_t s_edge[16];
 	__shared__ int s_chunk;
@@ -325,6 +334,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 		const ChunkCounts cc = A.chunks[chunk];
 		const uint32_t V = cc.n_verts;
 		const u64 cb = cc.cell_base, vb = cc.vert_base, ib = cc.ind_base;
+		// use counters of this chunk's vertices, 16 bits each, in the chunk's own stretch of the global array (V / 2 of its V words)
+		const uint32_t cap_aoff = (uint32_t)((d + 1) * L.wp + wc + (wc / 32) * 2); // words of the sign-word / offset region s_aoff takes over
+		const bool fits = V <= (uint32_t)FUSED_CAPV && V <= cap_aoff;
+		uint32_t* const cls32 = A.cls + vb; // accumulated with fire-and-forget global REDs (shared-memory atomics on the same words were slower: two
+		                                    // vertices per word and neighbouring triangles in one warp collide); phase 5e copies them to shared memory
 		BMF_FUSED_MARK(0);
 
 		// ---- phase 1: sign words (+ a zero plane at x = d: B == 0 outside the grid) and word counts -> shared memory; words that emit
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 				}
 			}
 			// every vertex's use counters (phase 5d adds to them) and normal start at zero: coalesced here instead of per vertex in 5c
-			for (uint32_t i = tid; i < V; i += NT) A.cls[(size_t)vb + i] = 0u;
+			for (uint32_t i = tid; i < (V + 1) / 2; i += NT) cls32[i] = 0u;
 			for (uint32_t i = tid; i < 3 * V; i += NT) A.normal[3 * (size_t)vb + i] = 0.0f;
 		}
 		__syncthreads();
@@ -524,7 +538,6 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 		// ---- phase 5d: indices (polygonize_cell, DMCChunk.cpp:537-576) + per-class use counts.  A warp takes 32 polygonizing cells and
 		// spreads their (cell, index) pairs over its lanes; the vertex id of an index is looked up in shared memory.
 		uint32_t* const inds_c = A.inds + ib;
-		uint32_t* const cls_c = A.cls + vb;
 		uint2 rec_nx = make_uint2(0u, 0u); // the record of the NEXT round is fetched while this round's pairs are processed
 		if ((uint32_t)tid < nic) rec_nx = __ldcg(il + tid);
 		for (uint32_t i0 = (uint32_t)wbase; i0 < nic; i0 += NT)
@@ -564,7 +577,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 				const uint32_t vid = vertex_id_smem(S, L, w, bit, (int)(ed >> 20));
 				inds_c[s_out[wbase + c] + t] = vid;
 				// init_valence++ (DMCChunk.cpp:573) per "cell class" 3 - (e & 3): see k_inds3 / k_adj_fill
-				atomicAdd(cls_c + vid, 1u << (8 * (3 - (e & 3))));
+				atomicAdd(cls32 + (vid >> 1), 1u << (4 * (3 - (e & 3)) + 16 * (vid & 1)));
 			}
 			__syncwarp();
 		}
@@ -582,8 +595,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 				for (int k = 0; k < VAL_ITEMS; k++)
 				{
 					const uint32_t i = base + k * NT + tid;
-					const uint32_t w = i < V ? __ldcg(A.cls + (size_t)vb + i) : 0u;
-					val[k] = (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
+					uint32_t w = 0;
+					if (i < V) w = (__ldcg(cls32 + (i >> 1)) >> (16 * (i & 1))) & 0xFFFFu;
+					if (fits && i < V) reinterpret_cast<uint16_t*>(s_cls)[i] = (uint16_t)w;
+					val[k] = (w & 15u) + ((w >> 4) & 15u) + ((w >> 8) & 15u) + (w >> 12);
 					sc[k] = val[k];
 				}
 				block_scan_nt<NT, VAL_ITEMS>(sc, rt, s_scan, s_scant);
@@ -596,6 +611,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 					{
 						A.valence[(size_t)vb + i] = (uint8_t)val[k];
 						A.adj_off[(size_t)vb + i] = run + sc[k];
+						if (fits) s_aoff[i] = run + sc[k];
 					}
 					run += rt[k];
 				}
@@ -610,6 +626,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 		// use counters / adjacency offset -> store, all through L2): UF pairs per lane are in flight at once.
 		const uint32_t* const aoff_c = A.adj_off + vb;
 		const uint32_t prim_c = (uint32_t)(ib / 3); // every cell emits whole triangles, so a chunk's and a cell's first index are multiples of 3
+		for (uint32_t t = tid; t < cc.n_inds / 3u; t += NT) A.prim_vbase[prim_c + t] = (uint32_t)vb; // Primitive -> its chunk's first vertex
 		rec_nx = make_uint2(0u, 0u);
 		if ((uint32_t)tid < nic) rec_nx = __ldcg(il + tid);
 		for (uint32_t i0 = (uint32_t)wbase; i0 < nic; i0 += NT)
@@ -656,23 +673,34 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 						const uint32_t t3 = (t * 11u) >> 5; // t / 3 for t < 15
 						const uint32_t lp = s_out[wbase + c] + t3;
 						prim[u] = prim_c + lp;
-						if (t == 3u * t3) A.prim_vbase[prim[u]] = (uint32_t)vb;
 						key[u] = ((3u - (e & 3u)) << 8) | ((uint32_t)(s_lc[wbase + c] >> (3 * t)) & 7u);
 						idx[u] = __ldcg(inds_c + 3u * s_out[wbase + c] + t);
+					}
+				}
+				if (fits)
+				{
+#pragma unroll
+					for (int u = 0; u < UF; u++)
+					{
+						cw[u] = reinterpret_cast<const uint16_t*>(s_cls)[idx[u]];
+						ao[u] = s_aoff[idx[u]];
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int u = 0; u < UF; u++)
+					{
+						cw[u] = __ldcg(cls32 + (idx[u] >> 1)) >> (16 * (idx[u] & 1));
+						ao[u] = __ldcg(aoff_c + idx[u]);
 					}
 				}
 #pragma unroll
 				for (int u = 0; u < UF; u++)
 				{
-					cw[u] = __ldcg(cls_c + idx[u]);
-					ao[u] = __ldcg(aoff_c + idx[u]);
-				}
-#pragma unroll
-				for (int u = 0; u < UF; u++)
-				{
 					if (p0 + 32 * u >= n_pairs) continue;
-					const uint32_t lower = cw[u] & ((1u << (8 * (key[u] >> 8))) - 1u);
-					const uint32_t before = (lower & 0xFF) + ((lower >> 8) & 0xFF) + ((lower >> 16) & 0xFF);
+					const uint32_t lower = cw[u] & ((1u << (4 * (key[u] >> 8))) - 1u);
+					const uint32_t before = (lower & 15u) + ((lower >> 4) & 15u) + ((lower >> 8) & 15u);
 					A.adj[ao[u] + before + (key[u] & 0xFFu)] = prim[u];
 				}
 			}

@@ -437,23 +437,37 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
                                                                    const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj,
                                                                    const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos,
                                                                    float* dp_global, int half_steps, int process_boundary, unsigned long long* tot,
-                                                                   unsigned int smem_floats, float* __restrict__ normal, int nan_step)
+                                                                   unsigned int smem_floats, float* __restrict__ normal, int nan_step,
+                                                                   const int* __restrict__ list /* the chunks that have vertices (k_chunk_count's emit list), or null */)
 {
 	extern __shared__ float sm_f[];
 	__shared__ int s_chunk;
 	if (tot[7]) return;
-	constexpr uint32_t BIG = 4096; // chunks with at least this many vertices are handed out first (longest first keeps the tail short)
+	// chunks are handed out longest first (three size classes, the candidates are walked once per class: a ticket that names a chunk of another
+	// class costs thread 0 one atomic and one 40-byte load).  With the emit list only mesh chunks are candidates; without it every chunk is.
+	const unsigned long long n_cand = list ? tot[10] : (unsigned long long)n_chunks;
 	for (;;)
 	{
-		if (threadIdx.x == 0) s_chunk = (int)atomicAdd(tot + 6, 1ull);
+		__syncthreads(); // the previous chunk's last half-step still reads shared memory
+		if (threadIdx.x == 0)
+		{
+			int k = -1;
+			for (;;)
+			{
+				const unsigned long long j = atomicAdd(tot + 6, 1ull);
+				if (j >= 3 * n_cand) break;
+				const int pass = (int)(j / n_cand), cand = (int)(j - (unsigned long long)pass * n_cand);
+				const int q = list ? list[cand] : cand;
+				const ChunkCounts t = chunks[q];
+				if (!t.contains_mesh || t.n_verts == 0 || t.n_inds < 3) continue;
+				if ((t.n_verts >= 6144u ? 0 : (t.n_verts >= 3072u ? 1 : 2)) == pass) { k = q; break; }
+			}
+			s_chunk = k;
+		}
 		__syncthreads();
-		const int w = s_chunk;
-		__syncthreads();
-		if (w >= 2 * n_chunks) return;
-		const int c = w < n_chunks ? w : w - n_chunks;
+		const int c = s_chunk;
+		if (c < 0) return;
 		const ChunkCounts cc = chunks[c];
-		if (!cc.contains_mesh || cc.n_verts == 0 || cc.n_inds < 3) continue;
-		if ((cc.n_verts >= BIG) != (w < n_chunks)) continue;
 		const uint32_t V = cc.n_verts, T = cc.n_inds / 3;
 		const size_t vb = (size_t)cc.vert_base, ib = (size_t)cc.ind_base;
 		const uint32_t prim0 = (uint32_t)(ib / 3);
