@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--chunks-per-axis", type=int, default=16)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (3-D noise, LOD rebuild, single 128^3, ...)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="e2e only: bmf_ctx_set_reserved_sms for both contexts (measured: no effect with the copy-engine download)")
     return ap.parse_args()
 
 
@@ -145,9 +146,11 @@ def kernel_bytes(name, st):
         "k_count": vox_mesh * 2 * w,
         # sign words + counts in, index bases out (+ 16 B vertex record per active word, + 8 B record per surface cell: ~ V/1.5 + I/9 cells)
         "k_bases": vox_mesh * 3 * w + 8.0 * (V / 1.5 + I / 9.0),
-        # fused front end (one CTA per mesh chunk): sign words in once, mesh out (13 B per vertex + 2 samples in, 4 B per index, valence + adjacency offsets 5 B per vertex,
-        # CSR 4 B per index + 4 B per triangle)
-        "k_chunk_mesh": vox_mesh * w + (13.0 + 8.0 + 5.0) * V + (4.0 + 4.0) * I + 4.0 * I / 3.0,
+        # per-chunk front end, dim <= 64 (csrc/fused.cuh).  count: sign words in, packed word counts out.  emit: sign words + word counts in; out: positions 12 B,
+        # zeroed normals 12 B, boundary 1 B, valence 1 B, adjacency offsets 4 B per vertex (+ two crossing-edge samples in, 8 B), indices 4 B + CSR 4 B per index,
+        # prim_vbase 4 B per triangle, and an 8-byte cell record written and read back per surface cell (~ V/1.5 vertex cells + I/9 index cells)
+        "k_chunk_count": vox_mesh * 2 * w,
+        "k_chunk_emit": vox_mesh * 2 * w + (12.0 + 12.0 + 1.0 + 1.0 + 4.0 + 8.0) * V + 8.0 * I + 4.0 * I / 3.0 + 16.0 * (V / 1.5 + I / 9.0),
         # 13 B per vertex out (position + boundary flag), two crossing-edge samples in
         "k_verts3": (13.0 + 8.0) * V,
         # 4 B per index out + 4 B use counter per vertex + one 8-byte cell record per ~9 indices
@@ -329,27 +332,33 @@ class SharedWorld:
         self.vox = self.n_total * dim ** 3
 
     def enqueue(self, c, slot):
+        """copy-engine download of c's resident batch into this rank's region of `slot` (the host waits for the batch's kernels first)"""
         b = self.g.buffers(slot)
         if self.compact:
-            c.download_enqueue(pos=b["pos"], inds16=b["inds"])
+            c.download_dma(pos=b["pos"], inds16=b["inds"])
         else:
-            c.download_enqueue(pos=b["pos"], color=b["color"], inds32=b["inds"])
+            c.download_dma(pos=b["pos"], color=b["color"], inds32=b["inds"])
 
     def run(self, steps, collect=True):
-        """the e2e loop of every rank: two contexts ping-pong, rank 0 gathers.  Returns rank 0's last (table, owner)."""
+        """the e2e loop of every rank: the NC contexts take the batches round robin, rank 0 gathers.  Returns rank 0's last (table, owner).
+        Iteration k: the kernels of batch k are queued on context k % NC; THEN the host waits for the kernels of batch k - LAG (another context) and
+        queues its DMA -- which runs beside the kernels of the batches after it; THEN the DMA of batch k - LAG - 1 is awaited, its chunk table
+        published and (rank 0) gathered.  LAG = NC - 2: a context is free again before its turn comes round, and kernels are queued LAG steps ahead
+        of their download (command fetch is slow while a download saturates the PCIe link: reads do not pass posted writes)."""
         g, last = self.g, None
-        prev = None
-        for k in range(steps):
-            c = self.ctxs[k & 1]
-            g.wait_slot_free(k)
-            if len(self.descs):
-                c.submit(self.descs, self.dim, iters=self.iters)
-                self.enqueue(c, k % g.SLOTS)
-            if prev is not None:
-                last = self._finish(k - 1, prev, collect)
-            prev = c
-        if prev is not None:
-            last = self._finish(steps - 1, prev, collect)
+        have = len(self.descs) > 0
+        nc = len(self.ctxs)
+        lag = max(1, nc - 2)
+        for k in range(steps + lag + 1):
+            if nc < 3 and k >= lag + 1:
+                last = self._finish(k - lag - 1, self.ctxs[(k - lag - 1) % nc], collect)
+            if k < steps and have:
+                self.ctxs[k % nc].submit(self.descs, self.dim, iters=self.iters)
+            if lag <= k < steps + lag and have:
+                g.wait_slot_free(k - lag)
+                self.enqueue(self.ctxs[(k - lag) % nc], (k - lag) % g.SLOTS)
+            if nc >= 3 and k >= lag + 1:
+                last = self._finish(k - lag - 1, self.ctxs[(k - lag - 1) % nc], collect)
         return last
 
     def _finish(self, step, c, collect):
@@ -424,7 +433,7 @@ def run_ours(args):
     if D.size > 1:
         args.gpus = D.size
     numa = pin_to_gpu_numa_node(D.local_rank)
-    ctxs = [Context(D.local_rank), Context(D.local_rank)]  # raises if the CUDA library or the device is missing: no fallback
+    ctxs = [Context(D.local_rank) for _ in range(3)]  # raises if the CUDA library or the device is missing: no fallback
     ctx = ctxs[0]
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", D.local_rank))
     kind = SAMPLERS[args.sampler]
@@ -455,6 +464,8 @@ def run_ours(args):
     V, I = sw.V, sw.I
 
     # ---- end to end (headline): compact download, device-driven, gathered on rank 0
+    for c in ctxs:
+        c.set_reserved_sms(args.reserve_sms)
     e2e_s, last = time_e2e(D, sw, K)
     d2h = sw.bytes_per_step()
     h2d = int(descs_all.nbytes + 16 * len(descs_all))  # descriptors (host ABI) + the geometry records the library uploads
@@ -470,8 +481,9 @@ def run_ours(args):
     clk = clocks.stop()  # sampled across both timed regions
     e2e = {"value": nvox * K / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3,
            "d2h_GB_per_s": d2h / (e2e_s / K) / 1e9,
-           "mode": "opt-in compact download (positions + uint16 chunk-local indices; colour == 1 and the chunk table say what was skipped), stored by a kernel "
-                   "straight into a shared pinned host segment, two contexts ping-pong, rank 0 assembles the batch-order chunk table",
+           "mode": "opt-in compact download (positions + uint16 chunk-local indices packed on the device; colour == 1 and the chunk table say what was skipped), "
+                   "copy engine straight into a shared pinned host segment (bmf_batch_download_dma), three contexts round robin so that the DMA of batch i runs beside "
+                   "the kernels of the batches after it, rank 0 assembles the batch-order chunk table",
            "gathered": verify}
     sw.close()
     # the reference-layout download (positions + colours + uint32 indices, GLChunk::format_data's arrays) through the same path
@@ -480,6 +492,8 @@ def run_ours(args):
     e2e["reference_layout"] = {"value": nvox * K / s2, "ms_per_step": s2 / K * 1e3, "d2h_bytes_per_step": sw2.bytes_per_step(),
                                "d2h_GB_per_s": sw2.bytes_per_step() / (s2 / K) / 1e9, "streams": "positions + colours + uint32 indices"}
     sw2.close()
+    for c in ctxs:
+        c.set_reserved_sms(0)
 
     result = {
         "metric": "voxels/sec sampled+meshed", "value": value, "unit": "voxels/s", "n_gpus": args.gpus, "steps": K, "warmup": W,

@@ -21,10 +21,10 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 # symbols include/bmf_b200.h declares (tests check that the library exports every one of them)
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
-           "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
+           "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_set_reserved_sms", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve", "bmf_sampler_gradient", "bmf_color_map", "bmf_mesh_collapse_bad_quads",
            "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue",
-           "bmf_batch_download_enqueue", "bmf_host_alloc", "bmf_host_free", "bmf_host_register", "bmf_host_unregister")
+           "bmf_batch_download_enqueue", "bmf_batch_download_dma", "bmf_host_alloc", "bmf_host_free", "bmf_host_register", "bmf_host_unregister")
 
 
 class SamplerDesc(C.Structure):
@@ -101,6 +101,7 @@ def load_library(path=SO):
     lib.bmf_ctx_launch_count.argtypes = [vp]
     lib.bmf_ctx_launch_count.restype = C.c_int64
     lib.bmf_ctx_set_kernel_timing.argtypes = [vp, C.c_int]
+    lib.bmf_ctx_set_reserved_sms.argtypes = [vp, C.c_int]
     lib.bmf_ctx_kernel_times.argtypes = [vp, C.c_int, vp, vp]
     lib.bmf_ctx_stream.argtypes = [vp]
     lib.bmf_ctx_stream.restype = vp
@@ -120,6 +121,7 @@ def load_library(path=SO):
     lib.bmf_seam_download.argtypes = [vp, vp]
     lib.bmf_seam_stage_ms.argtypes = [vp, vp]
     lib.bmf_batch_download_enqueue.argtypes = [vp, C.POINTER(DownloadDesc)]
+    lib.bmf_batch_download_dma.argtypes = [vp, C.POINTER(DownloadDesc)]
     lib.bmf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.bmf_host_free.argtypes = [vp]
     lib.bmf_host_free.restype = None
@@ -279,6 +281,21 @@ class Context:
         d.cap_verts, d.cap_inds = cap_v or 0, cap_i or 0
         self._check(self.lib.bmf_batch_download_enqueue(self.h, C.byref(d)))
 
+    def download_dma(self, pos=None, normal=None, color=None, boundary=None, valence=None, inds32=None, inds16=None):
+        """bmf_batch_download_dma: waits for the batch's kernels, enqueues copy-engine transfers into (pinned) numpy views, returns; wait() completes them"""
+        d = DownloadDesc()
+        cap_v, cap_i = None, None
+        for name, a, per in (("pos", pos, 3), ("normal", normal, 3), ("color", color, 3), ("boundary", boundary, 1), ("valence", valence, 1)):
+            if a is not None:
+                setattr(d, name, a.ctypes.data)
+                cap_v = a.size // per if cap_v is None else min(cap_v, a.size // per)
+        for name, a in (("indices32", inds32), ("indices16", inds16)):
+            if a is not None:
+                setattr(d, name, a.ctypes.data)
+                cap_i = a.size
+        d.cap_verts, d.cap_inds = cap_v or 0, cap_i or 0
+        self._check(self.lib.bmf_batch_download_dma(self.h, C.byref(d)))
+
     def copy_chunk(self, i, want=("verts", "inds", "bits")):
         info = ChunkInfo()
         self._check(self.lib.bmf_batch_chunk_info(self.h, i, C.byref(info)))
@@ -297,6 +314,10 @@ class Context:
         ms = np.zeros(len(STAGES), np.float32)
         self._check(self.lib.bmf_batch_stage_ms(self.h, _p(ms)))
         return dict(zip(STAGES, ms.tolist()))
+
+    def set_reserved_sms(self, n):
+        """leave n SMs partly free for another context's kernels (overlapped pipelines)"""
+        self._check(self.lib.bmf_ctx_set_reserved_sms(self.h, int(n)))
 
     def set_kernel_timing(self, on):
         self._check(self.lib.bmf_ctx_set_kernel_timing(self.h, int(on)))

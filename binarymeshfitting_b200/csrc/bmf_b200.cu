@@ -101,13 +101,18 @@ struct bmf_ctx
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	// fused per-chunk extraction (fused.cuh): one CTA per mesh chunk does label_edges + polygonize + MeshProcessor::init
-	int fused_extract = 1;    // BMF_FUSED=0: the multi-kernel path for every dim (it always serves dim 128 / 256 and quads)
+	int fused_extract = 1;    // per-chunk kernels for dim <= 64 triangle batches: 1 = when the batch has chunks for every SM several times over (a chunk is one
+	                          // CTA's serial job there: ~0.1 ms, so a few hundred chunks finish sooner spread over the whole GPU by the per-segment kernels),
+	                          // BMF_FUSED=0 never, BMF_FUSED=2 always
 	bool batch_fused = false; // the resident batch went through k_chunk_mesh
 	size_t fused_smem = 0;
 	DevBuf<unsigned long long> fz_prof;
 	DevBuf<int> emit_list, mixed_list;
+	DevBuf<uint16_t> pack16; // uint16 copy of the index buffer (bmf_batch_download_dma)
 	bool fused_prof = false; // BMF_FUSED_PROF=1: per-phase SM clocks of k_chunk_mesh, mean printed to stderr when the batch completes
 	int sm_count = 148;
+	int reserve_sms = 0; // bmf_ctx_set_reserved_sms: the persistent kernels leave this many SMs (partly) free for another context's kernels
+	int work_sms() const { return std::max(1, sm_count - reserve_sms); } // SMs the persistent kernels size their grids for
 	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
 	size_t smooth_smem = 0;    // dynamic shared memory of k_smooth_chunks
 	int smooth_cluster = 0;    // 1 (BMF_SMOOTH_CLUSTER=1): k_smooth_chunks2, two-CTA clusters with DSMEM for chunks that do not fit one SM -- correct but
@@ -359,7 +364,7 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 			           2 * iters, pb, tot, ctx->smooth_cnt.p, (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step);
 			return BMF_OK;
 		}
-		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->sm_count), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
+		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->work_sms()), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
 		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step,
 		           ctx->batch_fused ? ctx->emit_list.p : nullptr);
 		return BMF_OK;
@@ -457,6 +462,16 @@ int reserve_mesh(bmf_ctx* ctx, size_t cells, size_t verts, size_t inds)
 	return BMF_OK;
 }
 
+// last launch of a batch's sequence: totals and (once per batch) the chunk table to the host through mapped pinned memory (k_publish)
+int publish(bmf_ctx* ctx)
+{
+	const size_t words = ctx->counts_published ? 0 : (size_t)ctx->n * (sizeof(ChunkCounts) / sizeof(uint32_t));
+	BMF_LAUNCH(k_publish, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, ctx->totals_dev.p, ctx->totals_pinned->v,
+	           reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
+	ctx->counts_published = true;
+	return BMF_OK;
+}
+
 // K4 + K5 of the resident batch, sized by arena capacity and guarded on the device (k_check_caps): no host round trip
 int launch_mesh(bmf_ctx* ctx)
 {
@@ -470,10 +485,7 @@ int launch_mesh(bmf_ctx* ctx)
 	if (ctx->batch_fused)
 	{
 		// ---- dim <= 64, triangles: k_chunk_emit (fused.cuh) does label_edges' emission, polygonize and MeshProcessor::init of a chunk in one CTA
-		const size_t words = ctx->counts_published ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
-		BMF_LAUNCH(k_check_caps, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells,
-		           (unsigned long long)caps.verts, (unsigned long long)caps.inds, reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
-		ctx->counts_published = true;
+		BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
 		BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 		if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 		{
@@ -481,7 +493,7 @@ int launch_mesh(bmf_ctx* ctx)
 			BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 			BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 			BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-			return BMF_OK;
+			return publish(ctx);
 		}
 		if (ctx->color_ones < 3 * caps.verts)
 		{
@@ -510,7 +522,7 @@ int launch_mesh(bmf_ctx* ctx)
 			BMF_CUDA(cudaMemsetAsync(ctx->fz_prof.p, 0, 16 * (size_t)n * sizeof(unsigned long long), st));
 			A.prof = ctx->fz_prof.p;
 		}
-		BMF_LAUNCH(k_chunk_emit<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->sm_count), FUSED_NT, ctx->fused_smem, A);
+		BMF_LAUNCH(k_chunk_emit<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->work_sms()), FUSED_NT, ctx->fused_smem, A);
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		if (params->iters > 0)
@@ -520,19 +532,9 @@ int launch_mesh(bmf_ctx* ctx)
 			if (rc) return rc;
 		}
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return BMF_OK;
+		return publish(ctx);
 	}
-	// totals and the chunk table reach the host through mapped pinned memory written by the kernels themselves (UVA):
-	// no D2H transfer sits in this stream, so nothing here can queue behind another context's mesh download
-	{
-		// + the chunk table for the host (once per batch), in the same launch -- unless k_valence_offsets (one CTA per chunk, triangle
-		// path with allocated arenas) will hand it over for free further down
-		const bool later = !ctx->counts_published && !params->quads && caps.cells && caps.verts && caps.inds;
-		const size_t words = (ctx->counts_published || later) ? 0 : (size_t)n * (sizeof(ChunkCounts) / sizeof(uint32_t));
-		BMF_LAUNCH(k_check_caps, words ? std::min(grid_for(words, CTA), (unsigned)(ctx->sm_count * 2)) : 1u, CTA, 0, tot, ctx->totals_pinned->v, (unsigned long long)caps.cells,
-		           (unsigned long long)caps.verts, (unsigned long long)caps.inds, reinterpret_cast<const uint32_t*>(ctx->counts.p), reinterpret_cast<uint32_t*>(ctx->counts_pinned), words);
-		if (!later) ctx->counts_published = true;
-	}
+	BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 	{
@@ -541,7 +543,7 @@ int launch_mesh(bmf_ctx* ctx)
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return BMF_OK;
+		return publish(ctx);
 	}
 	const size_t V = caps.verts, I = caps.inds;
 	const size_t smem_count = (size_t)(L.P + 1) * L.wp * sizeof(uint32_t);
@@ -567,7 +569,7 @@ int launch_mesh(bmf_ctx* ctx)
 		           ctx->sampler, src, ctx->geom.p, ctx->pos.p, ctx->boundary.p, ctx->valence.p, ctx->inds.p, tot);
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-		return BMF_OK;
+		return publish(ctx);
 	}
 	if (L.wpt == 4)
 		BMF_LAUNCH(k_bases<4>, nseg, CTA, smem_bases, ctx->bits.p, L, ctx->wcnt.p, ctx->seg_tot.p, ctx->counts.p, ctx->wv4.p, ctx->wib.p, ctx->vcells.p,
@@ -585,9 +587,7 @@ int launch_mesh(bmf_ctx* ctx)
 		ctx->color_ones = ctx->color.cap;
 	}
 	BMF_LAUNCH(k_inds3, ctx->sm_count * 8, CTA, 0, L, ctx->wv4.p, ctx->wib.p, ctx->counts.p, ctx->icells.p, list_count, ctx->inds.p, ctx->cls.p, tot);
-	BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p, tot,
-	           ctx->counts_published ? nullptr : reinterpret_cast<uint32_t*>(ctx->counts_pinned));
-	ctx->counts_published = true;
+	BMF_LAUNCH(k_valence_offsets, n, CTA, 0, ctx->cls.p, ctx->counts.p, ctx->valence.p, ctx->adj_off.p, tot, nullptr);
 	BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 
 	// ---- K5 (+K6): MeshProcessor<3>(true, SMOOTH_NORMALS) as ChunkGenerator.cpp:110-124 drives it
@@ -598,7 +598,7 @@ int launch_mesh(bmf_ctx* ctx)
 		if (rc) return rc;
 	}
 	BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
-	return BMF_OK;
+	return publish(ctx);
 }
 
 // the in-loop primal step with set_colors (m == 3, or m == 0 when iters <= 3; MeshProcessor.cpp:229-232) turns the zero normals of the
@@ -748,7 +748,7 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 			ctx->smooth_cluster = 0;
 		}
 	}
-	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e) != 0;
+	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e);
 	if (const char* e = getenv("BMF_FUSED_PROF")) ctx->fused_prof = atoi(e) != 0;
 	ctx->fused_smem = fused_smem_bytes(make_layout(64), FUSED_NT);
 	if (cudaFuncSetAttribute(k_chunk_emit<FUSED_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
@@ -781,7 +781,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
 	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release(); ctx->smooth_cnt.release();
-	ctx->fz_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release();
+	ctx->fz_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release(); ctx->pack16.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
@@ -873,7 +873,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		g.oz = c.pos[2] - so;
 		ctx->geom_host[i] = g;
 	}
-	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64;
+	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64 && (ctx->fused_extract >= 2 || n >= 8 * ctx->sm_count);
 	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
@@ -1017,7 +1017,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	{
 		// chunks without a mesh keep chunk_tot = 0 (k_scan_chunks only reads the totals of mesh chunks); TOT_MESH / TOT_CTICKET restart
 		const bool have_cand = ctx->uni_valid; // the 2-D terrain classifier has listed the chunks it could not cull
-		BMF_LAUNCH(k_chunk_count<COUNT_NT>, (unsigned)std::min(n, 6 * ctx->sm_count), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+		BMF_LAUNCH(k_chunk_count<COUNT_NT>, (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
 		           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
 	}
 	else if (params->quads)
@@ -1180,6 +1180,42 @@ int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc)
 	return launch_download(ctx);
 }
 
+int bmf_batch_download_dma(bmf_ctx* ctx, const bmf_download_desc* desc)
+{
+	if (!ctx || !desc) return BMF_ERR_INVALID;
+	if (!ctx->have_batch) return fail(ctx, BMF_ERR_STATE, "bmf_batch_download_dma: no batch submitted");
+	if (desc->indices32 && desc->indices16) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_dma: pass indices32 or indices16, not both");
+	if (desc->cap_verts < 0 || desc->cap_inds < 0) return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_dma: negative capacity");
+	{
+		int frc = finish(ctx); // the host learns the sizes of the transfers here
+		if (frc) return frc;
+	}
+	BMF_CUDA(cudaSetDevice(ctx->device));
+	const size_t V = ctx->totals[1], I = ctx->totals[2];
+	const bool want_v = desc->pos || desc->normal || desc->color || desc->boundary || desc->valence, want_i = desc->indices32 || desc->indices16;
+	if ((want_v && V > (size_t)desc->cap_verts) || (want_i && I > (size_t)desc->cap_inds))
+		return fail(ctx, BMF_ERR_NOMEM, "bmf_batch_download_dma: host buffers too small for this batch (nothing was written)");
+	if (desc->indices16 && ctx->totals_pinned->v[TOT_MAXV] > 65535ull)
+		return fail(ctx, BMF_ERR_INVALID, "bmf_batch_download_dma: uint16 indices requested but a chunk has >= 65536 vertices (nothing was written)");
+	cudaStream_t st = ctx->stream;
+	if (V)
+	{
+		if (desc->pos) BMF_CUDA(cudaMemcpyAsync(desc->pos, ctx->pos.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (desc->normal) BMF_CUDA(cudaMemcpyAsync(desc->normal, ctx->normal.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (desc->color) BMF_CUDA(cudaMemcpyAsync(desc->color, ctx->color.p, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+		if (desc->boundary) BMF_CUDA(cudaMemcpyAsync(desc->boundary, ctx->boundary.p, V, cudaMemcpyDeviceToHost, st));
+		if (desc->valence) BMF_CUDA(cudaMemcpyAsync(desc->valence, ctx->valence.p, V, cudaMemcpyDeviceToHost, st));
+	}
+	if (I && desc->indices32) BMF_CUDA(cudaMemcpyAsync(desc->indices32, ctx->inds.p, sizeof(uint32_t) * I, cudaMemcpyDeviceToHost, st));
+	if (I && desc->indices16)
+	{
+		BMF_CUDA(ctx->pack16.reserve(I + 8));
+		BMF_LAUNCH(k_pack_indices16, std::min(grid_for((I + 7) / 8, CTA), (unsigned)(ctx->sm_count * 4)), CTA, 0, ctx->inds.p, I, ctx->pack16.p);
+		BMF_CUDA(cudaMemcpyAsync(desc->indices16, ctx->pack16.p, sizeof(uint16_t) * I, cudaMemcpyDeviceToHost, st));
+	}
+	return BMF_OK;
+}
+
 int bmf_host_alloc(size_t bytes, void** out)
 {
 	if (!out) return BMF_ERR_INVALID;
@@ -1314,6 +1350,14 @@ int bmf_ctx_kernel_times(bmf_ctx* ctx, int cap, const char** names, float* ms)
 		if (ms) ms[i] = t;
 	}
 	return n;
+}
+
+int bmf_ctx_set_reserved_sms(bmf_ctx* ctx, int n)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	if (n < 0 || n >= ctx->sm_count) return fail(ctx, BMF_ERR_INVALID, "bmf_ctx_set_reserved_sms: 0 <= n < number of SMs");
+	ctx->reserve_sms = n;
+	return BMF_OK;
 }
 
 void* bmf_ctx_stream(const bmf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

