@@ -111,6 +111,8 @@ struct bmf_ctx
 	DevBuf<uint16_t> pack16; // uint16 copy of the index buffer (bmf_batch_download_dma)
 	bool fused_prof = false; // BMF_FUSED_PROF=1: per-phase SM clocks of k_chunk_mesh, mean printed to stderr when the batch completes
 	int sm_count = 148;
+	int use_tma = 1;     // the per-chunk kernels stage a chunk's sign words / word counts with cp.async.bulk + mbarrier (TMA); BMF_TMA=0: 128-bit load loops
+	                     // (A/B on the 4096-chunk batch: k_chunk_count 0.058 -> 0.055 ms, k_chunk_emit 0.256 -> 0.249 ms, identical output)
 	int reserve_sms = 0; // bmf_ctx_set_reserved_sms: the persistent kernels leave this many SMs (partly) free for another context's kernels
 	int work_sms() const { return std::max(1, sm_count - reserve_sms); } // SMs the persistent kernels size their grids for
 	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
@@ -522,7 +524,10 @@ int launch_mesh(bmf_ctx* ctx)
 			BMF_CUDA(cudaMemsetAsync(ctx->fz_prof.p, 0, 16 * (size_t)n * sizeof(unsigned long long), st));
 			A.prof = ctx->fz_prof.p;
 		}
-		BMF_LAUNCH(k_chunk_emit<FUSED_NT>, (unsigned)std::min(n, 2 * ctx->work_sms()), FUSED_NT, ctx->fused_smem, A);
+		if (ctx->use_tma)
+			BMF_LAUNCH((k_chunk_emit<FUSED_NT, true>), (unsigned)std::min(n, 2 * ctx->work_sms()), FUSED_NT, ctx->fused_smem, A);
+		else
+			BMF_LAUNCH((k_chunk_emit<FUSED_NT, false>), (unsigned)std::min(n, 2 * ctx->work_sms()), FUSED_NT, ctx->fused_smem, A);
 		BMF_CUDA(cudaEventRecord(ctx->ev[4], st));
 		BMF_CUDA(cudaEventRecord(ctx->ev[5], st));
 		if (params->iters > 0)
@@ -750,8 +755,10 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 	}
 	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e);
 	if (const char* e = getenv("BMF_FUSED_PROF")) ctx->fused_prof = atoi(e) != 0;
+	if (const char* e = getenv("BMF_TMA")) ctx->use_tma = atoi(e) != 0;
 	ctx->fused_smem = fused_smem_bytes(make_layout(64), FUSED_NT);
-	if (cudaFuncSetAttribute(k_chunk_emit<FUSED_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_chunk_emit<FUSED_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_chunk_emit<FUSED_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->fused_smem) != cudaSuccess)
 	{
 		cudaGetLastError();
 		ctx->fused_extract = 0;
@@ -1017,8 +1024,12 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	{
 		// chunks without a mesh keep chunk_tot = 0 (k_scan_chunks only reads the totals of mesh chunks); TOT_MESH / TOT_CTICKET restart
 		const bool have_cand = ctx->uni_valid; // the 2-D terrain classifier has listed the chunks it could not cull
-		BMF_LAUNCH(k_chunk_count<COUNT_NT>, (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
-		           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
+		if (ctx->use_tma)
+			BMF_LAUNCH((k_chunk_count<COUNT_NT, true>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
+		else
+			BMF_LAUNCH((k_chunk_count<COUNT_NT, false>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
 	}
 	else if (params->quads)
 	{

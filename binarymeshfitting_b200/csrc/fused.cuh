@@ -159,7 +159,47 @@ __device__ __forceinline__ uint32_t vertex_id_smem(const FusedView& S, const Lay
 // once, DMCChunk.cpp:170-171) costs one ticket.  COUNT_NT threads per chunk so that six CTAs share an SM and no wave is left half empty.
 static constexpr int COUNT_NT = 256;
 
-template <int NT>
+// ---- TMA (bulk async copy) staging of a chunk's sign words: one elected thread arms an mbarrier with the byte count and issues ONE
+// cp.async.bulk global -> shared for the whole 4 / 32 KB image; everybody waits on the barrier's phase.  A/B against the 128-bit load loop:
+// BMF_TMA=1 (DESIGN.md section 4 has the numbers).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// the elected thread: arrive on the barrier announcing `bytes` of asynchronous transfers (all the bulk_copy calls of this phase together)
+__device__ __forceinline__ void mbar_expect(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic-proxy accesses to the destinations are ordered before the async writes
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes),
+	             "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar)
+{
+	mbar_expect(bar, bytes);
+	bulk_copy(dst_smem, src_global, bytes, bar);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	asm volatile("{\n"
+	             ".reg .pred p;\n"
+	             "BMF_WAIT_%=:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra BMF_DONE_%=;\n"
+	             "bra BMF_WAIT_%=;\n"
+	             "BMF_DONE_%=:\n"
+	             "}" ::"r"(smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+
+template <int NT, bool TMA>
 __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, int n, const int* __restrict__ cand,
                                                      const u64* __restrict__ cand_count, uint32_t* __restrict__ wcnt, uint32_t* __restrict__ chunk_tot,
                                                      uint8_t* __restrict__ masks, int* __restrict__ emit_list, u64* __restrict__ tot /* [TOT_MESH], [TOT_CTICKET] */)
@@ -168,9 +208,12 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 	__shared__ u64 s_tri[256];
 	__shared__ uint32_t s_red[3][NT / 32];
 	__shared__ int s_chunk;
+	__shared__ __align__(8) uint64_t s_bar;
 	const int d = L.d, wc = L.wc, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	uint32_t* sb = dyn;
 	for (int i = tid; i < 256; i += NT) s_tri[i] = g_tri_pack[i];
+	if (TMA && tid == 0) mbar_init(&s_bar, 1);
+	uint32_t phase = 0;
 	const u64 n_cand = cand ? *cand_count : (u64)n;
 	for (;;)
 	{
@@ -190,6 +233,14 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 		__syncthreads();
 		const int chunk = s_chunk;
 		if (chunk < 0) return;
+		if (TMA)
+		{
+			if (tid == 0) bulk_load(sb, bits + (size_t)chunk * wc, (uint32_t)wc * 4u, &s_bar);
+			for (int i = tid; i < L.wp; i += NT) sb[wc + i] = 0u; // plane x = d: B == 0 outside the grid
+			mbar_wait(&s_bar, phase);
+			phase ^= 1u;
+		}
+		else
 		{
 			const uint4* src = reinterpret_cast<const uint4*>(bits + (size_t)chunk * wc);
 			uint4* dst = reinterpret_cast<uint4*>(sb);
@@ -249,7 +300,7 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 	}
 }
 
-template <int NT>
+template <int NT, bool TMA>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArgs A)
 {
 	extern __shared__ __align__(16) uint32_t dyn[];
@@ -277,6 +328,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 	__shared__ uint32_t s_edge[16];
 	__shared__ int s_chunk;
 	__shared__ uint32_t s_njobs, s_nvc, s_nic;
+	__shared__ __align__(8) uint64_t s_bar;
 	__shared__ uint2 s_wtot[NW], s_woff[NW];
 	__shared__ uint32_t s_scan[VAL_ITEMS][NW], s_scant[VAL_ITEMS];
 	FusedView S;
@@ -299,6 +351,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 		s_tri[i] = tp;
 		s_loc[i] = lc;
 	}
+	if (TMA && tid == 0) mbar_init(&s_bar, 1);
+	uint32_t phase = 0;
 	if (tid < 12)
 	{
 		// edge e of a cell (EDGE_V, DMCChunk.cpp:32, 543-565): X-edges 0-3 at (y+hi, z+lo), Y-edges 4-7 at (x+hi, z+lo), Z-edges 8-11 at (x+hi, y+lo)
@@ -344,11 +398,42 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 		// ---- phase 1: sign words (+ a zero plane at x = d: B == 0 outside the grid) and word counts -> shared memory; words that emit
 		// anything -> job list (one shared-memory atomic per warp and step)
 		{
-			const uint4* src = reinterpret_cast<const uint4*>(A.bits + (size_t)chunk * wc);
-			uint4* dst = reinterpret_cast<uint4*>(sb);
-			for (int i = tid; i < wc / 4; i += NT) dst[i] = src[i];
-			for (int i = tid; i < L.wp; i += NT) sb[wc + i] = 0u;
 			const uint32_t* cnt = A.wcnt + (size_t)chunk * wc;
+			if (TMA)
+			{
+				// both 4 * wc byte images with two bulk copies; the stores below are issued while they are in flight
+				if (tid == 0)
+				{
+					mbar_expect(&s_bar, 8u * (uint32_t)wc);
+					bulk_copy(sb, A.bits + (size_t)chunk * wc, 4u * (uint32_t)wc, &s_bar);
+					bulk_copy(s_off, cnt, 4u * (uint32_t)wc, &s_bar);
+				}
+			}
+			else
+			{
+				const uint4* src = reinterpret_cast<const uint4*>(A.bits + (size_t)chunk * wc);
+				uint4* dst = reinterpret_cast<uint4*>(sb);
+				for (int i = tid; i < wc / 4; i += NT) dst[i] = src[i];
+			}
+			for (int i = tid; i < L.wp; i += NT) sb[wc + i] = 0u;
+			if (TMA)
+			{
+				for (uint32_t i = tid; i < (V + 1) / 2; i += NT) cls32[i] = 0u;
+				for (uint32_t i = tid; i < 3 * V; i += NT) A.normal[3 * (size_t)vb + i] = 0.0f;
+				mbar_wait(&s_bar, phase);
+				phase ^= 1u;
+				for (int w = tid; w < wc; w += NT)
+				{
+					const uint32_t c = s_off[w];
+					const uint32_t bal = __ballot_sync(0xffffffffu, c != 0u);
+					uint32_t o = 0;
+					if (lane == 0 && bal) o = atomicAdd(&s_njobs, (uint32_t)__popc(bal));
+					o = __shfl_sync(0xffffffffu, o, 0);
+					if (c) s_job[o + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)w;
+				}
+			}
+			else
+			{
 			constexpr int U1 = 8; // word counts in flight per thread
 			for (int w0 = tid; w0 < wc; w0 += U1 * NT)
 			{
@@ -371,6 +456,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 			// every vertex's use counters (phase 5d adds to them) and normal start at zero: coalesced here instead of per vertex in 5c
 			for (uint32_t i = tid; i < (V + 1) / 2; i += NT) cls32[i] = 0u;
 			for (uint32_t i = tid; i < 3 * V; i += NT) A.normal[3 * (size_t)vb + i] = 0.0f;
+			}
 		}
 		__syncthreads();
 		BMF_FUSED_MARK(1);

@@ -108,3 +108,23 @@ def test_fused_many_chunks_lookback_order():
     same(a, b)
     assert int(a[0]["contains_mesh"].sum()) > 2 * 148
     f.close(); m.close()
+
+
+def test_tma_staging_equals_load_loop():
+    """the per-chunk kernels stage the sign words / word counts with cp.async.bulk + mbarrier by default; BMF_TMA=0 is the 128-bit load loop"""
+    ps = grid(6, 32.0, -96.0)
+    outs = []
+    for tma in ("1", "0"):
+        old = os.environ.get("BMF_TMA")
+        os.environ["BMF_TMA"] = tma
+        try:
+            c = make_ctx(True)
+        finally:
+            if old is None:
+                del os.environ["BMF_TMA"]
+            else:
+                os.environ["BMF_TMA"] = old
+        outs.append(run(c, capi.TERRAIN2D_PERT, ps, 64, iters=2))
+        outs.append(run(c, capi.TERRAIN2D_PERT, ps, 32, iters=2))  # same context again: the barrier's phase keeps alternating
+        c.close()
+    assert same(outs[0], outs[2]) > 0 and same(outs[1], outs[3]) > 0
