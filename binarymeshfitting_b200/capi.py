@@ -329,7 +329,7 @@ class Context:
         n = self.lib.bmf_ctx_kernel_times(self.h, cap, names, _p(ms))
         if n < 0:
             self._check(n)
-        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
+        return [(names[i].decode().strip("()"), float(ms[i])) for i in range(min(n, cap))]  # (template kernels are launched as "(k<a, b>)")
 
     def device_ptrs(self):
         """device pointers (ints) of the resident batch: pos, indices, bits, density (0 if not materialised)"""

@@ -117,9 +117,6 @@ struct bmf_ctx
 	int work_sms() const { return std::max(1, sm_count - reserve_sms); } // SMs the persistent kernels size their grids for
 	int smooth_fused = 1;      // batch path: all smoothing half-steps of a chunk in one CTA out of shared memory (BMF_SMOOTH_FUSED=0: per-step kernels)
 	size_t smooth_smem = 0;    // dynamic shared memory of k_smooth_chunks
-	int smooth_cluster = 0;    // 1 (BMF_SMOOTH_CLUSTER=1): k_smooth_chunks2, two-CTA clusters with DSMEM for chunks that do not fit one SM -- correct but
-	                           // measured slower than one CTA per chunk (0.31 ms against 0.21 ms on the benchmark batch), so it is off by default
-	DevBuf<unsigned long long> smooth_cnt; // its two work counters
 	int smooth_ctas_per_sm = 8; // resident CTAs per SM of the grid-stride smoothing kernels (tuning knob: BMF_SMOOTH_CTAS_PER_SM)
 	DevBuf<float> density, hmap;
 	DevBuf<uint8_t> masks;
@@ -356,16 +353,6 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		// the in-loop primal step with set_colors (m == 3, or m == 0 when iters <= 3) turns the zero normals of the processed vertices into
 		// NaN in the reference (and in k_primal); nan_step = its half-step index, -1 if there is none
 		const int nan_step = nan_half_step(iters);
-		if (ctx->smooth_cluster)
-		{
-			// two-CTA clusters: chunks too large for one SM's shared memory are split over a pair of SMs (DSMEM)
-			BMF_CUDA(ctx->smooth_cnt.reserve(2));
-			BMF_CUDA(cudaMemsetAsync(ctx->smooth_cnt.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-			const unsigned grid = (unsigned)std::max(2, std::min(2 * ((n_chunks + 1) / 2), ctx->sm_count & ~1));
-			BMF_LAUNCH(k_smooth_chunks2, grid, SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p, valence, boundary, pos, ctx->dp.p,
-			           2 * iters, pb, tot, ctx->smooth_cnt.p, (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step);
-			return BMF_OK;
-		}
 		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->work_sms()), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
 		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step,
 		           ctx->batch_fused ? ctx->emit_list.p : nullptr);
@@ -746,12 +733,6 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 			cudaGetLastError();
 			ctx->smooth_fused = 0;
 		}
-		if (const char* e2 = getenv("BMF_SMOOTH_CLUSTER")) ctx->smooth_cluster = atoi(e2) != 0;
-		if (!ctx->smooth_fused || cudaFuncSetAttribute(k_smooth_chunks2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smooth_smem) != cudaSuccess)
-		{
-			cudaGetLastError();
-			ctx->smooth_cluster = 0;
-		}
 	}
 	if (const char* e = getenv("BMF_FUSED")) ctx->fused_extract = atoi(e);
 	if (const char* e = getenv("BMF_FUSED_PROF")) ctx->fused_prof = atoi(e) != 0;
@@ -787,7 +768,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->counts_pinned) cudaFreeHost(ctx->counts_pinned);
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
-	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release(); ctx->smooth_cnt.release();
+	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release();
 	ctx->fz_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release(); ctx->pack16.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();

@@ -492,196 +492,6 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
 	}
 }
 
-// ---- the same, for a CLUSTER of two CTAs (two SMs, 2 x 227 KB of shared memory, 2048 threads): chunks whose positions
-// and dual points do not fit one SM are split in halves -- CTA r keeps vertices / triangles [r * half, ...) -- and every
-// gather goes to the local half or, through distributed shared memory, to the peer's.  All writes are local; a cluster
-// barrier separates the half-steps.  Pass 1: the cluster takes the large chunks together (work counter cnt[0]); pass 2:
-// each CTA takes small chunks on its own (cnt[1]), exactly like k_smooth_chunks.
-struct SplitArray
-{
-	float* loc;      // this CTA's half
-	const float* rem; // the peer's half (DSMEM)
-	uint32_t split;  // elements held by rank 0
-	uint32_t rank;   // this CTA's rank
-	__device__ __forceinline__ f3 get(uint32_t i) const
-	{
-		const uint32_t r = i >= split ? 1u : 0u, j = i - (r ? split : 0u);
-		const float* b = r == rank ? loc : rem;
-		return { b[3 * j], b[3 * j + 1], b[3 * j + 2] };
-	}
-	__device__ __forceinline__ void put_local(uint32_t i, f3 v) const
-	{
-		const uint32_t j = i - (rank ? split : 0u);
-		loc[3 * j] = v.x; loc[3 * j + 1] = v.y; loc[3 * j + 2] = v.z;
-	}
-};
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SMOOTH_CTA, 1)
-    k_smooth_chunks2(const ChunkCounts* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off,
-                     const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos, float* dp_global,
-                     int half_steps, int process_boundary, const unsigned long long* __restrict__ tot, unsigned long long* __restrict__ cnt, unsigned int smem_floats,
-                     float* __restrict__ normal, int nan_step)
-{
-	namespace cg = cooperative_groups;
-	extern __shared__ float sm_f[];
-	__shared__ int s_chunk;
-	cg::cluster_group cluster = cg::this_cluster();
-	const uint32_t rank = cluster.block_rank();
-	if (tot[7]) return; // both CTAs of every cluster
-	constexpr int U = 4, KMAX = 8;
-	const float* sm_peer = cluster.map_shared_rank(sm_f, rank ^ 1u);
-	const int* chunk_of_rank0 = cluster.map_shared_rank(&s_chunk, 0);
-	// ---- pass 1: chunks too large for one SM, two CTAs per chunk
-	for (;;)
-	{
-		if (rank == 0 && threadIdx.x == 0) s_chunk = (int)atomicAdd(cnt, 1ull);
-		cluster.sync();
-		const int c = *chunk_of_rank0;
-		cluster.sync(); // rank 0 may overwrite s_chunk only after both have read it
-		if (c >= n_chunks) break;
-		const ChunkCounts cc = chunks[c];
-		if (!cc.contains_mesh || cc.n_verts == 0 || cc.n_inds < 3) continue;
-		const uint32_t V = cc.n_verts, T = cc.n_inds / 3;
-		if (3ull * ((unsigned long long)V + T) <= smem_floats) continue; // fits one SM: pass 2
-		const size_t vb = (size_t)cc.vert_base, ib = (size_t)cc.ind_base;
-		const uint32_t prim0 = (uint32_t)(ib / 3);
-		const uint32_t Vh = (V + 1) / 2, Th = (T + 1) / 2;
-		const uint32_t v_lo = rank ? Vh : 0u, v_hi = rank ? V : Vh, t_lo = rank ? Th : 0u, t_hi = rank ? T : Th;
-		const uint32_t* ci = inds + ib;
-		const uint32_t* ao = adj_off + vb;
-		const uint8_t* va = valence + vb;
-		const uint8_t* bo = boundary + vb;
-		float* gp = pos + 3 * vb;
-		if (3ull * ((unsigned long long)Vh + Th) > smem_floats)
-		{
-			// larger than two SMs' shared memory: the cluster works on the global arrays (the cluster barrier orders them)
-			float* gd = dp_global + 3 * (size_t)prim0;
-			for (int h = 0; h < half_steps; h++)
-			{
-				if ((h & 1) == 0)
-					for (uint32_t t = t_lo + threadIdx.x; t < t_hi; t += SMOOTH_CTA)
-					{
-						// L2 loads (ld.cg): the other SM of the cluster writes these arrays and L1 is not coherent across SMs
-						f3 sp = { 0, 0, 0 };
-						sp = add3(sp, ld3cg(gp, ci[3 * t]));
-						sp = add3(sp, ld3cg(gp, ci[3 * t + 1]));
-						sp = add3(sp, ld3cg(gp, ci[3 * t + 2]));
-						st3(gd, t, div3(sp, 3.0f));
-					}
-				else
-					for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += SMOOTH_CTA)
-					{
-						const int n = va[v];
-						if (n == 0 || (!process_boundary && bo[v])) continue;
-						const uint32_t* a = adj + ao[v];
-						f3 p = { 0, 0, 0 };
-						for (int k = 0; k < n; k++) p = add3(p, ld3cg(gd, a[k] - prim0));
-						st3(gp, v, div3(p, (float)n));
-						if (h == nan_step) st3(normal + 3 * vb, v, normalize3({ 0.0f, 0.0f, 0.0f }));
-					}
-				__threadfence();
-				cluster.sync();
-			}
-			continue;
-		}
-		SplitArray P, D;
-		P.loc = sm_f; P.rem = sm_peer; P.split = Vh; P.rank = rank;
-		D.loc = sm_f + 3 * (size_t)Vh; D.rem = sm_peer + 3 * (size_t)Vh; D.split = Th; D.rank = rank;
-		for (uint32_t i = 3 * v_lo + threadIdx.x; i < 3 * v_hi; i += SMOOTH_CTA) P.loc[i - 3 * v_lo] = gp[i];
-		cluster.sync();
-		for (int h = 0; h < half_steps; h++)
-		{
-			if ((h & 1) == 0)
-			{
-				for (uint32_t t0 = t_lo + threadIdx.x; t0 < t_hi; t0 += U * SMOOTH_CTA)
-				{
-					uint32_t id[U][3];
-#pragma unroll
-					for (int u = 0; u < U; u++)
-					{
-						const uint32_t t = t0 + u * SMOOTH_CTA;
-						const bool ok = t < t_hi;
-						id[u][0] = ok ? ci[3 * t] : 0u;
-						id[u][1] = ok ? ci[3 * t + 1] : 0u;
-						id[u][2] = ok ? ci[3 * t + 2] : 0u;
-					}
-#pragma unroll
-					for (int u = 0; u < U; u++)
-					{
-						const uint32_t t = t0 + u * SMOOTH_CTA;
-						if (t >= t_hi) continue;
-						f3 sp = { 0, 0, 0 };
-						sp = add3(sp, P.get(id[u][0]));
-						sp = add3(sp, P.get(id[u][1]));
-						sp = add3(sp, P.get(id[u][2]));
-						D.put_local(t, div3(sp, 3.0f));
-					}
-				}
-			}
-			else
-			{
-				for (uint32_t v0 = v_lo + threadIdx.x; v0 < v_hi; v0 += U * SMOOTH_CTA)
-				{
-					int n[U];
-					uint32_t off[U], a[U][KMAX];
-#pragma unroll
-					for (int u = 0; u < U; u++)
-					{
-						const uint32_t v = v0 + u * SMOOTH_CTA;
-						const bool ok = v < v_hi;
-						const int c0 = ok ? (int)va[v] : 0;
-						const bool skip = ok && !process_boundary && bo[v];
-						n[u] = skip ? 0 : c0;
-						off[u] = ok ? ao[v] : 0u;
-					}
-#pragma unroll
-					for (int u = 0; u < U; u++)
-#pragma unroll
-						for (int k = 0; k < KMAX; k++) a[u][k] = k < n[u] ? adj[off[u] + k] : prim0;
-#pragma unroll
-					for (int u = 0; u < U; u++)
-					{
-						if (n[u] == 0) continue;
-						f3 p = { 0, 0, 0 };
-#pragma unroll
-						for (int k = 0; k < KMAX; k++)
-							if (k < n[u]) p = add3(p, D.get(a[u][k] - prim0));
-						for (int k = KMAX; k < n[u]; k++) p = add3(p, D.get(adj[off[u] + k] - prim0));
-						P.put_local(v0 + u * SMOOTH_CTA, div3(p, (float)n[u]));
-						if (h == nan_step) st3(normal + 3 * vb, v0 + u * SMOOTH_CTA, normalize3({ 0.0f, 0.0f, 0.0f }));
-					}
-				}
-			}
-			cluster.sync();
-		}
-		for (uint32_t i = 3 * v_lo + threadIdx.x; i < 3 * v_hi; i += SMOOTH_CTA) gp[i] = P.loc[i - 3 * v_lo];
-		cluster.sync(); // the peer may still be reading this CTA's half
-	}
-	cluster.sync(); // no remote access after this point
-	// ---- pass 2: chunks that fit one SM, one CTA per chunk
-	for (;;)
-	{
-		__syncthreads();
-		if (threadIdx.x == 0) s_chunk = (int)atomicAdd(cnt + 1, 1ull);
-		__syncthreads();
-		const int c = s_chunk;
-		if (c >= n_chunks) break;
-		const ChunkCounts cc = chunks[c];
-		if (!cc.contains_mesh || cc.n_verts == 0 || cc.n_inds < 3) continue;
-		const uint32_t V = cc.n_verts, T = cc.n_inds / 3;
-		if (3ull * ((unsigned long long)V + T) > smem_floats) continue; // done in pass 1
-		const size_t vb = (size_t)cc.vert_base, ib = (size_t)cc.ind_base;
-		float* gp = pos + 3 * vb;
-		float* P = sm_f;
-		float* D = sm_f + 3 * (size_t)V;
-		for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) P[i] = gp[i];
-		__syncthreads();
-		smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, (uint32_t)(ib / 3), half_steps, process_boundary, normal + 3 * vb, nan_step);
-		for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) gp[i] = P[i];
-	}
-	cluster.sync(); // a CTA must not exit while its peer could still address its shared memory
-}
-
 // zero the first n (batch path: tot[idx] * mul) 32-bit words of p
 __global__ void __launch_bounds__(CTA) k_zero_u32(uint32_t* __restrict__ p, size_t n, const unsigned long long* __restrict__ tot, int idx, int mul)
 {

@@ -55,8 +55,10 @@ def test_sass_is_sm_100a_and_has_the_kernels():
     names = r.stdout
     for k in ("k_terrain2d_sheet", "k_terrain2d_bits", "k_terrain3d", "k_sample_implicit", "k_pack_density", "k_count", "k_scan_chunks", "k_bases", "k_verts3",
               "k_inds3", "k_valence_offsets", "k_adj_fill", "k_smooth_chunks", "k_dual", "k_primal", "k_qef_batch", "k_qef_place",
-              "k_seam_layers", "k_seam_cull", "k_seam_classify", "k_seam_pass", "k_q_count", "k_q_bases", "k_q_emit", "k_format_unwind", "k_ubench_issue"):
+              "k_seam_layers", "k_seam_cull", "k_seam_classify", "k_seam_pass", "k_q_count", "k_q_bases", "k_q_emit", "k_format_unwind", "k_ubench_issue",
+              "k_chunk_count", "k_chunk_emit", "k_publish", "k_pack_indices16", "k_download", "k_sampler_gradient", "k_dual_gradient", "k_color_map", "k_collapse_bad_quads"):
         assert k in names, k
+    assert "UBLKCP" in names, "the per-chunk kernels stage their chunk with cp.async.bulk (TMA): its SASS mnemonic must be present"
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -93,8 +93,8 @@ def test_growing_batches_all_samplers(gpu):
         assert sig == first
 
 
-def test_cluster_smoothing_variant_is_bit_identical(gpu):
-    """BMF_SMOOTH_CLUSTER=1: the two-CTA-cluster (DSMEM) form of the fused smoothing kernel gives the same bits"""
+def test_per_chunk_smoothing_equals_per_step_kernels(gpu):
+    """k_smooth_chunks (all half-steps of a chunk in one CTA) against the per-step kernels k_dual / k_primal (BMF_SMOOTH_FUSED=0), NaN-normal quirk included"""
     import os
     from binarymeshfitting_b200 import Context, capi, world
     ps = world.grid_chunks(8, 16.0, origin=(-64.0, -48.0, -64.0))  # 512 chunks: enough for the fused path
@@ -122,24 +122,7 @@ def test_cluster_smoothing_variant_is_bit_identical(gpu):
         np.testing.assert_array_equal(a["normal"], b["normal"])
         assert bool(np.isnan(b["normal"]).any()) == (iters in (2, 3, 5))
     ctx0.close()
-    gpu.submit(descs, 64, iters=3)
-    gpu.wait()
-    os.environ["BMF_SMOOTH_CLUSTER"] = "1"
-    try:
-        ctx = Context(0)
-    finally:
-        del os.environ["BMF_SMOOTH_CLUSTER"]
-    ctx.set_sampler(capi.TERRAIN2D_PERT)
-    ctx.set_kernel_timing(True)
-    ctx.submit(descs, 64, iters=3)
-    ctx.wait()
-    assert any(name == "k_smooth_chunks2" for name, _ in ctx.kernel_times())
-    got = ctx.download(want=("pos", "inds", "normal"))
-    ctx.close()
     assert len(want["pos"]) > 100000
-    np.testing.assert_array_equal(got["inds"], want["inds"])
-    np.testing.assert_array_equal(got["pos"].view(np.uint32), want["pos"].view(np.uint32))
-    np.testing.assert_array_equal(got["normal"], want["normal"])
 
 
 def test_mode_switching_on_one_context_keeps_every_result_right(gpu):
