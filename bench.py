@@ -471,7 +471,7 @@ def run_ours(args):
     clocks = ClockSampler(D.local_rank)
     clocks.start()
     t_max, wall = time_device(D, ctx, stream, step, K, W)
-    launches = ctx.launch_count() - launches0
+    launches = (ctx.launch_count() - launches0) * K // (K + W)  # time_device runs W warm-up steps first: count the K timed steps only
     value = nvox * K / t_max
     stage = ctx.stage_ms()
     infos_mine = ctx.chunk_infos() if len(sw.descs) else np.zeros(0, capi.CHUNK_INFO_DTYPE)

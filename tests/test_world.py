@@ -58,6 +58,25 @@ def test_partition_is_a_balanced_cover():
     assert W.partition(mc[:3], np.ones(3), 8)[0].size <= 1  # more parts than chunks: empty parts allowed
 
 
+def test_partition_balances_measured_costs():
+    """cost-balanced ranges ("cost ~ measured surface count from the previous rebuild"): with the bench's model 37 + n_verts
+    the heaviest part stays within one chunk's cost of the mean, and the cover / contiguity properties hold"""
+    rng = np.random.default_rng(1)
+    mc = W.grid_mortons(16)
+    nv = np.where(rng.random(len(mc)) < 0.15, rng.integers(1000, 9000, len(mc)), 0)  # ~15 % of the chunks carry a mesh, like the benchmark world
+    cost = 37.0 + nv
+    for n in (2, 4, 8):
+        parts = W.partition(mc, cost, n)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(mc)))
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() - cost.sum() / n <= cost.max() + 1e-9
+        equal = np.array([cost[p].sum() for p in W.partition(mc, np.ones(len(mc)), n)])
+        assert loads.max() <= equal.max() + 1e-9  # never worse than equal chunk counts
+        keys = [W.morton_key(c) for c in mc.tolist()]
+        flat = [keys[i] for p in parts for i in p]
+        assert flat == sorted(keys)
+
+
 def test_morton_key_orders_mixed_levels_along_one_curve():
     """a leaf's key lies between the keys of the leaves before / after its subtree: the raw sentinel-prefixed codes do not"""
     ps, lv, mc = W.split_leaves(W.WorldProperties(max_level=5))
