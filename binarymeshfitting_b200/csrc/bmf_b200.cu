@@ -744,6 +744,7 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 		cudaGetLastError();
 		ctx->fused_extract = 0;
 	}
+	cudaFuncSetAttribute(k_scan_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCAN_CTA * SCAN_PER_THREAD * sizeof(ChunkCounts)));
 	// k_bases keeps its segment's sign planes plus a work list of active words in dynamic shared memory (57 KB at dim 256)
 	cudaFuncSetAttribute(k_bases<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 	cudaFuncSetAttribute(k_bases<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -1027,7 +1028,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, 0, ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, (size_t)SCAN_CTA * SCAN_PER_THREAD * sizeof(ChunkCounts), ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
 	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
