@@ -1008,10 +1008,10 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		const bool have_cand = ctx->uni_valid; // the 2-D terrain classifier has listed the chunks it could not cull
 		if (ctx->use_tma)
 			BMF_LAUNCH((k_chunk_count<COUNT_NT, true>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
-			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p);
 		else
 			BMF_LAUNCH((k_chunk_count<COUNT_NT, false>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
-			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->emit_list.p, ctx->totals_dev.p);
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p);
 	}
 	else if (params->quads)
 	{
@@ -1028,7 +1028,8 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
-	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, (size_t)SCAN_CTA * SCAN_PER_THREAD * sizeof(ChunkCounts), ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p);
+	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, (size_t)SCAN_CTA * SCAN_PER_THREAD * sizeof(ChunkCounts), ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p,
+	           fused ? ctx->emit_list.p : nullptr);
 	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;

@@ -680,10 +680,16 @@ static constexpr int SCAN_CTA = 1024;
 
 static constexpr int SCAN_PER_THREAD = 4; // consecutive chunks per thread: 4096 chunks per tile, so the usual batch is one tile (one block scan, not four)
 
+static constexpr int SIZE_CLASSES = 32; // of the work list below: class = 31 - min(31, n_verts / 256), so class 0 holds the largest chunks
+
 __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __restrict__ chunk_tot, const uint32_t* __restrict__ flags, int n_chunks,
                                                            ChunkCounts* __restrict__ chunks,
-                                                           unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */)
+                                                           unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */,
+                                                           int* __restrict__ work_list /* or null: the chunks that have vertices, LARGEST FIRST (by size
+                                                           class) -- the order the per-chunk kernels take them in, so that the tail of their launches is short */)
 {
+	__shared__ uint32_t s_cls_cnt[SIZE_CLASSES], s_cls_pos[SIZE_CLASSES];
+	if (threadIdx.x < SIZE_CLASSES) s_cls_cnt[threadIdx.x] = 0;
 	// 64-bit throughout: a tile of dim-256 chunks can hold more than 2^32 indices (15 * 256^3 per chunk), and a sum that
 	// wrapped inside the tile would slip past the > 2^32 guard below
 	typedef unsigned long long u64;
@@ -695,6 +701,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 	__shared__ uint32_t s_maxv;
 	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 	if (t == 0) s_maxv = 0;
+	__syncthreads(); // the class counters are zero before the first chunk is counted
 	uint32_t maxv = 0;
 	u64 carry0 = 0, carry1 = 0, carry2 = 0;
 	for (int base = 0; base < n_chunks; base += SCAN_CTA * SCAN_PER_THREAD)
@@ -713,6 +720,7 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 			}
 			maxv = max(maxv, b[k]);
 			ia += a[k]; ib += b[k]; ic += c[k];
+			if (work_list && b[k]) atomicAdd(&s_cls_cnt[SIZE_CLASSES - 1 - min(SIZE_CLASSES - 1, (int)(b[k] >> 8))], 1u);
 		}
 		const u64 ta0 = ia, tb0 = ib, tc0 = ic; // this thread's totals
 #pragma unroll
@@ -765,6 +773,22 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 	for (int o = 16; o >= 1; o >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, o));
 	if (lane == 0 && maxv) atomicMax(&s_maxv, maxv);
 	__syncthreads();
+	if (work_list)
+	{
+		// counting sort by size class: class bases, then every chunk with vertices takes the next slot of its class (order inside a class is irrelevant)
+		if (t == 0)
+		{
+			uint32_t run = 0;
+			for (int k = 0; k < SIZE_CLASSES; k++) { s_cls_pos[k] = run; run += s_cls_cnt[k]; }
+			totals[10] = run; // TOT_MESH: length of the list
+		}
+		__syncthreads();
+		for (int i = t; i < n_chunks; i += SCAN_CTA)
+		{
+			const uint32_t nv = flags_contain_mesh(flags[i]) ? chunk_tot[3 * (size_t)i + 1] : 0u;
+			if (nv) work_list[atomicAdd(&s_cls_pos[SIZE_CLASSES - 1 - min(SIZE_CLASSES - 1, (int)(nv >> 8))], 1u)] = i;
+		}
+	}
 	if (t == 0)
 	{
 		const bool overflow = carry0 >= 0xFFFFFFFFull || carry1 >= 0xFFFFFFFFull || carry2 >= 0xFFFFFFFFull;

@@ -26,7 +26,7 @@ namespace bmf
 
 enum
 {
-	TOT_MESH = 10,    // length of the emit list (k_chunk_count)
+	TOT_MESH = 10,    // length of the work list (k_scan_chunks)
 	TOT_TICKET = 11,  // next emit-list position (k_chunk_emit)
 	TOT_CAND = 12,    // length of the candidate list (k_terrain2d_classify)
 	TOT_CTICKET = 13  // next candidate (k_chunk_count)
@@ -42,7 +42,7 @@ struct FusedArgs
 	int n;
 	const uint32_t* bits;
 	const uint32_t* wcnt;  // [n][wc] packed (vertices | indices << 16) of every word, written by k_chunk_count
-	const int* emit_list;  // the chunks that have vertices, in completion order of k_chunk_count (work distribution only: order is irrelevant)
+	const int* emit_list;  // the chunks that have vertices, largest first (k_scan_chunks)
 	const ChunkCounts* chunks;
 	u64* tot;
 	uint2* vcells;
@@ -202,7 +202,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 template <int NT, bool TMA>
 __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, int n, const int* __restrict__ cand,
                                                      const u64* __restrict__ cand_count, uint32_t* __restrict__ wcnt, uint32_t* __restrict__ chunk_tot,
-                                                     uint8_t* __restrict__ masks, int* __restrict__ emit_list, u64* __restrict__ tot /* [TOT_MESH], [TOT_CTICKET] */)
+                                                     uint8_t* __restrict__ masks, u64* __restrict__ tot /* [TOT_CTICKET] */)
 {
 	extern __shared__ __align__(16) uint32_t dyn[];
 	__shared__ u64 s_tri[256];
@@ -294,8 +294,7 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 		{
 			uint32_t t = 0;
 			for (int k = 0; k < NT / 32; k++) t += s_red[tid][k];
-			chunk_tot[3 * (size_t)chunk + tid] = t;
-			if (tid == 1 && t) emit_list[atomicAdd(tot + TOT_MESH, 1ull)] = chunk; // this chunk has vertices: k_chunk_emit will take it
+			chunk_tot[3 * (size_t)chunk + tid] = t; // (k_scan_chunks turns these into bases and into the largest-first work list of k_chunk_emit)
 		}
 	}
 }
@@ -364,22 +363,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 	for (;;)
 	{
 		__syncthreads(); // the previous chunk's last phase still reads shared memory
-		// ---- next chunk of the emit list, the large ones first (longest-processing-time order keeps the tail of the launch short): the
-		// list is walked once per size class, a ticket that names a chunk of another class costs one atomic
+		// ---- next chunk of the work list (k_scan_chunks has ordered it largest first: longest-processing-time order keeps the launch's tail short)
 		if (tid == 0)
 		{
-			const u64 M = A.tot[TOT_MESH];
-			int c = -1;
-			for (;;)
-			{
-				const u64 j = atomicAdd(A.tot + TOT_TICKET, 1ull);
-				if (j >= 3 * M) break;
-				const int pass = (int)(j / M), k = A.emit_list[j - (u64)pass * M];
-				const uint32_t nv = A.chunks[k].n_verts;
-				const int cls = nv >= 6144u ? 0 : (nv >= 3072u ? 1 : 2);
-				if (cls == pass) { c = k; break; }
-			}
-			s_chunk = c;
+			const u64 j = atomicAdd(A.tot + TOT_TICKET, 1ull);
+			s_chunk = j < A.tot[TOT_MESH] ? A.emit_list[j] : -1;
 			s_njobs = 0; s_nvc = 0; s_nic = 0;
 		}
 		__syncthreads();
@@ -640,6 +628,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 				s_xyz[tid] = rec.x & 0x3FFFFu; // word | bit << 13
 				s_out[tid] = rec.y;
 			}
+			// the unit of work is a TRIANGLE of a cell (three consecutive indices): the per-unit bookkeeping is paid once per three indices
+			n = (n * 11u) >> 5; // triangles of the cell (n / 3 for n <= 15)
 			uint32_t inc = n;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
@@ -651,19 +641,25 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 			if (lane == 0) pre[0] = 0;
 			for (uint32_t q = inc - n; q < inc; q++) own[q] = (uint8_t)lane;
 			__syncwarp();
-			const uint32_t n_pairs = pre[32];
-			for (uint32_t p = lane; p < n_pairs; p += 32)
+			const uint32_t n_tris = pre[32];
+			for (uint32_t p = lane; p < n_tris; p += 32)
 			{
 				const int c = own[p];
-				const uint32_t t = p - pre[c];
-				const uint32_t e = (uint32_t)(s_tp[wbase + c] >> (4 * t)) & 15u;
-				const uint32_t wb = s_xyz[wbase + c], ed = s_edge[e];
-				int w = (int)(wb & 0x1FFFu) + (int)(ed & 0xFFFFu), bit = (int)(wb >> 13) + (int)((ed >> 16) & 1u);
-				if (bit == 32) { w++; bit = 0; } // the z + 1 neighbour of the word's last cell
-				const uint32_t vid = vertex_id_smem(S, L, w, bit, (int)(ed >> 20));
-				inds_c[s_out[wbase + c] + t] = vid;
-				// init_valence++ (DMCChunk.cpp:573) per "cell class" 3 - (e & 3): see k_inds3 / k_adj_fill
-				atomicAdd(cls32 + (vid >> 1), 1u << (4 * (3 - (e & 3)) + 16 * (vid & 1)));
+				const uint32_t tt = p - pre[c];
+				const uint32_t e3 = (uint32_t)(s_tp[wbase + c] >> (12 * tt)) & 0xFFFu; // the triangle's three edge ids
+				const uint32_t wb = s_xyz[wbase + c];
+				uint32_t* const out = inds_c + s_out[wbase + c] + 3u * tt;
+#pragma unroll
+				for (int q = 0; q < 3; q++)
+				{
+					const uint32_t e = (e3 >> (4 * q)) & 15u, ed = s_edge[e];
+					int w = (int)(wb & 0x1FFFu) + (int)(ed & 0xFFFFu), bit = (int)(wb >> 13) + (int)((ed >> 16) & 1u);
+					if (bit == 32) { w++; bit = 0; } // the z + 1 neighbour of the word's last cell
+					const uint32_t vid = vertex_id_smem(S, L, w, bit, (int)(ed >> 20));
+					out[q] = vid;
+					// init_valence++ (DMCChunk.cpp:573) per "cell class" 3 - (e & 3): see k_inds3 / k_adj_fill
+					atomicAdd(cls32 + (vid >> 1), 1u << (4 * (3 - (e & 3)) + 16 * (vid & 1)));
+				}
 			}
 			__syncwarp();
 		}
@@ -730,6 +726,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 				s_lc[tid] = s_loc[m8];
 				s_out[tid] = rec.y / 3u; // the cell's first primitive inside the chunk
 			}
+			n = (n * 11u) >> 5; // triangles of the cell
 			uint32_t inc = n;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
@@ -741,53 +738,63 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_chunk_emit(FusedArg
 			if (lane == 0) pre[0] = 0;
 			for (uint32_t q = inc - n; q < inc; q++) own[q] = (uint8_t)lane;
 			__syncwarp();
-			const uint32_t n_pairs = pre[32];
-			constexpr int UF = 4;
-			for (uint32_t p0 = lane; p0 < n_pairs; p0 += 32 * UF)
+			const uint32_t n_tris = pre[32];
+			constexpr int UF = 2; // triangles per lane in flight (six index -> counter / offset -> store chains)
+			for (uint32_t p0 = lane; p0 < n_tris; p0 += 32 * UF)
 			{
-				uint32_t prim[UF], key[UF], idx[UF], cw[UF], ao[UF]; // key = class << 8 | rank among the same edge's uses inside the cell
+				uint32_t prim[UF], e3[UF], lc3[UF], idx[UF][3], cw[UF][3], ao[UF][3];
 #pragma unroll
 				for (int u = 0; u < UF; u++)
 				{
 					const uint32_t p = p0 + 32 * u;
-					idx[u] = 0; prim[u] = 0; key[u] = 0;
-					if (p < n_pairs)
+					prim[u] = 0; e3[u] = 0; lc3[u] = 0;
+					idx[u][0] = idx[u][1] = idx[u][2] = 0;
+					if (p < n_tris)
 					{
 						const int c = own[p];
-						const uint32_t t = p - pre[c];
-						const uint32_t e = (uint32_t)(s_tp[wbase + c] >> (4 * t)) & 15u;
-						const uint32_t t3 = (t * 11u) >> 5; // t / 3 for t < 15
-						const uint32_t lp = s_out[wbase + c] + t3;
+						const uint32_t tt = p - pre[c];
+						e3[u] = (uint32_t)(s_tp[wbase + c] >> (12 * tt)) & 0xFFFu;  // the triangle's three edge ids
+						lc3[u] = (uint32_t)(s_lc[wbase + c] >> (9 * tt)) & 0x1FFu; // their ranks among the same edge's uses inside the cell
+						const uint32_t lp = s_out[wbase + c] + tt;                // primitive inside the chunk
 						prim[u] = prim_c + lp;
-						key[u] = ((3u - (e & 3u)) << 8) | ((uint32_t)(s_lc[wbase + c] >> (3 * t)) & 7u);
-						idx[u] = __ldcg(inds_c + 3u * s_out[wbase + c] + t);
+						const uint32_t* src = inds_c + 3u * lp;
+						idx[u][0] = __ldcg(src); idx[u][1] = __ldcg(src + 1); idx[u][2] = __ldcg(src + 2);
 					}
 				}
 				if (fits)
 				{
 #pragma unroll
 					for (int u = 0; u < UF; u++)
-					{
-						cw[u] = reinterpret_cast<const uint16_t*>(s_cls)[idx[u]];
-						ao[u] = s_aoff[idx[u]];
-					}
+#pragma unroll
+						for (int q = 0; q < 3; q++)
+						{
+							cw[u][q] = reinterpret_cast<const uint16_t*>(s_cls)[idx[u][q]];
+							ao[u][q] = s_aoff[idx[u][q]];
+						}
 				}
 				else
 				{
 #pragma unroll
 					for (int u = 0; u < UF; u++)
-					{
-						cw[u] = __ldcg(cls32 + (idx[u] >> 1)) >> (16 * (idx[u] & 1));
-						ao[u] = __ldcg(aoff_c + idx[u]);
-					}
+#pragma unroll
+						for (int q = 0; q < 3; q++)
+						{
+							cw[u][q] = __ldcg(cls32 + (idx[u][q] >> 1)) >> (16 * (idx[u][q] & 1));
+							ao[u][q] = __ldcg(aoff_c + idx[u][q]);
+						}
 				}
 #pragma unroll
 				for (int u = 0; u < UF; u++)
 				{
-					if (p0 + 32 * u >= n_pairs) continue;
-					const uint32_t lower = cw[u] & ((1u << (4 * (key[u] >> 8))) - 1u);
-					const uint32_t before = (lower & 15u) + ((lower >> 4) & 15u) + ((lower >> 8) & 15u);
-					A.adj[ao[u] + before + (key[u] & 0xFFu)] = prim[u];
+					if (p0 + 32 * u >= n_tris) continue;
+#pragma unroll
+					for (int q = 0; q < 3; q++)
+					{
+						const uint32_t cl = 3u - ((e3[u] >> (4 * q)) & 3u); // class of the cell among the (at most four) cells around the vertex's edge
+						const uint32_t lower = cw[u][q] & ((1u << (4 * cl)) - 1u);
+						const uint32_t before = (lower & 15u) + ((lower >> 4) & 15u) + ((lower >> 8) & 15u);
+						A.adj[ao[u][q] + before + ((lc3[u] >> (3 * q)) & 7u)] = prim[u];
+					}
 				}
 			}
 			__syncwarp();

@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
 	extern __shared__ float sm_f[];
 	__shared__ int s_chunk;
 	if (tot[7]) return;
-	// chunks are handed out longest first (three size classes, the candidates are walked once per class: a ticket that names a chunk of another
-	// class costs thread 0 one atomic and one 40-byte load).  With the emit list only mesh chunks are candidates; without it every chunk is.
+	// chunks are handed out longest first: `list` is k_scan_chunks' work list (chunks with vertices, ordered by size class); without it (batches of the
+	// per-segment path with chunks for every SM) every chunk is a candidate and the candidates are walked once per size class (3 classes)
 	const unsigned long long n_cand = list ? tot[10] : (unsigned long long)n_chunks;
 	for (;;)
 	{
@@ -452,16 +452,21 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
 		if (threadIdx.x == 0)
 		{
 			int k = -1;
-			for (;;)
+			if (list)
 			{
 				const unsigned long long j = atomicAdd(tot + 6, 1ull);
-				if (j >= 3 * n_cand) break;
-				const int pass = (int)(j / n_cand), cand = (int)(j - (unsigned long long)pass * n_cand);
-				const int q = list ? list[cand] : cand;
-				const ChunkCounts t = chunks[q];
-				if (!t.contains_mesh || t.n_verts == 0 || t.n_inds < 3) continue;
-				if ((t.n_verts >= 6144u ? 0 : (t.n_verts >= 3072u ? 1 : 2)) == pass) { k = q; break; }
+				if (j < n_cand) k = list[j];
 			}
+			else
+				for (;;)
+				{
+					const unsigned long long j = atomicAdd(tot + 6, 1ull);
+					if (j >= 3 * n_cand) break;
+					const int pass = (int)(j / n_cand), q = (int)(j - (unsigned long long)pass * n_cand);
+					const ChunkCounts t = chunks[q];
+					if (!t.contains_mesh || t.n_verts == 0 || t.n_inds < 3) continue;
+					if ((t.n_verts >= 6144u ? 0 : (t.n_verts >= 3072u ? 1 : 2)) == pass) { k = q; break; }
+				}
 			s_chunk = k;
 		}
 		__syncthreads();
