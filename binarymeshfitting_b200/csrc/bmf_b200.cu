@@ -106,7 +106,8 @@ struct bmf_ctx
 	                          // BMF_FUSED=0 never, BMF_FUSED=2 always
 	bool batch_fused = false; // the resident batch went through k_chunk_mesh
 	size_t fused_smem = 0;
-	DevBuf<unsigned long long> fz_prof;
+	DevBuf<unsigned long long> fz_prof, sm_prof;
+	int sm_prof_n = 0;
 	DevBuf<int> emit_list, mixed_list;
 	DevBuf<uint16_t> pack16; // uint16 copy of the index buffer (bmf_batch_download_dma)
 	bool fused_prof = false; // BMF_FUSED_PROF=1: per-phase SM clocks of k_chunk_mesh, mean printed to stderr when the batch completes
@@ -292,6 +293,7 @@ bool is_implicit(int k) { return k >= BMF_SAMPLER_SPHERE && k <= BMF_SAMPLER_CSG
 
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 int nan_half_step(int iters);
+unsigned long long* smooth_prof(bmf_ctx* ctx, int n_chunks);
 
 // MeshProcessor<N> on device arrays (all batch-wide); chunks_dev maps index positions to vertex bases.
 template <int N>
@@ -355,7 +357,7 @@ int run_smooth(bmf_ctx* ctx, size_t n_verts, size_t n_inds, float* pos, float* c
 		const int nan_step = nan_half_step(iters);
 		BMF_LAUNCH(k_smooth_chunks, (unsigned)std::min(n_chunks, ctx->work_sms()), SMOOTH_CTA, ctx->smooth_smem, chunks_dev, n_chunks, inds, ctx->adj_off.p, ctx->adj.p,
 		           valence, boundary, pos, ctx->dp.p, 2 * iters, pb, const_cast<unsigned long long*>(tot), (unsigned)(ctx->smooth_smem / sizeof(float)), normal, nan_step,
-		           ctx->batch_fused ? ctx->emit_list.p : nullptr);
+		           ctx->batch_fused ? ctx->emit_list.p : nullptr, smooth_prof(ctx, n_chunks));
 		return BMF_OK;
 	}
 
@@ -420,7 +422,7 @@ MeshCaps mesh_caps(const bmf_ctx* ctx)
 	size_t i = ctx->inds.cap;
 	if (smoothing) i = std::min({ i, ctx->adj.cap, ctx->prim_vbase.cap * 3, ctx->dp.cap, need_dn ? ctx->dn.cap : (size_t)-1 });
 	c.verts = v > 32 ? v - 32 : 0; // the emitters touch up to 16 bytes past the last vertex (byte-packed words)
-	c.inds = i > 8 ? i - 8 : 0;
+	c.inds = i > 32 ? i - 32 : 0; // k_smooth_chunks reads the index / adjacency streams in aligned 16-byte words, up to 16 entries past a chunk's last one
 	return c;
 }
 
@@ -451,6 +453,16 @@ int reserve_mesh(bmf_ctx* ctx, size_t cells, size_t verts, size_t inds)
 	return BMF_OK;
 }
 
+// BMF_FUSED_PROF=1: per-chunk timeline of k_smooth_chunks (start / end ns, SM, path), summarised on stderr when the batch completes
+unsigned long long* smooth_prof(bmf_ctx* ctx, int n_chunks)
+{
+	if (!ctx->fused_prof) return nullptr;
+	if (ctx->sm_prof.reserve(4 * (size_t)n_chunks) != cudaSuccess) return nullptr;
+	cudaMemsetAsync(ctx->sm_prof.p, 0, 4 * (size_t)n_chunks * sizeof(unsigned long long), ctx->stream);
+	ctx->sm_prof_n = n_chunks;
+	return ctx->sm_prof.p;
+}
+
 // last launch of a batch's sequence: totals and (once per batch) the chunk table to the host through mapped pinned memory (k_publish)
 int publish(bmf_ctx* ctx)
 {
@@ -462,7 +474,7 @@ int publish(bmf_ctx* ctx)
 }
 
 // K4 + K5 of the resident batch, sized by arena capacity and guarded on the device (k_check_caps): no host round trip
-int launch_mesh(bmf_ctx* ctx)
+int launch_mesh(bmf_ctx* ctx, bool caps_checked /* k_scan_chunks, launched just before with the same capacities, has already formed the verdict */)
 {
 	const bmf_params* params = &ctx->params;
 	const Layout L = ctx->L;
@@ -474,7 +486,7 @@ int launch_mesh(bmf_ctx* ctx)
 	if (ctx->batch_fused)
 	{
 		// ---- dim <= 64, triangles: k_chunk_emit (fused.cuh) does label_edges' emission, polygonize and MeshProcessor::init of a chunk in one CTA
-		BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
+		if (!caps_checked) BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
 		BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 		if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 		{
@@ -526,7 +538,7 @@ int launch_mesh(bmf_ctx* ctx)
 		BMF_CUDA(cudaEventRecord(ctx->ev[6], st));
 		return publish(ctx);
 	}
-	BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
+	if (!caps_checked) BMF_LAUNCH(k_check_caps, 1, 32, 0, tot, (unsigned long long)caps.cells, (unsigned long long)caps.verts, (unsigned long long)caps.inds);
 	BMF_CUDA(cudaEventRecord(ctx->ev[3], st));
 	if (caps.cells == 0 || caps.verts == 0 || caps.inds == 0)
 	{
@@ -629,7 +641,7 @@ int finish(bmf_ctx* ctx)
 		int rc = reserve_mesh(ctx, (size_t)t.v[0], (size_t)t.v[1], (size_t)t.v[2]);
 		if (rc) return rc;
 		BMF_CUDA(cudaMemsetAsync(ctx->totals_dev.p + 4, 0, 2 * sizeof(unsigned long long), ctx->stream)); // list counters
-		rc = launch_mesh(ctx);
+		rc = launch_mesh(ctx, false);
 		if (rc) return rc;
 		if (ctx->dl_pending && !(ctx->params.quads && ctx->params.iters > 0))
 		{
@@ -671,6 +683,31 @@ int finish(bmf_ctx* ctx)
 		}
 		fprintf(stderr, "k_chunk_emit phases (mean SM cycles over %d chunks): stage %.0f scan %.0f lists %.0f verts %.0f inds %.0f valence %.0f adj %.0f\n",
 		        m, m ? sum[1] / m : 0, m ? sum[2] / m : 0, m ? sum[3] / m : 0, m ? sum[4] / m : 0, m ? sum[5] / m : 0, m ? sum[6] / m : 0, m ? sum[7] / m : 0);
+	}
+	if (ctx->fused_prof && ctx->sm_prof.p && ctx->sm_prof_n)
+	{
+		std::vector<unsigned long long> h(4 * (size_t)ctx->sm_prof_n);
+		cudaMemcpy(h.data(), ctx->sm_prof.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+		unsigned long long t0 = ~0ull, t1 = 0;
+		for (int j = 0; j < ctx->sm_prof_n; j++)
+			if (h[4 * (size_t)j + 1]) { t0 = std::min(t0, h[4 * (size_t)j]); t1 = std::max(t1, h[4 * (size_t)j + 1]); }
+		double busy[3] = {}, verts[3] = {};
+		int cnt[3] = {};
+		std::vector<double> sm_busy(1024, 0.0), sm_last(1024, 0.0);
+		for (int j = 0; j < ctx->sm_prof_n; j++)
+		{
+			const unsigned long long* r = &h[4 * (size_t)j];
+			if (!r[1]) continue;
+			const int path = (int)(r[2] >> 8) & 3, sm = (int)(r[2] & 255);
+			busy[path] += (double)(r[1] - r[0]); verts[path] += (double)r[3]; cnt[path]++;
+			sm_busy[sm] += (double)(r[1] - r[0]); sm_last[sm] = std::max(sm_last[sm], (double)(r[1] - t0));
+		}
+		double bsum = 0, bmax = 0, lmin = 1e30; int nsm = 0;
+		for (int k = 0; k < 1024; k++) if (sm_busy[k] > 0) { bsum += sm_busy[k]; bmax = std::max(bmax, sm_busy[k]); lmin = std::min(lmin, sm_last[k]); nsm++; }
+		fprintf(stderr, "k_smooth_chunks timeline: span %.1f us over %d SMs; busy per SM mean %.1f max %.1f us; earliest SM finished at %.1f us\n", (t1 - t0) * 1e-3, nsm, nsm ? bsum / nsm * 1e-3 : 0, bmax * 1e-3, lmin * 1e-3);
+		for (int k = 0; k < 3; k++)
+			fprintf(stderr, "   path %d (%s): %d chunks, %.0f verts, %.1f us CTA time, %.2f ns per vertex\n", k, k == 0 ? "P+D in smem" : k == 1 ? "D in smem" : "global", cnt[k], verts[k], busy[k] * 1e-3, verts[k] ? busy[k] / verts[k] : 0);
+		ctx->sm_prof_n = 0;
 	}
 	if (ctx->dl_pending)
 	{
@@ -770,7 +807,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (ctx->uni_pinned) cudaFreeHost(ctx->uni_pinned);
 	if (ctx->seam_total_pinned) cudaFreeHost(ctx->seam_total_pinned);
 	ctx->wq.release(); ctx->wqq.release(); ctx->wqv.release();
-	ctx->fz_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release(); ctx->pack16.release();
+	ctx->fz_prof.release(); ctx->sm_prof.release(); ctx->emit_list.release(); ctx->mixed_list.release(); ctx->pack16.release();
 	ctx->seam_chunks.release(); ctx->seam_map.release(); ctx->seam_group.release(); ctx->seam_clean.release(); ctx->seam_layers.release(); ctx->seam_active.release(); ctx->seam_counters.release(); ctx->seam_act.release(); ctx->seam_blk.release(); ctx->seam_cnt.release();
 	ctx->seam_base.release(); ctx->seam_tris.release();
 	for (cudaEvent_t e : ctx->seam_ev)
@@ -1028,12 +1065,13 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 
 	// ---- scan, then the emitters straight away: their launches are sized by the arenas' capacity and guarded on the
 	// device, so the host does not wait here (bmf_batch_wait / any query completes the batch)
+	const MeshCaps caps0 = mesh_caps(ctx); // the capacities launch_mesh is about to size the emitters with: the scan forms k_check_caps' verdict itself
 	BMF_LAUNCH(k_scan_chunks, 1, SCAN_CTA, (size_t)SCAN_CTA * SCAN_PER_THREAD * sizeof(ChunkCounts), ctx->chunk_tot.p, ctx->flags.p, n, ctx->counts.p, ctx->totals_dev.p,
-	           fused ? ctx->emit_list.p : nullptr);
+	           fused ? ctx->emit_list.p : nullptr, (unsigned long long)caps0.cells, (unsigned long long)caps0.verts, (unsigned long long)caps0.inds);
 	ctx->counts_published = false;
 	ctx->density_cur = density_dev;
 	ctx->have_batch = true;
-	int rc = launch_mesh(ctx);
+	int rc = launch_mesh(ctx, true);
 	if (rc)
 	{
 		ctx->have_batch = false;

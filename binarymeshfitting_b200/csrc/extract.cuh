@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_sheet(SamplerDev s, const Chu
 	float vx = (float)ix * sg + g.ox * s.g;
 	float vy = (float)0 * sg + 0.0f;
 	float vz = (float)iz * sg + g.oz * s.g;
-	const float n = noise_eval<BASE>(s.ns, vx, vy, vz);
+	__shared__ float4 s_corner[CTA / 32][8]; // gradient_perturb_warp: the lattice corners a warp shares
+	const float n = noise_eval_warp<BASE>(s.ns, vx, vy, vz, s_corner[threadIdx.x >> 5], threadIdx.x & 31);
 	hmap[i] = n;
 	// per-sheet range of t = n*height (the same product k_terrain2d_bits compares against)
 	const float t = n * s.nm;
@@ -402,7 +403,8 @@ __global__ void __launch_bounds__(CTA) k_terrain3d(SamplerDev s, const ChunkGeom
 	float vx = (float)x * sg + g.ox * s.g;
 	float vy = (float)y * sg + g.oy * s.g;
 	float vz = (float)z * sg + g.oz * s.g;
-	float n = noise_eval<BASE>(s.ns, vx, vy, vz);
+	__shared__ float4 s_corner[CTA / 32][8]; // gradient_perturb_warp: the lattice corners a warp shares
+	float n = noise_eval_warp<BASE>(s.ns, vx, vy, vz, s_corner[warp], lane);
 	float v = terrain_density(s, g, y, n);
 	density[(size_t)chunk * L.wc * 32 + (size_t)w * 32 + lane] = v;
 	uint32_t word = __ballot_sync(0xffffffffu, v < 0.0f);
@@ -686,7 +688,9 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
                                                            ChunkCounts* __restrict__ chunks,
                                                            unsigned long long* __restrict__ totals /* cells, verts, inds, overflow, list counters */,
                                                            int* __restrict__ work_list /* or null: the chunks that have vertices, LARGEST FIRST (by size
-                                                           class) -- the order the per-chunk kernels take them in, so that the tail of their launches is short */)
+                                                           class) -- the order the per-chunk kernels take them in, so that the tail of their launches is short */,
+                                                           unsigned long long cap_cells, unsigned long long cap_verts, unsigned long long cap_inds /* k_check_caps' verdict
+                                                           for the emitters that follow, formed here so that a submission has one launch less */)
 {
 	__shared__ uint32_t s_cls_cnt[SIZE_CLASSES], s_cls_pos[SIZE_CLASSES];
 	if (threadIdx.x < SIZE_CLASSES) s_cls_cnt[threadIdx.x] = 0;
@@ -797,6 +801,8 @@ __global__ void __launch_bounds__(SCAN_CTA) k_scan_chunks(const uint32_t* __rest
 		totals[8] = s_maxv;           // largest chunk (vertices): decides whether chunk-local indices fit 16 bits (download.cuh)
 		totals[9] = 0;                // download error flag
 		totals[11] = 0;               // chunk ticket of k_chunk_emit (fused.cuh)
+		totals[7] = (carry0 > cap_cells || carry1 > cap_verts || carry2 > cap_inds || overflow) ? 1ull : 0ull; // = k_check_caps
+		totals[6] = 0;                // chunk work counter of k_smooth_chunks
 	}
 }
 

@@ -240,8 +240,56 @@ __device__ __forceinline__ void gradient_perturb_single(int32_t seed, float amp,
 	z = __fmaf_rn(lerpf(gz0, gz1, zs) - 511.5f, amp, z);
 }
 
+// ---- the same octave, evaluated by a full converged warp.  A perturb lattice cell is many voxels wide at the low octaves (the world default
+// perturbs at 0.585 x 2^o cells per noise unit, a 64^3 chunk of the finest LOD steps 0.0006 noise units per voxel), so the 32 voxels of a warp
+// usually share ONE cell: then its 8 corner hashes and their 24 field conversions -- half of the octave's instructions -- are the same in every
+// lane.  Lanes 0..7 hash one corner each and leave its three fields in shared memory; everybody reads the eight records back as broadcast
+// 128-bit loads and does only the interpolation.  Same operations on the same operands as gradient_perturb_single, so the same bits; a warp
+// that straddles a cell boundary (or holds a NaN) takes gradient_perturb_single itself.  s_corner: 8 float4 owned by this warp.
+__device__ __forceinline__ void gradient_perturb_warp(int32_t seed, float amp, float freq, float& x, float& y, float& z, float4* s_corner, int lane)
+{
+	const float xf = x * freq, yf = y * freq, zf = z * freq;
+	float xs = floorf(xf), ys = floorf(yf), zs = floorf(zf);
+	const float xs0 = __shfl_sync(0xffffffffu, xs, 0), ys0 = __shfl_sync(0xffffffffu, ys, 0), zs0 = __shfl_sync(0xffffffffu, zs, 0);
+	if (!__all_sync(0xffffffffu, xs == xs0 && ys == ys0 && zs == zs0))
+	{
+		gradient_perturb_single(seed, amp, freq, x, y, z);
+		return;
+	}
+	if (lane < 8)
+	{
+		const int32_t x0 = (int32_t)((uint32_t)(int32_t)xs * (uint32_t)XPRIME);
+		const int32_t y0 = (int32_t)((uint32_t)(int32_t)ys * (uint32_t)YPRIME);
+		const int32_t z0 = (int32_t)((uint32_t)(int32_t)zs * (uint32_t)ZPRIME);
+		const int32_t xc = (int32_t)((uint32_t)x0 + ((lane & 1) ? (uint32_t)XPRIME : 0u));
+		const int32_t yc = (int32_t)((uint32_t)y0 + ((lane & 2) ? (uint32_t)YPRIME : 0u));
+		const int32_t zc = (int32_t)((uint32_t)z0 + ((lane & 4) ? (uint32_t)ZPRIME : 0u));
+		const int32_t h = hash_hb(seed, xc, yc, zc);
+		s_corner[lane] = make_float4(__int2float_rn(h & 1023), __int2float_rn((h >> 10) & 1023), __int2float_rn((h >> 20) & 1023), 0.0f);
+	}
+	__syncwarp();
+	const float4 c000 = s_corner[0], c100 = s_corner[1], c010 = s_corner[2], c110 = s_corner[3];
+	const float4 c001 = s_corner[4], c101 = s_corner[5], c011 = s_corner[6], c111 = s_corner[7];
+	__syncwarp(); // the next octave's corners may overwrite the records only after every lane has read them
+	xs = quintic(xf - xs);
+	ys = quintic(yf - ys);
+	zs = quintic(zf - zs);
+	const float gx0 = lerpf(lerpf(c000.x, c100.x, xs), lerpf(c010.x, c110.x, xs), ys);
+	const float gy0 = lerpf(lerpf(c000.y, c100.y, xs), lerpf(c010.y, c110.y, xs), ys);
+	const float gz0 = lerpf(lerpf(c000.z, c100.z, xs), lerpf(c010.z, c110.z, xs), ys);
+	const float gx1 = lerpf(lerpf(c001.x, c101.x, xs), lerpf(c011.x, c111.x, xs), ys);
+	const float gy1 = lerpf(lerpf(c001.y, c101.y, xs), lerpf(c011.y, c111.y, xs), ys);
+	const float gz1 = lerpf(lerpf(c001.z, c101.z, xs), lerpf(c011.z, c111.z, xs), ys);
+	x = __fmaf_rn(lerpf(gx0, gx1, zs) - 511.5f, amp, x);
+	y = __fmaf_rn(lerpf(gy0, gy1, zs) - 511.5f, amp, y);
+	z = __fmaf_rn(lerpf(gz0, gz1, zs) - 511.5f, amp, z);
+}
+
 // noise at raw vector-set coordinates (FillNoiseSet with sampleScale == 0 and zero offsets):
 // coord = fma(v, frequency, 0), then perturb, then the (fractal) base noise
+template <int BASE>
+__device__ __forceinline__ float noise_fractal(const NoiseState& s, float xF, float yF, float zF);
+
 template <int BASE>
 __device__ __forceinline__ float noise_eval(const NoiseState& s, float vx, float vy, float vz)
 {
@@ -267,7 +315,42 @@ __device__ __forceinline__ float noise_eval(const NoiseState& s, float vx, float
 			gradient_perturb_single(seedF, ampF, freqF, xF, yF, zF);
 		}
 	}
+	return noise_fractal<BASE>(s, xF, yF, zF);
+}
 
+// noise_eval for the sampling kernels, where a FULL CONVERGED warp evaluates 32 neighbouring points: the perturb octaves share their lattice
+// corners across the warp when they can (gradient_perturb_warp).  Bit-identical to noise_eval.
+template <int BASE>
+__device__ __forceinline__ float noise_eval_warp(const NoiseState& s, float vx, float vy, float vz, float4* s_corner, int lane)
+{
+	float xF = __fmaf_rn(vx, s.frequency, 0.0f);
+	float yF = __fmaf_rn(vy, s.frequency, 0.0f);
+	float zF = __fmaf_rn(vz, s.frequency, 0.0f);
+
+	if (s.perturb == 1)
+	{
+		gradient_perturb_warp(s.seed - 1, s.perturb_amp, s.perturb_frequency, xF, yF, zF, s_corner, lane);
+	}
+	else if (s.perturb == 2)
+	{
+		int32_t seedF = s.seed - 1;
+		float freqF = s.perturb_frequency;
+		float ampF = s.perturb_amp * s.perturb_bounding;
+		gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane);
+		for (int o = 1; o < s.perturb_octaves; o++)
+		{
+			freqF = freqF * s.perturb_lacunarity;
+			seedF = seedF - 1;
+			ampF = ampF * s.perturb_gain;
+			gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane);
+		}
+	}
+	return noise_fractal<BASE>(s, xF, yF, zF);
+}
+
+template <int BASE>
+__device__ __forceinline__ float noise_fractal(const NoiseState& s, float xF, float yF, float zF)
+{
 	if (!s.fractal)
 		return noise_single<BASE>(s.seed, xF, yF, zF);
 

@@ -354,10 +354,31 @@ __global__ void __launch_bounds__(CTA) k_primal(const uint32_t* __restrict__ adj
 // same loop on its global arrays (only this CTA touches them, so the CTA barrier is enough).  The arithmetic per
 // element -- and therefore every result bit -- is that of k_dual<3> / k_primal.
 static constexpr int SMOOTH_CTA = 1024;
+static constexpr int SMOOTH_RCP = 64; // reciprocal table: valences 1 .. SMOOTH_RCP - 1 take the short division
+
+// a / y for a small positive integer y, given c = RN(1 / y): q = RN(a c), r = a - y q (exact in one FMA), RN(q + r c) is the correctly
+// rounded quotient (Markstein's correction step).  Checked exhaustively -- every binary32 significand, y = 1 .. 63 -- against IEEE
+// division by tests/test_div_exact.py; the three operations replace the ~10-instruction division sequence with its slow-path branch, which was
+// a fifth of this kernel's instructions.  Only taken for finite components well inside the normal range (the proof needs r and q normal)
+// and away from zero (the sequence would turn -0 into +0); anything else goes through the IEEE division.
+__device__ __forceinline__ f3 div3_small(f3 a, float y, float c)
+{
+	const float ax = fabsf(a.x), ay = fabsf(a.y), az = fabsf(a.z);
+	const float hi = (ax + ay) + az;               // NaN / Inf in any component -> not < 2^100
+	const float lo = fminf(fminf(ax, ay), az);
+	if (hi < 0x1p100f && lo > 0x1p-100f)
+	{
+		const float qx = a.x * c, qy = a.y * c, qz = a.z * c;
+		const float rx = __fmaf_rn(-y, qx, a.x), ry = __fmaf_rn(-y, qy, a.y), rz = __fmaf_rn(-y, qz, a.z);
+		return { __fmaf_rn(rx, c, qx), __fmaf_rn(ry, c, qy), __fmaf_rn(rz, c, qz) };
+	}
+	return div3(a, y);
+}
 
 __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uint32_t* __restrict__ inds, const uint32_t* __restrict__ adj_off,
                                                    const uint32_t* __restrict__ adj, const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary,
-                                                   uint32_t V, uint32_t T, uint32_t prim0, int half_steps, int process_boundary, float* __restrict__ normal, int nan_step)
+                                                   uint32_t V, uint32_t T, uint32_t prim0, int half_steps, int process_boundary, float* __restrict__ normal, int nan_step,
+                                                   const float* __restrict__ s_rcp)
 {
 	// normal / nan_step: with smooth normals off the reference still "normalises" the zero normal of every processed vertex in
 	// the primal step that has set_colors (MeshProcessor.cpp:229-232, 296-303): normalize(0) = NaN and `n.y != 0` is true for a
@@ -366,6 +387,7 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 	// The index / adjacency streams come from global memory: SMOOTH_U elements per thread are in flight at once, all
 	// their loads issued before the first use, so a half-step costs a few memory round trips, not one per element.
 	constexpr int U = 4, KMAX = 8;
+	const float third = 1.0f / 3.0f;
 	for (int h = 0; h < half_steps; h++)
 	{
 		if ((h & 1) == 0)
@@ -391,7 +413,7 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 					sp = add3(sp, ld3(P, id[u][0]));
 					sp = add3(sp, ld3(P, id[u][1]));
 					sp = add3(sp, ld3(P, id[u][2]));
-					st3(D, t, div3(sp, 3.0f));
+					st3(D, t, div3_small(sp, 3.0f, third));
 				}
 			}
 		}
@@ -424,7 +446,7 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 					for (int k = 0; k < KMAX; k++)
 						if (k < cnt[u]) p = add3(p, ld3(D, a[u][k] - prim0));
 					for (int k = KMAX; k < cnt[u]; k++) p = add3(p, ld3(D, adj[off[u] + k] - prim0));
-					st3(P, v0 + u * SMOOTH_CTA, div3(p, (float)cnt[u]));
+					st3(P, v0 + u * SMOOTH_CTA, cnt[u] < SMOOTH_RCP ? div3_small(p, (float)cnt[u], s_rcp[cnt[u]]) : div3(p, (float)cnt[u]));
 					if (h == nan_step) st3(normal, v0 + u * SMOOTH_CTA, normalize3({ 0.0f, 0.0f, 0.0f }));
 				}
 			}
@@ -438,11 +460,14 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
                                                                    const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos,
                                                                    float* dp_global, int half_steps, int process_boundary, unsigned long long* tot,
                                                                    unsigned int smem_floats, float* __restrict__ normal, int nan_step,
-                                                                   const int* __restrict__ list /* the chunks that have vertices (k_chunk_count's emit list), or null */)
+                                                                   const int* __restrict__ list /* the chunks that have vertices (k_chunk_count's emit list), or null */,
+                                                                   unsigned long long* __restrict__ prof /* debugging aid (BMF_FUSED_PROF=1): [chunk][4] = start ns, end ns, SM | path << 8, n_verts; else null */)
 {
 	extern __shared__ float sm_f[];
 	__shared__ int s_chunk;
+	__shared__ float s_rcp[SMOOTH_RCP];
 	if (tot[7]) return;
+	if (threadIdx.x < SMOOTH_RCP) s_rcp[threadIdx.x] = 1.0f / (float)threadIdx.x; // IEEE division: the correctly rounded reciprocals div3_small needs (entry 0 is never used)
 	// chunks are handed out longest first: `list` is k_scan_chunks' work list (chunks with vertices, ordered by size class); without it (batches of the
 	// per-segment path with chunks for every SM) every chunk is a candidate and the candidates are walked once per size class (3 classes)
 	const unsigned long long n_cand = list ? tot[10] : (unsigned long long)n_chunks;
@@ -478,22 +503,37 @@ __global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCoun
 		const uint32_t prim0 = (uint32_t)(ib / 3);
 		float* gp = pos + 3 * vb;
 		float* gd = dp_global + 3 * (size_t)prim0;
+		unsigned long long t_start = 0;
+		int path = 2;
+		if (prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
 		if (3ull * ((unsigned long long)V + T) <= smem_floats)
 		{
+			path = 0;
 			// positions and dual points both in shared memory
 			float* P = sm_f;
 			float* D = sm_f + 3 * (size_t)V;
 			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) P[i] = gp[i];
 			__syncthreads();
-			smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
+			smooth_chunk_steps(P, D, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step, s_rcp);
 			for (uint32_t i = threadIdx.x; i < 3 * V; i += SMOOTH_CTA) gp[i] = P[i];
 			__syncthreads();
 		}
 		else if (3ull * T <= smem_floats)
+		{
 			// the dual points (the array the primal step gathers from) in shared memory, positions in place
-			smooth_chunk_steps(gp, sm_f, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
+			path = 1;
+			smooth_chunk_steps(gp, sm_f, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step, s_rcp);
+		}
 		else
-			smooth_chunk_steps(gp, gd, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step);
+			smooth_chunk_steps(gp, gd, inds + ib, adj_off + vb, adj, valence + vb, boundary + vb, V, T, prim0, half_steps, process_boundary, normal + 3 * vb, nan_step, s_rcp);
+		if (prof && threadIdx.x == 0)
+		{
+			unsigned long long t_end;
+			unsigned int smid;
+			asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+			asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+			prof[4 * (size_t)c] = t_start; prof[4 * (size_t)c + 1] = t_end; prof[4 * (size_t)c + 2] = smid | ((unsigned long long)path << 8); prof[4 * (size_t)c + 3] = V;
+		}
 	}
 }
 
