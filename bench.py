@@ -389,6 +389,25 @@ class SharedWorld:
             return out
         return None
 
+    def dma_only(self, K):
+        """the ceiling of the e2e loop on this box: the resident batches of two contexts downloaded again and again (no kernels besides the uint16
+        pack), all ranks at once.  Returns seconds per download (max over ranks)."""
+        D, cs = self.D, self.ctxs[:2]
+        have = len(self.descs) > 0
+        if have:
+            for c in cs:
+                c.submit(self.descs, self.dim, iters=self.iters)
+                c.wait()
+        D.barrier()
+        t0 = time.perf_counter()
+        if have:
+            for k in range(K):
+                self.enqueue(cs[k & 1], k % self.g.SLOTS)
+                cs[(k + 1) & 1].wait()
+            cs[(K - 1) & 1].wait()
+        D.barrier()
+        return D.max(time.perf_counter() - t0) / K
+
     def bytes_per_step(self):
         """D2H bytes of one step summed over ranks: what the GPUs really store (needs the per-rank totals)"""
         per = 12 * self.V + (2 if self.compact else 4) * self.I + (0 if self.compact else 12 * self.V) + 56 * len(self.descs) + 128
@@ -441,6 +460,34 @@ def time_device(D, ctx, stream, submit, K, W):
     return D.max(e0.elapsed_time(e1) * 1e-3), wall
 
 
+def time_device_pipelined(D, ctxs, streams, submit_on, K, W):
+    """K steps with len(ctxs) batches in flight: step k goes to context k % NC (its own stream and arenas), so the tail of one batch's launches
+    overlaps the head of the next one's.  Device time = from an event recorded before the first submit to the LAST of the events recorded
+    on every stream after the final submit; max over ranks."""
+    torch = D.torch
+    nc = len(ctxs)
+    for k in range(max(W, nc)):
+        submit_on(ctxs[k % nc])
+    for c in ctxs:
+        c.wait()
+    torch.cuda.synchronize()
+    D.barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    t0 = time.perf_counter()
+    e0.record(streams[0])
+    for k in range(K):
+        submit_on(ctxs[k % nc])
+    for e, s in zip(ends, streams):
+        e.record(s)
+    for c in ctxs:
+        c.wait()
+    torch.cuda.synchronize()
+    D.barrier()
+    wall = time.perf_counter() - t0
+    return D.max(max(e0.elapsed_time(e) for e in ends) * 1e-3), wall
+
+
 def run_ours(args):
     from binarymeshfitting_b200 import Context, capi, world
     D = Dist()
@@ -470,10 +517,18 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     clocks = ClockSampler(D.local_rank)
     clocks.start()
-    t_max, wall = time_device(D, ctx, stream, step, K, W)
+    t_one, wall_one = time_device(D, ctx, stream, step, K, W)
     launches = (ctx.launch_count() - launches0) * K // (K + W)  # time_device runs W warm-up steps first: count the K timed steps only
-    value = nvox * K / t_max
     stage = ctx.stage_ms()
+    # the same K steps with three batches in flight (one per context / stream): what a job that streams batches through the GPU gets
+    streams = [torch.cuda.ExternalStream(c.stream_ptr(), device=torch.device("cuda", D.local_rank)) for c in ctxs]
+
+    def submit_on(c):
+        if len(sw.descs):
+            c.submit(sw.descs, dim, iters=args.iters)
+
+    t_max, wall = time_device_pipelined(D, ctxs, streams, submit_on, K, W)
+    value = nvox * K / t_max
     infos_mine = ctx.chunk_infos() if len(sw.descs) else np.zeros(0, capi.CHUNK_INFO_DTYPE)
     n_mesh_mine = int((infos_mine["contains_mesh"] != 0).sum())
     V, I = sw.V, sw.I
@@ -500,6 +555,9 @@ def run_ours(args):
                    "copy engine straight into a shared pinned host segment (bmf_batch_download_dma), three contexts round robin so that the DMA of batch i runs beside "
                    "the kernels of the batches after it, rank 0 assembles the batch-order chunk table",
            "gathered": verify}
+    dma_s = sw.dma_only(K)
+    e2e["d2h_ceiling"] = {"ms_per_step": dma_s * 1e3, "GB_per_s": d2h / dma_s / 1e9, "voxels_per_s": nvox / dma_s,
+                          "what": "the same downloads without the kernels, all ranks at once: what the link(s) and the host memory of this box allow end to end"}
     sw.close()
     # the reference-layout download (positions + colours + uint32 indices, GLChunk::format_data's arrays) through the same path
     sw2 = SharedWorld(D, ctxs, descs_all, mortons, dim, args.iters, "ref", mode="reference_layout")
@@ -517,6 +575,9 @@ def run_ours(args):
         "config": config_of(args, overlap),
         "chunks_per_s": value / dim ** 3,
         "wall_ms_per_step": wall / K * 1e3,
+        "in_flight": {"batches": len(ctxs), "note": "step k is submitted to context k % 3 (own stream, own arenas); every step is a complete batch, consecutive steps overlap on the GPU",
+                      "single_stream": {"value": nvox * K / t_one, "ms_per_step": t_one / K * 1e3, "wall_ms_per_step": wall_one / K * 1e3,
+                                        "note": "the same K steps back to back on ONE stream: the latency of a step; kernels[], roofline and stage_ms are measured in this mode"}},
         "e2e": e2e,
         "gpu_launches": int(D.sum(float(launches))),
         "clocks": clk,

@@ -765,6 +765,13 @@ int bmf_ctx_create(int device, bmf_ctx** out)
 		int optin = 0;
 		cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
 		ctx->smooth_smem = optin > 4096 ? (size_t)optin - 1024 : 0; // leave room for the kernel's static shared memory
+		{
+			// ... and 8 KB for CTAs of other kernels (another stream's sampling kernel) beside a smoothing CTA; a chunk whose positions no longer fit next to its
+			// dual points keeps them in global memory, which costs the same per vertex.  BMF_SMOOTH_SMEM_LEAVE=<bytes> overrides.
+			size_t leave = 8192;
+			if (const char* e = getenv("BMF_SMOOTH_SMEM_LEAVE")) leave = (size_t)std::max(0, atoi(e));
+			if (leave + 65536 < ctx->smooth_smem) ctx->smooth_smem -= leave;
+		}
 		if (!ctx->smooth_smem || cudaFuncSetAttribute(k_smooth_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smooth_smem) != cudaSuccess)
 		{
 			cudaGetLastError();
@@ -900,6 +907,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		ctx->geom_host[i] = g;
 	}
 	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64 && (ctx->fused_extract >= 2 || n >= 8 * ctx->sm_count);
+	bool gen2d = false; // 2-D terrain on the per-chunk path: k_chunk_count makes the sign words itself, k_terrain2d_bits is not launched
 	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
@@ -1012,6 +1020,9 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 			BMF_CUDA(ctx->mixed_list.reserve(n));
 			BMF_LAUNCH(k_terrain2d_classify, grid_for(n, CTA), CTA, 0, ctx->sampler, ctx->geom.p, d, ctx->sheet_of.p, ctx->sheet_mm.p, n_sheets, n, ctx->flags.p, ctx->uni.p,
 			           ctx->mixed_list.p, ctx->totals_dev.p + TOT_CAND);
+			if (fused)
+				gen2d = true; // k_chunk_count makes the sign words of the listed chunks itself (fused.cuh, GEN)
+			else
 			{
 				const size_t groups = (size_t)n * L.d * L.zc * L.zc / (CTA / 32);
 				BMF_LAUNCH(k_terrain2d_bits, (unsigned)std::min(groups, (size_t)ctx->sm_count * 16), CTA, 0, ctx->sampler, ctx->geom.p, L, ctx->hmap.p, ctx->sheet_of.p,
@@ -1043,12 +1054,17 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	{
 		// chunks without a mesh keep chunk_tot = 0 (k_scan_chunks only reads the totals of mesh chunks); TOT_MESH / TOT_CTICKET restart
 		const bool have_cand = ctx->uni_valid; // the 2-D terrain classifier has listed the chunks it could not cull
-		if (ctx->use_tma)
-			BMF_LAUNCH((k_chunk_count<COUNT_NT, true>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
-			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p);
+		Gen2D G;
+		G.s = ctx->sampler; G.geom = ctx->geom.p; G.hmap = ctx->hmap.p; G.sheet_of = ctx->sheet_of.p;
+		if (gen2d)
+			BMF_LAUNCH((k_chunk_count<COUNT_NT, false, true>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+			           ctx->mixed_list.p, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p, G);
+		else if (ctx->use_tma)
+			BMF_LAUNCH((k_chunk_count<COUNT_NT, true, false>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p, G);
 		else
-			BMF_LAUNCH((k_chunk_count<COUNT_NT, false>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
-			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p);
+			BMF_LAUNCH((k_chunk_count<COUNT_NT, false, false>), (unsigned)std::min(n, 6 * ctx->work_sms()), COUNT_NT, (size_t)(L.d + 1) * L.wp * sizeof(uint32_t), ctx->bits.p, ctx->flags.p, L, n,
+			           have_cand ? ctx->mixed_list.p : nullptr, ctx->totals_dev.p + TOT_CAND, ctx->wcnt.p, ctx->chunk_tot.p, masks_w, ctx->totals_dev.p, G);
 	}
 	else if (params->quads)
 	{

@@ -313,15 +313,10 @@ __global__ void __launch_bounds__(CTA) k_terrain2d_density(SamplerDev s, const C
 // first y of ITS column where the bit turns on with a 5-step shuffle binary search, forms the column's 32-bit
 // y-mask with one shift, and a 5-stage warp bit-matrix transpose turns the 32 column masks into the 32 row
 // words -> one coalesced store.  ~70 instructions per 1024 voxels; a non-monotone tile falls back to 32 ballots.
-__device__ __forceinline__ void terrain2d_bits_task(const SamplerDev& s, const ChunkGeom* __restrict__ geom, const Layout& L, const float* __restrict__ hmap,
-                                                    const int* __restrict__ sheet_of, int chunk, int task /* (x, yb, zb) inside the chunk */, int lane,
-                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
+// the word of row y = yb * 32 + lane of the (x, yb, zb) tile; `sheet` = the chunk's d x d noise sheet
+__device__ __forceinline__ uint32_t terrain2d_tile_word(const SamplerDev& s, const ChunkGeom& g, const Layout& L, const float* __restrict__ sheet, int x, int yb, int zb, int lane)
 {
-	const int zb = task & (L.zc - 1);
-	const int yb = (task >> L.lzc) & (L.zc - 1);
-	const int x = (task >> (2 * L.lzc)) & (L.d - 1);
-	const ChunkGeom g = geom[chunk];
-	const float n = hmap[((size_t)sheet_of[chunk] << (2 * L.ld)) + ((size_t)x << L.ld) + zb * 32 + lane];
+	const float n = sheet[((size_t)x << L.ld) + zb * 32 + lane];
 	const float t = n * s.nm;
 	const int y = yb * 32 + lane;
 	float dy = ((float)y * g.delta + g.oy) * s.g;
@@ -369,6 +364,19 @@ __device__ __forceinline__ void terrain2d_bits_task(const SamplerDev& s, const C
 			if (lane == j) mine = word;
 		}
 	}
+	return mine;
+}
+
+__device__ __forceinline__ void terrain2d_bits_task(const SamplerDev& s, const ChunkGeom* __restrict__ geom, const Layout& L, const float* __restrict__ hmap,
+                                                    const int* __restrict__ sheet_of, int chunk, int task /* (x, yb, zb) inside the chunk */, int lane,
+                                                    uint32_t* __restrict__ bits, uint32_t* __restrict__ flags)
+{
+	const int zb = task & (L.zc - 1);
+	const int yb = (task >> L.lzc) & (L.zc - 1);
+	const int x = (task >> (2 * L.lzc)) & (L.d - 1);
+	const ChunkGeom g = geom[chunk];
+	const uint32_t mine = terrain2d_tile_word(s, g, L, hmap + ((size_t)sheet_of[chunk] << (2 * L.ld)), x, yb, zb, lane);
+	const int y = yb * 32 + lane;
 	bits[(size_t)chunk * L.wc + ((((size_t)x << L.ld) + y) << L.lzc) + zb] = mine;
 	merge_flags(word_flags(mine), flags + chunk);
 }

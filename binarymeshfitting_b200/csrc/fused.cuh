@@ -199,11 +199,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	             : "memory");
 }
 
-template <int NT, bool TMA>
-__global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ flags, Layout L, int n, const int* __restrict__ cand,
-                                                     const u64* __restrict__ cand_count, uint32_t* __restrict__ wcnt, uint32_t* __restrict__ chunk_tot,
-                                                     uint8_t* __restrict__ masks, u64* __restrict__ tot /* [TOT_CTICKET] */)
+// GEN (2-D noise terrains): the chunk's sign words are not loaded but MADE here, from its noise sheet and its y coordinates (terrain2d_tile_word,
+// a warp per 32 x 32 (y, z) tile), into shared memory and -- for the emitter and bmf_batch_copy_chunk -- into `bits`; the chunk's flags are formed
+// in the CTA.  That is the whole of k_terrain2d_bits, without its launch, its pass over the words and this kernel's load of them.
+struct Gen2D
 {
+	SamplerDev s;
+	const ChunkGeom* geom;
+	const float* hmap;
+	const int* sheet_of;
+};
+
+template <int NT, bool TMA, bool GEN>
+__global__ void __launch_bounds__(NT) k_chunk_count(uint32_t* __restrict__ bits, uint32_t* __restrict__ flags, Layout L, int n, const int* __restrict__ cand,
+                                                     const u64* __restrict__ cand_count, uint32_t* __restrict__ wcnt, uint32_t* __restrict__ chunk_tot,
+                                                     uint8_t* __restrict__ masks, u64* __restrict__ tot /* [TOT_CTICKET] */, Gen2D G)
+{
+	__shared__ uint32_t s_flags;
 	extern __shared__ __align__(16) uint32_t dyn[];
 	__shared__ u64 s_tri[256];
 	__shared__ uint32_t s_red[3][NT / 32];
@@ -226,14 +238,43 @@ __global__ void __launch_bounds__(NT) k_chunk_count(const uint32_t* __restrict__
 				const u64 j = atomicAdd(tot + TOT_CTICKET, 1ull);
 				if (j >= n_cand) break;
 				const int k = cand ? cand[j] : (int)j;
-				if (flags_contain_mesh(flags[k])) { c = k; break; }
+				if (GEN || flags_contain_mesh(flags[k])) { c = k; break; } // GEN: the flags are not known before the words are made
 			}
 			s_chunk = c;
+			s_flags = 0;
 		}
 		__syncthreads();
 		const int chunk = s_chunk;
 		if (chunk < 0) return;
-		if (TMA)
+		if (GEN)
+		{
+			const ChunkGeom g = G.geom[chunk];
+			const float* sheet = G.hmap + ((size_t)G.sheet_of[chunk] << (2 * L.ld));
+			uint32_t* out = bits + (size_t)chunk * wc;
+			uint32_t f = 0;
+			const int n_tasks = d << (2 * L.lzc); // (x, yb, zb)
+			for (int task = wid; task < n_tasks; task += NT / 32)
+			{
+				const int zb = task & (L.zc - 1), yb = (task >> L.lzc) & (L.zc - 1), x = task >> (2 * L.lzc);
+				const uint32_t mine = terrain2d_tile_word(G.s, g, L, sheet, x, yb, zb, lane);
+				const int w = ((((x << L.ld) + yb * 32 + lane)) << L.lzc) + zb;
+				sb[w] = mine;
+				out[w] = mine;
+				f |= word_flags(mine);
+			}
+			for (int i = tid; i < L.wp; i += NT) sb[wc + i] = 0u; // plane x = d: B == 0 outside the grid
+			f |= __shfl_xor_sync(0xffffffffu, f, 16);
+			f |= __shfl_xor_sync(0xffffffffu, f, 8);
+			f |= __shfl_xor_sync(0xffffffffu, f, 4);
+			f |= __shfl_xor_sync(0xffffffffu, f, 2);
+			f |= __shfl_xor_sync(0xffffffffu, f, 1);
+			if (lane == 0 && f) atomicOr(&s_flags, f);
+			__syncthreads();
+			const uint32_t fl = s_flags;
+			if (tid == 0) flags[chunk] = fl; // this CTA is the only writer: the classifier leaves the chunks it lists untouched
+			if (!flags_contain_mesh(fl)) continue; // (chunk_tot of such a chunk is never read)
+		}
+		else if (TMA)
 		{
 			if (tid == 0) bulk_load(sb, bits + (size_t)chunk * wc, (uint32_t)wc * 4u, &s_bar);
 			for (int i = tid; i < L.wp; i += NT) sb[wc + i] = 0u; // plane x = d: B == 0 outside the grid

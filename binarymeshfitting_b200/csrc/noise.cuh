@@ -246,13 +246,21 @@ __device__ __forceinline__ void gradient_perturb_single(int32_t seed, float amp,
 // lane.  Lanes 0..7 hash one corner each and leave its three fields in shared memory; everybody reads the eight records back as broadcast
 // 128-bit loads and does only the interpolation.  Same operations on the same operands as gradient_perturb_single, so the same bits; a warp
 // that straddles a cell boundary (or holds a NaN) takes gradient_perturb_single itself.  s_corner: 8 float4 owned by this warp.
-__device__ __forceinline__ void gradient_perturb_warp(int32_t seed, float amp, float freq, float& x, float& y, float& z, float4* s_corner, int lane)
+// `share` (warp-uniform): cleared by the first octave whose cell the warp does not share -- the octaves after it have twice the frequency each and
+// will not share theirs either, so they skip the test.
+__device__ __forceinline__ void gradient_perturb_warp(int32_t seed, float amp, float freq, float& x, float& y, float& z, float4* s_corner, int lane, bool& share)
 {
+	if (!share)
+	{
+		gradient_perturb_single(seed, amp, freq, x, y, z);
+		return;
+	}
 	const float xf = x * freq, yf = y * freq, zf = z * freq;
 	float xs = floorf(xf), ys = floorf(yf), zs = floorf(zf);
 	const float xs0 = __shfl_sync(0xffffffffu, xs, 0), ys0 = __shfl_sync(0xffffffffu, ys, 0), zs0 = __shfl_sync(0xffffffffu, zs, 0);
 	if (!__all_sync(0xffffffffu, xs == xs0 && ys == ys0 && zs == zs0))
 	{
+		share = false;
 		gradient_perturb_single(seed, amp, freq, x, y, z);
 		return;
 	}
@@ -327,22 +335,23 @@ __device__ __forceinline__ float noise_eval_warp(const NoiseState& s, float vx, 
 	float yF = __fmaf_rn(vy, s.frequency, 0.0f);
 	float zF = __fmaf_rn(vz, s.frequency, 0.0f);
 
+	bool share = true;
 	if (s.perturb == 1)
 	{
-		gradient_perturb_warp(s.seed - 1, s.perturb_amp, s.perturb_frequency, xF, yF, zF, s_corner, lane);
+		gradient_perturb_warp(s.seed - 1, s.perturb_amp, s.perturb_frequency, xF, yF, zF, s_corner, lane, share);
 	}
 	else if (s.perturb == 2)
 	{
 		int32_t seedF = s.seed - 1;
 		float freqF = s.perturb_frequency;
 		float ampF = s.perturb_amp * s.perturb_bounding;
-		gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane);
+		gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane, share);
 		for (int o = 1; o < s.perturb_octaves; o++)
 		{
 			freqF = freqF * s.perturb_lacunarity;
 			seedF = seedF - 1;
 			ampF = ampF * s.perturb_gain;
-			gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane);
+			gradient_perturb_warp(seedF, ampF, freqF, xF, yF, zF, s_corner, lane, share);
 		}
 	}
 	return noise_fractal<BASE>(s, xF, yF, zF);

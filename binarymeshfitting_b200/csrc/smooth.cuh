@@ -386,7 +386,7 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 	// half-step h: even = dual (centroids of the primitives), odd = primal (vertex = mean of its adjacent centroids).
 	// The index / adjacency streams come from global memory: SMOOTH_U elements per thread are in flight at once, all
 	// their loads issued before the first use, so a half-step costs a few memory round trips, not one per element.
-	constexpr int U = 4, KMAX = 8;
+	constexpr int U = 2, UP = 2, KMAX = 8; // triangles / vertices per thread in flight (two: 0.160 -> 0.150 ms against four, and no spills at 40 registers)
 	const float third = 1.0f / 3.0f;
 	for (int h = 0; h < half_steps; h++)
 	{
@@ -419,12 +419,12 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 		}
 		else
 		{
-			for (uint32_t v0 = threadIdx.x; v0 < V; v0 += U * SMOOTH_CTA)
+			for (uint32_t v0 = threadIdx.x; v0 < V; v0 += UP * SMOOTH_CTA)
 			{
-				int cnt[U];
-				uint32_t off[U], a[U][KMAX];
+				int cnt[UP];
+				uint32_t off[UP], a[UP][KMAX];
 #pragma unroll
-				for (int u = 0; u < U; u++)
+				for (int u = 0; u < UP; u++)
 				{
 					const uint32_t v = v0 + u * SMOOTH_CTA;
 					const bool ok = v < V;
@@ -434,11 +434,11 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 					off[u] = ok ? adj_off[v] : 0u;
 				}
 #pragma unroll
-				for (int u = 0; u < U; u++)
+				for (int u = 0; u < UP; u++)
 #pragma unroll
 					for (int k = 0; k < KMAX; k++) a[u][k] = k < cnt[u] ? adj[off[u] + k] : prim0;
 #pragma unroll
-				for (int u = 0; u < U; u++)
+				for (int u = 0; u < UP; u++)
 				{
 					if (cnt[u] == 0) continue;
 					f3 p = { 0, 0, 0 };
@@ -455,7 +455,10 @@ __device__ __forceinline__ void smooth_chunk_steps(float* P, float* D, const uin
 	}
 }
 
-__global__ void __launch_bounds__(SMOOTH_CTA, 1) k_smooth_chunks(const ChunkCounts* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ inds,
+// 40 registers per thread (not the 64 a 1024-thread CTA could have) and 8 KB of the SM's shared memory left unused (bmf_ctx_create): with several
+// batches in flight on different streams, CTAs of the NEXT batch's sampling kernel then fit beside a smoothing CTA -- an issue-bound kernel beside
+// this data-pipe-bound one: 0.497 -> 0.471 ms per batch with three batches in flight.
+__global__ void __maxnreg__(40) k_smooth_chunks(const ChunkCounts* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ inds,
                                                                    const uint32_t* __restrict__ adj_off, const uint32_t* __restrict__ adj,
                                                                    const uint8_t* __restrict__ valence, const uint8_t* __restrict__ boundary, float* pos,
                                                                    float* dp_global, int half_steps, int process_boundary, unsigned long long* tot,

@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # per-kernel counters of the steady state (the first batches grow the arenas and re-launch the emitters)
 ncu --metrics $M --clock-control none -s 60 -c 80 --csv --log-file $OUT/${TAG}_kernels.csv $B > $OUT/${TAG}_kernels.out 2>&1
 # full-set captures of the top kernels
-for k in k_chunk_emit k_smooth_chunks k_chunk_count k_terrain2d_sheet k_terrain2d_bits k_scan_chunks; do
+for k in k_chunk_emit k_smooth_chunks k_chunk_count k_terrain2d_sheet k_scan_chunks; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${TAG}_$k $B > $OUT/${TAG}_$k.out 2>&1
 done
 ncu --set full --clock-control none --import-source on -k regex:k_seam_pass -s 2 -c 1 -f -o $OUT/${TAG}_k_seam_pass python tools/seam_probe.py > $OUT/${TAG}_k_seam_pass.out 2>&1
@@ -23,5 +23,5 @@ python tools/ncu_summary.py $OUT/${TAG}_ncu_full_summary.txt $OUT/${TAG}_k_*.ncu
 for k in k_chunk_emit k_chunk_count k_smooth_chunks; do
   python tools/ncu_lines.py $OUT/${TAG}_$k.ncu-rep $k 40 --phases $( [ $k = k_smooth_chunks ] && echo smooth.cuh || echo fused.cuh ) > $OUT/${TAG}_${k}_lines.txt 2>&1
 done
-for k in k_chunk_count k_terrain2d_sheet k_terrain2d_bits k_scan_chunks k_seam_pass k_terrain3d; do rm -f $OUT/${TAG}_$k.ncu-rep; done
+for k in k_chunk_count k_terrain2d_sheet k_scan_chunks k_seam_pass k_terrain3d; do rm -f $OUT/${TAG}_$k.ncu-rep; done
 ls -la $OUT | grep $TAG
