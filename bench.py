@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--chunks-per-axis", type=int, default=16)
+    ap.add_argument("--in-flight", type=int, default=4, help="contexts (streams + arenas) the steps are dealt to round robin: batches in flight at once (>= 3)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (3-D noise, LOD rebuild, single 128^3, ...)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=0, help="e2e only: bmf_ctx_set_reserved_sms for both contexts (measured: no effect with the copy-engine download)")
@@ -428,7 +429,17 @@ class SharedWorld:
 
 
 def time_e2e(D, sw, K):
-    sw.run(3)
+    for c in sw.ctxs:
+        c.set_batches_in_flight(len(sw.ctxs))  # the contexts overlap their batches: least SM time first (bmf_ctx_set_batches_in_flight)
+    try:
+        return _time_e2e(D, sw, K)
+    finally:
+        for c in sw.ctxs:
+            c.set_batches_in_flight(1)
+
+
+def _time_e2e(D, sw, K):
+    sw.run(2 * len(sw.ctxs))  # untimed: every context meshes this world twice (the first submit of a new world grows its arenas and re-launches the emitters)
     D.barrier()
     sw.g.reset()
     D.barrier()
@@ -466,7 +477,7 @@ def time_device_pipelined(D, ctxs, streams, submit_on, K, W):
     on every stream after the final submit; max over ranks."""
     torch = D.torch
     nc = len(ctxs)
-    for k in range(max(W, nc)):
+    for k in range(max(W, 2 * nc)):  # every context twice: the first submit of a kind grows its arenas and re-launches
         submit_on(ctxs[k % nc])
     for c in ctxs:
         c.wait()
@@ -474,6 +485,7 @@ def time_device_pipelined(D, ctxs, streams, submit_on, K, W):
     D.barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     ends = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    l0 = sum(c.launch_count() for c in ctxs)
     t0 = time.perf_counter()
     e0.record(streams[0])
     for k in range(K):
@@ -485,7 +497,7 @@ def time_device_pipelined(D, ctxs, streams, submit_on, K, W):
     torch.cuda.synchronize()
     D.barrier()
     wall = time.perf_counter() - t0
-    return D.max(max(e0.elapsed_time(e) for e in ends) * 1e-3), wall
+    return D.max(max(e0.elapsed_time(e) for e in ends) * 1e-3), wall, sum(c.launch_count() for c in ctxs) - l0
 
 
 def run_ours(args):
@@ -495,7 +507,7 @@ def run_ours(args):
     if D.size > 1:
         args.gpus = D.size
     numa = pin_to_gpu_numa_node(D.local_rank)
-    ctxs = [Context(D.local_rank) for _ in range(3)]  # raises if the CUDA library or the device is missing: no fallback
+    ctxs = [Context(D.local_rank) for _ in range(args.in_flight)]  # raises if the CUDA library or the device is missing: no fallback
     ctx = ctxs[0]
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", D.local_rank))
     kind = SAMPLERS[args.sampler]
@@ -518,16 +530,19 @@ def run_ours(args):
     clocks = ClockSampler(D.local_rank)
     clocks.start()
     t_one, wall_one = time_device(D, ctx, stream, step, K, W)
-    launches = (ctx.launch_count() - launches0) * K // (K + W)  # time_device runs W warm-up steps first: count the K timed steps only
     stage = ctx.stage_ms()
-    # the same K steps with three batches in flight (one per context / stream): what a job that streams batches through the GPU gets
+    # the same K steps with several batches in flight (one per context / stream): what a job that streams batches through the GPU gets
     streams = [torch.cuda.ExternalStream(c.stream_ptr(), device=torch.device("cuda", D.local_rank)) for c in ctxs]
 
     def submit_on(c):
         if len(sw.descs):
             c.submit(sw.descs, dim, iters=args.iters)
 
-    t_max, wall = time_device_pipelined(D, ctxs, streams, submit_on, K, W)
+    for c in ctxs:
+        c.set_batches_in_flight(len(ctxs))
+    t_max, wall, launches = time_device_pipelined(D, ctxs, streams, submit_on, K, W)  # launches: this rank's kernels inside the timed region
+    for c in ctxs:
+        c.set_batches_in_flight(1)
     value = nvox * K / t_max
     infos_mine = ctx.chunk_infos() if len(sw.descs) else np.zeros(0, capi.CHUNK_INFO_DTYPE)
     n_mesh_mine = int((infos_mine["contains_mesh"] != 0).sum())
@@ -552,8 +567,8 @@ def run_ours(args):
     e2e = {"value": nvox * K / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3,
            "d2h_GB_per_s": d2h / (e2e_s / K) / 1e9,
            "mode": "opt-in compact download (positions + uint16 chunk-local indices packed on the device; colour == 1 and the chunk table say what was skipped), "
-                   "copy engine straight into a shared pinned host segment (bmf_batch_download_dma), three contexts round robin so that the DMA of batch i runs beside "
-                   "the kernels of the batches after it, rank 0 assembles the batch-order chunk table",
+                   "copy engine straight into a shared pinned host segment (bmf_batch_download_dma), %d contexts round robin so that the DMA of batch i runs beside "
+                   "the kernels of the batches after it, rank 0 assembles the batch-order chunk table" % len(ctxs),
            "gathered": verify}
     dma_s = sw.dma_only(K)
     e2e["d2h_ceiling"] = {"ms_per_step": dma_s * 1e3, "GB_per_s": d2h / dma_s / 1e9, "voxels_per_s": nvox / dma_s,
@@ -575,7 +590,7 @@ def run_ours(args):
         "config": config_of(args, overlap),
         "chunks_per_s": value / dim ** 3,
         "wall_ms_per_step": wall / K * 1e3,
-        "in_flight": {"batches": len(ctxs), "note": "step k is submitted to context k % 3 (own stream, own arenas); every step is a complete batch, consecutive steps overlap on the GPU",
+        "in_flight": {"batches": len(ctxs), "note": "step k is submitted to context k % NC (own stream, own arenas); every step is a complete batch, consecutive steps overlap on the GPU",
                       "single_stream": {"value": nvox * K / t_one, "ms_per_step": t_one / K * 1e3, "wall_ms_per_step": wall_one / K * 1e3,
                                         "note": "the same K steps back to back on ONE stream: the latency of a step; kernels[], roofline and stage_ms are measured in this mode"}},
         "e2e": e2e,

@@ -21,7 +21,7 @@ STAGES = ("sample", "count", "scan", "verts", "inds", "smooth", "total")
 # symbols include/bmf_b200.h declares (tests check that the library exports every one of them)
 EXPORTS = ("bmf_ctx_create", "bmf_ctx_destroy", "bmf_last_error", "bmf_version", "bmf_sampler_defaults", "bmf_sampler_set",
            "bmf_batch_submit", "bmf_batch_wait", "bmf_batch_totals", "bmf_batch_chunk_info", "bmf_batch_chunk_infos",
-           "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_set_reserved_sms", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
+           "bmf_batch_download", "bmf_batch_download_async", "bmf_batch_copy_chunk", "bmf_batch_stage_ms", "bmf_ctx_launch_count", "bmf_ctx_stream", "bmf_ctx_set_kernel_timing", "bmf_ctx_set_reserved_sms", "bmf_ctx_set_batches_in_flight", "bmf_ctx_kernel_times", "bmf_batch_device_ptrs",
            "bmf_mesh_process", "bmf_mesh_process_steps", "bmf_qef_solve", "bmf_sampler_gradient", "bmf_color_map", "bmf_mesh_collapse_bad_quads",
            "bmf_seam_overlap", "bmf_batch_stitch", "bmf_seam_download", "bmf_seam_stage_ms", "bmf_quads_to_tris", "bmf_batch_download_flat_quads", "bmf_ubench_issue",
            "bmf_batch_download_enqueue", "bmf_batch_download_dma", "bmf_host_alloc", "bmf_host_free", "bmf_host_register", "bmf_host_unregister")
@@ -102,6 +102,7 @@ def load_library(path=SO):
     lib.bmf_ctx_launch_count.restype = C.c_int64
     lib.bmf_ctx_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.bmf_ctx_set_reserved_sms.argtypes = [vp, C.c_int]
+    lib.bmf_ctx_set_batches_in_flight.argtypes = [vp, C.c_int]
     lib.bmf_ctx_kernel_times.argtypes = [vp, C.c_int, vp, vp]
     lib.bmf_ctx_stream.argtypes = [vp]
     lib.bmf_ctx_stream.restype = vp
@@ -318,6 +319,10 @@ class Context:
     def set_reserved_sms(self, n):
         """leave n SMs partly free for another context's kernels (overlapped pipelines)"""
         self._check(self.lib.bmf_ctx_set_reserved_sms(self.h, int(n)))
+
+    def set_batches_in_flight(self, n):
+        """hint: the caller keeps n batches in flight on this device (one context each): prefer the kernels with the least total SM time"""
+        self._check(self.lib.bmf_ctx_set_batches_in_flight(self.h, int(n)))
 
     def set_kernel_timing(self, on):
         self._check(self.lib.bmf_ctx_set_kernel_timing(self.h, int(on)))

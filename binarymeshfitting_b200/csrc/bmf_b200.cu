@@ -101,6 +101,7 @@ struct bmf_ctx
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
 	// fused per-chunk extraction (fused.cuh): one CTA per mesh chunk does label_edges + polygonize + MeshProcessor::init
+	int in_flight_hint = 1;   // bmf_ctx_set_batches_in_flight: > 1 = the caller overlaps batches on other contexts, total SM time matters more than latency
 	int fused_extract = 1;    // per-chunk kernels for dim <= 64 triangle batches: 1 = when the batch has chunks for every SM several times over (a chunk is one
 	                          // CTA's serial job there: ~0.1 ms, so a few hundred chunks finish sooner spread over the whole GPU by the per-segment kernels),
 	                          // BMF_FUSED=0 never, BMF_FUSED=2 always
@@ -906,7 +907,7 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		g.oz = c.pos[2] - so;
 		ctx->geom_host[i] = g;
 	}
-	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64 && (ctx->fused_extract >= 2 || n >= 8 * ctx->sm_count);
+	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64 && (ctx->fused_extract >= 2 || ctx->in_flight_hint > 1 || n >= 8 * ctx->sm_count);
 	bool gen2d = false; // 2-D terrain on the per-chunk path: k_chunk_count makes the sign words itself, k_terrain2d_bits is not launched
 	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
@@ -1405,6 +1406,13 @@ int bmf_ctx_set_reserved_sms(bmf_ctx* ctx, int n)
 	if (!ctx) return BMF_ERR_INVALID;
 	if (n < 0 || n >= ctx->sm_count) return fail(ctx, BMF_ERR_INVALID, "bmf_ctx_set_reserved_sms: 0 <= n < number of SMs");
 	ctx->reserve_sms = n;
+	return BMF_OK;
+}
+
+int bmf_ctx_set_batches_in_flight(bmf_ctx* ctx, int n)
+{
+	if (!ctx) return BMF_ERR_INVALID;
+	ctx->in_flight_hint = n > 1 ? n : 1;
 	return BMF_OK;
 }
 

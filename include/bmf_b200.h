@@ -209,6 +209,13 @@ int64_t bmf_ctx_launch_count(const bmf_ctx* ctx);
  * reference's generator and its GL upload never overlap (WorldWatcher.cpp:105-112). */
 int bmf_ctx_set_reserved_sms(bmf_ctx* ctx, int n);
 
+/* Scheduling hint for callers that keep SEVERAL batches in flight on this device (one ctx = one stream each, like bench.py does): with
+ * n > 1 the ctx picks, among kernel sets that give identical results, the one with the least total SM time -- the per-chunk kernels
+ * (csrc/fused.cuh) at any batch size -- instead of the one with the shortest latency for a batch that has the GPU to itself (per-segment
+ * kernels below 8 x SMs chunks).  Measured on a 512-chunk batch: 0.32 / 0.38 ms alone, 0.163 / 0.146 ms per batch with four in flight.
+ * n <= 1 (default): latency first.  No reference counterpart (the reference meshes one queue at a time, ChunkGenerator.cpp:27-60). */
+int bmf_ctx_set_batches_in_flight(bmf_ctx* ctx, int n);
+
 /* optional per-launch timing: when on, every kernel of the next batches is bracketed by its own event pair;
  * bmf_ctx_kernel_times returns the number of launches of the last batch and fills up to `cap` (name, ms) */
 int bmf_ctx_set_kernel_timing(bmf_ctx* ctx, int on);
