@@ -125,6 +125,43 @@ def test_per_chunk_smoothing_equals_per_step_kernels(gpu):
     assert len(want["pos"]) > 100000
 
 
+@pytest.mark.parametrize("kind", ["TERRAIN2D_PERT", "TERRAIN3D_PERT", "TORUS_Z"])
+def test_batches_in_flight_hint_changes_kernels_not_results(gpu, kind):
+    """bmf_ctx_set_batches_in_flight(n > 1) picks the per-chunk kernels for a batch of any size (for 2-D terrains: sign words made inside
+    k_chunk_count); everything a caller can read back must be identical to the latency-first kernels' output, sign words included."""
+    from binarymeshfitting_b200 import world
+    props = world.WorldProperties(max_level=4, chunk_resolution=64, process_iters=2)
+    lps, lv, mc = world.split_leaves(props)
+    descs = capi.make_chunk_descs(lps, overlaps=0.045, levels=lv)
+    assert len(descs) < 8 * 100  # small enough for the per-segment kernels by default
+    gpu.set_sampler(getattr(capi, kind))
+    got = []
+    for hint in (1, 4, 1):
+        gpu.set_batches_in_flight(hint)
+        gpu.set_kernel_timing(True)
+        gpu.submit(descs, 64, iters=2)
+        gpu.wait()
+        names = [n for n, _ in gpu.kernel_times()]
+        gpu.set_kernel_timing(False)
+        assert any("k_chunk_emit" in n for n in names) == (hint > 1), names
+        infos = gpu.chunk_infos()
+        out = gpu.download()
+        mesh = np.flatnonzero(infos["n_verts"] > 0)
+        bits = [gpu.copy_chunk(int(i), want=("bits",))["bits"] for i in list(mesh[:3]) + [0, len(descs) - 1]]
+        got.append((infos, out, bits))
+    gpu.set_batches_in_flight(1)
+    assert int(got[0][0]["n_verts"].sum()) > 10000
+    for infos, out, bits in got[1:]:
+        for f in ("contains_mesh", "n_cells", "n_verts", "n_inds", "vert_offset", "ind_offset", "flags"):
+            np.testing.assert_array_equal(infos[f], got[0][0][f])
+        for k in ("pos", "normal", "color"):
+            np.testing.assert_array_equal(out[k].view(np.uint32), got[0][1][k].view(np.uint32))
+        for k in ("inds", "boundary", "valence"):
+            np.testing.assert_array_equal(out[k], got[0][1][k])
+        for a, b in zip(bits, got[0][2]):
+            np.testing.assert_array_equal(a, b)
+
+
 def test_mode_switching_on_one_context_keeps_every_result_right(gpu):
     """one context, many kinds of batches back to back (triangles / quads / seams / smoothing variants / host density): no state
     of an earlier batch (colour fill, published chunk table, quad flags, arena contents) may leak into a later one"""
