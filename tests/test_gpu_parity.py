@@ -81,10 +81,16 @@ def test_recompute_path_matches_materialised(gpu, oracle):
 @pytest.mark.parametrize("kind", [ob.TERRAIN2D, ob.TERRAIN2D_PERT])
 @pytest.mark.parametrize("pos,size,dim,overlap", [((-64.0, -64.0, -64.0), 128.0, 64, 0.045), ((-256.0, -40.0, 100.0), 64.0, 32, 0.0), ((-256.0, -150.0, 100.0), 300.0, 32, 0.0),
                                                   ((3.5, -7.25, 11.0), 16.0, 128, 0.035), ((-16.0, 0.0, -16.0), 16.0, 64, 0.045)])
-def test_terrain2d_compare_only_sign_words(gpu, oracle, kind, pos, size, dim, overlap):
+@pytest.mark.parametrize("in_flight", [1, 4])
+def test_terrain2d_compare_only_sign_words(gpu, oracle, kind, pos, size, dim, overlap, in_flight):
     """The production 2-D terrain path never evaluates a density per voxel (bit = (-dy < n*height)); its sign
-    words, topology and positions must equal the oracle's, which evaluates -dy - n*height < 0 per voxel."""
-    g = gpu_chunk(gpu, kind, pos, size, dim, overlap, want_density=False)
+    words, topology and positions must equal the oracle's, which evaluates -dy - n*height < 0 per voxel.
+    in_flight = 4: the per-chunk kernels (dim <= 64), where k_chunk_count makes the sign words itself."""
+    gpu.set_batches_in_flight(in_flight)
+    try:
+        g = gpu_chunk(gpu, kind, pos, size, dim, overlap, want_density=False)
+    finally:
+        gpu.set_batches_in_flight(1)
     o = oracle.chunk(oracle.sampler(kind), pos, size, dim, overlap)
     assert_same_topology(g, o)
     assert_same_positions(g, o, dim)
