@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--chunks-per-axis", type=int, default=16)
-    ap.add_argument("--in-flight", type=int, default=4, help="contexts (streams + arenas) the steps are dealt to round robin: batches in flight at once (>= 3)")
+    ap.add_argument("--in-flight", type=int, default=0, help="contexts (streams + arenas) the steps are dealt to round robin: batches in flight at once (>= 3); "
+                    "default 4, 6 from four ranks up (a rank's share of the world is then a chain of short kernels: 0.117 / 0.094 ms per 400-chunk batch with 4 / 6 in flight)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (3-D noise, LOD rebuild, single 128^3, ...)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reserve-sms", type=int, default=0, help="e2e only: bmf_ctx_set_reserved_sms for both contexts (measured: no effect with the copy-engine download)")
@@ -322,11 +323,14 @@ class SharedWorld:
             if len(mine0):
                 c.submit(np.ascontiguousarray(descs_all[mine0]), dim, iters=iters)
                 nv0 = c.chunk_infos()["n_verts"].astype(np.int64)
-            cost = np.full(self.n_total, 37.0)
+            # ... for shares large enough for the per-chunk kernels on their own; a smaller share (from four ranks up) is a chain of short kernels whose time
+            # follows the number of chunks -- i.e. of noise sheets -- much more: 39 ns per chunk against 0.2 ns per vertex measured over the 8 ranks' own times
+            empty = 37.0 if self.n_total / D.size >= 8 * 148 else 160.0
+            cost = np.full(self.n_total, empty)
             for idx, nv in D.allgather((mine0, nv0)):
                 cost[idx] += nv
             parts = world.partition(mortons, cost, D.size)
-            self.cost_model = "37 + n_verts of the previous rebuild"
+            self.cost_model = "%d + n_verts of the previous rebuild" % empty
         self.parts = [np.sort(p) for p in parts]  # batch order inside a part
         self.mine = self.parts[D.rank]
         self.descs = np.ascontiguousarray(descs_all[self.mine])
@@ -497,7 +501,9 @@ def time_device_pipelined(D, ctxs, streams, submit_on, K, W):
     torch.cuda.synchronize()
     D.barrier()
     wall = time.perf_counter() - t0
-    return D.max(max(e0.elapsed_time(e) for e in ends) * 1e-3), wall, sum(c.launch_count() for c in ctxs) - l0
+    mine = max(e0.elapsed_time(e) for e in ends) * 1e-3
+    time_device_pipelined.per_rank_ms = [round(t / K * 1e3, 4) for t in D.allgather(mine)]  # every rank's own device time per step (the value uses the slowest)
+    return D.max(mine), wall, sum(c.launch_count() for c in ctxs) - l0
 
 
 def run_ours(args):
@@ -507,11 +513,13 @@ def run_ours(args):
     if D.size > 1:
         args.gpus = D.size
     numa = pin_to_gpu_numa_node(D.local_rank)
-    ctxs = [Context(D.local_rank) for _ in range(args.in_flight)]  # raises if the CUDA library or the device is missing: no fallback
+    n_ctx = max(3, args.in_flight) if args.in_flight else (6 if D.size >= 4 else 4)
+    ctxs_all = [Context(D.local_rank) for _ in range(n_ctx)]  # raises if the CUDA library or the device is missing: no fallback
+    ctxs = ctxs_all[:4]  # the end-to-end pipeline is download-bound: four contexts keep the copy engine busy, more only lengthen its ramp
     ctx = ctxs[0]
     stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", D.local_rank))
     kind = SAMPLERS[args.sampler]
-    for c in ctxs:
+    for c in ctxs_all:
         c.set_sampler(kind)
     ps, overlap = workload(args)
     descs_all = capi.make_chunk_descs(ps, overlaps=overlap)
@@ -532,16 +540,16 @@ def run_ours(args):
     t_one, wall_one = time_device(D, ctx, stream, step, K, W)
     stage = ctx.stage_ms()
     # the same K steps with several batches in flight (one per context / stream): what a job that streams batches through the GPU gets
-    streams = [torch.cuda.ExternalStream(c.stream_ptr(), device=torch.device("cuda", D.local_rank)) for c in ctxs]
+    streams = [torch.cuda.ExternalStream(c.stream_ptr(), device=torch.device("cuda", D.local_rank)) for c in ctxs_all]
 
     def submit_on(c):
         if len(sw.descs):
             c.submit(sw.descs, dim, iters=args.iters)
 
-    for c in ctxs:
-        c.set_batches_in_flight(len(ctxs))
-    t_max, wall, launches = time_device_pipelined(D, ctxs, streams, submit_on, K, W)  # launches: this rank's kernels inside the timed region
-    for c in ctxs:
+    for c in ctxs_all:
+        c.set_batches_in_flight(len(ctxs_all))
+    t_max, wall, launches = time_device_pipelined(D, ctxs_all, streams, submit_on, K, W)  # launches: this rank's kernels inside the timed region
+    for c in ctxs_all:
         c.set_batches_in_flight(1)
     value = nvox * K / t_max
     infos_mine = ctx.chunk_infos() if len(sw.descs) else np.zeros(0, capi.CHUNK_INFO_DTYPE)
@@ -590,7 +598,7 @@ def run_ours(args):
         "config": config_of(args, overlap),
         "chunks_per_s": value / dim ** 3,
         "wall_ms_per_step": wall / K * 1e3,
-        "in_flight": {"batches": len(ctxs), "note": "step k is submitted to context k % NC (own stream, own arenas); every step is a complete batch, consecutive steps overlap on the GPU",
+        "in_flight": {"batches": len(ctxs_all), "ms_per_step_per_rank": getattr(time_device_pipelined, "per_rank_ms", None), "note": "step k is submitted to context k % NC (own stream, own arenas); every step is a complete batch, consecutive steps overlap on the GPU",
                       "single_stream": {"value": nvox * K / t_one, "ms_per_step": t_one / K * 1e3, "wall_ms_per_step": wall_one / K * 1e3,
                                         "note": "the same K steps back to back on ONE stream: the latency of a step; kernels[], roofline and stage_ms are measured in this mode"}},
         "e2e": e2e,
@@ -637,7 +645,7 @@ def run_ours(args):
         result["extras"] = ex
     if D.rank == 0 and D.size == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(args, ps, overlap)
-    for c in ctxs:
+    for c in ctxs_all:
         c.close()
     D.close()
     if D.rank == 0:
