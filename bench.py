@@ -748,6 +748,26 @@ def extras_single(ctx, ctxs, args, capi, world, peaks, prof, clk, sms, D):
         ctx.submit(ld, 64, iters=2)
         ctx.wait()
         ex["lod_rebuild_232x64_%s" % name]["launches_per_rebuild"] = ctx.launch_count() - l0
+        if kind == capi.TERRAIN2D_PERT and len(ctxs) >= 4:
+            # the same rebuild when the host has several of them in flight (several worlds / frames ahead): four contexts round robin, per-chunk kernels
+            for c in ctxs[:4]:
+                c.set_sampler(kind)
+                c.set_batches_in_flight(4)
+            for k in range(8):
+                ctxs[k % 4].submit(ld, 64, iters=2)
+            best = 1e9
+            for rep in range(3):
+                for c in ctxs[:4]:
+                    c.wait()
+                t0 = time.perf_counter()
+                for k in range(40):
+                    ctxs[k % 4].submit(ld, 64, iters=2)
+                for c in ctxs[:4]:
+                    c.wait()
+                best = min(best, (time.perf_counter() - t0) / 40)
+            for c in ctxs[:4]:
+                c.set_batches_in_flight(1)
+            ex["lod_rebuild_232x64_%s" % name]["ms_per_rebuild_four_in_flight"] = best * 1e3
     # config 4 as named ("multi-level chunks + WorldStitcher seams")
     try:
         sdsc = capi.make_chunk_descs(lps, overlaps=ctx.seam_overlap(64), levels=lv)
