@@ -88,8 +88,12 @@ struct bmf_ctx
 	bool counts_published = false; // the chunk table of the resident batch has been queued for the host (once per batch, after the emitters)
 	size_t color_ones = 0; // the first color_ones floats of the colour arena are known to be exactly 1.0f
 
-	DevBuf<ChunkGeom> geom, sheet_geom;
-	DevBuf<int> sheet_of;
+	// per-batch host -> device upload: chunk geometry, sheet geometry and the chunk -> sheet map are ONE device block filled by ONE copy (three
+	// copies of pageable memory were 20 us of a submit's 90 us on the host); geom / sheet_geom / sheet_of point into it
+	DevBuf<unsigned char> upload;
+	std::vector<unsigned char> upload_host;
+	struct { ChunkGeom* p = nullptr; } geom, sheet_geom;
+	struct { int* p = nullptr; } sheet_of;
 	DevBuf<uint32_t> sheet_mm;
 	DevBuf<uint8_t> uni, gflags;
 	uint8_t* uni_pinned = nullptr;
@@ -804,7 +808,7 @@ void bmf_ctx_destroy(bmf_ctx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->geom.release(); ctx->sheet_geom.release(); ctx->sheet_of.release(); ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wv4.release(); ctx->wib.release();
+	ctx->upload.release(); ctx->geom.p = ctx->sheet_geom.p = nullptr; ctx->sheet_of.p = nullptr; ctx->flags.release(); ctx->bits.release(); ctx->wcnt.release(); ctx->wv4.release(); ctx->wib.release();
 	ctx->seg_tot.release(); ctx->chunk_tot.release(); ctx->vcells.release(); ctx->icells.release(); ctx->density.release(); ctx->hmap.release(); ctx->masks.release();
 	ctx->counts.release(); ctx->totals_dev.release(); ctx->pos.release(); ctx->color.release(); ctx->normal.release();
 	ctx->boundary.release(); ctx->valence.release(); ctx->inds.release(); ctx->adj_off.release(); ctx->cls.release(); ctx->cursor.release();
@@ -909,7 +913,6 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 	const bool fused = ctx->batch_fused = ctx->fused_extract && !params->quads && d <= 64 && (ctx->fused_extract >= 2 || ctx->in_flight_hint > 1 || n >= 8 * ctx->sm_count);
 	bool gen2d = false; // 2-D terrain on the per-chunk path: k_chunk_count makes the sign words itself, k_terrain2d_bits is not launched
-	BMF_CUDA(ctx->geom.reserve(n));
 	BMF_CUDA(ctx->flags.reserve(n));
 	BMF_CUDA(ctx->bits.reserve(n_words));
 	BMF_CUDA(ctx->wcnt.reserve(n_words));
@@ -971,8 +974,6 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 		}
 		n_sheets = (int)ctx->sheet_geom_host.size();
 		BMF_CUDA(ctx->hmap.reserve((size_t)n_sheets * d * d));
-		BMF_CUDA(ctx->sheet_geom.reserve(n_sheets));
-		BMF_CUDA(ctx->sheet_of.reserve(n));
 		BMF_CUDA(ctx->sheet_mm.reserve(3 * (size_t)n_sheets));
 		BMF_CUDA(ctx->uni.reserve(n));
 		if ((size_t)n > ctx->uni_pinned_cap)
@@ -986,17 +987,28 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	}
 
 	cudaStream_t st = ctx->stream;
-	BMF_CUDA(cudaMemcpyAsync(ctx->geom.p, ctx->geom_host.data(), sizeof(ChunkGeom) * n, cudaMemcpyHostToDevice, st));
+	{
+		// [geom n][sheet_geom n_sheets][sheet_of n] (16-byte records first: every part stays aligned)
+		const size_t off_sg = sizeof(ChunkGeom) * (size_t)n, off_so = off_sg + sizeof(ChunkGeom) * (size_t)n_sheets, up_bytes = off_so + sizeof(int) * (size_t)(n_sheets ? n : 0);
+		ctx->upload_host.resize(up_bytes);
+		memcpy(ctx->upload_host.data(), ctx->geom_host.data(), off_sg);
+		if (n_sheets)
+		{
+			memcpy(ctx->upload_host.data() + off_sg, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * (size_t)n_sheets);
+			memcpy(ctx->upload_host.data() + off_so, ctx->sheet_of_host.data(), sizeof(int) * (size_t)n);
+		}
+		BMF_CUDA(ctx->upload.reserve(up_bytes));
+		ctx->geom.p = reinterpret_cast<ChunkGeom*>(ctx->upload.p);
+		ctx->sheet_geom.p = reinterpret_cast<ChunkGeom*>(ctx->upload.p + off_sg);
+		ctx->sheet_of.p = reinterpret_cast<int*>(ctx->upload.p + off_so);
+		BMF_CUDA(cudaMemcpyAsync(ctx->upload.p, ctx->upload_host.data(), up_bytes, cudaMemcpyHostToDevice, st));
+	}
 	if (host_density && !params->density_on_device)
 		BMF_CUDA(cudaMemcpyAsync(ctx->density.p, density_in, sizeof(float) * n * nvox, cudaMemcpyHostToDevice, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->flags.p, 0, sizeof(uint32_t) * n, st));
 	BMF_CUDA(cudaMemsetAsync(ctx->totals_dev.p + TOT_MESH, 0, 4 * sizeof(unsigned long long), st)); // list lengths and tickets: TOT_MESH, TOT_TICKET, TOT_CAND, TOT_CTICKET
 	if (!fused) BMF_CUDA(cudaMemsetAsync(ctx->chunk_tot.p, 0, sizeof(uint32_t) * 3 * n, st)); // k_count adds to it; k_chunk_count stores
-	if (n_sheets)
-	{
-		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_geom.p, ctx->sheet_geom_host.data(), sizeof(ChunkGeom) * n_sheets, cudaMemcpyHostToDevice, st));
-		BMF_CUDA(cudaMemcpyAsync(ctx->sheet_of.p, ctx->sheet_of_host.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
-	}
+
 
 	// ---- K1 / K2
 	BMF_CUDA(cudaEventRecord(ctx->ev[0], st));
