@@ -185,7 +185,7 @@ int bmf_batch_download_enqueue(bmf_ctx* ctx, const bmf_download_desc* desc);
  * errors are reported at once (BMF_ERR_NOMEM: buffers too small; BMF_ERR_INVALID: a chunk has >= 65536 vertices and indices16 was asked).
  * Measured on B200 / PCIe 5: 56 GB/s and no slow-down of another context's kernels, against 51 GB/s for the kernel-driven form, whose
  * stores to host memory slow concurrent kernels down by ~2.7x -- so pipelines that overlap batch i's download with batch i+1's kernels
- * (two contexts, bench.py's e2e) use this call, and bmf_batch_download_enqueue is for callers that must not block the host. */
+ * (several contexts round robin, bench.py's e2e) use this call, and bmf_batch_download_enqueue is for callers that must not block the host. */
 int bmf_batch_download_dma(bmf_ctx* ctx, const bmf_download_desc* desc);
 /* page-locked, device-mapped host memory for the call above (cudaHostAlloc portable + mapped) -- so that a host program needs no
  * CUDA headers -- and registration of memory the caller already owns (e.g. a shared-memory segment several ranks write into) */
