@@ -306,12 +306,14 @@ def pin_to_gpu_numa_node(local_rank):
 class SharedWorld:
     """ONE batch of chunks partitioned over the ranks + the shared host segment its meshes are gathered in."""
 
-    def __init__(self, D, ctxs, descs_all, mortons, dim, iters, tag, mode="compact"):
+    def __init__(self, D, ctxs, descs_all, mortons, dim, iters, tag, mode="compact", columns=False):
         from binarymeshfitting_b200 import gather, world
         self.D, self.ctxs, self.dim, self.iters, self.mode = D, ctxs, dim, iters, mode
         self.descs_all = descs_all
         self.n_total = len(descs_all)
-        parts = world.partition(mortons, np.ones(self.n_total), D.size) if D.size > 1 else [np.arange(self.n_total)]
+        # columns: heightfield sampler -> ranges of the column-major curve (whole chunk columns per rank: no noise sheet is sampled twice)
+        self.columns = columns
+        parts = world.partition(mortons, np.ones(self.n_total), D.size, columns) if D.size > 1 else [np.arange(self.n_total)]
         c = ctxs[0]
         self.cost_model = None
         if D.size > 1:
@@ -329,7 +331,7 @@ class SharedWorld:
             cost = np.full(self.n_total, empty)
             for idx, nv in D.allgather((mine0, nv0)):
                 cost[idx] += nv
-            parts = world.partition(mortons, cost, D.size)
+            parts = world.partition(mortons, cost, D.size, columns)
             self.cost_model = "%d + n_verts of the previous rebuild" % empty
         self.parts = [np.sort(p) for p in parts]  # batch order inside a part
         self.mine = self.parts[D.rank]
@@ -526,7 +528,8 @@ def run_ours(args):
     mortons = world.grid_mortons(args.chunks_per_axis)
     descs_all["morton"] = mortons
     dim, K, W = args.dim, args.steps, max(args.warmup, 3)
-    sw = SharedWorld(D, ctxs, descs_all, mortons, dim, args.iters, "main", mode="compact")
+    columns = args.sampler.startswith("terrain2d")
+    sw = SharedWorld(D, ctxs, descs_all, mortons, dim, args.iters, "main", mode="compact", columns=columns)
     nvox = sw.vox
 
     def step():
@@ -583,7 +586,7 @@ def run_ours(args):
                           "what": "the same downloads without the kernels, all ranks at once: what the link(s) and the host memory of this box allow end to end"}
     sw.close()
     # the reference-layout download (positions + colours + uint32 indices, GLChunk::format_data's arrays) through the same path
-    sw2 = SharedWorld(D, ctxs, descs_all, mortons, dim, args.iters, "ref", mode="reference_layout")
+    sw2 = SharedWorld(D, ctxs, descs_all, mortons, dim, args.iters, "ref", mode="reference_layout", columns=columns)
     s2, _ = time_e2e(D, sw2, K)
     e2e["reference_layout"] = {"value": nvox * K / s2, "ms_per_step": s2 / K * 1e3, "d2h_bytes_per_step": sw2.bytes_per_step(),
                                "d2h_GB_per_s": sw2.bytes_per_step() / (s2 / K) / 1e9, "streams": "positions + colours + uint32 indices"}
@@ -604,7 +607,8 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": int(D.sum(float(launches))),
         "clocks": clk,
-        "partition": {"scheme": "world.partition: contiguous ranges of the depth-normalised Morton order, balanced by cost (%s); no data-path collective" % (sw.cost_model or "one rank"),
+        "partition": {"scheme": "world.partition: contiguous ranges of the depth-normalised Morton order%s, balanced by cost (%s); no data-path collective" % (
+                          " regrouped column-major ((z, x) bits before the y bits: a rank owns whole chunk columns and no noise sheet is sampled twice)" if sw.columns else "", sw.cost_model or "one rank"),
                       "chunks_per_rank": [int(len(p)) for p in sw.parts], "mesh_chunks_per_rank": [int(x) for x in D.allgather(n_mesh_mine)],
                       "numa": numa},
         "l2": "working set per step (sign words of the mesh chunks + per-word records + meshes, > 200 MB at N=1) exceeds the 126 MB L2; no explicit flush",
@@ -937,7 +941,7 @@ def extras_multi(D, ctxs, args, capi, world, stream):
         dd = capi.make_chunk_descs(dps, overlaps=overlap)
         mc = world.grid_mortons(n)
         dd["morton"] = mc
-        sw = SharedWorld(D, ctxs, dd, mc, dim, args.iters, "dense")
+        sw = SharedWorld(D, ctxs, dd, mc, dim, args.iters, "dense", columns=args.sampler.startswith("terrain2d"))
         t, _ = time_device(D, ctx, stream, lambda: ctx.submit(sw.descs, dim, iters=args.iters), 5, 3)
         s, last = time_e2e(D, sw, 5)
         rec = {"chunks": len(dd), "chunks_per_rank": [int(len(p)) for p in sw.parts], "device_ms_per_step": t / 5 * 1e3, "voxels_per_s": sw.vox * 5 / t,

@@ -112,8 +112,26 @@ def morton_key(code):
     return ((code ^ (1 << (3 * level))) << (3 * (MORTON_MAX_LEVEL - level)), level)
 
 
-def morton_order(mortons):
-    keys = [morton_key(c) for c in np.asarray(mortons, np.uint64).tolist()]
+def column_key(code):
+    """Sort key for heightfield worlds: the same digits, regrouped -- the (z, x) bits of all levels first (a 2-D Z-curve over the chunk
+    COLUMNS), the y bits after them.  A contiguous range of this order is a bundle of whole columns (plus at most one cut column at
+    each end), so the ranks of a 2-D noise terrain do not sample each other's noise sheets: with the octree's own order (z, y, x) the
+    second cut is along y and two ranks compute every sheet twice."""
+    code = int(code)
+    level = (code.bit_length() - 1) // 3
+    zx = yy = 0
+    for l in range(level - 1, -1, -1):
+        d = (code >> (3 * l)) & 7
+        zx = (zx << 2) | (((d >> 2) & 1) << 1) | (d & 1)
+        yy = (yy << 1) | ((d >> 1) & 1)
+    zx <<= 2 * (MORTON_MAX_LEVEL - level)
+    yy <<= MORTON_MAX_LEVEL - level
+    return ((zx << MORTON_MAX_LEVEL) | yy, level)
+
+
+def morton_order(mortons, columns=False):
+    kf = column_key if columns else morton_key
+    keys = [kf(c) for c in np.asarray(mortons, np.uint64).tolist()]
     return np.array(sorted(range(len(keys)), key=keys.__getitem__), np.int64)
 
 
@@ -130,10 +148,11 @@ def grid_mortons(n_per_axis):
     return code
 
 
-def partition(mortons, costs, n_parts):
+def partition(mortons, costs, n_parts, columns=False):
     """Multi-GPU sharding by octree node: sort leaves along the Z-curve (depth-normalised Morton key) and deal
-    contiguous, cost-balanced ranges.  Returns a list of index arrays (into the original order), one per part."""
-    order = morton_order(mortons)
+    contiguous, cost-balanced ranges.  Returns a list of index arrays (into the original order), one per part.
+    columns=True: the column-major variant of the curve (column_key) for heightfield samplers."""
+    order = morton_order(mortons, columns)
     c = np.asarray(costs, np.float64)[order]
     cum = np.cumsum(c)
     total = cum[-1] if len(cum) else 0.0

@@ -58,6 +58,32 @@ def test_partition_is_a_balanced_cover():
     assert W.partition(mc[:3], np.ones(3), 8)[0].size <= 1  # more parts than chunks: empty parts allowed
 
 
+def test_column_major_partition_keeps_chunk_columns_together():
+    """columns=True: ranges of the column-major curve are bundles of whole (x, z) columns -- at most one column is shared by two
+    neighbouring ranks -- while the octree's own order (z, y, x) cuts along y from four parts on; cover and balance as before"""
+    n = 16
+    mc = W.grid_mortons(n)
+    i = np.arange(n)
+    X, Y, Z = (a.ravel() for a in np.meshgrid(i, i, i, indexing="ij"))
+    col = X * n + Z
+    for parts_n in (2, 4, 8):
+        parts = W.partition(mc, np.ones(len(mc)), parts_n, columns=True)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(len(mc)))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1
+        owners = [set(col[p].tolist()) for p in parts]
+        assert sum(len(o) for o in owners) <= n * n + parts_n - 1  # every column on one rank, cut columns aside
+        plain = [set(col[p].tolist()) for p in W.partition(mc, np.ones(len(mc)), parts_n)]
+        if parts_n >= 4:
+            assert sum(len(o) for o in plain) >= 2 * n * n  # the plain Z-curve: every column sampled by two ranks
+    # mixed levels: still a cover, contiguous in the column-major key
+    ps, lv, mc2 = W.split_leaves(W.WorldProperties(max_level=5))
+    parts = W.partition(mc2, np.ones(len(mc2)), 4, columns=True)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(len(mc2)))
+    keys = [W.column_key(c) for c in mc2.tolist()]
+    assert [keys[i] for p in parts for i in p] == sorted(keys)
+
+
 def test_partition_balances_measured_costs():
     """cost-balanced ranges ("cost ~ measured surface count from the previous rebuild"): with the bench's model 37 + n_verts
     the heaviest part stays within one chunk's cost of the mean, and the cover / contiguity properties hold"""
