@@ -100,7 +100,7 @@ struct bmf_ctx
 	size_t uni_pinned_cap = 0;
 	bool uni_valid = false;
 	std::vector<ChunkGeom> sheet_geom_host;
-	std::vector<int> sheet_of_host;
+	std::vector<int> sheet_of_host, sheet_tab;
 	DevBuf<uint32_t> flags, bits, wcnt, wib, seg_tot, chunk_tot;
 	DevBuf<uint4> wv4; // per-word vertex record {first vertex id, ex, ey, ez}
 	DevBuf<uint2> vcells, icells; // compact surface-cell lists (sized after the scan: <= cells each)
@@ -956,21 +956,34 @@ int bmf_batch_submit(bmf_ctx* ctx, const bmf_chunk_desc* chunks, int n, const bm
 	if (is_terrain2d(kind))
 	{
 		// the noise sheet is a function of (overlap_pos.x, overlap_pos.z, delta) only: one sheet per unique triple
-		std::map<std::array<uint32_t, 3>, int> seen;
+		// (open-addressing table over the three 32-bit patterns; sheets are numbered in order of first appearance.  A std::map here was a fifth of a
+		// small batch's submit time on the host)
+		size_t cap = 64;
+		while (cap < 2 * (size_t)n) cap <<= 1;
+		ctx->sheet_tab.assign(cap, -1);
 		ctx->sheet_of_host.resize(n);
 		ctx->sheet_geom_host.clear();
 		for (int i = 0; i < n; i++)
 		{
 			const ChunkGeom& g = ctx->geom_host[i];
-			std::array<uint32_t, 3> key;
-			memcpy(&key[0], &g.ox, 4); memcpy(&key[1], &g.oz, 4); memcpy(&key[2], &g.delta, 4);
-			auto it = seen.find(key);
-			if (it == seen.end())
+			uint32_t k[3];
+			memcpy(&k[0], &g.ox, 4); memcpy(&k[1], &g.oz, 4); memcpy(&k[2], &g.delta, 4);
+			uint64_t h = (uint64_t)k[0] * 0x9E3779B97F4A7C15ull ^ (uint64_t)k[1] * 0xC2B2AE3D27D4EB4Full ^ (uint64_t)k[2] * 0x165667B19E3779F9ull;
+			size_t slot = (size_t)((h ^ (h >> 29)) & (cap - 1));
+			for (;;)
 			{
-				it = seen.emplace(key, (int)ctx->sheet_geom_host.size()).first;
-				ctx->sheet_geom_host.push_back(g);
+				const int s = ctx->sheet_tab[slot];
+				if (s < 0)
+				{
+					ctx->sheet_tab[slot] = (int)ctx->sheet_geom_host.size();
+					ctx->sheet_geom_host.push_back(g);
+					break;
+				}
+				const ChunkGeom& q = ctx->sheet_geom_host[s];
+				if (memcmp(&q.ox, &g.ox, 4) == 0 && memcmp(&q.oz, &g.oz, 4) == 0 && memcmp(&q.delta, &g.delta, 4) == 0) break;
+				slot = (slot + 1) & (cap - 1);
 			}
-			ctx->sheet_of_host[i] = it->second;
+			ctx->sheet_of_host[i] = ctx->sheet_tab[slot];
 		}
 		n_sheets = (int)ctx->sheet_geom_host.size();
 		BMF_CUDA(ctx->hmap.reserve((size_t)n_sheets * d * d));
